@@ -1,0 +1,133 @@
+/*
+ * include/mww.h -- C-ABI of libmww_b200.so: the drop-in boundary for microWakeWord's streaming
+ * inference hot path on B200 (sm_100a).
+ *
+ * The reference crosses into native code at three places, all un-vendored third-party libraries
+ * (SURVEY.md 2.1); each entry point below names the reference call site it replaces:
+ *
+ *   microwakeword/inference.py:36-39    tf.lite.Interpreter(model_path) + allocate_tensors()  -> mww_create
+ *   microwakeword/inference.py:41-45    get_input_details()/get_output_details()              -> mww_get_info
+ *   microwakeword/audio/audio_utils.py:52      MicroFrontend()   (fresh state)               -> mww_reset
+ *   microwakeword/audio/audio_utils.py:57-62   MicroFrontend.ProcessSamples(160 samples)     -> mww_features
+ *   microwakeword/audio/audio_utils.py:69-81   frontend_op.audio_microfrontend(...)          -> mww_features
+ *   microwakeword/inference.py:113-119  set_tensor / invoke / get_tensor, once per 30 ms      -> mww_infer_features
+ *   microwakeword/inference.py:66-80    predict_clip (features + predict_spectrogram)         -> mww_predict_clip[_host]
+ *
+ * Conventions
+ *   - plain C types only; every d_* pointer is DEVICE memory on the handle's GPU (for PyTorch
+ *     callers: tensor.data_ptr()), every h_* pointer is HOST memory.  The caller owns all I/O
+ *     buffers; the library owns weights, per-stream state and scratch.
+ *   - return 0 on success, a negative MWW_E* code on failure; mww_last_error() gives the message.
+ *   - calls are asynchronous on `cu_stream` (a cudaStream_t / CUstream passed as void*, NULL = the
+ *     legacy default stream) unless the name ends in _host.  One handle per GPU per host thread.
+ *   - a handle carries `n_streams` independent audio streams that advance IN LOCKSTEP: every
+ *     stateful call processes all of them with the same number of samples / rows.
+ *   - there is no CPU fallback: without a CUDA device mww_create fails with MWW_ECUDA.
+ */
+#ifndef MWW_H_
+#define MWW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MWW_OK 0
+#define MWW_EINVAL (-1)      /* bad argument */
+#define MWW_EMODEL (-2)      /* malformed / unsupported model container */
+#define MWW_ECUDA (-3)       /* CUDA runtime error (message has the cudaError string) */
+#define MWW_ENOMEM (-4)
+#define MWW_EUNSUPPORTED (-5)
+
+#define MWW_NUM_FEATURES 40
+#define MWW_HOP_SAMPLES 160      /* 10 ms */
+#define MWW_WINDOW_SAMPLES 480   /* 30 ms */
+
+/* feature-row element types accepted by mww_infer_features (inference.py:93-96,110) */
+#define MWW_ROWS_U16 0   /* raw frontend output; scaled by 0.0390625 on load (inference.py:94) */
+#define MWW_ROWS_F32 1   /* already-scaled float features */
+#define MWW_ROWS_I8 2    /* pre-quantised int8 rows for a quantised model (inference.py:110) */
+
+typedef struct mww_handle mww_t;
+
+typedef struct mww_info {
+    int32_t n_streams;             /* streams carried by the handle */
+    int32_t device;
+    int32_t is_quantized;          /* inference.py:44 */
+    int32_t input_feature_slices;  /* inference.py:45  (= first-conv stride, modes.py:62-63) */
+    int32_t num_features;          /* 40 */
+    float input_scale;             /* int8 models: quantisation of the input tensor (utils.py:308-313) */
+    int32_t input_zero_point;
+    float output_scale;            /* int8 models: 1/256 (TFLite LOGISTIC); the reference dequantises with /255 */
+    int32_t output_zero_point;
+    int32_t state_bytes_per_stream;
+    int32_t frontend_buffered;     /* samples currently held in the window carry (0..479) */
+    int32_t pending_rows;          /* feature rows waiting for a full stride */
+    int32_t sm_count;
+    int32_t macs_per_step;
+} mww_info;
+
+/* Parse an MWW model container (microwakeword_b200/model_file.py), upload the weights to `device`
+ * and allocate zeroed state for `n_streams` streams.  model_blob == NULL creates a frontend-only
+ * handle (mww_features works, the NN entry points return MWW_EINVAL).  On failure *out is NULL and
+ * mww_last_error(NULL) describes why. */
+int mww_create(const void *model_blob, size_t n_bytes, int device, int n_streams, mww_t **out);
+int mww_destroy(mww_t *h);
+const char *mww_last_error(const mww_t *h);
+int mww_get_info(const mww_t *h, mww_info *out);
+
+/* Fresh frontend + zero ring buffers.  ids == NULL (n ignored): all streams, and the lockstep
+ * counters (buffered samples, pending rows) return to 0 -- the exact analogue of a new
+ * MicroFrontend() / a freshly loaded interpreter.  ids != NULL: h_ids[0..n) streams get zeroed
+ * state but keep the shared counters (their history reads as silence). */
+int mww_reset(mww_t *h, const int32_t *h_ids, int n, void *cu_stream);
+
+/* Fresh frontend only (what a new MicroFrontend() per clip gives the reference, audio_utils.py:52):
+ * zero window buffer, zero noise estimates, buffered-sample counter 0.  NN rings are untouched --
+ * the reference never resets the interpreter between clips (inference.py:52-64, test.py:335-341). */
+int mww_reset_frontend(mww_t *h, void *cu_stream);
+
+/* Frontend only.  d_audio: int16 [n_streams][n_samples] with row pitch `audio_stride` samples.
+ * Appends the samples to every stream's window buffer and emits one uint16[40] row per completed
+ * 10 ms hop into d_feat [n_streams][max_rows][40].  *h_rows_out = rows emitted per stream
+ * ((buffered + n_samples - 480) / 160 + 1 when that is >= 1, else 0).  Does not touch the NN state. */
+int mww_features(mww_t *h, const int16_t *d_audio, int n_samples, long long audio_stride,
+                 uint16_t *d_feat, int max_rows, int *h_rows_out, void *cu_stream);
+
+/* NN only.  d_rows: [n_streams][n_rows][40] of `row_type`, stream pitch `rows_stride` rows.
+ * Rows are appended to the pending rows; every full `input_feature_slices` rows run one model step.
+ * d_probs [n_streams][max_probs] receives one probability per step (for a quantised model the
+ * uint8 output already divided by 255 as inference.py:162-170 does).  *h_probs_out = steps run. */
+int mww_infer_features(mww_t *h, const void *d_rows, int row_type, int n_rows, long long rows_stride,
+                       float *d_probs, int max_probs, int *h_probs_out, void *cu_stream);
+
+/* Frontend + NN on device buffers (scratch features stay inside the library). */
+int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long audio_stride,
+                     float *d_probs, int max_probs, int *h_probs_out, void *cu_stream);
+
+/* Same, from/to HOST buffers: the library tiles the streams, overlaps the host->device copy of one
+ * tile with the kernels of the previous one, and returns when h_probs is complete.  Pinned host
+ * memory gives full-rate copies; pageable memory works too. */
+int mww_predict_clip_host(mww_t *h, const int16_t *h_audio, int n_samples, long long audio_stride,
+                          float *h_probs, int max_probs, int *h_probs_out);
+
+/* Per-stream state snapshot for checkpoint / tests (host buffers, synchronous).
+ *   h_carry    int16 [n_streams][480]   window buffer (first `frontend_buffered` samples valid)
+ *   h_estimate uint32 [n_streams][40]   noise estimates
+ *   h_nn       float [n_streams][4176] (fp32 model) or int8 [n_streams][4176] (quantised): ring buffers,
+ *              layer order first-conv, block 0..3, head; each [row][channel], oldest row first
+ *   h_pending  float/int8 [n_streams][2][40]
+ * NULL pointers are skipped. */
+int mww_get_state(mww_t *h, int16_t *h_carry, uint32_t *h_estimate, void *h_nn, void *h_pending);
+int mww_set_state(mww_t *h, const int16_t *h_carry, int frontend_buffered, const uint32_t *h_estimate,
+                  const void *h_nn, const void *h_pending, int pending_rows);
+
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+long long mww_launch_count(const mww_t *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MWW_H_ */

@@ -1,0 +1,67 @@
+"""Drop-in for the hot-path part of ``microwakeword.audio.audio_utils``
+(reference: microwakeword/audio/audio_utils.py:28-84).  ``save_clip`` / ``remove_silence_webrtc``
+(:87-140) are training-data preparation and out of scope."""
+
+from __future__ import annotations
+
+import numpy as np
+
+from ..model_file import FEATURE_SCALE
+
+_engine = None
+
+
+def to_int16(audio_samples: np.ndarray) -> np.ndarray:
+    """audio_utils.py:47-48: float clips are scaled by 32768 and clipped; int16 passes through."""
+    if audio_samples.dtype in (np.float32, np.float64):
+        return np.clip((audio_samples * 32768), -32768, 32767).astype(np.int16)
+    if audio_samples.dtype != np.int16:
+        raise ValueError("audio must be int16 PCM or float in [-1, 1]")
+    return audio_samples
+
+
+def clip_samples_fed(n_samples: int) -> int:
+    """Samples the reference's chunk loop hands to the frontend: 160-sample chunks while
+    ``audio_idx + 320 < num_audio_bytes`` (strict '<', audio_utils.py:56) -- the last exact chunk is skipped."""
+    n_bytes = 2 * n_samples
+    if n_bytes <= 320:
+        return 0
+    chunks = (n_bytes - 320 - 1) // 320 + 1
+    return min(160 * chunks, n_samples)
+
+
+def _frontend_engine(device: int = 0):
+    global _engine
+    if _engine is None or _engine.device != device:
+        from ..engine import StreamEngine
+        _engine = StreamEngine(None, n_streams=1, device=device)
+    return _engine
+
+
+def generate_features_for_clip(audio_samples: np.ndarray, step_ms: int = 20, use_c: bool = True, device: int = 0):
+    """Generates spectrogram features for the given audio data on the GPU.
+
+    use_c=True  (default): pymicro_features semantics -- fresh frontend, 10 ms hop regardless of
+                ``step_ms`` (the reference ignores it on this path), strict-'<' chunk loop; returns
+                float32 [T, 40] = uint16 features * 0.0390625.
+    use_c=False: TensorFlow audio_microfrontend op semantics (audio_utils.py:69-81) -- every full window
+                of the clip, returns uint16 [T, 40]; only window_step = 10 ms is available here.
+    """
+    import torch
+
+    audio = to_int16(np.asarray(audio_samples)).reshape(-1)
+    eng = _frontend_engine(device)
+    eng.reset_frontend()
+    if use_c:
+        fed = clip_samples_fed(audio.size)
+    else:
+        if step_ms != 10:
+            raise ValueError("the B200 frontend implements the 10 ms hop all shipped models use (SURVEY.md Appendix D.2)")
+        fed = audio.size
+    if fed == 0:
+        return np.zeros((0, 40), np.float32 if use_c else np.uint16)
+    dev = torch.from_numpy(np.ascontiguousarray(audio[:fed])).to(eng._dev()).unsqueeze(0)
+    feat = eng.features(dev)[0].view(torch.int16).cpu().numpy().view(np.uint16)
+    if use_c:
+        return feat.astype(np.float32) * np.float32(FEATURE_SCALE)
+    return feat

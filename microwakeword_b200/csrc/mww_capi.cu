@@ -1,0 +1,581 @@
+// mww_capi.cu -- the extern "C" boundary declared in include/mww.h.
+//
+// Host-side orchestration only: model-container parsing, weight/table upload, per-stream state,
+// stream tiling against a scratch budget, and the pipelined host-buffer path.  All arithmetic is
+// in the kernels (mww_frontend.cu, mww_nn.cu, mww_nn_int8.cu); there is no CPU fallback.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/mww.h"
+#include "mww_kernels.h"
+
+using namespace mww;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DirEntry { char name[48]; uint32_t dtype, ndim, shape[4]; uint64_t offset, nbytes; };
+static_assert(sizeof(DirEntry) == 88, "container directory entry layout");
+
+struct Tensor { const uint8_t *data = nullptr; uint32_t dtype = 0, ndim = 0, shape[4] = {0, 0, 0, 0}; uint64_t nbytes = 0; };
+
+bool find_tensor(const uint8_t *blob, size_t n, const char *name, Tensor *out) {
+    if (n < 24 || memcmp(blob, "MWWB200", 8) != 0) return false;
+    uint32_t hdr[4];
+    memcpy(hdr, blob + 8, 16);
+    if (hdr[0] != 1) return false;
+    const uint32_t count = hdr[1], dir_off = hdr[2];
+    for (uint32_t i = 0; i < count; ++i) {
+        if ((size_t)dir_off + (size_t)(i + 1) * sizeof(DirEntry) > n) return false;
+        DirEntry e;
+        memcpy(&e, blob + dir_off + (size_t)i * sizeof e, sizeof e);
+        if (strncmp(e.name, name, 48) == 0) {
+            if (e.offset > n || e.nbytes > n - e.offset) return false;
+            out->data = blob + e.offset; out->dtype = e.dtype; out->ndim = e.ndim; out->nbytes = e.nbytes;
+            memcpy(out->shape, e.shape, sizeof e.shape);
+            return true;
+        }
+    }
+    return false;
+}
+
+const int32_t kOkayNabuArch[30] = {32, 5, 3, 40, 4, 17, 64, 1, 5, 0, 0, 0, 64, 2, 7, 11, 0, 0, 64, 2, 9, 15, 0, 0, 64, 1, 23, 0, 0, 0};
+
+}  // namespace
+
+struct mww_handle {
+    int device = 0, n_streams = 0, sm_count = 148;
+    bool quantized = false;
+    bool has_nn = true;
+    std::string err;
+    // constant tables
+    uint8_t *d_tables = nullptr;
+    FrontendParams P;
+    int fb_coef_len = 0;
+    // weights
+    uint8_t *d_weights = nullptr;
+    NnWeightsF32 W;
+    NnWeightsI8 Wq;
+    float in_scale = 0.f, out_scale = 0.f;
+    int in_zp = 0, out_zp = 0;
+    // per-stream state
+    int16_t *d_carry = nullptr;
+    uint32_t *d_estimate = nullptr;
+    void *d_nn_state = nullptr;     // float or int8 [S][4176]
+    void *d_pend = nullptr;         // float or int8 [S][2][40]
+    int used = 0, n_pend = 0;
+    // scratch
+    uint32_t *d_v = nullptr; size_t v_bytes = 0;
+    uint16_t *d_feat = nullptr; size_t feat_bytes = 0;
+    size_t scratch_budget = (size_t)2048 << 20;
+    // host-buffer pipeline
+    cudaStream_t st_h2d = nullptr, st_compute = nullptr, st_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    int16_t *d_audio_tile[2] = {nullptr, nullptr}; size_t audio_tile_bytes = 0;
+    float *d_probs_tile[2] = {nullptr, nullptr}; size_t probs_tile_bytes = 0;
+    long long launches = 0;
+};
+
+namespace {
+
+int fail(mww_t *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(mww_t *h, cudaError_t e, const char *what) {
+    return fail(h, MWW_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(h, e_, #call); } while (0)
+
+size_t elem_size(const mww_t *h) { return h->quantized ? 1 : 4; }
+
+int ensure_scratch(mww_t *h, size_t v_bytes, size_t feat_bytes) {
+    if (v_bytes > h->v_bytes) {
+        if (h->d_v) cudaFree(h->d_v);
+        h->d_v = nullptr; h->v_bytes = 0;
+        CU(h, cudaMalloc(&h->d_v, v_bytes));
+        h->v_bytes = v_bytes;
+    }
+    if (feat_bytes > h->feat_bytes) {
+        if (h->d_feat) cudaFree(h->d_feat);
+        h->d_feat = nullptr; h->feat_bytes = 0;
+        CU(h, cudaMalloc(&h->d_feat, feat_bytes));
+        h->feat_bytes = feat_bytes;
+    }
+    return MWW_OK;
+}
+
+int frames_for(int used, int n_samples) {
+    const long long total = (long long)used + n_samples;
+    return total >= kWindow ? (int)((total - kWindow) / kHop + 1) : 0;
+}
+
+// streams per tile so that the K1->K2 scratch (and optional feature scratch) fits the budget
+int tile_streams(const mww_t *h, int n_frames, bool need_feat) {
+    const size_t per_stream = (size_t)std::max(n_frames, 1) * kNumChannels * (4 + (need_feat ? 2 : 0));
+    size_t t = h->scratch_budget / per_stream;
+    if (t < 1) t = 1;
+    if (t > (size_t)h->n_streams) t = (size_t)h->n_streams;
+    return (int)t;
+}
+
+// frontend for streams [first, first+n): audio tile pointer is already offset to the tile's first stream
+int run_frontend_tile(mww_t *h, int first, int n, const int16_t *d_audio, long long audio_stride, int n_samples,
+                      int n_frames, uint16_t *d_feat, long long feat_stream_stride, cudaStream_t st) {
+    if (n_frames <= 0) return MWW_OK;
+    CU(h, launch_k1(h->P, h->fb_coef_len, h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n,
+                    n_frames, h->d_v, h->sm_count, st));
+    CU(h, launch_k2(h->P, h->d_v, n, n_frames, h->d_estimate + (size_t)first * kNumChannels, d_feat, feat_stream_stride, st));
+    h->launches += 2;
+    return MWW_OK;
+}
+
+int run_carry_tile(mww_t *h, int first, int n, const int16_t *d_audio, long long audio_stride, int n_samples, int n_frames,
+                   cudaStream_t st) {
+    const int consumed = n_frames * kHop;
+    const int new_used = h->used + n_samples - consumed;
+    CU(h, launch_carry_update(h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n, consumed, new_used, st));
+    h->launches += 1;
+    return MWW_OK;
+}
+
+int run_nn_tile(mww_t *h, int first, int n, const void *d_rows, int row_type, long long rows_stream_stride_rows, int n_rows,
+                float *d_probs, long long probs_stride, cudaStream_t st) {
+    if (h->quantized) {
+        if (row_type == MWW_ROWS_F32 || row_type == MWW_ROWS_U16 || row_type == MWW_ROWS_I8) {
+            const size_t rb = row_type == MWW_ROWS_F32 ? 4 : (row_type == MWW_ROWS_U16 ? 2 : 1);
+            CU(h, launch_nn_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state) + (size_t)first * kStateFloats,
+                               static_cast<int8_t *>(h->d_pend) + (size_t)first * 2 * kNumChannels, h->n_pend, d_rows,
+                               rows_stream_stride_rows * kNumChannels * (long long)rb, n_rows, row_type, d_probs, probs_stride, n, st));
+            h->launches += 1;
+            return MWW_OK;
+        }
+        return fail(h, MWW_EINVAL, "unknown row_type");
+    }
+    if (row_type == MWW_ROWS_I8) return fail(h, MWW_EINVAL, "int8 rows need a quantised model (inference.py:110)");
+    const size_t rb = row_type == MWW_ROWS_F32 ? 4 : 2;
+    CU(h, launch_nn_f32(h->W, static_cast<float *>(h->d_nn_state) + (size_t)first * kStateFloats,
+                        static_cast<float *>(h->d_pend) + (size_t)first * 2 * kNumChannels, h->n_pend, d_rows,
+                        rows_stream_stride_rows * kNumChannels * (long long)rb, n_rows, row_type == MWW_ROWS_F32, d_probs, probs_stride,
+                        nullptr, n, st));
+    h->launches += 1;
+    return MWW_OK;
+}
+
+template <typename T>
+bool upload(uint8_t *base, size_t &cursor, const void *src, size_t bytes, const T **dev_out, cudaError_t *err) {
+    cursor = (cursor + 255) / 256 * 256;
+    *err = cudaMemcpy(base + cursor, src, bytes, cudaMemcpyHostToDevice);
+    *dev_out = reinterpret_cast<const T *>(base + cursor);
+    cursor += bytes;
+    return *err == cudaSuccess;
+}
+
+int upload_tables(mww_t *h) {
+    HostTables t;
+    build_host_tables(&t);
+    if (!t.ok || t.fb_coef.size() > (size_t)kFbCoefMax) return fail(h, MWW_EINVAL, "frontend table construction failed");
+    h->fb_coef_len = (int)t.fb_coef.size();
+    const size_t total = 64 * 1024;
+    CU(h, cudaMalloc(&h->d_tables, total));
+    size_t cur = 0;
+    cudaError_t e;
+    bool ok = upload(h->d_tables, cur, t.win_pairs, sizeof t.win_pairs, &h->P.win_pairs, &e) &&
+              upload(h->d_tables, cur, t.tw, sizeof t.tw, &h->P.tw, &e) &&
+              upload(h->d_tables, cur, t.super_tw, sizeof t.super_tw, &h->P.super_tw, &e) &&
+              upload(h->d_tables, cur, t.fb_coef.data(), t.fb_coef.size() * sizeof(int16_t), &h->P.fb_coef, &e) &&
+              upload(h->d_tables, cur, &t.fb_slots[0][0], sizeof t.fb_slots, &h->P.fb_slots, &e) &&
+              upload(h->d_tables, cur, t.gain_lut, sizeof t.gain_lut, &h->P.gain_lut, &e) &&
+              upload(h->d_tables, cur, t.log_lut, sizeof t.log_lut, &h->P.log_lut, &e);
+    if (!ok) return cuda_fail(h, e, "table upload");
+    memcpy(h->P.tw2, t.tw2, sizeof h->P.tw2);
+    memcpy(h->P.fb_slot_len, t.fb_slot_len, sizeof h->P.fb_slot_len);
+    return MWW_OK;
+}
+
+struct Need { const char *name; uint32_t dtype; size_t count; };
+
+int upload_weights(mww_t *h, const uint8_t *blob, size_t n) {
+    Tensor arch;
+    if (!find_tensor(blob, n, "arch", &arch) || arch.dtype != 2) return fail(h, MWW_EMODEL, "model container: missing 'arch' tensor or bad magic/version");
+    if (arch.nbytes != sizeof kOkayNabuArch || memcmp(arch.data, kOkayNabuArch, sizeof kOkayNabuArch) != 0)
+        return fail(h, MWW_EUNSUPPORTED,
+                    "this build is compiled for the okay_nabu MixedNet (first conv 32x5 stride 3; MixConv [5],[7,11],[9,15],[23]; "
+                    "pointwise 64x4; 17-row head); the container describes another architecture");
+    Tensor probe;
+    h->quantized = find_tensor(blob, n, "q/scales", &probe);
+    const size_t total = 1 << 20;
+    CU(h, cudaMalloc(&h->d_weights, total));
+    size_t cur = 0;
+    cudaError_t e = cudaSuccess;
+    char name[64];
+    auto get = [&](const char *nm, uint32_t dtype, size_t count, const void **dev) -> int {
+        Tensor t;
+        static const size_t esz[6] = {4, 1, 4, 1, 2, 2};
+        if (!find_tensor(blob, n, nm, &t)) return fail(h, MWW_EMODEL, std::string("model container: missing tensor ") + nm);
+        if (t.dtype != dtype || t.nbytes != count * esz[dtype]) return fail(h, MWW_EMODEL, std::string("model container: wrong dtype/size for ") + nm);
+        if (!upload(h->d_weights, cur, t.data, (size_t)t.nbytes, reinterpret_cast<const uint8_t **>(dev), &e)) return cuda_fail(h, e, "weight upload");
+        return MWW_OK;
+    };
+    static const int cin[4] = {32, 64, 64, 64}, kmax[4] = {5, 11, 15, 23};
+    int rc;
+    if (!h->quantized) {
+        if ((rc = get("first_conv/w", 0, 5 * 40 * 32, (const void **)&h->W.w0))) return rc;
+        for (int i = 0; i < 4; ++i) {
+            snprintf(name, sizeof name, "b%d/dw/w", i); if ((rc = get(name, 0, (size_t)kmax[i] * cin[i], (const void **)&h->W.dw_w[i]))) return rc;
+            snprintf(name, sizeof name, "b%d/dw/b", i); if ((rc = get(name, 0, cin[i], (const void **)&h->W.dw_b[i]))) return rc;
+            snprintf(name, sizeof name, "b%d/pw/w", i); if ((rc = get(name, 0, (size_t)cin[i] * 64, (const void **)&h->W.pw_w[i]))) return rc;
+            snprintf(name, sizeof name, "b%d/pw/b", i); if ((rc = get(name, 0, 64, (const void **)&h->W.pw_b[i]))) return rc;
+        }
+        if ((rc = get("head/w", 0, 17 * 64, (const void **)&h->W.head_w))) return rc;
+        if ((rc = get("head/b", 0, 1, (const void **)&h->W.head_b))) return rc;
+    } else {
+        NnWeightsI8 &Q = h->Wq;
+        if ((rc = get("q/first_conv/w", 1, 5 * 40 * 32, (const void **)&Q.w0))) return rc;
+        if ((rc = get("q/first_conv/bias", 2, 32, (const void **)&Q.b0))) return rc;
+        if ((rc = get("q/first_conv/mult", 2, 32, (const void **)&Q.m0))) return rc;
+        if ((rc = get("q/first_conv/shift", 2, 32, (const void **)&Q.s0))) return rc;
+        for (int i = 0; i < 4; ++i) {
+            snprintf(name, sizeof name, "q/b%d/dw/w", i); if ((rc = get(name, 1, (size_t)kmax[i] * cin[i], (const void **)&Q.dw_w[i]))) return rc;
+            snprintf(name, sizeof name, "q/b%d/dw/bias", i); if ((rc = get(name, 2, cin[i], (const void **)&Q.dw_b[i]))) return rc;
+            snprintf(name, sizeof name, "q/b%d/dw/mult", i); if ((rc = get(name, 2, cin[i], (const void **)&Q.dw_m[i]))) return rc;
+            snprintf(name, sizeof name, "q/b%d/dw/shift", i); if ((rc = get(name, 2, cin[i], (const void **)&Q.dw_s[i]))) return rc;
+            snprintf(name, sizeof name, "q/b%d/pw/w", i); if ((rc = get(name, 1, (size_t)cin[i] * 64, (const void **)&Q.pw_w[i]))) return rc;
+            snprintf(name, sizeof name, "q/b%d/pw/bias", i); if ((rc = get(name, 2, 64, (const void **)&Q.pw_b[i]))) return rc;
+            snprintf(name, sizeof name, "q/b%d/pw/mult", i); if ((rc = get(name, 2, 64, (const void **)&Q.pw_m[i]))) return rc;
+            snprintf(name, sizeof name, "q/b%d/pw/shift", i); if ((rc = get(name, 2, 64, (const void **)&Q.pw_s[i]))) return rc;
+        }
+        if ((rc = get("q/head/w", 1, 17 * 64, (const void **)&Q.head_w))) return rc;
+        if ((rc = get("q/logistic_lut", 1, 256, (const void **)&Q.lut))) return rc;
+        Tensor t;
+        if (!find_tensor(blob, n, "q/head/bias", &t) || t.nbytes != 4) return fail(h, MWW_EMODEL, "model container: q/head/bias");
+        memcpy(&Q.head_bias, t.data, 4);
+        if (!find_tensor(blob, n, "q/head/mult", &t) || t.nbytes != 4) return fail(h, MWW_EMODEL, "model container: q/head/mult");
+        memcpy(&Q.head_mult, t.data, 4);
+        if (!find_tensor(blob, n, "q/head/shift", &t) || t.nbytes != 4) return fail(h, MWW_EMODEL, "model container: q/head/shift");
+        memcpy(&Q.head_shift, t.data, 4);
+        Tensor sc, zp;
+        if (!find_tensor(blob, n, "q/scales", &sc) || sc.nbytes != 12 * 4 || !find_tensor(blob, n, "q/zps", &zp) || zp.nbytes != 12 * 4)
+            return fail(h, MWW_EMODEL, "model container: q/scales / q/zps must hold 12 entries");
+        float scales[12];
+        memcpy(scales, sc.data, sizeof scales);
+        memcpy(Q.zp, zp.data, sizeof Q.zp);
+        Q.in_scale = scales[0];
+        h->in_scale = scales[0]; h->in_zp = Q.zp[0];
+        h->out_scale = scales[11]; h->out_zp = 0;   // uint8 output tensor: zero point -128 + 128 (utils.py:338)
+    }
+    return MWW_OK;
+}
+
+int zero_state(mww_t *h, cudaStream_t st) {
+    const size_t S = (size_t)h->n_streams;
+    CU(h, cudaMemsetAsync(h->d_carry, 0, S * kWindow * sizeof(int16_t), st));
+    CU(h, cudaMemsetAsync(h->d_estimate, 0, S * kNumChannels * sizeof(uint32_t), st));
+    h->used = 0;
+    h->n_pend = 0;
+    if (!h->has_nn) return MWW_OK;
+    if (h->quantized) {
+        CU(h, launch_fill_state_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state), static_cast<int8_t *>(h->d_pend), nullptr, h->n_streams, st));
+        h->launches += 1;
+    } else {
+        CU(h, cudaMemsetAsync(h->d_nn_state, 0, S * kStateFloats * 4, st));
+        CU(h, cudaMemsetAsync(h->d_pend, 0, S * 2 * kNumChannels * 4, st));
+    }
+    h->used = 0;
+    h->n_pend = 0;
+    return MWW_OK;
+}
+
+void destroy_impl(mww_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_tables); cudaFree(h->d_weights); cudaFree(h->d_carry); cudaFree(h->d_estimate);
+    cudaFree(h->d_nn_state); cudaFree(h->d_pend); cudaFree(h->d_v); cudaFree(h->d_feat);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(h->d_audio_tile[b]); cudaFree(h->d_probs_tile[b]);
+        if (h->ev_h2d[b]) cudaEventDestroy(h->ev_h2d[b]);
+        if (h->ev_compute[b]) cudaEventDestroy(h->ev_compute[b]);
+        if (h->ev_d2h[b]) cudaEventDestroy(h->ev_d2h[b]);
+    }
+    if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
+    if (h->st_compute) cudaStreamDestroy(h->st_compute);
+    if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
+    delete h;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mww_create(const void *model_blob, size_t n_bytes, int device, int n_streams, mww_t **out) {
+    if (out) *out = nullptr;
+    if (!out || n_streams < 1) return fail(nullptr, MWW_EINVAL, "mww_create: bad arguments");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, MWW_ECUDA, std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, MWW_EINVAL, "mww_create: device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    mww_t *h = new mww_handle();
+    h->device = device;
+    h->n_streams = n_streams;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char *mb = getenv("MWW_SCRATCH_MB")) { const long v = atol(mb); if (v > 0) h->scratch_budget = (size_t)v << 20; }
+    h->has_nn = model_blob != nullptr;
+    int rc = upload_tables(h);
+    if (rc == MWW_OK && h->has_nn) rc = upload_weights(h, static_cast<const uint8_t *>(model_blob), n_bytes);
+    if (rc == MWW_OK) {
+        const size_t S = (size_t)n_streams;
+        cudaError_t a = cudaMalloc(&h->d_carry, S * kWindow * sizeof(int16_t));
+        if (a == cudaSuccess) a = cudaMalloc(&h->d_estimate, S * kNumChannels * sizeof(uint32_t));
+        if (a == cudaSuccess && h->has_nn) a = cudaMalloc(&h->d_nn_state, S * kStateFloats * elem_size(h));
+        if (a == cudaSuccess && h->has_nn) a = cudaMalloc(&h->d_pend, S * 2 * kNumChannels * elem_size(h));
+        if (a != cudaSuccess) rc = fail(h, a == cudaErrorMemoryAllocation ? MWW_ENOMEM : MWW_ECUDA, std::string("state allocation: ") + cudaGetErrorString(a));
+    }
+    if (rc == MWW_OK) rc = zero_state(h, nullptr);
+    if (rc == MWW_OK) { cudaError_t s = cudaDeviceSynchronize(); if (s != cudaSuccess) rc = cuda_fail(h, s, "cudaDeviceSynchronize"); }
+    if (rc != MWW_OK) { g_create_error = h->err; destroy_impl(h); return rc; }
+    *out = h;
+    return MWW_OK;
+}
+
+int mww_destroy(mww_t *h) { destroy_impl(h); return MWW_OK; }
+
+const char *mww_last_error(const mww_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+long long mww_launch_count(const mww_t *h) { return h ? h->launches : 0; }
+
+int mww_get_info(const mww_t *h, mww_info *o) {
+    if (!h || !o) return MWW_EINVAL;
+    memset(o, 0, sizeof *o);
+    o->n_streams = h->n_streams; o->device = h->device; o->is_quantized = h->quantized;
+    o->input_feature_slices = 3; o->num_features = kNumChannels;
+    o->input_scale = h->in_scale; o->input_zero_point = h->in_zp;
+    o->output_scale = h->out_scale; o->output_zero_point = h->out_zp;
+    o->state_bytes_per_stream = (int)(kStateFloats * elem_size(h));
+    o->frontend_buffered = h->used; o->pending_rows = h->n_pend;
+    o->sm_count = h->sm_count; o->macs_per_step = 24800;
+    return MWW_OK;
+}
+
+int mww_reset(mww_t *h, const int32_t *h_ids, int n, void *cu_stream) {
+    if (!h) return MWW_EINVAL;
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cu_stream);
+    if (!h_ids) return zero_state(h, st);
+    for (int i = 0; i < n; ++i) {
+        const int id = h_ids[i];
+        if (id < 0 || id >= h->n_streams) return fail(h, MWW_EINVAL, "mww_reset: stream id out of range");
+        CU(h, cudaMemsetAsync(h->d_carry + (size_t)id * kWindow, 0, kWindow * sizeof(int16_t), st));
+        CU(h, cudaMemsetAsync(h->d_estimate + (size_t)id * kNumChannels, 0, kNumChannels * sizeof(uint32_t), st));
+        if (!h->has_nn) continue;
+        if (h->quantized) {
+            CU(h, launch_fill_state_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state) + (size_t)id * kStateFloats,
+                                       static_cast<int8_t *>(h->d_pend) + (size_t)id * 2 * kNumChannels, nullptr, 1, st));
+            h->launches += 1;
+        } else {
+            CU(h, cudaMemsetAsync(static_cast<float *>(h->d_nn_state) + (size_t)id * kStateFloats, 0, kStateFloats * 4, st));
+            CU(h, cudaMemsetAsync(static_cast<float *>(h->d_pend) + (size_t)id * 2 * kNumChannels, 0, 2 * kNumChannels * 4, st));
+        }
+    }
+    return MWW_OK;
+}
+
+int mww_reset_frontend(mww_t *h, void *cu_stream) {
+    if (!h) return MWW_EINVAL;
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cu_stream);
+    const size_t S = (size_t)h->n_streams;
+    CU(h, cudaMemsetAsync(h->d_carry, 0, S * kWindow * sizeof(int16_t), st));
+    CU(h, cudaMemsetAsync(h->d_estimate, 0, S * kNumChannels * sizeof(uint32_t), st));
+    h->used = 0;
+    return MWW_OK;
+}
+
+int mww_features(mww_t *h, const int16_t *d_audio, int n_samples, long long audio_stride, uint16_t *d_feat, int max_rows,
+                 int *h_rows_out, void *cu_stream) {
+    if (!h) return MWW_EINVAL;
+    if (n_samples < 0 || (n_samples > 0 && !d_audio) || audio_stride < n_samples) return fail(h, MWW_EINVAL, "mww_features: bad audio arguments");
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cu_stream);
+    const int n_frames = frames_for(h->used, n_samples);
+    if (n_frames > max_rows || (n_frames > 0 && !d_feat)) return fail(h, MWW_EINVAL, "mww_features: feature buffer too small for the rows this call emits");
+    const int tile = tile_streams(h, n_frames, false);
+    int rc = ensure_scratch(h, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4, 0);
+    if (rc) return rc;
+    for (int first = 0; first < h->n_streams; first += tile) {
+        const int n = std::min(tile, h->n_streams - first);
+        rc = run_frontend_tile(h, first, n, d_audio + (size_t)first * audio_stride, audio_stride, n_samples, n_frames,
+                               d_feat + (size_t)first * max_rows * kNumChannels, (long long)max_rows * kNumChannels, st);
+        if (rc) return rc;
+    }
+    if (n_samples > 0) {
+        rc = run_carry_tile(h, 0, h->n_streams, d_audio, audio_stride, n_samples, n_frames, st);
+        if (rc) return rc;
+    }
+    h->used = h->used + n_samples - n_frames * kHop;
+    if (h_rows_out) *h_rows_out = n_frames;
+    return MWW_OK;
+}
+
+int mww_infer_features(mww_t *h, const void *d_rows, int row_type, int n_rows, long long rows_stride, float *d_probs,
+                       int max_probs, int *h_probs_out, void *cu_stream) {
+    if (!h) return MWW_EINVAL;
+    if (n_rows < 0 || (n_rows > 0 && !d_rows) || rows_stride < n_rows) return fail(h, MWW_EINVAL, "mww_infer_features: bad row arguments");
+    if (row_type < 0 || row_type > 2) return fail(h, MWW_EINVAL, "mww_infer_features: unknown row_type");
+    if (!h->has_nn) return fail(h, MWW_EINVAL, "mww_infer_features: frontend-only handle (created without a model)");
+    CU(h, cudaSetDevice(h->device));
+    const int n_steps = (h->n_pend + n_rows) / 3;
+    if (n_steps > max_probs || (n_steps > 0 && !d_probs)) return fail(h, MWW_EINVAL, "mww_infer_features: probability buffer too small");
+    int rc = run_nn_tile(h, 0, h->n_streams, d_rows, row_type, rows_stride, n_rows, d_probs, max_probs, static_cast<cudaStream_t>(cu_stream));
+    if (rc) return rc;
+    h->n_pend = (h->n_pend + n_rows) % 3;
+    if (h_probs_out) *h_probs_out = n_steps;
+    return MWW_OK;
+}
+
+int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long audio_stride, float *d_probs, int max_probs,
+                     int *h_probs_out, void *cu_stream) {
+    if (!h) return MWW_EINVAL;
+    if (n_samples < 0 || (n_samples > 0 && !d_audio) || audio_stride < n_samples) return fail(h, MWW_EINVAL, "mww_predict_clip: bad audio arguments");
+    if (!h->has_nn) return fail(h, MWW_EINVAL, "mww_predict_clip: frontend-only handle (created without a model)");
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cu_stream);
+    const int n_frames = frames_for(h->used, n_samples);
+    const int n_steps = (h->n_pend + n_frames) / 3;
+    if (n_steps > max_probs || (n_steps > 0 && !d_probs)) return fail(h, MWW_EINVAL, "mww_predict_clip: probability buffer too small");
+    const int tile = tile_streams(h, n_frames, true);
+    int rc = ensure_scratch(h, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 2);
+    if (rc) return rc;
+    for (int first = 0; first < h->n_streams; first += tile) {
+        const int n = std::min(tile, h->n_streams - first);
+        rc = run_frontend_tile(h, first, n, d_audio + (size_t)first * audio_stride, audio_stride, n_samples, n_frames, h->d_feat,
+                               (long long)n_frames * kNumChannels, st);
+        if (rc) return rc;
+        rc = run_nn_tile(h, first, n, h->d_feat, MWW_ROWS_U16, n_frames, n_frames, d_probs + (size_t)first * max_probs, max_probs, st);
+        if (rc) return rc;
+    }
+    if (n_samples > 0) {
+        rc = run_carry_tile(h, 0, h->n_streams, d_audio, audio_stride, n_samples, n_frames, st);
+        if (rc) return rc;
+    }
+    h->used = h->used + n_samples - n_frames * kHop;
+    h->n_pend = (h->n_pend + n_frames) % 3;
+    if (h_probs_out) *h_probs_out = n_steps;
+    return MWW_OK;
+}
+
+int mww_predict_clip_host(mww_t *h, const int16_t *h_audio, int n_samples, long long audio_stride, float *h_probs, int max_probs,
+                          int *h_probs_out) {
+    if (!h) return MWW_EINVAL;
+    if (n_samples < 0 || (n_samples > 0 && !h_audio) || audio_stride < n_samples) return fail(h, MWW_EINVAL, "mww_predict_clip_host: bad audio arguments");
+    if (!h->has_nn) return fail(h, MWW_EINVAL, "mww_predict_clip_host: frontend-only handle (created without a model)");
+    CU(h, cudaSetDevice(h->device));
+    const int n_frames = frames_for(h->used, n_samples);
+    const int n_steps = (h->n_pend + n_frames) / 3;
+    if (n_steps > max_probs || (n_steps > 0 && !h_probs)) return fail(h, MWW_EINVAL, "mww_predict_clip_host: probability buffer too small");
+    if (!h->st_compute) {
+        CU(h, cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
+        CU(h, cudaStreamCreateWithFlags(&h->st_compute, cudaStreamNonBlocking));
+        CU(h, cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CU(h, cudaEventCreateWithFlags(&h->ev_h2d[b], cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&h->ev_compute[b], cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming));
+        }
+    }
+    // tile so that copies and kernels of neighbouring tiles overlap: at least 8 tiles when there are enough streams
+    int tile = tile_streams(h, n_frames, true);
+    tile = std::max(1, std::min(tile, (h->n_streams + 7) / 8));
+    int rc = ensure_scratch(h, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 2);
+    if (rc) return rc;
+    const size_t a_bytes = (size_t)tile * std::max(n_samples, 1) * sizeof(int16_t);
+    const size_t p_bytes = (size_t)tile * std::max(n_steps, 1) * sizeof(float);
+    if (a_bytes > h->audio_tile_bytes || p_bytes > h->probs_tile_bytes) {
+        CU(h, cudaDeviceSynchronize());
+        for (int b = 0; b < 2; ++b) {
+            cudaFree(h->d_audio_tile[b]); cudaFree(h->d_probs_tile[b]);
+            h->d_audio_tile[b] = nullptr; h->d_probs_tile[b] = nullptr;
+        }
+        h->audio_tile_bytes = h->probs_tile_bytes = 0;
+        for (int b = 0; b < 2; ++b) {
+            CU(h, cudaMalloc(&h->d_audio_tile[b], a_bytes));
+            CU(h, cudaMalloc(&h->d_probs_tile[b], p_bytes));
+        }
+        h->audio_tile_bytes = a_bytes; h->probs_tile_bytes = p_bytes;
+    }
+    int it = 0;
+    for (int first = 0; first < h->n_streams; first += tile, ++it) {
+        const int n = std::min(tile, h->n_streams - first);
+        const int b = it & 1;
+        // the audio buffer is free once the kernels of the tile that used it two iterations ago are done
+        if (it >= 2) CU(h, cudaStreamWaitEvent(h->st_h2d, h->ev_compute[b], 0));
+        if (n_samples > 0)
+            CU(h, cudaMemcpy2DAsync(h->d_audio_tile[b], (size_t)n_samples * 2, h_audio + (size_t)first * audio_stride, (size_t)audio_stride * 2,
+                                    (size_t)n_samples * 2, n, cudaMemcpyHostToDevice, h->st_h2d));
+        CU(h, cudaEventRecord(h->ev_h2d[b], h->st_h2d));
+        CU(h, cudaStreamWaitEvent(h->st_compute, h->ev_h2d[b], 0));
+        if (it >= 2) CU(h, cudaStreamWaitEvent(h->st_compute, h->ev_d2h[b], 0));   // probs buffer drained
+        rc = run_frontend_tile(h, first, n, h->d_audio_tile[b], n_samples, n_samples, n_frames, h->d_feat, (long long)n_frames * kNumChannels, h->st_compute);
+        if (rc) return rc;
+        rc = run_nn_tile(h, first, n, h->d_feat, MWW_ROWS_U16, n_frames, n_frames, h->d_probs_tile[b], std::max(n_steps, 1), h->st_compute);
+        if (rc) return rc;
+        if (n_samples > 0) {
+            rc = run_carry_tile(h, first, n, h->d_audio_tile[b], n_samples, n_samples, n_frames, h->st_compute);
+            if (rc) return rc;
+        }
+        CU(h, cudaEventRecord(h->ev_compute[b], h->st_compute));
+        CU(h, cudaStreamWaitEvent(h->st_d2h, h->ev_compute[b], 0));
+        if (n_steps > 0)
+            CU(h, cudaMemcpy2DAsync(h_probs + (size_t)first * max_probs, (size_t)max_probs * 4, h->d_probs_tile[b], (size_t)std::max(n_steps, 1) * 4,
+                                    (size_t)n_steps * 4, n, cudaMemcpyDeviceToHost, h->st_d2h));
+        CU(h, cudaEventRecord(h->ev_d2h[b], h->st_d2h));
+    }
+    CU(h, cudaStreamSynchronize(h->st_d2h));
+    CU(h, cudaStreamSynchronize(h->st_compute));
+    h->used = h->used + n_samples - n_frames * kHop;
+    h->n_pend = (h->n_pend + n_frames) % 3;
+    if (h_probs_out) *h_probs_out = n_steps;
+    return MWW_OK;
+}
+
+int mww_get_state(mww_t *h, int16_t *h_carry, uint32_t *h_estimate, void *h_nn, void *h_pending) {
+    if (!h) return MWW_EINVAL;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());
+    const size_t S = (size_t)h->n_streams;
+    if (h_carry) CU(h, cudaMemcpy(h_carry, h->d_carry, S * kWindow * 2, cudaMemcpyDeviceToHost));
+    if (h_estimate) CU(h, cudaMemcpy(h_estimate, h->d_estimate, S * kNumChannels * 4, cudaMemcpyDeviceToHost));
+    if ((h_nn || h_pending) && !h->has_nn) return fail(h, MWW_EINVAL, "frontend-only handle has no NN state");
+    if (h_nn) CU(h, cudaMemcpy(h_nn, h->d_nn_state, S * kStateFloats * elem_size(h), cudaMemcpyDeviceToHost));
+    if (h_pending) CU(h, cudaMemcpy(h_pending, h->d_pend, S * 2 * kNumChannels * elem_size(h), cudaMemcpyDeviceToHost));
+    return MWW_OK;
+}
+
+int mww_set_state(mww_t *h, const int16_t *h_carry, int frontend_buffered, const uint32_t *h_estimate, const void *h_nn,
+                  const void *h_pending, int pending_rows) {
+    if (!h) return MWW_EINVAL;
+    if (frontend_buffered < 0 || frontend_buffered >= kWindow || pending_rows < 0 || pending_rows > 2)
+        return fail(h, MWW_EINVAL, "mww_set_state: counters out of range");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());
+    const size_t S = (size_t)h->n_streams;
+    if (h_carry) CU(h, cudaMemcpy(h->d_carry, h_carry, S * kWindow * 2, cudaMemcpyHostToDevice));
+    if (h_estimate) CU(h, cudaMemcpy(h->d_estimate, h_estimate, S * kNumChannels * 4, cudaMemcpyHostToDevice));
+    if ((h_nn || h_pending) && !h->has_nn) return fail(h, MWW_EINVAL, "frontend-only handle has no NN state");
+    if (h_nn) CU(h, cudaMemcpy(h->d_nn_state, h_nn, S * kStateFloats * elem_size(h), cudaMemcpyHostToDevice));
+    if (h_pending) CU(h, cudaMemcpy(h->d_pend, h_pending, S * 2 * kNumChannels * elem_size(h), cudaMemcpyHostToDevice));
+    h->used = frontend_buffered;
+    h->n_pend = pending_rows;
+    return MWW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// mww_frontend.cu -- sm_100a kernels of the batched micro-frontend (see mww_frontend_dev.cuh for the
+// phase decomposition and the reference citations).
+#include <cuda_runtime.h>
+
+#include "mww_frontend_dev.cuh"
+#include "mww_kernels.h"
+
+namespace mww {
+
+// K1: grid = (streams, group_chunks); 256 threads; 16 frames of one stream per iteration.
+__global__ void __launch_bounds__(kK1Threads, 3)
+k1_spectral_kernel(FrontendParams P, int fb_coef_len, const int16_t *__restrict__ carry, int used,
+                   const int16_t *__restrict__ audio, long long audio_stride, int n_samples, int n_frames,
+                   int groups_per_block, uint32_t *__restrict__ vout) {
+    __shared__ K1Smem sm;
+    const int tid = threadIdx.x;
+    const long long s = blockIdx.x;
+    K1Lane lane;
+    k1_lane_init(tid, P, lane);
+    for (int i = tid; i < fb_coef_len; i += kK1Threads) sm.fb_coef[i] = P.fb_coef[i];
+
+    const int n_groups = (n_frames + kFramesPerGroup - 1) / kFramesPerGroup;
+    const int g_begin = blockIdx.y * groups_per_block;
+    const int g_end = min(g_begin + groups_per_block, n_groups);
+    const int16_t *my_carry = carry + s * kWindow;
+    const int16_t *my_audio = audio + s * audio_stride;
+    for (int g = g_begin; g < g_end; ++g) {
+        const int f0 = g * kFramesPerGroup;
+        k1_load_audio(tid, sm, my_carry, used, my_audio, n_samples, f0);
+        __syncthreads();
+        k1_window(tid, sm, P);
+        __syncthreads();
+        k1_fft_pass1(tid, sm, P);
+        __syncthreads();
+        k1_fft_pass2(tid, sm, lane);
+        __syncthreads();
+        k1_real_energy(tid, sm, P);
+        __syncthreads();
+        const int f = f0 + (tid >> 4);
+        k1_filterbank(tid, sm, P, f < n_frames ? vout + (s * n_frames + f) * kNumChannels : nullptr);
+        // no trailing barrier needed: the next iteration touches audio/A/lane_max only after its own
+        // barriers, and B/shift are rewritten two barriers later (see DESIGN.md, K1 hazards)
+    }
+}
+
+// K2: one thread per (stream, channel); frames are scanned in order, noise estimate kept in a register.
+__global__ void __launch_bounds__(256)
+k2_temporal_kernel(FrontendParams P, const uint32_t *__restrict__ vin, int n_streams, int n_frames,
+                   uint32_t *__restrict__ estimate, uint16_t *__restrict__ feat, long long feat_stream_stride) {
+    __shared__ int16_t gain_lut[128];
+    __shared__ uint16_t log_lut[132];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) gain_lut[i] = P.gain_lut[i];
+    for (int i = threadIdx.x; i < 132; i += blockDim.x) log_lut[i] = P.log_lut[i];
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_streams * kNumChannels) return;
+    const long long s = idx / kNumChannels;
+    const int ch = (int)(idx - s * kNumChannels);
+    const uint32_t smoothing = (ch & 1) ? kOddSmoothing : kEvenSmoothing;
+    uint32_t est = estimate[idx];
+    const uint32_t *v = vin + s * (long long)n_frames * kNumChannels + ch;
+    uint16_t *out = feat + s * feat_stream_stride + ch;
+    int f = 0;
+    for (; f + 4 <= n_frames; f += 4) {
+        uint32_t x[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[q] = __ldcs(v + (long long)(f + q) * kNumChannels);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) out[(long long)(f + q) * kNumChannels] = k2_channel_step(x[q], est, smoothing, gain_lut, log_lut);
+    }
+    for (; f < n_frames; ++f) out[(long long)f * kNumChannels] = k2_channel_step(v[(long long)f * kNumChannels], est, smoothing, gain_lut, log_lut);
+    estimate[idx] = est;
+}
+
+// carry update: keep the samples that did not complete a hop (one CTA of 128 threads per stream)
+__global__ void __launch_bounds__(128)
+carry_update_kernel(int16_t *__restrict__ carry, int used, const int16_t *__restrict__ audio, long long audio_stride,
+                    int n_samples, int consumed, int new_used) {
+    const long long s = blockIdx.x;
+    int16_t *c = carry + s * kWindow;
+    const int16_t *a = audio + s * audio_stride;
+    int16_t tmp[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = threadIdx.x + 128 * q;
+        int16_t val = 0;
+        if (i < new_used) {
+            const int vi = consumed + i;
+            val = vi < used ? c[vi] : a[vi - used];
+        }
+        tmp[q] = val;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = threadIdx.x + 128 * q;
+        if (i < kWindow) c[i] = tmp[q];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+
+cudaError_t launch_k1(const FrontendParams &P, int fb_coef_len, const int16_t *carry, int used, const int16_t *audio,
+                      long long audio_stride, int n_samples, int n_streams, int n_frames, uint32_t *vout, int sm_count,
+                      cudaStream_t st) {
+    if (n_frames <= 0 || n_streams <= 0) return cudaSuccess;
+    const int n_groups = (n_frames + kFramesPerGroup - 1) / kFramesPerGroup;
+    // enough CTAs to fill the chip a few times over, but keep per-CTA setup amortised when streams abound
+    int chunks = 1;
+    const long long want = (long long)sm_count * 3 * 4;
+    if (n_streams < want) chunks = (int)min((long long)n_groups, (want + n_streams - 1) / n_streams);
+    const int gpb = (n_groups + chunks - 1) / chunks;
+    chunks = (n_groups + gpb - 1) / gpb;
+    dim3 grid((unsigned)n_streams, (unsigned)chunks);
+    k1_spectral_kernel<<<grid, kK1Threads, 0, st>>>(P, fb_coef_len, carry, used, audio, audio_stride, n_samples, n_frames, gpb, vout);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k2(const FrontendParams &P, const uint32_t *vin, int n_streams, int n_frames, uint32_t *estimate,
+                      uint16_t *feat, long long feat_stream_stride, cudaStream_t st) {
+    if (n_frames <= 0 || n_streams <= 0) return cudaSuccess;
+    const long long total = (long long)n_streams * kNumChannels;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    k2_temporal_kernel<<<blocks, 256, 0, st>>>(P, vin, n_streams, n_frames, estimate, feat, feat_stream_stride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_carry_update(int16_t *carry, int used, const int16_t *audio, long long audio_stride, int n_samples,
+                                int n_streams, int consumed, int new_used, cudaStream_t st) {
+    if (n_streams <= 0) return cudaSuccess;
+    carry_update_kernel<<<(unsigned)n_streams, 128, 0, st>>>(carry, used, audio, audio_stride, n_samples, consumed, new_used);
+    return cudaGetLastError();
+}
+
+}  // namespace mww

@@ -1,0 +1,351 @@
+// mww_frontend_dev.cuh -- device-side micro-frontend, written as per-thread PHASE functions.
+//
+// Replaces the per-frame arithmetic that pymicro_features.MicroFrontend.ProcessSamples performs
+// when called from microwakeword/audio/audio_utils.py:57-62 (algorithm: SURVEY.md Appendix B).
+//
+// Work decomposition (B200-first, not a translation of the scalar C library):
+//   * kernel K1 "spectral": every 10 ms frame is independent up to the filterbank sqrt, so a CTA of
+//     256 threads processes 16 frames of one stream at a time, 16 lanes per frame:
+//       P0  coalesced int16 loads of the 18-hop audio span into shared memory
+//       P1  Q12 Hann window, packed int16x2, per-lane |max|
+//       P2  input scaling + radix-4 stages 1,2 of the 256-point complex FFT on 16 register-resident
+//           points per lane (bit-exact Q15 roundings of KissFFT FIXED_POINT=16)
+//       P3  transpose through padded shared memory, radix-4 stages 3,4
+//       P4  real-FFT post pass + |X|^2 (uint32)
+//       P5  41-band triangular mel accumulation (64-bit), exact rounded integer sqrt, >> shift
+//   * kernel K2 "temporal": noise-reduction IIR, PCAN gain and log scaling are the only parts that
+//     carry state from frame to frame; one thread per (stream, channel) scans the frames.
+//
+// All functions are __host__ __device__: tests/host_emul runs them thread by thread on the CPU.
+#pragma once
+
+#include "mww_common.h"
+#include "mww_tables.h"
+
+#if !defined(__CUDA_ARCH__)
+#include <math.h>
+#endif
+
+namespace mww {
+
+constexpr int kFramesPerGroup = 16;
+constexpr int kK1Threads = 256;
+constexpr int kRowWords = 272;   // 256 + 16: two frames of one warp land in disjoint bank halves
+constexpr int kGroupSamples = (kFramesPerGroup + 2) * kHop;   // 2880
+
+
+struct K1Smem {
+    uint32_t A[kFramesPerGroup][kRowWords];
+    uint32_t B[kFramesPerGroup][kRowWords];
+    int16_t audio[kGroupSamples];
+    uint16_t lane_max[kFramesPerGroup][16];
+    int32_t shift[kFramesPerGroup];
+    int16_t fb_coef[kFbCoefMax];
+};
+
+// per-thread constants that do not depend on the frame (kept in registers across groups)
+struct K1Lane {
+    int32_t t3r[3], t3i[3];     // stage-3 twiddles tw[4b], tw[8b], tw[12b]
+    int32_t t4r[12], t4i[12];   // stage-4 twiddles tw[k'], tw[2k'], tw[3k'] for k' = 16j + b
+};
+
+// ---------------------------------------------------------------------------------------------
+// Q15 primitives of KissFFT FIXED_POINT=16
+
+// C_FIXDIV(x, 4): x * (32767/4) rounded;  input must already be a valid int16 value
+MWW_HD int32_t fixdiv4(int32_t x) { return (x * 8191 + 16384) >> 15; }
+MWW_HD int32_t fixdiv2(int32_t x) { return (x * 16383 + 16384) >> 15; }
+
+// C_MUL: one rounding per component
+MWW_HD void cmul_q15(int32_t ar, int32_t ai, int32_t wr, int32_t wi, int32_t &mr, int32_t &mi) {
+    mr = (ar * wr - ai * wi + 16384) >> 15;
+    mi = (ar * wi + ai * wr + 16384) >> 15;
+}
+
+// radix-4 forward butterfly on pre-divided, pre-twiddled inputs.  Sums are left un-wrapped: every
+// consumer either re-wraps (sext16 before the next multiply) or packs to int16 (implicit wrap),
+// and add/sub commute with the mod-2^16 wrap, so results equal int16-storing KissFFT bit for bit.
+MWW_HD void bfly4_core(int32_t &r0, int32_t &i0, int32_t &r1, int32_t &i1, int32_t &r2, int32_t &i2, int32_t &r3, int32_t &i3) {
+    // scratch[0..2] = r1,r2,r3 (already multiplied by their twiddles)
+    const int32_t s5r = r0 - r2, s5i = i0 - i2;
+    const int32_t f0r = r0 + r2, f0i = i0 + i2;
+    const int32_t s3r = r1 + r3, s3i = i1 + i3;
+    const int32_t s4r = r1 - r3, s4i = i1 - i3;
+    r2 = f0r - s3r; i2 = f0i - s3i;
+    r0 = f0r + s3r; i0 = f0i + s3i;
+    r1 = s5r + s4i; i1 = s5i - s4r;
+    r3 = s5r - s4i; i3 = s5i + s4r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact integer sqrt with the library's round-half-up (remainder > root) rule
+
+MWW_HD uint32_t isqrt64_round(uint64_t x) {
+    if (x == 0) return 0;
+#if defined(__CUDA_ARCH__)
+    const float xf = __ull2float_rn(x);
+    const float rf = __fsqrt_rn(xf);
+    uint64_t r = (uint64_t)__float2ull_rz(rf);
+#else
+    const float xf = (float)x;
+    const float rf = sqrtf(xf);
+    uint64_t r = (uint64_t)rf;
+#endif
+    if (r > 0xFFFFFFFFull) r = 0xFFFFFFFFull;
+    if (r == 0) r = 1;
+    // one float Newton correction: r is within ~2^-23 relative, the residual fits a float exactly enough
+    {
+        const int64_t d = (int64_t)(x - r * r);
+#if defined(__CUDA_ARCH__)
+        const float c = __ll2float_rn(d) * __frcp_rn(2.0f * __ull2float_rn(r));
+        r = (uint64_t)((int64_t)r + (int64_t)__float2ll_rd(c));
+#else
+        const float c = (float)d * (1.0f / (2.0f * (float)r));
+        r = (uint64_t)((int64_t)r + (int64_t)floorf(c));
+#endif
+        if (r > 0xFFFFFFFFull) r = 0xFFFFFFFFull;
+    }
+    // exact fix-up (each loop runs at most a couple of times; kept as loops for safety)
+    while (r * r > x) --r;
+    uint64_t rem = x - r * r;
+    while (rem > 2 * r) { rem -= 2 * r + 1; ++r; }
+    // rounding: the 32-bit fast path of the library cannot exceed 0xFFFF, the 64-bit one 0xFFFFFFFF
+    const uint64_t cap = (x >> 32) == 0 ? 0xFFFFull : 0xFFFFFFFFull;
+    if (rem > r && r != cap) ++r;
+    if (r > cap) r = cap;
+    return (uint32_t)r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 phases
+
+MWW_HD void k1_lane_init(int tid, const FrontendParams &P, K1Lane &L) {
+    const int b = tid & 15;
+    for (int j = 0; j < 3; ++j) {
+        const uint32_t w = P.tw[4 * b * (j + 1)];
+        L.t3r[j] = unpack_lo(w); L.t3i[j] = unpack_hi(w);
+    }
+    for (int j = 0; j < 4; ++j) {
+        const int kp = 16 * j + b;
+        for (int q = 0; q < 3; ++q) {
+            const uint32_t w = P.tw[kp * (q + 1)];
+            L.t4r[3 * j + q] = unpack_lo(w); L.t4i[3 * j + q] = unpack_hi(w);
+        }
+    }
+}
+
+// P0: bring the group's audio span into shared memory.  The stream's sample sequence is
+// carry[0 .. used) followed by audio[0 .. n_samples); group g needs samples [160*f0, 160*f0 + 2880).
+MWW_HD void k1_load_audio(int tid, K1Smem &sm, const int16_t *carry, int used, const int16_t *audio, int n_samples, int f0) {
+    const int base = kHop * f0;
+    for (int i = tid; i < kGroupSamples; i += kK1Threads) {
+        const int vi = base + i;
+        int16_t s = 0;
+        if (vi < used) s = carry[vi];
+        else if (vi - used < n_samples) s = audio[vi - used];
+        sm.audio[i] = s;
+    }
+}
+
+// P1: Hann window in Q12 (window coefficient pairs come straight from the read-only table)
+MWW_HD void k1_window(int tid, K1Smem &sm, const FrontendParams &P) {
+    const int fl = tid >> 4, l = tid & 15;
+    const uint32_t *pairs = reinterpret_cast<const uint32_t *>(sm.audio) + (kHop / 2) * fl;
+    int32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 15; ++j) {
+        const int p = l + 16 * j;
+        const uint32_t sw = pairs[p];
+        const uint32_t cw = P.win_pairs[p];
+        const int32_t v0 = (unpack_lo(sw) * unpack_lo(cw)) >> 12;
+        const int32_t v1 = (unpack_hi(sw) * unpack_hi(cw)) >> 12;
+        sm.A[fl][p] = pack16(v0, v1);
+        // |v| with the int16 wrap of the library: |-32768| stays negative and never wins the max
+        const int32_t a0 = v0 < 0 ? sext16(-v0) : v0;
+        const int32_t a1 = v1 < 0 ? sext16(-v1) : v1;
+        m = a0 > m ? a0 : m;
+        m = a1 > m ? a1 : m;
+    }
+    sm.lane_max[fl][l] = (uint16_t)m;
+}
+
+// P2: scale to 15 significant bits, FFT stages 1 and 2 on 16 local points
+MWW_HD void k1_fft_pass1(int tid, K1Smem &sm, const FrontendParams &P) {
+    const int fl = tid >> 4, a = tid & 15;
+    int32_t mx = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const int32_t v = sm.lane_max[fl][i]; mx = v > mx ? v : mx; }
+    const int shift = 15 - msb32((uint32_t)mx);
+    if (a == 0) sm.shift[fl] = shift;
+
+    const int c = (a >> 2) + 4 * (a & 3);     // complex sample index modulo 16 owned by this lane
+    int32_t xr[16], xi[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        const int j = (b >> 2) + 4 * (b & 3);  // position 4*n2+n3 holds sample c + 16*n2 + 64*n3
+        if (j == 15) { xr[b] = 0; xi[b] = 0; }                 // samples 480..511 are the zero padding
+        else {
+            const uint32_t w = sm.A[fl][c + 16 * j];
+            xr[b] = sext16(unpack_lo(w) << shift);
+            xi[b] = sext16(unpack_hi(w) << shift);
+        }
+    }
+    // stage 1 (m = 1): unit twiddles; C_MUL by (32767, 0) is the identity on the pre-divided range
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { xr[4 * g + q] = fixdiv4(xr[4 * g + q]); xi[4 * g + q] = fixdiv4(xi[4 * g + q]); }
+        bfly4_core(xr[4 * g], xi[4 * g], xr[4 * g + 1], xi[4 * g + 1], xr[4 * g + 2], xi[4 * g + 2], xr[4 * g + 3], xi[4 * g + 3]);
+    }
+    // stage 2 (m = 4): butterfly k on points k, k+4, k+8, k+12; |stage-1 sums| <= 4*8191, no wrap possible
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { xr[k + 4 * q] = fixdiv4(xr[k + 4 * q]); xi[k + 4 * q] = fixdiv4(xi[k + 4 * q]); }
+        if (k > 0) {
+#pragma unroll
+            for (int q = 1; q < 4; ++q) {
+                int32_t mr, mi;
+                cmul_q15(xr[k + 4 * q], xi[k + 4 * q], P.tw2[(k - 1) * 3 + (q - 1)][0], P.tw2[(k - 1) * 3 + (q - 1)][1], mr, mi);
+                xr[k + 4 * q] = mr; xi[k + 4 * q] = mi;
+            }
+        }
+        bfly4_core(xr[k], xi[k], xr[k + 4], xi[k + 4], xr[k + 8], xi[k + 8], xr[k + 12], xi[k + 12]);
+    }
+#pragma unroll
+    for (int b = 0; b < 16; ++b) sm.B[fl][17 * a + b] = pack16(xr[b], xi[b]);
+}
+
+// P3: transpose (lane b gathers position b of every 16-point block), FFT stages 3 and 4
+MWW_HD void k1_fft_pass2(int tid, K1Smem &sm, const K1Lane &L) {
+    const int fl = tid >> 4, b = tid & 15;
+    int32_t yr[16], yi[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+        const uint32_t w = sm.B[fl][17 * a + b];
+        yr[a] = unpack_lo(w); yi[a] = unpack_hi(w);
+    }
+    // stage 3 (m = 16, fstride 4): butterfly index k = b inside each 64-block c, points a = 4c + q
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { yr[4 * c + q] = fixdiv4(yr[4 * c + q]); yi[4 * c + q] = fixdiv4(yi[4 * c + q]); }
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+            int32_t mr, mi;
+            cmul_q15(yr[4 * c + q], yi[4 * c + q], L.t3r[q - 1], L.t3i[q - 1], mr, mi);
+            yr[4 * c + q] = mr; yi[4 * c + q] = mi;
+        }
+        bfly4_core(yr[4 * c], yi[4 * c], yr[4 * c + 1], yi[4 * c + 1], yr[4 * c + 2], yi[4 * c + 2], yr[4 * c + 3], yi[4 * c + 3]);
+    }
+    // stage 4 (m = 64, fstride 1): butterfly index k' = 16j + b, points a = 4q + j.
+    // Stage-3 sums may exceed int16; the library stored them as int16, so wrap before multiplying.
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { yr[4 * q + j] = fixdiv4(sext16(yr[4 * q + j])); yi[4 * q + j] = fixdiv4(sext16(yi[4 * q + j])); }
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+            int32_t mr, mi;
+            cmul_q15(yr[4 * q + j], yi[4 * q + j], L.t4r[3 * j + q - 1], L.t4i[3 * j + q - 1], mr, mi);
+            yr[4 * q + j] = mr; yi[4 * q + j] = mi;
+        }
+        bfly4_core(yr[j], yi[j], yr[4 + j], yi[4 + j], yr[8 + j], yi[8 + j], yr[12 + j], yi[12 + j]);
+    }
+    // point a = 4q + j now holds bin k' + 64q = b + 16a
+#pragma unroll
+    for (int a = 0; a < 16; ++a) sm.A[fl][b + 16 * a] = pack16(yr[a], yi[a]);
+}
+
+// P4: split the packed complex FFT into the real spectrum and take |X|^2
+MWW_HD void k1_real_energy(int tid, K1Smem &sm, const FrontendParams &P) {
+    const int fl = tid >> 4, l = tid & 15;
+    if (l == 0) sm.B[fl][0] = 0;   // DC is never read with a non-zero weight; keep it defined
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int k = 1 + 16 * t + l;
+        const uint32_t wk = sm.A[fl][k];
+        const uint32_t wn = sm.A[fl][kNcfft - k];
+        const uint32_t ws = P.super_tw[k - 1];
+        const int32_t pr = fixdiv2(unpack_lo(wk)), pi = fixdiv2(unpack_hi(wk));
+        const int32_t nr = fixdiv2(unpack_lo(wn)), ni = fixdiv2(sext16(-unpack_hi(wn)));
+        const int32_t f1r = pr + nr, f1i = pi + ni;          // |.| <= 2*16383: no wrap
+        const int32_t f2r = pr - nr, f2i = pi - ni;
+        int32_t tr, ti;
+        cmul_q15(f2r, f2i, unpack_lo(ws), unpack_hi(ws), tr, ti);
+        tr = sext16(tr); ti = sext16(ti);                    // C_MUL stores into int16
+        const int32_t ar = sext16((f1r + tr) >> 1), ai = sext16((f1i + ti) >> 1);
+        const int32_t br = sext16((f1r - tr) >> 1), bi = sext16((ti - f1i) >> 1);
+        sm.B[fl][k] = (uint32_t)(ar * ar) + (uint32_t)(ai * ai);
+        sm.B[fl][kNcfft - k] = (uint32_t)(br * br) + (uint32_t)(bi * bi);   // for k = 128 this (later) store wins, as in the library
+    }
+}
+
+// P5: mel filterbank (64-bit accumulate), rounded sqrt, undo the input scaling
+MWW_HD void k1_filterbank(int tid, K1Smem &sm, const FrontendParams &P, uint32_t *vout_frame /* [40] or nullptr */) {
+    const int fl = tid >> 4, l = tid & 15;
+    const int sh = sm.shift[fl];
+#pragma unroll
+    for (int s = 0; s < kFbSlots; ++s) {
+        const FbSlot slot = P.fb_slots[l * kFbSlots + s];
+        const int n = P.fb_slot_len[s];
+        int64_t acc = 0;
+        const uint32_t *e = &sm.B[fl][slot.bin0];
+        const int16_t *cf = &sm.fb_coef[slot.coef_off];
+        for (int j = 0; j < n; ++j) acc = mad_wide_s32((int32_t)e[j], (int32_t)cf[j], acc);   // energy widened as int32, like the library
+        if (slot.ch >= 0 && vout_frame) vout_frame[slot.ch] = isqrt64_round((uint64_t)acc) >> sh;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: per-(stream, channel) temporal chain
+
+MWW_HD int32_t wide_dynamic_function(uint32_t x, const int16_t *lut) {
+    if (x <= 2) return lut[x];
+    const int interval = msb32(x);
+    const int16_t *p = lut + 4 * interval - 6;
+    const int32_t frac = (int32_t)(((interval < 11) ? (x << (11 - interval)) : (x >> (interval - 11))) & 0x3FF);
+    int32_t r = ((int32_t)p[2] * frac) >> 5;
+    r += (int32_t)((uint32_t)(int32_t)p[1] << 5);
+    r *= frac;
+    r = (r + (1 << 14)) >> 15;
+    r += p[0];
+    return (int32_t)(int16_t)r;
+}
+
+MWW_HD uint32_t pcan_shrink(uint32_t x) {
+    if (x < (2u << 12)) return (x * x) >> 20;
+    return (x >> 6) - 64u;
+}
+
+MWW_HD uint32_t log_scale(uint32_t x, const uint16_t *lut) {
+    // natural log of x, scaled by 2^scale_shift
+    const uint32_t integer = (uint32_t)msb32(x) - 1;
+    int32_t frac = (int32_t)(x - (1u << integer));
+    if (integer < 16) frac <<= (16 - integer); else frac >>= (integer - 16);
+    const uint32_t seg = (uint32_t)frac >> 9;
+    const int32_t c0 = lut[seg], c1 = lut[seg + 1];
+    const int32_t rel = ((c1 - c0) * (frac - (int32_t)(seg << 9))) >> 16;
+    const uint32_t log2v = (integer << 16) + (uint32_t)(frac + c0 + rel);
+    const uint32_t loge = (uint32_t)((45426ull * log2v + 32768u) >> 16);
+    return ((loge << kLogScaleShift) + 32768u) >> 16;
+}
+
+// one frame of noise reduction + PCAN + log for one channel; `est` is the persistent noise estimate
+MWW_HD uint16_t k2_channel_step(uint32_t v, uint32_t &est, uint32_t smoothing, const int16_t *gain_lut, const uint16_t *log_lut) {
+    const uint32_t scaled = v << kSmoothingBits;
+    uint32_t e = (uint32_t)((((uint64_t)scaled * smoothing) + ((uint64_t)est * ((1u << kNoiseBits) - smoothing))) >> kNoiseBits);
+    est = e;
+    if (e > scaled) e = scaled;
+    const uint32_t fl = (uint32_t)(((uint64_t)v * kMinSignalRemaining) >> kNoiseBits);
+    const uint32_t sub = (scaled - e) >> kSmoothingBits;
+    uint32_t sig = sub > fl ? sub : fl;
+    const uint32_t gain = (uint32_t)wide_dynamic_function(est, gain_lut);
+    const uint32_t snr = (uint32_t)(((uint64_t)sig * gain) >> kPcanSnrShift);
+    sig = pcan_shrink(snr);
+    sig <<= kLogCorrectionBits;
+    sig = sig > 1 ? log_scale(sig, log_lut) : 0;
+    return (uint16_t)(sig < 0xFFFFu ? sig : 0xFFFFu);
+}
+
+}  // namespace mww

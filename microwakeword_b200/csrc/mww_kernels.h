@@ -1,0 +1,34 @@
+// mww_kernels.h -- launcher prototypes shared by the C-ABI layer (mww_capi.cu) and the kernel files.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mww_tables.h"
+
+namespace mww {
+
+cudaError_t launch_k1(const FrontendParams &P, int fb_coef_len, const int16_t *carry, int used, const int16_t *audio,
+                      long long audio_stride, int n_samples, int n_streams, int n_frames, uint32_t *vout, int sm_count,
+                      cudaStream_t st);
+cudaError_t launch_k2(const FrontendParams &P, const uint32_t *vin, int n_streams, int n_frames, uint32_t *estimate,
+                      uint16_t *feat, long long feat_stream_stride, cudaStream_t st);
+cudaError_t launch_carry_update(int16_t *carry, int used, const int16_t *audio, long long audio_stride, int n_samples,
+                                int n_streams, int consumed, int new_used, cudaStream_t st);
+
+}  // namespace mww
+
+#include "mww_nn_dev.cuh"
+namespace mww {
+cudaError_t launch_nn_f32(const NnWeightsF32 &W, float *state, float *pend, int n_pend, const void *rows,
+                          long long rows_stream_stride_bytes, int n_rows, int rows_are_f32, float *probs,
+                          long long probs_stream_stride, float *logits, int n_streams, cudaStream_t st);
+}  // namespace mww
+
+#include "mww_nn_i8_dev.cuh"
+namespace mww {
+cudaError_t launch_nn_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, int n_pend, const void *rows,
+                         long long rows_stream_stride_bytes, int n_rows, int row_type, float *probs,
+                         long long probs_stream_stride, int n_streams, cudaStream_t st);
+cudaError_t launch_fill_state_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, void *unused, int n_streams, cudaStream_t st);
+}  // namespace mww

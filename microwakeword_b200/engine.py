@@ -1,0 +1,188 @@
+"""StreamEngine: many independent audio streams on one B200, behind the C-ABI of include/mww.h.
+
+Host-side mirror of what the reference does one stream at a time:
+  * frontend  ...... microwakeword/audio/audio_utils.py:50-64 (ProcessSamples loop)
+  * model step ..... microwakeword/inference.py:109-123 (set_tensor / invoke / get_tensor)
+batched over `n_streams` streams that advance in lockstep.  PyTorch tensors are used only as
+device buffers (`.data_ptr()`) and for the current CUDA stream; all arithmetic is in
+libmww_b200.so.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .model_file import NUM_FEATURES
+
+HOP = 160
+WINDOW = 480
+STATE_ELEMENTS = 4176
+
+
+def _torch():
+    import torch  # deferred: `import microwakeword_b200` must work without initialising CUDA
+    return torch
+
+
+class StreamEngine:
+    """`model`: path to an MWW container, its bytes, or None for a frontend-only engine."""
+
+    def __init__(self, model, n_streams: int = 1, device: int = 0):
+        if isinstance(model, (bytes, bytearray, memoryview)):
+            blob = bytes(model)
+        elif model is None:
+            blob = None
+        else:
+            with open(model, "rb") as f:
+                blob = f.read()
+        self._L = _lib.lib()
+        self._h = ctypes.c_void_p()
+        self._blob = blob  # keep alive during create
+        rc = self._L.mww_create(blob, len(blob) if blob else 0, int(device), int(n_streams), ctypes.byref(self._h))
+        if rc != 0:
+            msg = self._L.mww_last_error(None)
+            raise _lib.MwwError(rc, msg.decode() if msg else "mww_create failed")
+        self.n_streams = int(n_streams)
+        self.device = int(device)
+        self.info = self._info()
+        self.is_quantized = bool(self.info.is_quantized)
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mww_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _info(self):
+        info = _lib.MwwInfo()
+        _lib.check(self._h, self._L.mww_get_info(self._h, ctypes.byref(info)))
+        return info
+
+    def _cu_stream(self):
+        torch = _torch()
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self):
+        return _torch().device("cuda", self.device)
+
+    @property
+    def frontend_buffered(self) -> int:
+        return self._info().frontend_buffered
+
+    @property
+    def pending_rows(self) -> int:
+        return self._info().pending_rows
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.mww_launch_count(self._h))
+
+    def _check_audio(self, audio):
+        torch = _torch()
+        if audio.dtype != torch.int16 or audio.dim() != 2 or audio.shape[0] != self.n_streams or not audio.is_cuda:
+            raise ValueError("audio must be a CUDA int16 tensor of shape [n_streams=%d, n_samples]" % self.n_streams)
+        if audio.stride(1) != 1 and audio.shape[1] > 1:
+            raise ValueError("audio samples must be contiguous along the last dimension")
+        return audio.shape[1], (audio.stride(0) if audio.shape[1] > 0 else 0)
+
+    # ------------------------------------------------------------------ operations
+    def reset(self, stream_ids=None):
+        """Fresh frontend + zero rings for all streams (None) or for the given stream ids."""
+        if stream_ids is None:
+            _lib.check(self._h, self._L.mww_reset(self._h, None, 0, self._cu_stream()))
+        else:
+            ids = np.ascontiguousarray(stream_ids, np.int32)
+            _lib.check(self._h, self._L.mww_reset(self._h, ids.ctypes.data, ids.size, self._cu_stream()))
+
+    def reset_frontend(self):
+        _lib.check(self._h, self._L.mww_reset_frontend(self._h, self._cu_stream()))
+
+    def features(self, audio):
+        """int16 CUDA tensor [S, N] -> uint16 CUDA tensor [S, rows, 40] (rows may be 0)."""
+        torch = _torch()
+        n, stride = self._check_audio(audio)
+        rows = max((self.frontend_buffered + n - WINDOW) // HOP + 1, 0) if self.frontend_buffered + n >= WINDOW else 0
+        out = torch.empty((self.n_streams, max(rows, 1), NUM_FEATURES), dtype=torch.uint16, device=self._dev())
+        got = ctypes.c_int(0)
+        _lib.check(self._h, self._L.mww_features(self._h, audio.data_ptr(), n, max(stride, n), out.data_ptr(), max(rows, 1),
+                                                 ctypes.byref(got), self._cu_stream()))
+        return out[:, :got.value]
+
+    def infer(self, rows):
+        """feature rows [S, R, 40] (uint16 / float32 / int8 CUDA tensor) -> float32 probabilities [S, steps]."""
+        torch = _torch()
+        kinds = {torch.uint16: _lib.MWW_ROWS_U16, torch.float32: _lib.MWW_ROWS_F32, torch.int8: _lib.MWW_ROWS_I8}
+        if rows.dtype not in kinds or rows.dim() != 3 or rows.shape[0] != self.n_streams or rows.shape[2] != NUM_FEATURES or not rows.is_cuda:
+            raise ValueError("rows must be a CUDA uint16/float32/int8 tensor of shape [n_streams, R, 40]")
+        rows = rows.contiguous()
+        r = rows.shape[1]
+        steps = (self.pending_rows + r) // 3
+        probs = torch.empty((self.n_streams, max(steps, 1)), dtype=torch.float32, device=self._dev())
+        got = ctypes.c_int(0)
+        _lib.check(self._h, self._L.mww_infer_features(self._h, rows.data_ptr(), kinds[rows.dtype], r, max(r, 0), probs.data_ptr(),
+                                                       max(steps, 1), ctypes.byref(got), self._cu_stream()))
+        return probs[:, :got.value]
+
+    def predict_clip(self, audio, out=None):
+        """int16 CUDA tensor [S, N] -> float32 probabilities [S, steps]; state carries over between calls."""
+        torch = _torch()
+        n, stride = self._check_audio(audio)
+        buffered = self.frontend_buffered
+        rows = (buffered + n - WINDOW) // HOP + 1 if buffered + n >= WINDOW else 0
+        steps = (self.pending_rows + rows) // 3
+        if out is None:
+            out = torch.empty((self.n_streams, max(steps, 1)), dtype=torch.float32, device=self._dev())
+        got = ctypes.c_int(0)
+        _lib.check(self._h, self._L.mww_predict_clip(self._h, audio.data_ptr(), n, max(stride, n), out.data_ptr(), out.shape[1],
+                                                     ctypes.byref(got), self._cu_stream()))
+        return out[:, :got.value]
+
+    step = predict_clip  # the live "one chunk of new audio per call" surface (north_star step())
+
+    def predict_clip_host(self, audio: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """int16 HOST array [S, N] -> float32 HOST array [S, steps]; copies are pipelined inside the library."""
+        if audio.dtype != np.int16 or audio.ndim != 2 or audio.shape[0] != self.n_streams:
+            raise ValueError("audio must be an int16 array of shape [n_streams=%d, n_samples]" % self.n_streams)
+        if audio.strides[1] != 2 and audio.shape[1] > 1:
+            audio = np.ascontiguousarray(audio)
+        n = audio.shape[1]
+        buffered = self.frontend_buffered
+        rows = (buffered + n - WINDOW) // HOP + 1 if buffered + n >= WINDOW else 0
+        steps = (self.pending_rows + rows) // 3
+        if out is None:
+            out = np.empty((self.n_streams, max(steps, 1)), np.float32)
+        got = ctypes.c_int(0)
+        _lib.check(self._h, self._L.mww_predict_clip_host(self._h, audio.ctypes.data, n, audio.strides[0] // 2 if n else 0, out.ctypes.data,
+                                                          out.shape[1], ctypes.byref(got)))
+        return out[:, :got.value]
+
+    # ------------------------------------------------------------------ state (checkpoint / tests)
+    def state_dict(self) -> dict:
+        S = self.n_streams
+        nn_dtype = np.int8 if self.is_quantized else np.float32
+        d = dict(carry=np.zeros((S, WINDOW), np.int16), estimate=np.zeros((S, NUM_FEATURES), np.uint32),
+                 nn=np.zeros((S, STATE_ELEMENTS), nn_dtype), pending=np.zeros((S, 2, NUM_FEATURES), nn_dtype))
+        _lib.check(self._h, self._L.mww_get_state(self._h, d["carry"].ctypes.data, d["estimate"].ctypes.data, d["nn"].ctypes.data,
+                                                  d["pending"].ctypes.data))
+        info = self._info()
+        d["frontend_buffered"] = info.frontend_buffered
+        d["pending_rows"] = info.pending_rows
+        return d
+
+    def load_state_dict(self, d: dict) -> None:
+        nn_dtype = np.int8 if self.is_quantized else np.float32
+        carry = np.ascontiguousarray(d["carry"], np.int16)
+        est = np.ascontiguousarray(d["estimate"], np.uint32)
+        nn = np.ascontiguousarray(d["nn"], nn_dtype)
+        pend = np.ascontiguousarray(d["pending"], nn_dtype)
+        _lib.check(self._h, self._L.mww_set_state(self._h, carry.ctypes.data, int(d["frontend_buffered"]), est.ctypes.data, nn.ctypes.data,
+                                                  pend.ctypes.data, int(d["pending_rows"])))

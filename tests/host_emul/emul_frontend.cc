@@ -1,0 +1,114 @@
+// tests/host_emul/emul_frontend.cc -- TEST INFRASTRUCTURE.
+//
+// Executes the product's frontend PHASE functions (microwakeword_b200/csrc/mww_frontend_dev.cuh --
+// the very code the sm_100a kernels run) on the CPU, thread by thread with barriers modelled as
+// "finish the phase for all 256 threads", so index math / bit-exactness can be validated against
+// the oracle in the GPU-less authoring container.  Never used by the product.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../microwakeword_b200/csrc/mww_frontend_dev.cuh"
+
+using namespace mww;
+
+namespace {
+HostTables g_tables;
+FrontendParams g_params;
+bool g_ready = false;
+
+void ensure_tables() {
+    if (g_ready) return;
+    build_host_tables(&g_tables);
+    g_params.win_pairs = g_tables.win_pairs;
+    g_params.tw = g_tables.tw;
+    g_params.super_tw = g_tables.super_tw;
+    g_params.fb_coef = g_tables.fb_coef.data();
+    g_params.fb_slots = &g_tables.fb_slots[0][0];
+    g_params.gain_lut = g_tables.gain_lut;
+    g_params.log_lut = g_tables.log_lut;
+    memcpy(g_params.tw2, g_tables.tw2, sizeof g_params.tw2);
+    memcpy(g_params.fb_slot_len, g_tables.fb_slot_len, sizeof g_params.fb_slot_len);
+    g_ready = true;
+}
+}  // namespace
+
+extern "C" {
+
+int emul_tables(int16_t *window480, int16_t *bin_weight257, int16_t *bin_unweight257, int16_t *chan_start42,
+                int16_t *gain_lut125, uint16_t *log_lut129, int16_t *tw512, int16_t *super256, int32_t *info8) {
+    ensure_tables();
+    const HostTables &t = g_tables;
+    memcpy(window480, t.window, sizeof t.window);
+    memcpy(bin_weight257, t.bin_weight, sizeof t.bin_weight);
+    memcpy(bin_unweight257, t.bin_unweight, sizeof t.bin_unweight);
+    memcpy(chan_start42, t.chan_start, sizeof t.chan_start);
+    memcpy(gain_lut125, t.gain_lut, 125 * sizeof(int16_t));
+    memcpy(log_lut129, t.log_lut, 129 * sizeof(uint16_t));
+    for (int k = 0; k < 256; ++k) { tw512[2 * k] = (int16_t)unpack_lo(t.tw[k]); tw512[2 * k + 1] = (int16_t)unpack_hi(t.tw[k]); }
+    for (int k = 0; k < 128; ++k) { super256[2 * k] = (int16_t)unpack_lo(t.super_tw[k]); super256[2 * k + 1] = (int16_t)unpack_hi(t.super_tw[k]); }
+    info8[0] = t.start_index; info8[1] = t.end_index; info8[2] = t.ok;
+    info8[3] = (int)t.fb_coef.size();
+    for (int s = 0; s < kFbSlots; ++s) info8[4 + s] = t.fb_slot_len[s];
+    return 0;
+}
+
+uint32_t emul_isqrt64_round(uint64_t x) { return isqrt64_round(x); }
+
+// Mirrors mww_features(): streams advance in lockstep; returns the number of feature rows per stream.
+int emul_features(const int16_t *audio, int n_streams, int n_samples, int16_t *carry, int used, uint32_t *estimate,
+                  uint16_t *feat, int max_rows, int *new_used_out) {
+    ensure_tables();
+    const int total = used + n_samples;
+    const int n_frames = total >= kWindow ? (total - kWindow) / kHop + 1 : 0;
+    const int consumed = n_frames * kHop;
+    const int new_used = total - consumed;
+    std::vector<uint32_t> v((size_t)n_streams * (n_frames > 0 ? n_frames : 1) * kNumChannels);
+    K1Smem *sm = new K1Smem;
+    std::vector<K1Lane> lanes(kK1Threads);
+    const int n_groups = (n_frames + kFramesPerGroup - 1) / kFramesPerGroup;
+    for (int s = 0; s < n_streams; ++s) {
+        memset(sm, 0xA5, sizeof *sm);   // poison: phases must not depend on stale shared memory
+        for (int tid = 0; tid < kK1Threads; ++tid) k1_lane_init(tid, g_params, lanes[tid]);
+        for (size_t i = 0; i < g_tables.fb_coef.size(); ++i) sm->fb_coef[i] = g_tables.fb_coef[i];
+        const int16_t *my_carry = carry + (size_t)s * kWindow;
+        const int16_t *my_audio = audio + (size_t)s * n_samples;
+        for (int g = 0; g < n_groups; ++g) {
+            const int f0 = g * kFramesPerGroup;
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_load_audio(tid, *sm, my_carry, used, my_audio, n_samples, f0);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_window(tid, *sm, g_params);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_fft_pass1(tid, *sm, g_params);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_fft_pass2(tid, *sm, lanes[tid]);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_real_energy(tid, *sm, g_params);
+            for (int tid = 0; tid < kK1Threads; ++tid) {
+                const int f = f0 + (tid >> 4);
+                k1_filterbank(tid, *sm, g_params, f < n_frames ? &v[((size_t)s * n_frames + f) * kNumChannels] : nullptr);
+            }
+        }
+    }
+    delete sm;
+    for (int s = 0; s < n_streams; ++s)
+        for (int ch = 0; ch < kNumChannels; ++ch) {
+            uint32_t est = estimate[(size_t)s * kNumChannels + ch];
+            const uint32_t smoothing = (ch & 1) ? kOddSmoothing : kEvenSmoothing;
+            for (int f = 0; f < n_frames && f < max_rows; ++f)
+                feat[((size_t)s * max_rows + f) * kNumChannels + ch] =
+                    k2_channel_step(v[((size_t)s * n_frames + f) * kNumChannels + ch], est, smoothing, g_tables.gain_lut, g_tables.log_lut);
+            estimate[(size_t)s * kNumChannels + ch] = est;
+        }
+    // carry update
+    for (int s = 0; s < n_streams; ++s) {
+        int16_t tmp[kWindow] = {0};
+        int16_t *c = carry + (size_t)s * kWindow;
+        for (int i = 0; i < new_used; ++i) {
+            const int vi = consumed + i;
+            tmp[i] = vi < used ? c[vi] : audio[(size_t)s * n_samples + (vi - used)];
+        }
+        memcpy(c, tmp, sizeof tmp);
+    }
+    if (new_used_out) *new_used_out = new_used;
+    return n_frames;
+}
+
+}  // extern "C"

@@ -1,0 +1,255 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every call goes through the C-ABI of
+include/mww.h (via microwakeword_b200.engine / .inference) and is compared with the CPU oracle on the
+same seeded inputs and with the committed golden fixtures.
+
+Bars: uint16 features bit-exact; int8 model bit-exact; fp32 probabilities within 1e-5 of the fp32
+oracle (north_star allows 1e-3; the only difference is fma / summation order)."""
+
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, edge_case_audio, synth_audio
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _blob(name):
+    with open(os.path.join(GOLDEN, name), "rb") as f:
+        return f.read()
+
+
+def _u16(t):
+    import torch
+    return t.view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+def _dev_u16(a, torch):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int16)).cuda().view(torch.uint16)
+
+
+def test_library_loaded_and_device_is_blackwell(torch_cuda):
+    from microwakeword_b200 import _lib
+    assert os.path.exists(_lib.SO_PATH)
+    L = _lib.lib()
+    for sym in _lib.EXPORTS:
+        assert hasattr(L, sym)
+    assert torch_cuda.cuda.get_device_capability(0)[0] >= 10
+
+
+def test_features_bit_exact_random_and_edge(torch_cuda):
+    from microwakeword_b200.engine import StreamEngine
+    torch = torch_cuda
+    audio = np.concatenate([np.stack([synth_audio(16000, 200 + i) for i in range(50)]), edge_case_audio(16000)])
+    eng = StreamEngine(None, n_streams=audio.shape[0])
+    got = _u16(eng.features(torch.from_numpy(audio).cuda()))
+    want, _ = oracle.run_pipeline(None, audio, want_probs=False, threads=8)
+    assert got.shape == want.shape == (audio.shape[0], 98, 40)
+    assert np.array_equal(got, want)
+    assert eng.frontend_buffered == 320
+
+
+def test_features_golden_config0(torch_cuda):
+    from microwakeword_b200.audio.audio_utils import generate_features_for_clip
+    clip = np.load(os.path.join(GOLDEN, "config0_audio.npy"))
+    want = np.load(os.path.join(GOLDEN, "config0_features.npy"))
+    got = generate_features_for_clip(clip)                      # float32 = uint16 * 0.0390625
+    assert got.dtype == np.float32 and got.shape == (997, 40)
+    assert np.array_equal(got, want.astype(np.float32) * np.float32(0.0390625))
+    got_tf = generate_features_for_clip(clip, step_ms=10, use_c=False)   # TF-op semantics: all 998 windows, uint16
+    assert got_tf.dtype == np.uint16 and got_tf.shape == (998, 40)
+    assert np.array_equal(got_tf[:997], want)
+    # float input path (audio_utils.py:47-48)
+    got_f = generate_features_for_clip(clip.astype(np.float32) / 32768.0)
+    assert np.array_equal(got_f, got)
+
+
+def test_features_chunking_invariance_and_state(torch_cuda):
+    from microwakeword_b200.engine import StreamEngine
+    torch = torch_cuda
+    audio = np.stack([synth_audio(24000, 300 + i) for i in range(9)])
+    whole, _ = oracle.run_pipeline(None, audio, want_probs=False)
+    eng = StreamEngine(None, n_streams=9)
+    rng = np.random.default_rng(4)
+    pos, parts = 0, []
+    while pos < audio.shape[1]:
+        n = int(rng.integers(1, 1500))
+        chunk = np.ascontiguousarray(audio[:, pos:pos + n])
+        parts.append(_u16(eng.features(torch.from_numpy(chunk).cuda())))
+        pos += chunk.shape[1]
+    got = np.concatenate(parts, 1)
+    assert np.array_equal(got, whole)
+    # state equals the oracle's after the same audio
+    st = eng.state_dict()
+    fe = oracle.Frontend()
+    fe.stream(audio[3])
+    buf, used, est = fe.state()
+    assert st["frontend_buffered"] == used
+    assert np.array_equal(st["carry"][3][:used], buf[:used])
+    assert np.array_equal(st["estimate"][3], est)
+
+
+@pytest.mark.parametrize("kind", ["f32", "int8"])
+def test_model_golden_config0(torch_cuda, kind):
+    from microwakeword.inference import Model               # the reference's import path
+    m = Model(os.path.join(GOLDEN, "okay_nabu_synth_%s.mww" % kind))
+    assert m.is_quantized_model == (kind == "int8") and m.input_feature_slices == 3 and m.stride == 3
+    feats = np.load(os.path.join(GOLDEN, "config0_features.npy"))
+    want = np.load(os.path.join(GOLDEN, "config0_probs_%s.npy" % kind))
+    got = m.predict_spectrogram(feats)
+    assert isinstance(got, list) and len(got) == 332 and isinstance(got[0], np.float32)
+    if kind == "int8":
+        assert np.array_equal(np.asarray(got), want)
+    else:
+        assert np.abs(np.asarray(got) - want).max() <= F32_TOL
+    # state persists across calls (inference.py never resets): a second pass differs from a fresh one
+    again = np.asarray(m.predict_spectrogram(feats[:30]))
+    m.reset()
+    fresh = np.asarray(m.predict_spectrogram(feats[:30]))
+    assert np.array_equal(fresh, np.asarray(got[:10])) if kind == "int8" else np.abs(fresh - np.asarray(got[:10])).max() <= F32_TOL
+    assert not np.array_equal(again, fresh)
+    # predict_clip = fresh frontend + NN (state carried): after reset equals the golden chain
+    m.reset()
+    clip = np.load(os.path.join(GOLDEN, "config0_audio.npy"))
+    pc = np.asarray(m.predict_clip(clip))
+    assert pc.shape == (332,)
+    assert np.array_equal(pc, want) if kind == "int8" else np.abs(pc - want).max() <= F32_TOL
+
+
+def test_predict_spectrogram_dtypes_and_quirks(torch_cuda):
+    from microwakeword_b200.inference import Model
+    feats = np.load(os.path.join(GOLDEN, "config0_features.npy"))[:92]
+    m = Model(os.path.join(GOLDEN, "okay_nabu_synth_f32.mww"))
+    a = np.asarray(m.predict_spectrogram(feats)); m.reset()
+    b = np.asarray(m.predict_spectrogram(feats.astype(np.float32) * np.float32(0.0390625))); m.reset()
+    c = np.asarray(m.predict_spectrogram(feats.astype(np.float64) * 0.0390625)); m.reset()
+    assert len(a) == 30 and np.array_equal(a, b) and np.array_equal(a, c)        # 92 rows -> 30 chunks, 2 rows dropped
+    assert m.predict_spectrogram(feats[:2]) == []
+    # stride 1: overlapping chunks, each is one invoke (inference.py:98-105)
+    m1 = Model(os.path.join(GOLDEN, "okay_nabu_synth_f32.mww"), stride=1)
+    got = np.asarray(m1.predict_spectrogram(feats[:12]))
+    from oracle import mixednet_ref as R
+    from microwakeword_b200 import model_file as MF
+    om = R.FoldedStreamingF32(MF.load(os.path.join(GOLDEN, "okay_nabu_synth_f32.mww")))
+    want = np.asarray(R.predict_spectrogram(om, feats[:12], stride=1))
+    assert got.shape == want.shape == (10,) and np.abs(got - want).max() <= F32_TOL
+    # int8 model: float rows are quantised with the truncating rule; pre-quantised int8 rows bypass it (inference.py:110)
+    q = Model(os.path.join(GOLDEN, "okay_nabu_synth_int8.mww"))
+    pa = np.asarray(q.predict_spectrogram(feats)); q.reset()
+    rows_q = q.quantize_input_data(feats.astype(np.float32) * np.float32(0.0390625), q.input_details[0])
+    assert rows_q.dtype == np.int8
+    pb = np.asarray(q.predict_spectrogram(rows_q))
+    assert np.array_equal(pa, pb)
+    assert q.dequantize_output_data(np.uint8(255), q.output_details[0]) == np.float32(1.0)
+
+
+@pytest.mark.parametrize("kind", ["f32", "int8"])
+def test_batch_pipeline_device_and_host_paths(torch_cuda, kind):
+    from microwakeword_b200.engine import StreamEngine
+    torch = torch_cuda
+    blob = _blob("okay_nabu_synth_%s.mww" % kind)
+    audio = np.concatenate([np.stack([synth_audio(30000, 400 + i) for i in range(40)]), edge_case_audio(30000)])
+    _, want = oracle.run_pipeline(blob, audio, want_features=False, threads=8)
+    S = audio.shape[0]
+    eng = StreamEngine(blob, n_streams=S)
+    got = eng.predict_clip(torch.from_numpy(audio).cuda()).cpu().numpy()
+    assert got.shape == want.shape
+    ok = np.array_equal(got, want) if kind == "int8" else np.abs(got - want).max() <= F32_TOL
+    assert ok
+    # host-buffer path with forced small tiles -> many pipelined tiles, same answer
+    os.environ["MWW_SCRATCH_MB"] = "1"
+    try:
+        eng2 = StreamEngine(blob, n_streams=S)
+    finally:
+        del os.environ["MWW_SCRATCH_MB"]
+    got2 = eng2.predict_clip_host(audio)
+    assert np.array_equal(got2, got)
+    # live-step mode: 480 new samples per call == the clip result
+    eng3 = StreamEngine(blob, n_streams=S)
+    dev = torch.from_numpy(audio).cuda()
+    parts = [eng3.step(dev[:, i:i + 480].contiguous()) for i in range(0, audio.shape[1] - 479, 480)]
+    got3 = torch.cat(parts, 1).cpu().numpy()
+    n = got3.shape[1]
+    assert n >= want.shape[1] - 1 and np.array_equal(got3, got[:, :n])
+
+
+def test_golden_batch_fixture(torch_cuda):
+    from microwakeword_b200.engine import StreamEngine
+    torch = torch_cuda
+    audio = np.load(os.path.join(GOLDEN, "batch_audio.npy"))
+    eng = StreamEngine(_blob("okay_nabu_synth_int8.mww"), n_streams=audio.shape[0])
+    assert np.array_equal(eng.predict_clip(torch.from_numpy(audio).cuda()).cpu().numpy(), np.load(os.path.join(GOLDEN, "batch_probs_int8.npy")))
+    eng = StreamEngine(_blob("okay_nabu_synth_f32.mww"), n_streams=audio.shape[0])
+    got = eng.predict_clip(torch.from_numpy(audio).cuda()).cpu().numpy()
+    assert np.abs(got - np.load(os.path.join(GOLDEN, "batch_probs_f32.npy"))).max() <= F32_TOL
+    fe = StreamEngine(None, n_streams=audio.shape[0])
+    assert np.array_equal(_u16(fe.features(torch.from_numpy(audio).cuda())), np.load(os.path.join(GOLDEN, "batch_features.npy")))
+
+
+def test_nn_state_roundtrip_and_reset_ids(torch_cuda):
+    from microwakeword_b200.engine import StreamEngine
+    torch = torch_cuda
+    blob = _blob("okay_nabu_synth_f32.mww")
+    audio = np.stack([synth_audio(20000, 500 + i) for i in range(5)])
+    dev = torch.from_numpy(audio).cuda()
+    a = StreamEngine(blob, n_streams=5)
+    first = a.predict_clip(dev[:, :9000].contiguous()).cpu().numpy()
+    snap = a.state_dict()
+    rest = a.predict_clip(dev[:, 9000:].contiguous()).cpu().numpy()
+    b = StreamEngine(blob, n_streams=5)
+    b.load_state_dict(snap)
+    assert np.array_equal(b.predict_clip(dev[:, 9000:].contiguous()).cpu().numpy(), rest)
+    _, whole = oracle.run_pipeline(blob, audio, want_features=False)
+    assert np.abs(np.concatenate([first, rest], 1) - whole).max() <= F32_TOL
+    # per-stream reset zeroes that stream's state only
+    a.reset([2])
+    st = a.state_dict()
+    assert not st["nn"][2].any() and not st["estimate"][2].any() and st["nn"][1].any()
+
+
+def test_errors_are_loud(torch_cuda):
+    from microwakeword_b200 import _lib
+    from microwakeword_b200.engine import StreamEngine
+    with pytest.raises(_lib.MwwError):
+        StreamEngine(b"not a model", n_streams=1)
+    eng = StreamEngine(None, n_streams=2)
+    with pytest.raises(_lib.MwwError):
+        eng.infer(torch_cuda.zeros((2, 3, 40), dtype=torch_cuda.float32, device="cuda"))
+    with pytest.raises(ValueError):
+        eng.features(torch_cuda.zeros((3, 480), dtype=torch_cuda.int16, device="cuda"))
+
+
+def test_full_size_properties(torch_cuda):
+    """BASELINE.json configs[1] scale (65 536 streams), checked through size-independent properties:
+    replicated streams give identical outputs, silence gives the model's fixed silence response,
+    a sample of streams matches the oracle, and chunked == whole."""
+    from microwakeword_b200.engine import StreamEngine
+    torch = torch_cuda
+    S, N = 65536, 4800
+    base = np.concatenate([np.stack([synth_audio(N, 600 + i) for i in range(60)]), edge_case_audio(N)[:4]])   # 64 distinct streams
+    reps = S // base.shape[0]
+    dev = torch.from_numpy(base).cuda().repeat(reps, 1)
+    blob = _blob("okay_nabu_synth_int8.mww")
+    eng = StreamEngine(blob, n_streams=S)
+    got = eng.predict_clip(dev)
+    assert got.shape == (S, 9)
+    g = got.view(reps, base.shape[0], 9)
+    assert bool((g == g[0:1]).all())                      # every replica identical -> no cross-stream leakage
+    _, want = oracle.run_pipeline(blob, base, want_features=False, threads=8)
+    assert np.array_equal(g[0].cpu().numpy(), want)
+    # chunked streaming at full size equals the whole-clip call
+    eng.reset()
+    a = eng.predict_clip(dev[:, :1760].contiguous())
+    b = eng.predict_clip(dev[:, 1760:].contiguous())
+    assert bool((torch.cat([a, b], 1) == got).all())
