@@ -124,6 +124,13 @@ int mww_get_state(mww_t *h, int16_t *h_carry, uint32_t *h_estimate, void *h_nn, 
 int mww_set_state(mww_t *h, const int16_t *h_carry, int frontend_buffered, const uint32_t *h_estimate,
                   const void *h_nn, const void *h_pending, int pending_rows);
 
+/* Per-kernel device timing for roofline reporting.  While enabled, every launch of the four kernel
+ * classes is bracketed by CUDA events on the launching stream.  mww_profile_read synchronises the
+ * device, adds the elapsed milliseconds into ms[4] and the launch counts into counts[4]
+ * (index 0 spectral K1, 1 temporal K2, 2 MixedNet, 3 window-carry update) and clears the record. */
+int mww_profile_enable(mww_t *h, int on);
+int mww_profile_read(mww_t *h, double *ms4, long long *counts4);
+
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 long long mww_launch_count(const mww_t *h);
 

@@ -19,7 +19,7 @@ MWW_ROWS_U16, MWW_ROWS_F32, MWW_ROWS_I8 = 0, 1, 2
 EXPORTS = (
     "mww_create", "mww_destroy", "mww_last_error", "mww_get_info", "mww_reset", "mww_reset_frontend",
     "mww_features", "mww_infer_features", "mww_predict_clip", "mww_predict_clip_host",
-    "mww_get_state", "mww_set_state", "mww_launch_count",
+    "mww_get_state", "mww_set_state", "mww_launch_count", "mww_profile_enable", "mww_profile_read",
 )
 
 
@@ -77,6 +77,10 @@ def lib() -> ctypes.CDLL:
     L.mww_get_state.argtypes = [vp, vp, vp, vp, vp]
     L.mww_set_state.restype = i32
     L.mww_set_state.argtypes = [vp, vp, i32, vp, vp, vp, i32]
+    L.mww_profile_enable.restype = i32
+    L.mww_profile_enable.argtypes = [vp, i32]
+    L.mww_profile_read.restype = i32
+    L.mww_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
     L.mww_launch_count.restype = ll
     L.mww_launch_count.argtypes = [vp]
     _lib = L

@@ -81,6 +81,9 @@ struct mww_handle {
     int16_t *d_audio_tile[2] = {nullptr, nullptr}; size_t audio_tile_bytes = 0;
     float *d_probs_tile[2] = {nullptr, nullptr}; size_t probs_tile_bytes = 0;
     long long launches = 0;
+    // optional per-kernel timing (mww_profile_*)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev[4];   // start/stop pairs per kernel class
 };
 
 namespace {
@@ -95,6 +98,20 @@ int cuda_fail(mww_t *h, cudaError_t e, const char *what) {
 #define CU(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(h, e_, #call); } while (0)
 
 size_t elem_size(const mww_t *h) { return h->quantized ? 1 : 4; }
+
+// RAII bracket: records an event pair around a launch when profiling is on
+struct ProfScope {
+    mww_t *h; int cls; cudaStream_t st; cudaEvent_t stop = nullptr;
+    ProfScope(mww_t *h_, int cls_, cudaStream_t st_) : h(h_), cls(cls_), st(st_) {
+        if (!h->profiling) return;
+        cudaEvent_t a = nullptr;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) { stop = nullptr; return; }
+        cudaEventRecord(a, st);
+        h->prof_ev[cls].push_back(a);
+        h->prof_ev[cls].push_back(stop);
+    }
+    ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
+};
 
 int ensure_scratch(mww_t *h, size_t v_bytes, size_t feat_bytes) {
     if (v_bytes > h->v_bytes) {
@@ -130,9 +147,15 @@ int tile_streams(const mww_t *h, int n_frames, bool need_feat) {
 int run_frontend_tile(mww_t *h, int first, int n, const int16_t *d_audio, long long audio_stride, int n_samples,
                       int n_frames, uint16_t *d_feat, long long feat_stream_stride, cudaStream_t st) {
     if (n_frames <= 0) return MWW_OK;
-    CU(h, launch_k1(h->P, h->fb_coef_len, h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n,
-                    n_frames, h->d_v, h->sm_count, st));
-    CU(h, launch_k2(h->P, h->d_v, n, n_frames, h->d_estimate + (size_t)first * kNumChannels, d_feat, feat_stream_stride, st));
+    {
+        ProfScope p(h, 0, st);
+        CU(h, launch_k1(h->P, h->fb_coef_len, h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n,
+                        n_frames, h->d_v, h->sm_count, st));
+    }
+    {
+        ProfScope p(h, 1, st);
+        CU(h, launch_k2(h->P, h->d_v, n, n_frames, h->d_estimate + (size_t)first * kNumChannels, d_feat, feat_stream_stride, st));
+    }
     h->launches += 2;
     return MWW_OK;
 }
@@ -141,6 +164,7 @@ int run_carry_tile(mww_t *h, int first, int n, const int16_t *d_audio, long long
                    cudaStream_t st) {
     const int consumed = n_frames * kHop;
     const int new_used = h->used + n_samples - consumed;
+    ProfScope p(h, 3, st);
     CU(h, launch_carry_update(h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n, consumed, new_used, st));
     h->launches += 1;
     return MWW_OK;
@@ -148,6 +172,7 @@ int run_carry_tile(mww_t *h, int first, int n, const int16_t *d_audio, long long
 
 int run_nn_tile(mww_t *h, int first, int n, const void *d_rows, int row_type, long long rows_stream_stride_rows, int n_rows,
                 float *d_probs, long long probs_stride, cudaStream_t st) {
+    ProfScope p(h, 2, st);
     if (h->quantized) {
         if (row_type == MWW_ROWS_F32 || row_type == MWW_ROWS_U16 || row_type == MWW_ROWS_I8) {
             const size_t rb = row_type == MWW_ROWS_F32 ? 4 : (row_type == MWW_ROWS_U16 ? 2 : 1);
@@ -304,6 +329,7 @@ void destroy_impl(mww_t *h) {
         if (h->ev_compute[b]) cudaEventDestroy(h->ev_compute[b]);
         if (h->ev_d2h[b]) cudaEventDestroy(h->ev_d2h[b]);
     }
+    for (int c = 0; c < 4; ++c) for (cudaEvent_t e : h->prof_ev[c]) cudaEventDestroy(e);
     if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
     if (h->st_compute) cudaStreamDestroy(h->st_compute);
     if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
@@ -352,6 +378,28 @@ int mww_destroy(mww_t *h) { destroy_impl(h); return MWW_OK; }
 const char *mww_last_error(const mww_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 long long mww_launch_count(const mww_t *h) { return h ? h->launches : 0; }
+
+int mww_profile_enable(mww_t *h, int on) {
+    if (!h) return MWW_EINVAL;
+    h->profiling = on != 0;
+    return MWW_OK;
+}
+
+int mww_profile_read(mww_t *h, double *ms4, long long *counts4) {
+    if (!h || !ms4 || !counts4) return MWW_EINVAL;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());
+    for (int c = 0; c < 4; ++c) {
+        std::vector<cudaEvent_t> &v = h->prof_ev[c];
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, v[i], v[i + 1]) == cudaSuccess) { ms4[c] += ms; counts4[c] += 1; }
+            cudaEventDestroy(v[i]); cudaEventDestroy(v[i + 1]);
+        }
+        v.clear();
+    }
+    return MWW_OK;
+}
 
 int mww_get_info(const mww_t *h, mww_info *o) {
     if (!h || !o) return MWW_EINVAL;

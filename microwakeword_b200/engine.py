@@ -165,14 +165,30 @@ class StreamEngine:
                                                           out.shape[1], ctypes.byref(got)))
         return out[:, :got.value]
 
+    # ------------------------------------------------------------------ per-kernel device timing
+    KERNEL_CLASSES = ("k1_spectral", "k2_temporal", "mixednet", "carry_update")
+
+    def profile(self, on: bool) -> None:
+        _lib.check(self._h, self._L.mww_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self) -> dict:
+        """{class: (total_ms, launches)} accumulated since the last read (synchronises the device)."""
+        ms = (ctypes.c_double * 4)(0, 0, 0, 0)
+        cnt = (ctypes.c_longlong * 4)(0, 0, 0, 0)
+        _lib.check(self._h, self._L.mww_profile_read(self._h, ms, cnt))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
     # ------------------------------------------------------------------ state (checkpoint / tests)
     def state_dict(self) -> dict:
         S = self.n_streams
         nn_dtype = np.int8 if self.is_quantized else np.float32
-        d = dict(carry=np.zeros((S, WINDOW), np.int16), estimate=np.zeros((S, NUM_FEATURES), np.uint32),
-                 nn=np.zeros((S, STATE_ELEMENTS), nn_dtype), pending=np.zeros((S, 2, NUM_FEATURES), nn_dtype))
-        _lib.check(self._h, self._L.mww_get_state(self._h, d["carry"].ctypes.data, d["estimate"].ctypes.data, d["nn"].ctypes.data,
-                                                  d["pending"].ctypes.data))
+        d = dict(carry=np.zeros((S, WINDOW), np.int16), estimate=np.zeros((S, NUM_FEATURES), np.uint32))
+        if self._blob is not None:
+            d["nn"] = np.zeros((S, STATE_ELEMENTS), nn_dtype)
+            d["pending"] = np.zeros((S, 2, NUM_FEATURES), nn_dtype)
+        _lib.check(self._h, self._L.mww_get_state(self._h, d["carry"].ctypes.data, d["estimate"].ctypes.data,
+                                                  d["nn"].ctypes.data if "nn" in d else None,
+                                                  d["pending"].ctypes.data if "pending" in d else None))
         info = self._info()
         d["frontend_buffered"] = info.frontend_buffered
         d["pending_rows"] = info.pending_rows
@@ -182,7 +198,8 @@ class StreamEngine:
         nn_dtype = np.int8 if self.is_quantized else np.float32
         carry = np.ascontiguousarray(d["carry"], np.int16)
         est = np.ascontiguousarray(d["estimate"], np.uint32)
-        nn = np.ascontiguousarray(d["nn"], nn_dtype)
-        pend = np.ascontiguousarray(d["pending"], nn_dtype)
-        _lib.check(self._h, self._L.mww_set_state(self._h, carry.ctypes.data, int(d["frontend_buffered"]), est.ctypes.data, nn.ctypes.data,
-                                                  pend.ctypes.data, int(d["pending_rows"])))
+        nn = np.ascontiguousarray(d["nn"], nn_dtype) if "nn" in d else None
+        pend = np.ascontiguousarray(d["pending"], nn_dtype) if "pending" in d else None
+        _lib.check(self._h, self._L.mww_set_state(self._h, carry.ctypes.data, int(d["frontend_buffered"]), est.ctypes.data,
+                                                  nn.ctypes.data if nn is not None else None, pend.ctypes.data if pend is not None else None,
+                                                  int(d.get("pending_rows", 0))))
