@@ -285,7 +285,8 @@ def run_gpu(args):
         achieved = K1_ALG_BYTES_PER_FRAME * frames_per_launch / (k1_ms / k1_n / 1e3) / 1e9
         tr = ncu_traffic()
         roof = {"bound": "hbm", "kernel": "k1_spectral_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": (tr or {}).get("dram_bytes_per_launch"),
+                "peak_source": peak_src, "traffic": ((tr or {}).get("dram_bytes_per_unit") or 0) * frames_per_launch or None,
+                "traffic_source": (tr or {}).get("source"),
                 "alg_bytes_per_frame": K1_ALG_BYTES_PER_FRAME, "frames_per_launch": frames_per_launch,
                 "share_of_step": k1_ms / max(sum(v[0] for v in prof.values()), 1e-9),
                 "note": "K1 is integer-ALU bound by construction (~25k integer ops per 320-byte frame); see DESIGN.md and profiles/ for issue-slot utilisation"}

@@ -1,0 +1,123 @@
+"""ctypes front-end of tests/host_emul/*.cc -- TEST INFRASTRUCTURE.
+
+Builds (g++) and loads a host executable version of the product's device PHASE functions
+(microwakeword_b200/csrc/*_dev.cuh) so that the kernels' index math and bit-exactness can be
+checked against the oracle without a GPU.  Nothing in the product imports this."""
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "microwakeword_b200", "csrc")
+SO = os.path.join(HERE, "_build", "libemul.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        srcs = [os.path.join(HERE, "emul_frontend.cc"), os.path.join(HERE, "emul_nn.cc"), os.path.join(CSRC, "mww_tables.cc")]
+        deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+        if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+            os.makedirs(os.path.dirname(SO), exist_ok=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + srcs, check=True)
+        L = ctypes.CDLL(SO)
+        L.emul_features.restype = ctypes.c_int
+        L.emul_nn_f32.restype = ctypes.c_int
+        L.emul_nn_i8.restype = ctypes.c_int
+        L.emul_isqrt64_round.restype = ctypes.c_uint32
+        L.emul_isqrt64_round.argtypes = [ctypes.c_uint64]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def tables():
+    t = dict(window=np.zeros(480, np.int16), bin_weight=np.zeros(257, np.int16), bin_unweight=np.zeros(257, np.int16),
+             chan_start=np.zeros(42, np.int16), gain_lut=np.zeros(125, np.int16), log_lut=np.zeros(129, np.uint16),
+             twiddles=np.zeros((256, 2), np.int16), super_twiddles=np.zeros((128, 2), np.int16), info=np.zeros(8, np.int32))
+    lib().emul_tables(*[_p(t[k]) for k in ("window", "bin_weight", "bin_unweight", "chan_start", "gain_lut", "log_lut", "twiddles", "super_twiddles", "info")])
+    return t
+
+
+class Frontend:
+    """Emulated mww_features state machine for S lockstep streams."""
+
+    def __init__(self, n_streams):
+        self.S = n_streams
+        self.carry = np.zeros((n_streams, 480), np.int16)
+        self.estimate = np.zeros((n_streams, 40), np.uint32)
+        self.used = 0
+
+    def features(self, audio):
+        audio = np.ascontiguousarray(audio, np.int16)
+        S, N = audio.shape
+        rows = (self.used + N) // 160 + 1
+        feat = np.zeros((S, rows, 40), np.uint16)
+        nu = ctypes.c_int(0)
+        n = lib().emul_features(_p(audio), S, N, _p(self.carry), self.used, _p(self.estimate), _p(feat), rows, ctypes.byref(nu))
+        self.used = nu.value
+        return feat[:, :n]
+
+
+F32_NAMES = ["first_conv/w"] + ["b%d/dw/w" % i for i in range(4)] + ["b%d/dw/b" % i for i in range(4)] + \
+            ["b%d/pw/w" % i for i in range(4)] + ["b%d/pw/b" % i for i in range(4)] + ["head/w", "head/b"]
+
+
+class NnF32:
+    def __init__(self, tensors, n_streams):
+        self.arrs = [np.ascontiguousarray(tensors[n], np.float32) for n in F32_NAMES]
+        self.wp = (ctypes.c_void_p * len(self.arrs))(*[a.ctypes.data for a in self.arrs])
+        self.state = np.zeros((n_streams, 4176), np.float32)
+        self.pend = np.zeros((n_streams, 80), np.float32)
+        self.n_pend = 0
+
+    def infer(self, rows):
+        rows = np.ascontiguousarray(rows)
+        S, n_rows = rows.shape[:2]
+        probs = np.zeros((S, (self.n_pend + n_rows) // 3 + 1), np.float32)
+        n = lib().emul_nn_f32(self.wp, _p(self.state), _p(self.pend), self.n_pend, _p(rows), n_rows, int(rows.dtype == np.float32), S,
+                              _p(probs), probs.shape[1], None)
+        self.n_pend = (self.n_pend + n_rows) % 3
+        return probs[:, :n]
+
+
+def i8_names():
+    names = ["q/first_conv/w", "q/first_conv/bias", "q/first_conv/mult", "q/first_conv/shift"]
+    for i in range(4):
+        names += ["q/b%d/dw/%s" % (i, x) for x in ("w", "bias", "mult", "shift")] + ["q/b%d/pw/%s" % (i, x) for x in ("w", "bias", "mult", "shift")]
+    return names + ["q/head/w", "q/logistic_lut"]
+
+
+class NnI8:
+    def __init__(self, q, n_streams):
+        self.arrs = [np.ascontiguousarray(q[n]) for n in i8_names()]
+        self.wp = (ctypes.c_void_p * len(self.arrs))(*[a.ctypes.data for a in self.arrs])
+        self.zp = np.ascontiguousarray(q["q/zps"], np.int32)
+        self.head3 = np.array([q["q/head/bias"][0], q["q/head/mult"][0], q["q/head/shift"][0]], np.int32)
+        self.in_scale = float(q["q/scales"][0])
+        self.state = np.zeros((n_streams, 4176), np.int8)
+        self.pend = np.zeros((n_streams, 80), np.int8)
+        self.n_pend = 0
+        self.reset()
+
+    def reset(self):
+        lib().emul_fill_state_i8(_p(self.zp), _p(self.state), _p(self.pend), self.state.shape[0])
+        self.n_pend = 0
+
+    def infer(self, rows):
+        rows = np.ascontiguousarray(rows)
+        S, n_rows = rows.shape[:2]
+        rt = {np.dtype(np.uint16): 0, np.dtype(np.float32): 1, np.dtype(np.int8): 2}[rows.dtype]
+        probs = np.zeros((S, (self.n_pend + n_rows) // 3 + 1), np.float32)
+        n = lib().emul_nn_i8(self.wp, _p(self.zp), _p(self.head3), ctypes.c_float(self.in_scale), _p(self.state), _p(self.pend), self.n_pend,
+                             _p(rows), n_rows, rt, S, _p(probs), probs.shape[1])
+        self.n_pend = (self.n_pend + n_rows) % 3
+        return probs[:, :n]

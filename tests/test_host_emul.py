@@ -1,0 +1,99 @@
+"""CPU tests of the PRODUCT's kernel logic: the __host__ __device__ phase functions that the sm_100a
+kernels execute (microwakeword_b200/csrc/*_dev.cuh) are run thread-by-thread on the host
+(tests/host_emul) and compared with the oracle.  This is what lets index math and bit-exactness be
+iterated without a GPU; the GPU runs of the very same functions are in tests/test_gpu_parity.py."""
+
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, edge_case_audio, synth_audio
+from host_emul import emul
+from microwakeword_b200 import model_file as MF
+
+
+def test_product_tables_equal_oracle_tables():
+    t, o = emul.tables(), oracle.Frontend().tables()
+    for k in ("window", "bin_weight", "bin_unweight", "chan_start", "gain_lut", "log_lut", "twiddles", "super_twiddles"):
+        assert np.array_equal(t[k], o[k]), k
+    assert t["info"][0] == 5 and t["info"][1] == 241 and t["info"][2] == 1
+    assert t["info"][3] <= 1024           # span coefficients fit the shared-memory copy
+    assert sum(t["info"][4:8]) <= 48      # per-lane trip count of the balanced filterbank schedule
+
+
+def test_isqrt_matches_library_rule():
+    L, O = emul.lib(), oracle.lib()
+    rng = np.random.default_rng(0)
+    vals = [0, 1, 2, 3, (1 << 32) - 1, 1 << 32, (1 << 64) - 1, 1 << 63, 65535 ** 2 + 65535, 65535 ** 2 + 65536,
+            (2 ** 32 - 1) ** 2, (2 ** 32 - 1) ** 2 + 2 ** 32 - 1, (2 ** 32 - 1) ** 2 + 2 ** 32]
+    vals += [int(v) for v in rng.integers(0, 1 << 62, 5000)] + [int(v) for v in rng.integers(0, 1 << 36, 5000)]
+    vals += [int(r) * int(r) + int(r) + int(d) for r, d in zip(rng.integers(1, 1 << 31, 5000), rng.integers(-2, 3, 5000))]
+    for v in vals:
+        assert L.emul_isqrt64_round(v) == O.mwwo_sqrt64(v), v
+
+
+def test_frontend_phases_bit_exact_random_edge_and_adversarial():
+    rng = np.random.default_rng(0)
+    n = 3200
+    t = np.arange(n)
+    rows = [synth_audio(n, 40 + i) for i in range(12)] + list(edge_case_audio(n))
+    for i in range(120):                     # full-scale patterns that overflow int16 inside the FFT butterflies
+        kind = i % 4
+        if kind == 0:
+            x = rng.choice([-32768, 32767], n)
+        elif kind == 1:
+            x = rng.integers(-32768, 32768, n)
+        elif kind == 2:
+            w = rng.choice([np.pi / 2, np.pi / 4, np.pi / 8, 3 * np.pi / 8, rng.uniform(0, np.pi)])
+            x = 32767 * np.sign(np.cos(w * (t // 2) + rng.uniform(0, 6.28) + (t % 2) * np.pi / 2) + 1e-12)
+        else:
+            x = np.clip(rng.normal(0, 30000, n), -32768, 32767)
+        rows.append(np.clip(np.round(x), -32768, 32767).astype(np.int16))
+    audio = np.stack(rows)
+    got = emul.Frontend(audio.shape[0]).features(audio)
+    want, _ = oracle.run_pipeline(None, audio, want_probs=False)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_frontend_phases_chunked_stream_and_multi_group():
+    audio = np.stack([synth_audio(16000, 70 + i) for i in range(3)])     # 98 frames -> 7 groups of 16
+    want, _ = oracle.run_pipeline(None, audio, want_probs=False)
+    fe = emul.Frontend(3)
+    rng = np.random.default_rng(1)
+    pos, parts = 0, []
+    while pos < audio.shape[1]:
+        n = int(rng.integers(1, 2500))
+        parts.append(fe.features(audio[:, pos:pos + n]))
+        pos += n
+    assert np.array_equal(np.concatenate(parts, 1), want)
+    assert fe.used == 320
+
+
+def test_nn_f32_phases_match_oracle_and_golden():
+    t = MF.load(os.path.join(GOLDEN, "okay_nabu_synth_f32.mww"))
+    feats = np.load(os.path.join(GOLDEN, "config0_features.npy"))
+    want = np.load(os.path.join(GOLDEN, "config0_probs_f32.npy"))
+    nn = emul.NnF32(t, 1)
+    got = nn.infer(feats[None, :996])                 # 332 steps = 10 full chunks of 32 + a ragged one
+    assert got.shape == (1, 332) and np.abs(got[0] - want).max() <= 1e-5
+    # ragged calls leave pending rows; the chain continues exactly
+    nn = emul.NnF32(t, 1)
+    parts = [nn.infer(feats[None, a:b]) for a, b in ((0, 1), (1, 5), (5, 100), (100, 101), (101, 997))]
+    assert np.array_equal(np.concatenate(parts, 1), got)
+    # float32 rows == uint16 rows * 0.0390625
+    nn = emul.NnF32(t, 1)
+    assert np.array_equal(nn.infer((feats[None, :996].astype(np.float32) * np.float32(0.0390625))), got)
+
+
+def test_nn_int8_phases_bit_exact():
+    q = MF.load(os.path.join(GOLDEN, "okay_nabu_synth_int8.mww"))
+    feats = np.load(os.path.join(GOLDEN, "batch_features.npy"))
+    want = np.load(os.path.join(GOLDEN, "batch_probs_int8.npy"))
+    nn = emul.NnI8(q, feats.shape[0])
+    assert np.array_equal(nn.infer(feats), want)
+    f0 = np.load(os.path.join(GOLDEN, "config0_features.npy"))
+    nn = emul.NnI8(q, 1)
+    parts = [nn.infer(f0[None, a:b]) for a, b in ((0, 2), (2, 300), (300, 301), (301, 997))]
+    assert np.array_equal(np.concatenate(parts, 1)[0], np.load(os.path.join(GOLDEN, "config0_probs_int8.npy")))
