@@ -1,0 +1,75 @@
+"""Host-side sharding logic with world_size-2 gloo process groups on CPU: the contiguous stream
+partition, scatter of int16 audio, gather of float32 scores, and "N shards == 1 process" on the oracle
+standing in for the per-rank engine (the GPU engine itself is covered by tests/test_gpu_parity.py)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from microwakeword_b200.sharding import partition
+
+
+def test_partition_is_contiguous_and_balanced():
+    for n in (0, 1, 7, 64, 65536, 524288, 100001):
+        for w in (1, 2, 3, 4, 8):
+            parts = partition(n, w)
+            assert len(parts) == w and parts[0][0] == 0 and sum(c for _, c in parts) == n
+            assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+    assert partition(524288, 8) == [(65536 * r, 65536) for r in range(8)]
+    with pytest.raises(ValueError):
+        partition(4, 0)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_streams, q):
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    from microwakeword_b200.sharding import gather_probs, scatter_audio
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        audio = np.load(os.path.join(GOLDEN, "batch_audio.npy"))[:n_streams]
+        blob = open(os.path.join(GOLDEN, "okay_nabu_synth_int8.mww"), "rb").read()
+        full = torch.from_numpy(audio) if rank == 0 else None
+        local = scatter_audio(full, n_streams, audio.shape[1], src=0)
+        start, count = partition(n_streams, world)[rank]
+        assert local.shape == (count, audio.shape[1]) and np.array_equal(local.numpy(), audio[start:start + count])
+        _, probs = oracle.run_pipeline(blob, local.numpy(), want_features=False)      # stand-in for the rank's GPU engine
+        out = gather_probs(torch.from_numpy(probs), n_streams, dst=0)
+        if rank == 0:
+            q.put(out.numpy())
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_streams", [12, 11])
+def test_two_rank_scatter_compute_gather_equals_single_process(n_streams):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_streams, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    want = np.load(os.path.join(GOLDEN, "batch_probs_int8.npy"))[:n_streams]
+    assert np.array_equal(got, want)
