@@ -207,6 +207,8 @@ int upload_tables(mww_t *h) {
     HostTables t;
     build_host_tables(&t);
     if (!t.ok || t.fb_coef.size() > (size_t)kFbCoefMax) return fail(h, MWW_EINVAL, "frontend table construction failed");
+    for (int s = 0; s < kFbSlots; ++s)
+        if (t.fb_slot_len[s] != kFbLen[s]) return fail(h, MWW_EINVAL, "filterbank schedule differs from the trip counts the kernel was compiled for");
     h->fb_coef_len = (int)t.fb_coef.size();
     const size_t total = 64 * 1024;
     CU(h, cudaMalloc(&h->d_tables, total));

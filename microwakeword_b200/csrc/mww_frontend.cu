@@ -7,12 +7,35 @@
 
 namespace mww {
 
+// 16-byte async copies global -> shared (LDGSTS): the next group's audio lands while this one is computed
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit_and_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// vectorised variant of k1_load_audio: valid when `used`, `n_samples` and the row pitch are multiples of 8
+// samples and both base pointers are 16-byte aligned, so no 8-sample vector straddles a source boundary
+__device__ __forceinline__ void k1_load_audio_async(int tid, K1Smem &sm, int buf, const int16_t *carry, int used,
+                                                    const int16_t *audio, int n_samples, int f0) {
+    const int base = kHop * f0;
+    for (int v = tid; v < kGroupSamples / 8; v += kK1Threads) {
+        const int vi = base + 8 * v;
+        int16_t *dst = &sm.audio[buf][8 * v];
+        if (vi < used) cp_async16(dst, carry + vi);
+        else if (vi - used < n_samples) cp_async16(dst, audio + (vi - used));
+        else *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
+    }
+}
+
 // K1: grid = (streams, group_chunks); 256 threads; 16 frames of one stream per iteration.
 __global__ void __launch_bounds__(kK1Threads, 3)
 k1_spectral_kernel(FrontendParams P, int fb_coef_len, const int16_t *__restrict__ carry, int used,
                    const int16_t *__restrict__ audio, long long audio_stride, int n_samples, int n_frames,
-                   int groups_per_block, uint32_t *__restrict__ vout) {
-    __shared__ K1Smem sm;
+                   int groups_per_block, int vec_ok, uint32_t *__restrict__ vout) {
+    __shared__ __align__(16) K1Smem sm;
     const int tid = threadIdx.x;
     const long long s = blockIdx.x;
     K1Lane lane;
@@ -24,13 +47,21 @@ k1_spectral_kernel(FrontendParams P, int fb_coef_len, const int16_t *__restrict_
     const int g_end = min(g_begin + groups_per_block, n_groups);
     const int16_t *my_carry = carry + s * kWindow;
     const int16_t *my_audio = audio + s * audio_stride;
+    if (g_begin < g_end) {
+        if (vec_ok) k1_load_audio_async(tid, sm, 0, my_carry, used, my_audio, n_samples, g_begin * kFramesPerGroup);
+        else k1_load_audio(tid, sm, 0, my_carry, used, my_audio, n_samples, g_begin * kFramesPerGroup);
+    }
     for (int g = g_begin; g < g_end; ++g) {
+        const int buf = (g - g_begin) & 1;
+        cp_async_commit_and_wait_all();
+        __syncthreads();                       // audio[buf] visible; everyone is done with the previous group
+        if (g + 1 < g_end) {                   // prefetch: audio[buf^1] was last read two barriers ago
+            if (vec_ok) k1_load_audio_async(tid, sm, buf ^ 1, my_carry, used, my_audio, n_samples, (g + 1) * kFramesPerGroup);
+            else k1_load_audio(tid, sm, buf ^ 1, my_carry, used, my_audio, n_samples, (g + 1) * kFramesPerGroup);
+        }
         const int f0 = g * kFramesPerGroup;
-        k1_load_audio(tid, sm, my_carry, used, my_audio, n_samples, f0);
-        __syncthreads();
-        k1_window(tid, sm, P);
-        __syncthreads();
-        k1_fft_pass1(tid, sm, P);
+        K1Pass1Ctx ctx;
+        k1_window_fft1<2>(tid, sm, buf, P, ctx);
         __syncthreads();
         k1_fft_pass2(tid, sm, lane);
         __syncthreads();
@@ -38,8 +69,8 @@ k1_spectral_kernel(FrontendParams P, int fb_coef_len, const int16_t *__restrict_
         __syncthreads();
         const int f = f0 + (tid >> 4);
         k1_filterbank(tid, sm, P, f < n_frames ? vout + (s * n_frames + f) * kNumChannels : nullptr);
-        // no trailing barrier needed: the next iteration touches audio/A/lane_max only after its own
-        // barriers, and B/shift are rewritten two barriers later (see DESIGN.md, K1 hazards)
+        // hazards: the next iteration's top barrier orders filterbank's reads of B/shift before the next
+        // window_fft1 rewrites them; A is rewritten only after two more barriers
     }
 }
 
@@ -113,7 +144,9 @@ cudaError_t launch_k1(const FrontendParams &P, int fb_coef_len, const int16_t *c
     const int gpb = (n_groups + chunks - 1) / chunks;
     chunks = (n_groups + gpb - 1) / gpb;
     dim3 grid((unsigned)n_streams, (unsigned)chunks);
-    k1_spectral_kernel<<<grid, kK1Threads, 0, st>>>(P, fb_coef_len, carry, used, audio, audio_stride, n_samples, n_frames, gpb, vout);
+    const int vec_ok = (used % 8 == 0) && (n_samples % 8 == 0) && (audio_stride % 8 == 0) &&
+                       (reinterpret_cast<uintptr_t>(audio) % 16 == 0) && (reinterpret_cast<uintptr_t>(carry) % 16 == 0);
+    k1_spectral_kernel<<<grid, kK1Threads, 0, st>>>(P, fb_coef_len, carry, used, audio, audio_stride, n_samples, n_frames, gpb, vec_ok, vout);
     return cudaGetLastError();
 }
 

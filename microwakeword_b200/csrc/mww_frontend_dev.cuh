@@ -37,7 +37,7 @@ constexpr int kGroupSamples = (kFramesPerGroup + 2) * kHop;   // 2880
 struct K1Smem {
     uint32_t A[kFramesPerGroup][kRowWords];
     uint32_t B[kFramesPerGroup][kRowWords];
-    int16_t audio[kGroupSamples];
+    int16_t audio[2][kGroupSamples];   // double buffered: group g+1 is prefetched (cp.async) while g is processed
     uint16_t lane_max[kFramesPerGroup][16];
     int32_t shift[kFramesPerGroup];
     int16_t fb_coef[kFbCoefMax];
@@ -105,9 +105,12 @@ MWW_HD uint32_t isqrt64_round(uint64_t x) {
 #endif
         if (r > 0xFFFFFFFFull) r = 0xFFFFFFFFull;
     }
-    // exact fix-up (each loop runs at most a couple of times; kept as loops for safety)
+    // exact fix-up: the estimate is within +-1 after the correction; straight-line steps first, the loops
+    // are a safety net that is not expected to iterate
+    if (r * r > x) --r;
     while (r * r > x) --r;
     uint64_t rem = x - r * r;
+    if (rem > 2 * r) { rem -= 2 * r + 1; ++r; }
     while (rem > 2 * r) { rem -= 2 * r + 1; ++r; }
     // rounding: the 32-bit fast path of the library cannot exceed 0xFFFF, the 64-bit one 0xFFFFFFFF
     const uint64_t cap = (x >> 32) == 0 ? 0xFFFFull : 0xFFFFFFFFull;
@@ -136,60 +139,61 @@ MWW_HD void k1_lane_init(int tid, const FrontendParams &P, K1Lane &L) {
 
 // P0: bring the group's audio span into shared memory.  The stream's sample sequence is
 // carry[0 .. used) followed by audio[0 .. n_samples); group g needs samples [160*f0, 160*f0 + 2880).
-MWW_HD void k1_load_audio(int tid, K1Smem &sm, const int16_t *carry, int used, const int16_t *audio, int n_samples, int f0) {
+MWW_HD void k1_load_audio(int tid, K1Smem &sm, int buf, const int16_t *carry, int used, const int16_t *audio, int n_samples, int f0) {
     const int base = kHop * f0;
     for (int i = tid; i < kGroupSamples; i += kK1Threads) {
         const int vi = base + i;
         int16_t s = 0;
         if (vi < used) s = carry[vi];
         else if (vi - used < n_samples) s = audio[vi - used];
-        sm.audio[i] = s;
+        sm.audio[buf][i] = s;
     }
 }
 
-// P1: Hann window in Q12 (window coefficient pairs come straight from the read-only table)
-MWW_HD void k1_window(int tid, K1Smem &sm, const FrontendParams &P) {
-    const int fl = tid >> 4, l = tid & 15;
-    const uint32_t *pairs = reinterpret_cast<const uint32_t *>(sm.audio) + (kHop / 2) * fl;
-    int32_t m = 0;
-#pragma unroll
-    for (int j = 0; j < 15; ++j) {
-        const int p = l + 16 * j;
-        const uint32_t sw = pairs[p];
-        const uint32_t cw = P.win_pairs[p];
-        const int32_t v0 = (unpack_lo(sw) * unpack_lo(cw)) >> 12;
-        const int32_t v1 = (unpack_hi(sw) * unpack_hi(cw)) >> 12;
-        sm.A[fl][p] = pack16(v0, v1);
-        // |v| with the int16 wrap of the library: |-32768| stays negative and never wins the max
-        const int32_t a0 = v0 < 0 ? sext16(-v0) : v0;
-        const int32_t a1 = v1 < 0 ? sext16(-v1) : v1;
-        m = a0 > m ? a0 : m;
-        m = a1 > m ? a1 : m;
-    }
-    sm.lane_max[fl][l] = (uint16_t)m;
-}
+// P1+P2 fused: Hann window (Q12) on the 15 sample pairs this lane owns in FFT pass 1, |max| across the
+// frame's 16 lanes (half a warp), scaling to 15 significant bits, radix-4 stages 1 and 2 on the 16
+// register-resident points.  PART 0 / 1 are the two halves for the host emulation (the half-warp exchange
+// of lane maxima through shared memory sits between them); PART 2 is the device version.
+struct K1Pass1Ctx { int32_t xr[16], xi[16]; };
 
-// P2: scale to 15 significant bits, FFT stages 1 and 2 on 16 local points
-MWW_HD void k1_fft_pass1(int tid, K1Smem &sm, const FrontendParams &P) {
+template <int PART>
+MWW_HD void k1_window_fft1(int tid, K1Smem &sm, int buf, const FrontendParams &P, K1Pass1Ctx &ctx) {
     const int fl = tid >> 4, a = tid & 15;
+    const int c = (a >> 2) + 4 * (a & 3);     // complex sample index modulo 16 owned by this lane
+    int32_t (&xr)[16] = ctx.xr;
+    int32_t (&xi)[16] = ctx.xi;
+    if (PART != 1) {
+        const uint32_t *pairs = reinterpret_cast<const uint32_t *>(sm.audio[buf]) + (kHop / 2) * fl;
+        int32_t m = 0;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const int j = (b >> 2) + 4 * (b & 3);  // position 4*n2+n3 holds complex sample c + 16*n2 + 64*n3
+            if (j == 15) { xr[b] = 0; xi[b] = 0; continue; }        // samples 480..511 are the zero padding
+            const int p = c + 16 * j;
+            const uint32_t sw = pairs[p];
+            const uint32_t cw = P.win_pairs[p];
+            const int32_t v0 = sext16((unpack_lo(sw) * unpack_lo(cw)) >> 12);
+            const int32_t v1 = sext16((unpack_hi(sw) * unpack_hi(cw)) >> 12);
+            xr[b] = v0; xi[b] = v1;
+            // |v| with the int16 wrap of the library: |-32768| stays negative and never wins the max
+            const int32_t a0 = v0 < 0 ? sext16(-v0) : v0;
+            const int32_t a1 = v1 < 0 ? sext16(-v1) : v1;
+            m = a0 > m ? a0 : m;
+            m = a1 > m ? a1 : m;
+        }
+        sm.lane_max[fl][a] = (uint16_t)m;
+    }
+#if defined(__CUDA_ARCH__)
+    if (PART == 2) __syncwarp();
+#endif
+    if (PART == 0) return;
     int32_t mx = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) { const int32_t v = sm.lane_max[fl][i]; mx = v > mx ? v : mx; }
     const int shift = 15 - msb32((uint32_t)mx);
     if (a == 0) sm.shift[fl] = shift;
-
-    const int c = (a >> 2) + 4 * (a & 3);     // complex sample index modulo 16 owned by this lane
-    int32_t xr[16], xi[16];
 #pragma unroll
-    for (int b = 0; b < 16; ++b) {
-        const int j = (b >> 2) + 4 * (b & 3);  // position 4*n2+n3 holds sample c + 16*n2 + 64*n3
-        if (j == 15) { xr[b] = 0; xi[b] = 0; }                 // samples 480..511 are the zero padding
-        else {
-            const uint32_t w = sm.A[fl][c + 16 * j];
-            xr[b] = sext16(unpack_lo(w) << shift);
-            xi[b] = sext16(unpack_hi(w) << shift);
-        }
-    }
+    for (int b = 0; b < 16; ++b) { xr[b] = sext16(xr[b] << shift); xi[b] = sext16(xi[b] << shift); }
     // stage 1 (m = 1): unit twiddles; C_MUL by (32767, 0) is the identity on the pre-divided range
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -287,12 +291,18 @@ MWW_HD void k1_filterbank(int tid, K1Smem &sm, const FrontendParams &P, uint32_t
     const int sh = sm.shift[fl];
 #pragma unroll
     for (int s = 0; s < kFbSlots; ++s) {
+        if (fb_len(s) == 0) continue;
         const FbSlot slot = P.fb_slots[l * kFbSlots + s];
-        const int n = P.fb_slot_len[s];
         int64_t acc = 0;
         const uint32_t *e = &sm.B[fl][slot.bin0];
-        const int16_t *cf = &sm.fb_coef[slot.coef_off];
-        for (int j = 0; j < n; ++j) acc = mad_wide_s32((int32_t)e[j], (int32_t)cf[j], acc);   // energy widened as int32, like the library
+        const uint32_t *cf = reinterpret_cast<const uint32_t *>(&sm.fb_coef[slot.coef_off]);   // coef_off is even
+#pragma unroll
+        for (int j = 0; j < fb_len(s) / 2; ++j) {
+            const uint32_t cw = cf[j];
+            // energy widened as int32, like the library
+            acc = mad_wide_s32((int32_t)e[2 * j], unpack_lo(cw), acc);
+            acc = mad_wide_s32((int32_t)e[2 * j + 1], unpack_hi(cw), acc);
+        }
         if (slot.ch >= 0 && vout_frame) vout_frame[slot.ch] = isqrt64_round((uint64_t)acc) >> sh;
     }
 }

@@ -101,6 +101,7 @@ bool make_filterbank(HostTables *t) {
         t->fb_slot_len[s] = 0;
         for (int l = 0; l < kFbLanes; ++l)
             if ((int)lane[l].size() > s) t->fb_slot_len[s] = std::max(t->fb_slot_len[s], lane[l][s].n);
+        t->fb_slot_len[s] = (t->fb_slot_len[s] + 1) & ~1;   // even: coefficients are fetched two per word
     }
     t->fb_coef.clear();
     for (int l = 0; l < kFbLanes; ++l)
@@ -110,8 +111,8 @@ bool make_filterbank(HostTables *t) {
             if ((int)lane[l].size() > s) {
                 const Span &sp = lane[l][s];
                 slot.ch = (int16_t)sp.ch; slot.bin0 = (int16_t)sp.bin0; slot.n = (int16_t)sp.n;
-                // keep padded reads inside the 256-word energy row
-                if (slot.bin0 + t->fb_slot_len[s] > 256) return false;
+                // keep padded reads inside the 272-word energy row
+                if (slot.bin0 + t->fb_slot_len[s] > 272) return false;
                 for (int j = 0; j < t->fb_slot_len[s]; ++j) {
                     const int b = sp.bin0 + j;
                     int16_t c = 0;

@@ -16,6 +16,11 @@ namespace mww {
 constexpr int kFbLanes = 16;       // lanes that cooperate on one frame
 constexpr int kFbSlots = 4;        // max channels one lane accumulates
 constexpr int kFbCoefMax = 1024;   // capacity of the shared-memory copy of the span coefficients
+// Trip counts of the balanced filterbank schedule (mww_tables.cc LPT assignment), padded to even so the
+// Q12 coefficients can be fetched two per 32-bit load.  mww_create verifies the table builder agrees.
+constexpr int kFbLen[kFbSlots] = {28, 12, 6, 0};
+MWW_HD constexpr int fb_len(int s) { return s == 0 ? 28 : (s == 1 ? 12 : (s == 2 ? 6 : 0)); }
+static_assert(fb_len(0) == kFbLen[0] && fb_len(1) == kFbLen[1] && fb_len(2) == kFbLen[2] && fb_len(3) == kFbLen[3], "fb_len");
 
 struct FbSlot {
     int16_t ch;        // output channel 0..39, -1 = unused slot

@@ -50,6 +50,7 @@ int emul_tables(int16_t *window480, int16_t *bin_weight257, int16_t *bin_unweigh
     for (int k = 0; k < 128; ++k) { super256[2 * k] = (int16_t)unpack_lo(t.super_tw[k]); super256[2 * k + 1] = (int16_t)unpack_hi(t.super_tw[k]); }
     info8[0] = t.start_index; info8[1] = t.end_index; info8[2] = t.ok;
     info8[3] = (int)t.fb_coef.size();
+    for (int s = 0; s < kFbSlots; ++s) if (t.fb_slot_len[s] != kFbLen[s]) return -1;
     for (int s = 0; s < kFbSlots; ++s) info8[4 + s] = t.fb_slot_len[s];
     return 0;
 }
@@ -76,9 +77,11 @@ int emul_features(const int16_t *audio, int n_streams, int n_samples, int16_t *c
         const int16_t *my_audio = audio + (size_t)s * n_samples;
         for (int g = 0; g < n_groups; ++g) {
             const int f0 = g * kFramesPerGroup;
-            for (int tid = 0; tid < kK1Threads; ++tid) k1_load_audio(tid, *sm, my_carry, used, my_audio, n_samples, f0);
-            for (int tid = 0; tid < kK1Threads; ++tid) k1_window(tid, *sm, g_params);
-            for (int tid = 0; tid < kK1Threads; ++tid) k1_fft_pass1(tid, *sm, g_params);
+            const int buf = g & 1;
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_load_audio(tid, *sm, buf, my_carry, used, my_audio, n_samples, f0);
+            std::vector<K1Pass1Ctx> ctx(kK1Threads);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_window_fft1<0>(tid, *sm, buf, g_params, ctx[tid]);   // half-warp exchange between
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_window_fft1<1>(tid, *sm, buf, g_params, ctx[tid]);
             for (int tid = 0; tid < kK1Threads; ++tid) k1_fft_pass2(tid, *sm, lanes[tid]);
             for (int tid = 0; tid < kK1Threads; ++tid) k1_real_energy(tid, *sm, g_params);
             for (int tid = 0; tid < kK1Threads; ++tid) {
