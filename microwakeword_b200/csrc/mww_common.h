@@ -39,6 +39,9 @@ MWW_HD uint32_t pack16(int32_t lo, int32_t hi) { return ((uint32_t)lo & 0xFFFFu)
 MWW_HD int32_t unpack_lo(uint32_t w) { return (int32_t)(int16_t)(w & 0xFFFFu); }
 MWW_HD int32_t unpack_hi(uint32_t w) { return ((int32_t)w) >> 16; }
 
+MWW_HD int32_t max3i(int32_t a, int32_t b, int32_t c) { const int32_t m = a > b ? a : b; return m > c ? m : c; }
+MWW_HD int32_t min3i(int32_t a, int32_t b, int32_t c) { const int32_t m = a < b ? a : b; return m < c ? m : c; }
+
 MWW_HD int64_t mad_wide_s32(int32_t a, int32_t b, int64_t c) { return (int64_t)a * (int64_t)b + c; }
 
 }  // namespace mww

@@ -80,43 +80,42 @@ MWW_HD void bfly4_core(int32_t &r0, int32_t &i0, int32_t &r1, int32_t &i1, int32
 // ---------------------------------------------------------------------------------------------
 // exact integer sqrt with the library's round-half-up (remainder > root) rule
 
+MWW_HD uint64_t sq32(uint32_t r) { return (uint64_t)r * r; }   // one 32x32->64 multiply
+
 MWW_HD uint32_t isqrt64_round(uint64_t x) {
     if (x == 0) return 0;
+    // float estimate (relative error ~2^-23), then one float Newton correction from the exact residual
 #if defined(__CUDA_ARCH__)
-    const float xf = __ull2float_rn(x);
-    const float rf = __fsqrt_rn(xf);
-    uint64_t r = (uint64_t)__float2ull_rz(rf);
+    const float rf = __fsqrt_rn(__ull2float_rn(x));
+    uint32_t r = rf >= 4294967040.0f ? 0xFFFFFFFFu : __float2uint_rz(rf);
 #else
-    const float xf = (float)x;
-    const float rf = sqrtf(xf);
-    uint64_t r = (uint64_t)rf;
+    const float rf = sqrtf((float)x);
+    uint32_t r = rf >= 4294967040.0f ? 0xFFFFFFFFu : (uint32_t)rf;
 #endif
-    if (r > 0xFFFFFFFFull) r = 0xFFFFFFFFull;
     if (r == 0) r = 1;
-    // one float Newton correction: r is within ~2^-23 relative, the residual fits a float exactly enough
     {
-        const int64_t d = (int64_t)(x - r * r);
+        const int64_t d = (int64_t)(x - sq32(r));
 #if defined(__CUDA_ARCH__)
-        const float c = __ll2float_rn(d) * __frcp_rn(2.0f * __ull2float_rn(r));
-        r = (uint64_t)((int64_t)r + (int64_t)__float2ll_rd(c));
+        const float c = __ll2float_rn(d) * __frcp_rn(2.0f * __uint2float_rn(r));
+        const int64_t r2 = (int64_t)r + (int64_t)__float2int_rd(c);
 #else
         const float c = (float)d * (1.0f / (2.0f * (float)r));
-        r = (uint64_t)((int64_t)r + (int64_t)floorf(c));
+        const int64_t r2 = (int64_t)r + (int64_t)floorf(c);
 #endif
-        if (r > 0xFFFFFFFFull) r = 0xFFFFFFFFull;
+        r = r2 > 0xFFFFFFFFll ? 0xFFFFFFFFu : (r2 < 1 ? 1u : (uint32_t)r2);
     }
     // exact fix-up: the estimate is within +-1 after the correction; straight-line steps first, the loops
     // are a safety net that is not expected to iterate
-    if (r * r > x) --r;
-    while (r * r > x) --r;
-    uint64_t rem = x - r * r;
-    if (rem > 2 * r) { rem -= 2 * r + 1; ++r; }
-    while (rem > 2 * r) { rem -= 2 * r + 1; ++r; }
+    if (sq32(r) > x) --r;
+    while (sq32(r) > x) --r;
+    uint64_t rem = x - sq32(r);
+    if (rem > 2ull * r) { rem -= 2ull * r + 1; ++r; }
+    while (rem > 2ull * r) { rem -= 2ull * r + 1; ++r; }
     // rounding: the 32-bit fast path of the library cannot exceed 0xFFFF, the 64-bit one 0xFFFFFFFF
-    const uint64_t cap = (x >> 32) == 0 ? 0xFFFFull : 0xFFFFFFFFull;
+    const uint32_t cap = (x >> 32) == 0 ? 0xFFFFu : 0xFFFFFFFFu;
     if (rem > r && r != cap) ++r;
     if (r > cap) r = cap;
-    return (uint32_t)r;
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -164,7 +163,10 @@ MWW_HD void k1_window_fft1(int tid, K1Smem &sm, int buf, const FrontendParams &P
     int32_t (&xi)[16] = ctx.xi;
     if (PART != 1) {
         const uint32_t *pairs = reinterpret_cast<const uint32_t *>(sm.audio[buf]) + (kHop / 2) * fl;
-        int32_t m = 0;
+        // max |v| as max(mx, -mn); a windowed value of -32768 (only reachable where the Q12 coefficient is
+        // exactly 4096: samples 238..241 = pairs 119, 120 = the j == 7 column) must not win, because the
+        // library's int16 negate leaves it negative.
+        int32_t mx = 0, mn = 0;
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
             const int j = (b >> 2) + 4 * (b & 3);  // position 4*n2+n3 holds complex sample c + 16*n2 + 64*n3
@@ -172,33 +174,44 @@ MWW_HD void k1_window_fft1(int tid, K1Smem &sm, int buf, const FrontendParams &P
             const int p = c + 16 * j;
             const uint32_t sw = pairs[p];
             const uint32_t cw = P.win_pairs[p];
-            const int32_t v0 = sext16((unpack_lo(sw) * unpack_lo(cw)) >> 12);
-            const int32_t v1 = sext16((unpack_hi(sw) * unpack_hi(cw)) >> 12);
+            const int32_t v0 = (unpack_lo(sw) * unpack_lo(cw)) >> 12;   // |s| <= 32768, c <= 4096: fits int16
+            const int32_t v1 = (unpack_hi(sw) * unpack_hi(cw)) >> 12;
             xr[b] = v0; xi[b] = v1;
-            // |v| with the int16 wrap of the library: |-32768| stays negative and never wins the max
-            const int32_t a0 = v0 < 0 ? sext16(-v0) : v0;
-            const int32_t a1 = v1 < 0 ? sext16(-v1) : v1;
-            m = a0 > m ? a0 : m;
-            m = a1 > m ? a1 : m;
+            if (j == 7) {
+                const int32_t m0 = v0 == -32768 ? 0 : v0, m1 = v1 == -32768 ? 0 : v1;
+                mx = max3i(mx, m0, m1); mn = min3i(mn, m0, m1);
+            } else {
+                mx = max3i(mx, v0, v1); mn = min3i(mn, v0, v1);
+            }
         }
+        const int32_t m = mx > -mn ? mx : -mn;
         sm.lane_max[fl][a] = (uint16_t)m;
     }
 #if defined(__CUDA_ARCH__)
     if (PART == 2) __syncwarp();
 #endif
     if (PART == 0) return;
-    int32_t mx = 0;
+    int32_t mxa = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { const int32_t v = sm.lane_max[fl][i]; mx = v > mx ? v : mx; }
-    const int shift = 15 - msb32((uint32_t)mx);
+    for (int i = 0; i < 16; ++i) { const int32_t v = sm.lane_max[fl][i]; mxa = v > mxa ? v : mxa; }
+    const int shift = 15 - msb32((uint32_t)mxa);
     if (a == 0) sm.shift[fl] = shift;
-#pragma unroll
-    for (int b = 0; b < 16; ++b) { xr[b] = sext16(xr[b] << shift); xi[b] = sext16(xi[b] << shift); }
-    // stage 1 (m = 1): unit twiddles; C_MUL by (32767, 0) is the identity on the pre-divided range
+    // stage 1 (m = 1): unit twiddles; C_MUL by (32767, 0) is the identity on the pre-divided range.
+    // The input scaling int16(uint16(v) << shift) is folded into C_FIXDIV's multiplier: v << shift cannot leave
+    // int16 (shift comes from the maximum) except for a -32768 in the j == 7 column, which wraps like the library.
+    const int32_t k4 = 8191 << shift;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { xr[4 * g + q] = fixdiv4(xr[4 * g + q]); xi[4 * g + q] = fixdiv4(xi[4 * g + q]); }
+        for (int q = 0; q < 4; ++q) {
+            const int b = 4 * g + q;
+            const int j = (b >> 2) + 4 * (b & 3);
+            if (j == 7) {
+                xr[b] = fixdiv4(sext16(xr[b] << shift)); xi[b] = fixdiv4(sext16(xi[b] << shift));
+            } else {
+                xr[b] = (xr[b] * k4 + 16384) >> 15; xi[b] = (xi[b] * k4 + 16384) >> 15;
+            }
+        }
         bfly4_core(xr[4 * g], xi[4 * g], xr[4 * g + 1], xi[4 * g + 1], xr[4 * g + 2], xi[4 * g + 2], xr[4 * g + 3], xi[4 * g + 3]);
     }
     // stage 2 (m = 4): butterfly k on points k, k+4, k+8, k+12; |stage-1 sums| <= 4*8191, no wrap possible

@@ -34,15 +34,18 @@ nn_f32_clip_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
         const int n = min(kTT, n_steps - step0);
         nn_load_features(tid, sm, in, step0, n);
         __syncthreads();
-        nn_first_conv(tid, sm, W);
+        float fc[2][4];
+        nn_first_conv_a(tid, sm, W, fc);
         __syncthreads();
-        nn_depthwise<0>(tid, sm, W); __syncthreads();
+        nn_first_conv_b(tid, sm, fc);
+        __syncthreads();
+        nn_stage_pw_weights<0>(tid, sm, W); nn_depthwise<0>(tid, sm, W); __syncthreads();
         nn_pointwise<0>(tid, sm, W); __syncthreads();
-        nn_depthwise<1>(tid, sm, W); __syncthreads();
+        nn_stage_pw_weights<1>(tid, sm, W); nn_depthwise<1>(tid, sm, W); __syncthreads();
         nn_pointwise<1>(tid, sm, W); __syncthreads();
-        nn_depthwise<2>(tid, sm, W); __syncthreads();
+        nn_stage_pw_weights<2>(tid, sm, W); nn_depthwise<2>(tid, sm, W); __syncthreads();
         nn_pointwise<2>(tid, sm, W); __syncthreads();
-        nn_depthwise<3>(tid, sm, W); __syncthreads();
+        nn_stage_pw_weights<3>(tid, sm, W); nn_depthwise<3>(tid, sm, W); __syncthreads();
         nn_pointwise<3>(tid, sm, W); __syncthreads();
         nn_head_partial(tid, sm, W);
         __syncthreads();

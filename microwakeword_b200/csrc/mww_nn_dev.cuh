@@ -12,9 +12,16 @@
 // buffers live in shared memory for the entire clip and touch HBM once per call, instead of the
 // reference's 4 176-element state shuffle on every step (stream.py:586-590).
 //
-// Shared-memory activation layout is channel-major [c][LD] with time contiguous; columns
-// [HP-R, HP) hold the ring history, columns [HP, HP+TT) the chunk's new outputs (HP = R rounded up to
-// a multiple of 4 so float4 accesses stay aligned; LD/4 is odd to spread 128-bit accesses over banks).
+// One CTA = one stream, 288 threads, chunks of 36 model steps (1 s of audio = 34 steps = one chunk).
+// Shared-memory activation layout is channel-major [c][LD] with time contiguous; columns [0, R) hold the
+// ring history, columns [R, R+TT) the chunk's new outputs.  LD is odd, so the depthwise stage -- one lane per
+// channel sliding along time -- reads without bank conflicts.  The depthwise output D[c][t] (the A operand
+// of the 1x1 contraction) has a 16-byte aligned pitch; the 1x1 weights of the current block are staged in
+// shared memory (in the region the feature planes occupied) so every thread accumulates a
+// 4 (out channels) x 2 (time steps) register tile from one 128-bit and one 64-bit load per k.
+// Feature rows are de-interleaved into three planes by (row mod 3) so that the stride-3 first conv reads
+// consecutive time steps from consecutive addresses; its K = 200 contraction is split over two thread groups
+// (taps 0-2 | taps 3-4) whose partial sums meet in shared memory.
 #pragma once
 
 #include "mww_common.h"
@@ -25,31 +32,28 @@
 
 namespace mww {
 
-constexpr int kNnThreads = 128;
-constexpr int kTT = 32;            // model steps per chunk
-
-// okay_nabu MixedNet (notebooks/basic_training_notebook.ipynb:503-509)
-struct ArchOkayNabu {
-    static constexpr int C0 = 32, K0 = 5, STRIDE = 3, NB = 4, CP = 64, HEAD = 17;
-    static constexpr int ring0_rows = 2;
-};
+constexpr int kNnThreads = 288;
+constexpr int kTT = 36;            // model steps per chunk
 
 struct NnLayerGeom { int cin, kmax, ring, hp, ld, off; };   // off: float offset of the buffer in smem
 
 // geometry of the five ring-carrying activation buffers: inputs of block 0..3 and of the head
+// (okay_nabu MixedNet, notebooks/basic_training_notebook.ipynb:503-509)
 constexpr NnLayerGeom kGeom[5] = {
-    {32, 5, 4, 4, 36, 0},
-    {64, 11, 10, 12, 44, 32 * 36},
-    {64, 15, 14, 16, 52, 32 * 36 + 64 * 44},
-    {64, 23, 22, 24, 60, 32 * 36 + 64 * 44 + 64 * 52},
-    {64, 17, 16, 16, 52, 32 * 36 + 64 * 44 + 64 * 52 + 64 * 60},
+    {32, 5, 4, 4, 41, 0},
+    {64, 11, 10, 10, 47, 32 * 41},
+    {64, 15, 14, 14, 51, 32 * 41 + 64 * 47},
+    {64, 23, 22, 22, 59, 32 * 41 + 64 * 47 + 64 * 51},
+    {64, 17, 16, 16, 53, 32 * 41 + 64 * 47 + 64 * 51 + 64 * 59},
 };
-constexpr int kXFloats = 32 * 36 + 64 * 44 + 64 * 52 + 64 * 60 + 64 * 52;   // 14464
+constexpr int kXFloats = 32 * 41 + 64 * (47 + 51 + 59 + 53);   // 14752
 constexpr int kDLd = 36;
 constexpr int kDFloats = 64 * kDLd;
-constexpr int kFeatFloats = 5 * kNumChannels * kTT;   // im2col'ed feature planes [j][f][t]
+constexpr int kUS = 40;                                       // pitch of a feature plane row (u index)
+constexpr int kFeatFloats = 3 * kNumChannels * kUS;           // 4800 >= 64*64 staged 1x1 weights
 constexpr int kNnSmemFloats = kXFloats + kDFloats + kFeatFloats;
-constexpr int kNnSmemBytes = kNnSmemFloats * 4;       // 92.4 KB -> 2 CTAs / SM
+constexpr int kNnSmemBytes = kNnSmemFloats * 4;               // 87.4 KB -> 2 CTAs / SM
+static_assert(kXFloats % 4 == 0 && kDFloats % 4 == 0 && kFeatFloats >= 64 * 64, "smem carve-up");
 
 // per-stream state layout in HBM (floats), oldest row first, [row][channel] -- identical to the oracle
 constexpr int kStateOff[6] = {0, 80, 80 + 128, 80 + 128 + 640, 80 + 128 + 640 + 896, 80 + 128 + 640 + 896 + 1408};
@@ -99,61 +103,115 @@ MWW_HD void nn_load_state(int tid, float *sm, const float *state) {
     nn_load_state_l<3>(tid, sm, state); nn_load_state_l<4>(tid, sm, state);
 }
 
-// ---- phase: im2col the chunk's feature rows: featJ[j][f][t] = row(3*(t0+t) + j - 2) ----
+// ---- phase: de-interleave the chunk's feature rows into three planes ----
+// Chunk-relative row q = 0 .. 3n+1 is virtual row 3*step0 + q - 2 (q = 0, 1: the first-conv ring or the
+// previous chunk's last two rows); plane[q % 3][f][q / 3].  Step t, tap j reads q = 3t + j.
 MWW_HD void nn_load_features(int tid, float *sm, const NnInput &in, int step0, int n) {
     float *feat = sm + kXFloats + kDFloats;
-    for (int e = tid; e < 5 * kNumChannels * kTT; e += kNnThreads) {
-        const int t = e % kTT;
-        const int f = (e / kTT) % kNumChannels;
-        const int j = e / (kTT * kNumChannels);
-        float v = 0.f;
-        if (t < n) v = nn_virtual_row(in, 3 * (step0 + t) + j - 2, f);
-        feat[(j * kNumChannels + f) * kTT + t] = v;
+    const int n_q = 3 * n + 2;
+    // one thread handles 8 consecutive features of one row: a single 16-byte load on the uint16 fast path
+    for (int e = tid; e < n_q * 5; e += kNnThreads) {
+        const int q = e / 5, f0 = 8 * (e - 5 * q);
+        const int vr = 3 * step0 + q - 2;
+        float *dst = feat + ((q % 3) * kNumChannels + f0) * kUS + q / 3;
+        const int r = vr - in.n_pend;
+        if (vr >= in.n_pend && !in.rows_are_f32) {
+            const uint16_t *src = static_cast<const uint16_t *>(in.rows) + (long long)r * kNumChannels + f0;
+#if defined(__CUDA_ARCH__)
+            const uint4 v = *reinterpret_cast<const uint4 *>(src);      // rows are 80 B apart, f0 * 2 is 16 B aligned
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                dst[(2 * i) * kUS] = (float)(w[i] & 0xFFFFu) * kFeatureScale;
+                dst[(2 * i + 1) * kUS] = (float)(w[i] >> 16) * kFeatureScale;
+            }
+#else
+            for (int i = 0; i < 8; ++i) dst[i * kUS] = (float)src[i] * kFeatureScale;
+#endif
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i * kUS] = nn_virtual_row(in, vr, f0 + i);
+        }
     }
 }
 
-// ---- phase: first conv (5x1, stride 3, 40 -> 32, no bias) + ReLU ----
-MWW_HD void nn_first_conv(int tid, float *sm, const NnWeightsF32 &W) {
+// ---- phases: first conv (5x1, stride 3, 40 -> 32, no bias) + ReLU ----
+// thread tile 2 out-channels x 4 steps; threads [0,144) contract taps 0..2 (aligned float4 reads of the planes),
+// threads [144,288) taps 3..4 (plane index + 1: scalar reads) and park their partial sums in D.
+MWW_HD void nn_first_conv_a(int tid, float *sm, const NnWeightsF32 &W, float (&acc)[2][4]) {
     const float *feat = sm + kXFloats + kDFloats;
-    const int o = tid & 31, q = tid >> 5;          // 8 steps per thread
-    float acc[8];
+    const int half = tid >= 144, r = tid - 144 * half;
+    const int o0 = 2 * (r & 15), t0 = 4 * (r >> 4);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int k = 0; k < 5 * kNumChannels; ++k) {
-        const float w = W.w0[k * 32 + o];
-        const float *x = feat + k * kTT + 8 * q;
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, x[i], acc[i]);
+        for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+    const int j_begin = half ? 3 : 0, j_end = half ? 5 : 3;
+    for (int j = j_begin; j < j_end; ++j) {
+        const float *plane = feat + (j % 3) * kNumChannels * kUS + t0 + j / 3;
+        const float *w = W.w0 + j * kNumChannels * 32 + o0;
+#pragma unroll 8
+        for (int f = 0; f < kNumChannels; ++f) {
+            const float w0 = w[f * 32], w1 = w[f * 32 + 1];
+            const float *x = plane + f * kUS;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { acc[0][q] = fmaf(w0, x[q], acc[0][q]); acc[1][q] = fmaf(w1, x[q], acc[1][q]); }
+        }
     }
-    float *dst = sm + kGeom[0].off + o * kGeom[0].ld + kGeom[0].hp + 8 * q;
+    if (half) {
+        float *part = sm + kXFloats;      // D region is idle until the first depthwise
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dst[i] = acc[i] > 0.f ? acc[i] : 0.f;
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) part[(o0 + i) * kDLd + t0 + q] = acc[i][q];
+    }
+}
+MWW_HD void nn_first_conv_b(int tid, float *sm, const float (&acc)[2][4]) {
+    if (tid >= 144) return;
+    const int o0 = 2 * (tid & 15), t0 = 4 * (tid >> 4);
+    const float *part = sm + kXFloats;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float *dst = sm + kGeom[0].off + (o0 + i) * kGeom[0].ld + kGeom[0].hp + t0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float v = acc[i][q] + part[(o0 + i) * kDLd + t0 + q];
+            dst[q] = v > 0.f ? v : 0.f;
+        }
+    }
+}
+
+// ---- phase helper: stage block L's 1x1 weights [cin][64] into shared memory (feature region, free by now) ----
+template <int L>
+MWW_HD void nn_stage_pw_weights(int tid, float *sm, const NnWeightsF32 &W) {
+    float *wsm = sm + kXFloats + kDFloats;
+    constexpr int n = kGeom[L].cin * 64;
+    for (int e = tid; e < n; e += kNnThreads) wsm[e] = W.pw_w[L][e];
 }
 
 // ---- phase: depthwise conv over (ring ++ chunk) for block L; output D[c][t] ----
-template <int L>
-MWW_HD void nn_depthwise(int tid, float *sm, const NnWeightsF32 &W) {
+// MixConv groups (mixednet.py:132-136): block 1 = 7 | 11 taps, block 2 = 9 | 15, blocks 0 and 3 uniform.  The
+// container stores kernels zero padded at the front to kmax taps, so a K-tap group reads weights [kmax-K, kmax).
+// cin = 64: 4 threads per channel x 9 steps (threads 256..287 idle); cin = 32: 9 threads per channel x 4 steps.
+template <int L, int K, int TN>
+MWW_HD void nn_depthwise_k(int c, int t0, float *sm, const NnWeightsF32 &W) {
     constexpr NnLayerGeom g = kGeom[L];
-    constexpr int TPC = kNnThreads / g.cin;        // threads per channel
-    constexpr int TN = kTT / TPC;                  // steps per thread
-    const int c = tid % g.cin, part = tid / g.cin;
-    const int t0 = part * TN;
-    float w[g.kmax];
+    float w[K];
 #pragma unroll
-    for (int j = 0; j < g.kmax; ++j) w[j] = W.dw_w[L][j * g.cin + c];
+    for (int j = 0; j < K; ++j) w[j] = W.dw_w[L][(g.kmax - K + j) * g.cin + c];
     const float bias = W.dw_b[L][c];
     float acc[TN];
 #pragma unroll
     for (int i = 0; i < TN; ++i) acc[i] = 0.f;
-    // output step t reads columns hp - (kmax-1) + t + j, j = 0..kmax-1 (oldest tap first, like the ring concat)
-    const float *x = sm + g.off + c * g.ld + (g.hp - (g.kmax - 1)) + t0;
+    // output step t reads columns hp - (K-1) + t + j, j = 0..K-1 (oldest tap first, like the ring concat)
+    const float *x = sm + g.off + c * g.ld + (g.hp - (K - 1)) + t0;
 #pragma unroll
-    for (int i = 0; i < TN + g.kmax - 1; ++i) {
+    for (int i = 0; i < TN + K - 1; ++i) {
         const float xv = x[i];
 #pragma unroll
         for (int tt = 0; tt < TN; ++tt) {
             const int j = i - tt;
-            if (j >= 0 && j < g.kmax) acc[tt] = fmaf(w[j], xv, acc[tt]);
+            if (j >= 0 && j < K) acc[tt] = fmaf(w[j], xv, acc[tt]);
         }
     }
     float *d = sm + kXFloats + c * kDLd + t0;
@@ -161,60 +219,80 @@ MWW_HD void nn_depthwise(int tid, float *sm, const NnWeightsF32 &W) {
     for (int i = 0; i < TN; ++i) d[i] = acc[i] + bias;
 }
 
+template <int L>
+MWW_HD void nn_depthwise(int tid, float *sm, const NnWeightsF32 &W) {
+    constexpr NnLayerGeom g = kGeom[L];
+    if (L == 0) {
+        nn_depthwise_k<L, g.kmax, 4>(tid & 31, 4 * (tid >> 5), sm, W);
+    } else {
+        if (tid >= 256) return;
+        const int c = tid & 63, t0 = 9 * (tid >> 6);
+        if (L == 1) { if (c < 32) nn_depthwise_k<L, 7, 9>(c, t0, sm, W); else nn_depthwise_k<L, 11, 9>(c, t0, sm, W); }
+        else if (L == 2) { if (c < 32) nn_depthwise_k<L, 9, 9>(c, t0, sm, W); else nn_depthwise_k<L, 15, 9>(c, t0, sm, W); }
+        else nn_depthwise_k<L, g.kmax, 9>(c, t0, sm, W);
+    }
+}
+
 // ---- phase: pointwise 1x1 (cin -> 64) + folded-BN bias + ReLU into the next ring buffer ----
+// thread tile: 4 output channels x 2 steps; 16 x 18 threads cover 64 x 36.
 template <int L>
 MWW_HD void nn_pointwise(int tid, float *sm, const NnWeightsF32 &W) {
     constexpr int cin = kGeom[L].cin;
     constexpr NnLayerGeom gn = kGeom[L + 1];
-    const int o = tid & 63, h = tid >> 6;          // 16 steps per thread
-    float acc[16];
+    const int o0 = 4 * (tid & 15), t0 = 2 * (tid >> 4);
+    const float *wsm = sm + kXFloats + kDFloats + o0;
+    const float *d = sm + kXFloats + t0;
+    float acc[4][2];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-    const float *d = sm + kXFloats + 16 * h;
+    for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+#pragma unroll 8
     for (int k = 0; k < cin; ++k) {
-        const float w = W.pw_w[L][k * 64 + o];
+        const float *w = wsm + k * 64;
         const float *x = d + k * kDLd;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = fmaf(w, x[i], acc[i]);
+        const float w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+        const float x0 = x[0], x1 = x[1];
+        acc[0][0] = fmaf(w0, x0, acc[0][0]); acc[0][1] = fmaf(w0, x1, acc[0][1]);
+        acc[1][0] = fmaf(w1, x0, acc[1][0]); acc[1][1] = fmaf(w1, x1, acc[1][1]);
+        acc[2][0] = fmaf(w2, x0, acc[2][0]); acc[2][1] = fmaf(w2, x1, acc[2][1]);
+        acc[3][0] = fmaf(w3, x0, acc[3][0]); acc[3][1] = fmaf(w3, x1, acc[3][1]);
     }
-    const float bias = W.pw_b[L][o];
-    float *dst = sm + gn.off + o * gn.ld + gn.hp + 16 * h;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { const float v = acc[i] + bias; dst[i] = v > 0.f ? v : 0.f; }
+    for (int i = 0; i < 4; ++i) {
+        const float bias = W.pw_b[L][o0 + i];
+        float *dst = sm + gn.off + (o0 + i) * gn.ld + gn.hp + t0;
+        const float v0 = acc[i][0] + bias, v1 = acc[i][1] + bias;
+        dst[0] = v0 > 0.f ? v0 : 0.f;
+        dst[1] = v1 > 0.f ? v1 : 0.f;
+    }
 }
 
 // ---- phase: head, part 1: per-channel 17-tap partial sums into D[c][t] ----
 MWW_HD void nn_head_partial(int tid, float *sm, const NnWeightsF32 &W) {
     constexpr NnLayerGeom g = kGeom[4];
-    const int c = tid & 63, h = tid >> 6;
+    if (tid >= 256) return;
+    const int c = tid & 63, t0 = 9 * (tid >> 6);
     float w[17];
 #pragma unroll
     for (int j = 0; j < 17; ++j) w[j] = W.head_w[j * 64 + c];
-    float acc[16];
+    float acc[9];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-    const float *x = sm + g.off + c * g.ld + (g.hp - 16) + 16 * h;
+    for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+    const float *x = sm + g.off + c * g.ld + (g.hp - 16) + t0;
 #pragma unroll
-    for (int i = 0; i < 16 + 16; ++i) {
+    for (int i = 0; i < 9 + 16; ++i) {
         const float xv = x[i];
 #pragma unroll
-        for (int tt = 0; tt < 16; ++tt) {
+        for (int tt = 0; tt < 9; ++tt) {
             const int j = i - tt;
             if (j >= 0 && j < 17) acc[tt] = fmaf(w[j], xv, acc[tt]);
         }
     }
-    float *d = sm + kXFloats + c * kDLd + 16 * h;
+    float *d = sm + kXFloats + c * kDLd + t0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) d[i] = acc[i];
+    for (int i = 0; i < 9; ++i) d[i] = acc[i];
 }
 
-MWW_HD float nn_sigmoid(float x) {
-#if defined(__CUDA_ARCH__)
-    return 1.0f / (1.0f + expf(-x));
-#else
-    return 1.0f / (1.0f + expf(-x));
-#endif
-}
+MWW_HD float nn_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ---- phase: head, part 2: reduce over channels, bias, sigmoid ----
 MWW_HD void nn_head_finish(int tid, float *sm, const NnWeightsF32 &W, int n, float *probs_out /* step0-relative */, float *logits_out) {
@@ -228,7 +306,7 @@ MWW_HD void nn_head_finish(int tid, float *sm, const NnWeightsF32 &W, int n, flo
 }
 
 // ---- phase pair: slide the ring histories left by n steps (read -> barrier -> write) ----
-constexpr int kShiftPerThread = 11;   // ceil(64*22 / 128)
+constexpr int kShiftPerThread = 5;   // ceil(64*22 / 288)
 template <int L>
 MWW_HD void nn_shift_read_l(int tid, const float *sm, int n, float (&tmp)[kShiftPerThread]) {
     constexpr NnLayerGeom g = kGeom[L];
@@ -274,29 +352,21 @@ MWW_HD void nn_store_state_l(int tid, const float *sm, float *state) {
 }
 // The new first-conv ring (two rows preceding the next unconsumed row) and the new pending rows are
 // gathered from the OLD ring/pending/rows first; a barrier separates this from nn_tail_write.
-struct NnTail { float ring_new[2], pend_new[2]; };
+struct NnTail { float ring_new, pend_new; };
 MWW_HD void nn_tail_read(int tid, const NnInput &in, int n_steps, int n_virtual_rows, NnTail &t) {
     const int consumed = 3 * n_steps;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int e = tid + q * kNnThreads;
-        t.ring_new[q] = 0.f; t.pend_new[q] = 0.f;
-        if (e < 2 * kNumChannels) {
-            const int r = e / kNumChannels, f = e - r * kNumChannels;
-            t.ring_new[q] = nn_virtual_row(in, consumed - 2 + r, f);
-            const int vr = consumed + r;
-            t.pend_new[q] = vr < n_virtual_rows ? nn_virtual_row(in, vr, f) : 0.f;
-        }
+    t.ring_new = 0.f; t.pend_new = 0.f;
+    if (tid < 2 * kNumChannels) {
+        const int r = tid / kNumChannels, f = tid - r * kNumChannels;
+        t.ring_new = nn_virtual_row(in, consumed - 2 + r, f);
+        const int vr = consumed + r;
+        t.pend_new = vr < n_virtual_rows ? nn_virtual_row(in, vr, f) : 0.f;
     }
 }
 MWW_HD void nn_tail_write(int tid, const float *sm, float *state, float *pend_out, const NnTail &t) {
     nn_store_state_l<0>(tid, sm, state); nn_store_state_l<1>(tid, sm, state); nn_store_state_l<2>(tid, sm, state);
     nn_store_state_l<3>(tid, sm, state); nn_store_state_l<4>(tid, sm, state);
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int e = tid + q * kNnThreads;
-        if (e < 2 * kNumChannels) { state[e] = t.ring_new[q]; pend_out[e] = t.pend_new[q]; }
-    }
+    if (tid < 2 * kNumChannels) { state[tid] = t.ring_new; pend_out[tid] = t.pend_new; }
 }
 
 }  // namespace mww

@@ -101,57 +101,82 @@ MWW_HD void nnq_load_state(int tid, int32_t *sm, const int8_t *state, const NnWe
     nnq_load_state_l<3>(tid, sm, state, W); nnq_load_state_l<4>(tid, sm, state, W);
 }
 
+// de-interleave the chunk's rows into three planes of (q - zp_in) words (same indexing as the fp32 path)
 MWW_HD void nnq_load_features(int tid, int32_t *sm, const NnInputI8 &in, const NnWeightsI8 &W, int step0, int n) {
     int32_t *feat = sm + kXFloats + kDFloats;
-    for (int e = tid; e < 5 * kNumChannels * kTT; e += kNnThreads) {
-        const int t = e % kTT;
-        const int f = (e / kTT) % kNumChannels;
-        const int j = e / (kTT * kNumChannels);
-        int32_t v = 0;
-        if (t < n) v = nnq_virtual_row(in, W, 3 * (step0 + t) + j - 2, f);
-        feat[(j * kNumChannels + f) * kTT + t] = v;
+    const int n_q = 3 * n + 2;
+    for (int e = tid; e < n_q * kNumChannels; e += kNnThreads) {
+        const int q = e / kNumChannels, f = e - q * kNumChannels;
+        feat[((q % 3) * kNumChannels + f) * kUS + q / 3] = nnq_virtual_row(in, W, 3 * step0 + q - 2, f);
     }
 }
 
-MWW_HD void nnq_first_conv(int tid, int32_t *sm, const NnWeightsI8 &W) {
+// first conv, K split over two thread groups (taps 0..2 | 3..4); integer partial sums meet in D
+MWW_HD void nnq_first_conv_a(int tid, int32_t *sm, const NnWeightsI8 &W, int32_t (&acc)[2][4]) {
     const int32_t *feat = sm + kXFloats + kDFloats;
-    const int o = tid & 31, q = tid >> 5;
-    int32_t acc[8];
+    const int half = tid >= 144, r = tid - 144 * half;
+    const int o0 = 2 * (r & 15), t0 = 4 * (r >> 4);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0;
-    for (int k = 0; k < 5 * kNumChannels; ++k) {
-        const int32_t w = W.w0[k * 32 + o];
-        const int32_t *x = feat + k * kTT + 8 * q;
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += w * x[i];
+        for (int q = 0; q < 4; ++q) acc[i][q] = 0;
+    const int j_begin = half ? 3 : 0, j_end = half ? 5 : 3;
+    for (int j = j_begin; j < j_end; ++j) {
+        const int32_t *plane = feat + (j % 3) * kNumChannels * kUS + t0 + j / 3;
+        const int8_t *w = W.w0 + j * kNumChannels * 32 + o0;
+#pragma unroll 8
+        for (int f = 0; f < kNumChannels; ++f) {
+            const int32_t w0 = w[f * 32], w1 = w[f * 32 + 1];
+            const int32_t *x = plane + f * kUS;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { acc[0][q] += w0 * x[q]; acc[1][q] += w1 * x[q]; }
+        }
     }
-    const int32_t b = W.b0[o], m = W.m0[o], s = W.s0[o];
-    int32_t *dst = sm + kGeom[0].off + o * kGeom[0].ld + kGeom[0].hp + 8 * q;
+    if (half) {
+        int32_t *part = sm + kXFloats;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dst[i] = requant_rel(acc[i] + b, m, s, W.zp[1], true);
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) part[(o0 + i) * kDLd + t0 + q] = acc[i][q];
+    }
+}
+MWW_HD void nnq_first_conv_b(int tid, int32_t *sm, const NnWeightsI8 &W, const int32_t (&acc)[2][4]) {
+    if (tid >= 144) return;
+    const int o0 = 2 * (tid & 15), t0 = 4 * (tid >> 4);
+    const int32_t *part = sm + kXFloats;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int32_t b = W.b0[o0 + i], m = W.m0[o0 + i], s = W.s0[o0 + i];
+        int32_t *dst = sm + kGeom[0].off + (o0 + i) * kGeom[0].ld + kGeom[0].hp + t0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = requant_rel(acc[i][q] + part[(o0 + i) * kDLd + t0 + q] + b, m, s, W.zp[1], true);
+    }
 }
 
 template <int L>
-MWW_HD void nnq_depthwise(int tid, int32_t *sm, const NnWeightsI8 &W) {
+MWW_HD void nnq_stage_pw_weights(int tid, int32_t *sm, const NnWeightsI8 &W) {
+    int32_t *wsm = sm + kXFloats + kDFloats;
+    constexpr int n = kGeom[L].cin * 64;
+    for (int e = tid; e < n; e += kNnThreads) wsm[e] = W.pw_w[L][e];
+}
+
+template <int L, int K, int TN>
+MWW_HD void nnq_depthwise_k(int c, int t0, int32_t *sm, const NnWeightsI8 &W) {
     constexpr NnLayerGeom g = kGeom[L];
-    constexpr int TPC = kNnThreads / g.cin;
-    constexpr int TN = kTT / TPC;
-    const int c = tid % g.cin, part = tid / g.cin;
-    const int t0 = part * TN;
-    int32_t w[g.kmax];
+    int32_t w[K];
 #pragma unroll
-    for (int j = 0; j < g.kmax; ++j) w[j] = W.dw_w[L][j * g.cin + c];
+    for (int j = 0; j < K; ++j) w[j] = W.dw_w[L][(g.kmax - K + j) * g.cin + c];
     int32_t acc[TN];
 #pragma unroll
     for (int i = 0; i < TN; ++i) acc[i] = 0;
-    const int32_t *x = sm + g.off + c * g.ld + (g.hp - (g.kmax - 1)) + t0;
+    const int32_t *x = sm + g.off + c * g.ld + (g.hp - (K - 1)) + t0;
 #pragma unroll
-    for (int i = 0; i < TN + g.kmax - 1; ++i) {
+    for (int i = 0; i < TN + K - 1; ++i) {
         const int32_t xv = x[i];
 #pragma unroll
         for (int tt = 0; tt < TN; ++tt) {
             const int j = i - tt;
-            if (j >= 0 && j < g.kmax) acc[tt] += w[j] * xv;
+            if (j >= 0 && j < K) acc[tt] += w[j] * xv;
         }
     }
     const int32_t b = W.dw_b[L][c], m = W.dw_m[L][c], s = W.dw_s[L][c];
@@ -161,48 +186,69 @@ MWW_HD void nnq_depthwise(int tid, int32_t *sm, const NnWeightsI8 &W) {
 }
 
 template <int L>
+MWW_HD void nnq_depthwise(int tid, int32_t *sm, const NnWeightsI8 &W) {
+    constexpr NnLayerGeom g = kGeom[L];
+    if (L == 0) {
+        nnq_depthwise_k<L, g.kmax, 4>(tid & 31, 4 * (tid >> 5), sm, W);
+    } else {
+        if (tid >= 256) return;
+        const int c = tid & 63, t0 = 9 * (tid >> 6);
+        if (L == 1) { if (c < 32) nnq_depthwise_k<L, 7, 9>(c, t0, sm, W); else nnq_depthwise_k<L, 11, 9>(c, t0, sm, W); }
+        else if (L == 2) { if (c < 32) nnq_depthwise_k<L, 9, 9>(c, t0, sm, W); else nnq_depthwise_k<L, 15, 9>(c, t0, sm, W); }
+        else nnq_depthwise_k<L, g.kmax, 9>(c, t0, sm, W);
+    }
+}
+
+template <int L>
 MWW_HD void nnq_pointwise(int tid, int32_t *sm, const NnWeightsI8 &W) {
     constexpr int cin = kGeom[L].cin;
     constexpr NnLayerGeom gn = kGeom[L + 1];
-    const int o = tid & 63, h = tid >> 6;
-    int32_t acc[16];
+    const int o0 = 4 * (tid & 15), t0 = 2 * (tid >> 4);
+    const int32_t *wsm = sm + kXFloats + kDFloats + o0;
+    const int32_t *d = sm + kXFloats + t0;
+    int32_t acc[4][2];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0;
-    const int32_t *d = sm + kXFloats + 16 * h;
+    for (int i = 0; i < 4; ++i) { acc[i][0] = 0; acc[i][1] = 0; }
+#pragma unroll 8
     for (int k = 0; k < cin; ++k) {
-        const int32_t w = W.pw_w[L][k * 64 + o];
+        const int32_t *w = wsm + k * 64;
         const int32_t *x = d + k * kDLd;
+        const int32_t x0 = x[0], x1 = x[1];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] += w * x[i];
+        for (int i = 0; i < 4; ++i) { acc[i][0] += w[i] * x0; acc[i][1] += w[i] * x1; }
     }
-    const int32_t b = W.pw_b[L][o], m = W.pw_m[L][o], s = W.pw_s[L][o];
-    int32_t *dst = sm + gn.off + o * gn.ld + gn.hp + 16 * h;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) dst[i] = requant_rel(acc[i] + b, m, s, W.zp[3 + 2 * L], true);
+    for (int i = 0; i < 4; ++i) {
+        const int32_t b = W.pw_b[L][o0 + i], m = W.pw_m[L][o0 + i], s = W.pw_s[L][o0 + i];
+        int32_t *dst = sm + gn.off + (o0 + i) * gn.ld + gn.hp + t0;
+        dst[0] = requant_rel(acc[i][0] + b, m, s, W.zp[3 + 2 * L], true);
+        dst[1] = requant_rel(acc[i][1] + b, m, s, W.zp[3 + 2 * L], true);
+    }
 }
 
 MWW_HD void nnq_head_partial(int tid, int32_t *sm, const NnWeightsI8 &W) {
     constexpr NnLayerGeom g = kGeom[4];
-    const int c = tid & 63, h = tid >> 6;
+    if (tid >= 256) return;
+    const int c = tid & 63, t0 = 9 * (tid >> 6);
     int32_t w[17];
 #pragma unroll
     for (int j = 0; j < 17; ++j) w[j] = W.head_w[j * 64 + c];
-    int32_t acc[16];
+    int32_t acc[9];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0;
-    const int32_t *x = sm + g.off + c * g.ld + (g.hp - 16) + 16 * h;
+    for (int i = 0; i < 9; ++i) acc[i] = 0;
+    const int32_t *x = sm + g.off + c * g.ld + (g.hp - 16) + t0;
 #pragma unroll
-    for (int i = 0; i < 16 + 16; ++i) {
+    for (int i = 0; i < 9 + 16; ++i) {
         const int32_t xv = x[i];
 #pragma unroll
-        for (int tt = 0; tt < 16; ++tt) {
+        for (int tt = 0; tt < 9; ++tt) {
             const int j = i - tt;
             if (j >= 0 && j < 17) acc[tt] += w[j] * xv;
         }
     }
-    int32_t *d = sm + kXFloats + c * kDLd + 16 * h;
+    int32_t *d = sm + kXFloats + c * kDLd + t0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) d[i] = acc[i];
+    for (int i = 0; i < 9; ++i) d[i] = acc[i];
 }
 
 // FULLY_CONNECTED requant -> LOGISTIC LUT -> QUANTIZE to uint8 -> Model.dequantize_output_data (/255)
@@ -227,29 +273,21 @@ MWW_HD void nnq_store_state_l(int tid, const int32_t *sm, int8_t *state, const N
     }
 }
 
-struct NnTailI8 { int8_t ring_new[2], pend_new[2]; };
+struct NnTailI8 { int8_t ring_new, pend_new; };
 MWW_HD void nnq_tail_read(int tid, const NnInputI8 &in, const NnWeightsI8 &W, int n_steps, int n_virtual_rows, NnTailI8 &t) {
     const int consumed = 3 * n_steps;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int e = tid + q * kNnThreads;
-        t.ring_new[q] = 0; t.pend_new[q] = 0;
-        if (e < 2 * kNumChannels) {
-            const int r = e / kNumChannels, f = e - r * kNumChannels;
-            t.ring_new[q] = (int8_t)(nnq_virtual_row(in, W, consumed - 2 + r, f) + W.zp[0]);
-            const int vr = consumed + r;
-            t.pend_new[q] = vr < n_virtual_rows ? (int8_t)(nnq_virtual_row(in, W, vr, f) + W.zp[0]) : (int8_t)W.zp[0];
-        }
+    t.ring_new = 0; t.pend_new = 0;
+    if (tid < 2 * kNumChannels) {
+        const int r = tid / kNumChannels, f = tid - r * kNumChannels;
+        t.ring_new = (int8_t)(nnq_virtual_row(in, W, consumed - 2 + r, f) + W.zp[0]);
+        const int vr = consumed + r;
+        t.pend_new = vr < n_virtual_rows ? (int8_t)(nnq_virtual_row(in, W, vr, f) + W.zp[0]) : (int8_t)W.zp[0];
     }
 }
 MWW_HD void nnq_tail_write(int tid, const int32_t *sm, int8_t *state, int8_t *pend_out, const NnWeightsI8 &W, const NnTailI8 &t) {
     nnq_store_state_l<0>(tid, sm, state, W); nnq_store_state_l<1>(tid, sm, state, W); nnq_store_state_l<2>(tid, sm, state, W);
     nnq_store_state_l<3>(tid, sm, state, W); nnq_store_state_l<4>(tid, sm, state, W);
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int e = tid + q * kNnThreads;
-        if (e < 2 * kNumChannels) { state[e] = t.ring_new[q]; pend_out[e] = t.pend_new[q]; }
-    }
+    if (tid < 2 * kNumChannels) { state[tid] = t.ring_new; pend_out[tid] = t.pend_new; }
 }
 
 // value every state byte takes after a reset: the zero point of the tensor it buffers

@@ -30,15 +30,18 @@ nn_i8_clip_kernel(NnWeightsI8 W, int8_t *__restrict__ state, int8_t *__restrict_
         const int n = min(kTT, n_steps - step0);
         nnq_load_features(tid, smi, in, W, step0, n);
         __syncthreads();
-        nnq_first_conv(tid, smi, W);
+        int32_t fc[2][4];
+        nnq_first_conv_a(tid, smi, W, fc);
         __syncthreads();
-        nnq_depthwise<0>(tid, smi, W); __syncthreads();
+        nnq_first_conv_b(tid, smi, W, fc);
+        __syncthreads();
+        nnq_stage_pw_weights<0>(tid, smi, W); nnq_depthwise<0>(tid, smi, W); __syncthreads();
         nnq_pointwise<0>(tid, smi, W); __syncthreads();
-        nnq_depthwise<1>(tid, smi, W); __syncthreads();
+        nnq_stage_pw_weights<1>(tid, smi, W); nnq_depthwise<1>(tid, smi, W); __syncthreads();
         nnq_pointwise<1>(tid, smi, W); __syncthreads();
-        nnq_depthwise<2>(tid, smi, W); __syncthreads();
+        nnq_stage_pw_weights<2>(tid, smi, W); nnq_depthwise<2>(tid, smi, W); __syncthreads();
         nnq_pointwise<2>(tid, smi, W); __syncthreads();
-        nnq_depthwise<3>(tid, smi, W); __syncthreads();
+        nnq_stage_pw_weights<3>(tid, smi, W); nnq_depthwise<3>(tid, smi, W); __syncthreads();
         nnq_pointwise<3>(tid, smi, W); __syncthreads();
         nnq_head_partial(tid, smi, W);
         __syncthreads();

@@ -35,11 +35,13 @@ extern "C" int emul_nn_f32(const float *const *wp /* w0, dw_w[4], dw_b[4], pw_w[
         for (int step0 = 0; step0 < n_steps; step0 += kTT) {
             const int n = n_steps - step0 < kTT ? n_steps - step0 : kTT;
             ALL(nn_load_features(tid, sm, in, step0, n));
-            ALL(nn_first_conv(tid, sm, W));
-            ALL(nn_depthwise<0>(tid, sm, W)); ALL(nn_pointwise<0>(tid, sm, W));
-            ALL(nn_depthwise<1>(tid, sm, W)); ALL(nn_pointwise<1>(tid, sm, W));
-            ALL(nn_depthwise<2>(tid, sm, W)); ALL(nn_pointwise<2>(tid, sm, W));
-            ALL(nn_depthwise<3>(tid, sm, W)); ALL(nn_pointwise<3>(tid, sm, W));
+            std::vector<float> fc((size_t)kNnThreads * 8);
+            ALL(nn_first_conv_a(tid, sm, W, *reinterpret_cast<float(*)[2][4]>(&fc[(size_t)tid * 8])));
+            ALL(nn_first_conv_b(tid, sm, *reinterpret_cast<float(*)[2][4]>(&fc[(size_t)tid * 8])));
+            ALL(nn_stage_pw_weights<0>(tid, sm, W)); ALL(nn_depthwise<0>(tid, sm, W)); ALL(nn_pointwise<0>(tid, sm, W));
+            ALL(nn_stage_pw_weights<1>(tid, sm, W)); ALL(nn_depthwise<1>(tid, sm, W)); ALL(nn_pointwise<1>(tid, sm, W));
+            ALL(nn_stage_pw_weights<2>(tid, sm, W)); ALL(nn_depthwise<2>(tid, sm, W)); ALL(nn_pointwise<2>(tid, sm, W));
+            ALL(nn_stage_pw_weights<3>(tid, sm, W)); ALL(nn_depthwise<3>(tid, sm, W)); ALL(nn_pointwise<3>(tid, sm, W));
             ALL(nn_head_partial(tid, sm, W));
             ALL(nn_head_finish(tid, sm, W, n, probs + (size_t)s * max_probs + step0, logits ? logits + (size_t)s * max_probs + step0 : nullptr));
             std::vector<float> tmp((size_t)kNnThreads * 5 * kShiftPerThread);
@@ -89,11 +91,13 @@ extern "C" int emul_nn_i8(const void *const *wp /* see order below */, const int
         for (int step0 = 0; step0 < n_steps; step0 += kTT) {
             const int n = n_steps - step0 < kTT ? n_steps - step0 : kTT;
             ALL(nnq_load_features(tid, sm, in, W, step0, n));
-            ALL(nnq_first_conv(tid, sm, W));
-            ALL(nnq_depthwise<0>(tid, sm, W)); ALL(nnq_pointwise<0>(tid, sm, W));
-            ALL(nnq_depthwise<1>(tid, sm, W)); ALL(nnq_pointwise<1>(tid, sm, W));
-            ALL(nnq_depthwise<2>(tid, sm, W)); ALL(nnq_pointwise<2>(tid, sm, W));
-            ALL(nnq_depthwise<3>(tid, sm, W)); ALL(nnq_pointwise<3>(tid, sm, W));
+            std::vector<int32_t> fc((size_t)kNnThreads * 8);
+            ALL(nnq_first_conv_a(tid, sm, W, *reinterpret_cast<int32_t(*)[2][4]>(&fc[(size_t)tid * 8])));
+            ALL(nnq_first_conv_b(tid, sm, W, *reinterpret_cast<int32_t(*)[2][4]>(&fc[(size_t)tid * 8])));
+            ALL(nnq_stage_pw_weights<0>(tid, sm, W)); ALL(nnq_depthwise<0>(tid, sm, W)); ALL(nnq_pointwise<0>(tid, sm, W));
+            ALL(nnq_stage_pw_weights<1>(tid, sm, W)); ALL(nnq_depthwise<1>(tid, sm, W)); ALL(nnq_pointwise<1>(tid, sm, W));
+            ALL(nnq_stage_pw_weights<2>(tid, sm, W)); ALL(nnq_depthwise<2>(tid, sm, W)); ALL(nnq_pointwise<2>(tid, sm, W));
+            ALL(nnq_stage_pw_weights<3>(tid, sm, W)); ALL(nnq_depthwise<3>(tid, sm, W)); ALL(nnq_pointwise<3>(tid, sm, W));
             ALL(nnq_head_partial(tid, sm, W));
             ALL(nnq_head_finish(tid, sm, W, n, probs + (size_t)s * max_probs + step0));
             std::vector<float> tmp((size_t)kNnThreads * 5 * kShiftPerThread);
