@@ -82,40 +82,39 @@ MWW_HD void bfly4_core(int32_t &r0, int32_t &i0, int32_t &r1, int32_t &i1, int32
 
 MWW_HD uint64_t sq32(uint32_t r) { return (uint64_t)r * r; }   // one 32x32->64 multiply
 
+// Branch-free: float estimate r0 (|r0 - sqrt x| <= ~1.5e3 for x < 2^64), one Newton step in float on the EXACT
+// integer residual (lands within +-1 of floor(sqrt x): the float error of the correction is < 1e-3), then two
+// predicated exact fix-ups.  A third defensive pass costs a few predicated instructions and never fires.
 MWW_HD uint32_t isqrt64_round(uint64_t x) {
-    if (x == 0) return 0;
-    // float estimate (relative error ~2^-23), then one float Newton correction from the exact residual
 #if defined(__CUDA_ARCH__)
-    const float rf = __fsqrt_rn(__ull2float_rn(x));
-    uint32_t r = rf >= 4294967040.0f ? 0xFFFFFFFFu : __float2uint_rz(rf);
+    const float xf = __ull2float_rn(x);
+    const float rs = rsqrtf(xf);                       // MUFU.RSQ; inf for x == 0 (handled by the final select)
+    uint32_t r = __float2uint_rz(xf * rs);             // saturates at 0xFFFFFFFF
+    const int64_t d = (int64_t)(x - sq32(r));
+    const int64_t r1 = (int64_t)r + (int64_t)__float2int_rd(__ll2float_rn(d) * (0.5f * rs));
 #else
-    const float rf = sqrtf((float)x);
+    const float xf = (float)x;
+    const float rs = x ? 1.0f / sqrtf(xf) : 0.0f;
+    const float rf = xf * rs;
     uint32_t r = rf >= 4294967040.0f ? 0xFFFFFFFFu : (uint32_t)rf;
+    const int64_t d = (int64_t)(x - sq32(r));
+    const int64_t r1 = (int64_t)r + (int64_t)floorf((float)d * (0.5f * rs));
 #endif
-    if (r == 0) r = 1;
-    {
-        const int64_t d = (int64_t)(x - sq32(r));
-#if defined(__CUDA_ARCH__)
-        const float c = __ll2float_rn(d) * __frcp_rn(2.0f * __uint2float_rn(r));
-        const int64_t r2 = (int64_t)r + (int64_t)__float2int_rd(c);
-#else
-        const float c = (float)d * (1.0f / (2.0f * (float)r));
-        const int64_t r2 = (int64_t)r + (int64_t)floorf(c);
-#endif
-        r = r2 > 0xFFFFFFFFll ? 0xFFFFFFFFu : (r2 < 1 ? 1u : (uint32_t)r2);
-    }
-    // exact fix-up: the estimate is within +-1 after the correction; straight-line steps first, the loops
-    // are a safety net that is not expected to iterate
-    if (sq32(r) > x) --r;
-    while (sq32(r) > x) --r;
+    r = r1 > 0xFFFFFFFFll ? 0xFFFFFFFFu : (r1 < 0 ? 0u : (uint32_t)r1);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) r -= (sq32(r) > x) ? 1u : 0u;
     uint64_t rem = x - sq32(r);
-    if (rem > 2ull * r) { rem -= 2ull * r + 1; ++r; }
-    while (rem > 2ull * r) { rem -= 2ull * r + 1; ++r; }
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool up = rem > 2ull * r;
+        rem -= up ? 2ull * r + 1 : 0ull;
+        r += up ? 1u : 0u;
+    }
     // rounding: the 32-bit fast path of the library cannot exceed 0xFFFF, the 64-bit one 0xFFFFFFFF
     const uint32_t cap = (x >> 32) == 0 ? 0xFFFFu : 0xFFFFFFFFu;
-    if (rem > r && r != cap) ++r;
-    if (r > cap) r = cap;
-    return r;
+    r += (rem > r && r < cap) ? 1u : 0u;
+    r = r > cap ? cap : r;
+    return x == 0 ? 0u : r;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -38,14 +38,18 @@ nn_f32_clip_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
         nn_first_conv_a(tid, sm, W, fc);
         __syncthreads();
         nn_first_conv_b(tid, sm, fc);
+        nn_stage_pw_weights<0>(tid, sm, W);          // feature planes are dead: block 0's weights land there
+        nn_stage_pw_weights<1>(tid, sm, W);
         __syncthreads();
-        nn_stage_pw_weights<0>(tid, sm, W); nn_depthwise<0>(tid, sm, W); __syncthreads();
+        nn_depthwise<0>(tid, sm, W); nn_wait_weights<1>(); __syncthreads();
         nn_pointwise<0>(tid, sm, W); __syncthreads();
-        nn_stage_pw_weights<1>(tid, sm, W); nn_depthwise<1>(tid, sm, W); __syncthreads();
+        nn_stage_pw_weights<2>(tid, sm, W);          // buffer of block 0 is free again
+        nn_depthwise<1>(tid, sm, W); nn_wait_weights<1>(); __syncthreads();
         nn_pointwise<1>(tid, sm, W); __syncthreads();
-        nn_stage_pw_weights<2>(tid, sm, W); nn_depthwise<2>(tid, sm, W); __syncthreads();
+        nn_stage_pw_weights<3>(tid, sm, W);
+        nn_depthwise<2>(tid, sm, W); nn_wait_weights<1>(); __syncthreads();
         nn_pointwise<2>(tid, sm, W); __syncthreads();
-        nn_stage_pw_weights<3>(tid, sm, W); nn_depthwise<3>(tid, sm, W); __syncthreads();
+        nn_depthwise<3>(tid, sm, W); nn_wait_weights<0>(); __syncthreads();
         nn_pointwise<3>(tid, sm, W); __syncthreads();
         nn_head_partial(tid, sm, W);
         __syncthreads();

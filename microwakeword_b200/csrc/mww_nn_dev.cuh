@@ -51,8 +51,9 @@ constexpr int kDLd = 36;
 constexpr int kDFloats = 64 * kDLd;
 constexpr int kUS = 40;                                       // pitch of a feature plane row (u index)
 constexpr int kFeatFloats = 3 * kNumChannels * kUS;           // 4800 >= 64*64 staged 1x1 weights
-constexpr int kNnSmemFloats = kXFloats + kDFloats + kFeatFloats;
-constexpr int kNnSmemBytes = kNnSmemFloats * 4;               // 87.4 KB -> 2 CTAs / SM
+constexpr int kWBFloats = 64 * 64;                            // second staging buffer for the 1x1 weights
+constexpr int kNnSmemFloats = kXFloats + kDFloats + kFeatFloats + kWBFloats;
+constexpr int kNnSmemBytes = kNnSmemFloats * 4;               // 103.8 KB -> 2 CTAs / SM
 static_assert(kXFloats % 4 == 0 && kDFloats % 4 == 0 && kFeatFloats >= 64 * 64, "smem carve-up");
 
 // per-stream state layout in HBM (floats), oldest row first, [row][channel] -- identical to the oracle
@@ -146,16 +147,45 @@ MWW_HD void nn_first_conv_a(int tid, float *sm, const NnWeightsF32 &W, float (&a
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
-    const int j_begin = half ? 3 : 0, j_end = half ? 5 : 3;
-    for (int j = j_begin; j < j_end; ++j) {
-        const float *plane = feat + (j % 3) * kNumChannels * kUS + t0 + j / 3;
-        const float *w = W.w0 + j * kNumChannels * 32 + o0;
+    if (!half) {
+        // taps 0..2: plane j, u = t -> 16-byte aligned float4 of four consecutive steps
+#pragma unroll 1
+        for (int j = 0; j < 3; ++j) {
+            const float *plane = feat + j * kNumChannels * kUS + t0;
+            const float *w = W.w0 + j * kNumChannels * 32 + o0;
 #pragma unroll 8
-        for (int f = 0; f < kNumChannels; ++f) {
-            const float w0 = w[f * 32], w1 = w[f * 32 + 1];
-            const float *x = plane + f * kUS;
+            for (int f = 0; f < kNumChannels; ++f) {
+#if defined(__CUDA_ARCH__)
+                const float2 ww = __ldg(reinterpret_cast<const float2 *>(w + f * 32));
+                const float4 xx = *reinterpret_cast<const float4 *>(plane + f * kUS);
+                const float w0 = ww.x, w1 = ww.y;
+                const float x[4] = {xx.x, xx.y, xx.z, xx.w};
+#else
+                const float w0 = w[f * 32], w1 = w[f * 32 + 1];
+                const float *x = plane + f * kUS;
+#endif
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { acc[0][q] = fmaf(w0, x[q], acc[0][q]); acc[1][q] = fmaf(w1, x[q], acc[1][q]); }
+                for (int q = 0; q < 4; ++q) { acc[0][q] = fmaf(w0, x[q], acc[0][q]); acc[1][q] = fmaf(w1, x[q], acc[1][q]); }
+            }
+        }
+    } else {
+        // taps 3, 4: plane j - 3, u = t + 1 -> unaligned, scalar reads
+#pragma unroll 1
+        for (int j = 3; j < 5; ++j) {
+            const float *plane = feat + (j - 3) * kNumChannels * kUS + t0 + 1;
+            const float *w = W.w0 + j * kNumChannels * 32 + o0;
+#pragma unroll 8
+            for (int f = 0; f < kNumChannels; ++f) {
+#if defined(__CUDA_ARCH__)
+                const float2 ww = __ldg(reinterpret_cast<const float2 *>(w + f * 32));
+                const float w0 = ww.x, w1 = ww.y;
+#else
+                const float w0 = w[f * 32], w1 = w[f * 32 + 1];
+#endif
+                const float *x = plane + f * kUS;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { acc[0][q] = fmaf(w0, x[q], acc[0][q]); acc[1][q] = fmaf(w1, x[q], acc[1][q]); }
+            }
         }
     }
     if (half) {
@@ -181,12 +211,36 @@ MWW_HD void nn_first_conv_b(int tid, float *sm, const float (&acc)[2][4]) {
     }
 }
 
-// ---- phase helper: stage block L's 1x1 weights [cin][64] into shared memory (feature region, free by now) ----
+// ---- phase helper: stage block L's 1x1 weights [cin][64] into shared memory ----
+// Two staging buffers alternate (even blocks: the feature-plane region, free once the first conv is done;
+// odd blocks: a dedicated buffer) so block L+1's weights stream in (cp.async, no register round trip)
+// while block L computes.
+template <int L>
+MWW_HD float *nn_pw_weight_buffer(float *sm) {
+    return (L & 1) ? sm + kXFloats + kDFloats + kFeatFloats : sm + kXFloats + kDFloats;
+}
 template <int L>
 MWW_HD void nn_stage_pw_weights(int tid, float *sm, const NnWeightsF32 &W) {
-    float *wsm = sm + kXFloats + kDFloats;
-    constexpr int n = kGeom[L].cin * 64;
-    for (int e = tid; e < n; e += kNnThreads) wsm[e] = W.pw_w[L][e];
+    float *wsm = nn_pw_weight_buffer<L>(sm);
+    constexpr int n4 = kGeom[L].cin * 64 / 4;
+    for (int e = tid; e < n4; e += kNnThreads) {
+#if defined(__CUDA_ARCH__)
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(wsm + 4 * e);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(W.pw_w[L] + 4 * e));
+#else
+        for (int i = 0; i < 4; ++i) wsm[4 * e + i] = W.pw_w[L][4 * e + i];
+#endif
+    }
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+// wait until at most N of this thread's cp.async groups are still in flight (no-op on the host)
+template <int N>
+MWW_HD void nn_wait_weights() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
 }
 
 // ---- phase: depthwise conv over (ring ++ chunk) for block L; output D[c][t] ----
@@ -240,7 +294,7 @@ MWW_HD void nn_pointwise(int tid, float *sm, const NnWeightsF32 &W) {
     constexpr int cin = kGeom[L].cin;
     constexpr NnLayerGeom gn = kGeom[L + 1];
     const int o0 = 4 * (tid & 15), t0 = 2 * (tid >> 4);
-    const float *wsm = sm + kXFloats + kDFloats + o0;
+    const float *wsm = nn_pw_weight_buffer<L>(sm) + o0;
     const float *d = sm + kXFloats + t0;
     float acc[4][2];
 #pragma unroll

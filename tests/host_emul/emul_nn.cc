@@ -38,10 +38,13 @@ extern "C" int emul_nn_f32(const float *const *wp /* w0, dw_w[4], dw_b[4], pw_w[
             std::vector<float> fc((size_t)kNnThreads * 8);
             ALL(nn_first_conv_a(tid, sm, W, *reinterpret_cast<float(*)[2][4]>(&fc[(size_t)tid * 8])));
             ALL(nn_first_conv_b(tid, sm, *reinterpret_cast<float(*)[2][4]>(&fc[(size_t)tid * 8])));
-            ALL(nn_stage_pw_weights<0>(tid, sm, W)); ALL(nn_depthwise<0>(tid, sm, W)); ALL(nn_pointwise<0>(tid, sm, W));
-            ALL(nn_stage_pw_weights<1>(tid, sm, W)); ALL(nn_depthwise<1>(tid, sm, W)); ALL(nn_pointwise<1>(tid, sm, W));
-            ALL(nn_stage_pw_weights<2>(tid, sm, W)); ALL(nn_depthwise<2>(tid, sm, W)); ALL(nn_pointwise<2>(tid, sm, W));
-            ALL(nn_stage_pw_weights<3>(tid, sm, W)); ALL(nn_depthwise<3>(tid, sm, W)); ALL(nn_pointwise<3>(tid, sm, W));
+            ALL(nn_stage_pw_weights<0>(tid, sm, W)); ALL(nn_stage_pw_weights<1>(tid, sm, W));
+            ALL(nn_depthwise<0>(tid, sm, W)); ALL(nn_pointwise<0>(tid, sm, W));
+            ALL(nn_stage_pw_weights<2>(tid, sm, W));
+            ALL(nn_depthwise<1>(tid, sm, W)); ALL(nn_pointwise<1>(tid, sm, W));
+            ALL(nn_stage_pw_weights<3>(tid, sm, W));
+            ALL(nn_depthwise<2>(tid, sm, W)); ALL(nn_pointwise<2>(tid, sm, W));
+            ALL(nn_depthwise<3>(tid, sm, W)); ALL(nn_pointwise<3>(tid, sm, W));
             ALL(nn_head_partial(tid, sm, W));
             ALL(nn_head_finish(tid, sm, W, n, probs + (size_t)s * max_probs + step0, logits ? logits + (size_t)s * max_probs + step0 : nullptr));
             std::vector<float> tmp((size_t)kNnThreads * 5 * kShiftPerThread);
