@@ -16,12 +16,11 @@
 // Shared-memory activation layout is channel-major [c][LD] with time contiguous; columns [0, R) hold the
 // ring history, columns [R, R+TT) the chunk's new outputs.  LD is odd, so the depthwise stage -- one lane per
 // channel sliding along time -- reads without bank conflicts.  The depthwise output D[c][t] (the A operand
-// of the 1x1 contraction) has a 16-byte aligned pitch; the 1x1 weights of the current block are staged in
-// shared memory (in the region the feature planes occupied) so every thread accumulates a
-// 4 (out channels) x 2 (time steps) register tile from one 128-bit and one 64-bit load per k.
+// of the 1x1 contraction) and the 1x1 weights staged in shared memory feed warp-level tensor-core MMAs
+// (mww_nn_mma.cuh); their pitches (40 and 72 floats) make the fragment loads bank-conflict free.
 // Feature rows are de-interleaved into three planes by (row mod 3) so that the stride-3 first conv reads
-// consecutive time steps from consecutive addresses; its K = 200 contraction is split over two thread groups
-// (taps 0-2 | taps 3-4) whose partial sums meet in shared memory.
+// consecutive time steps from consecutive addresses; its K = 200 contraction is split over three warp groups
+// whose partial sums meet in shared memory.
 #pragma once
 
 #include "mww_common.h"
@@ -47,14 +46,15 @@ constexpr NnLayerGeom kGeom[5] = {
     {64, 17, 16, 16, 53, 32 * 41 + 64 * 47 + 64 * 51 + 64 * 59},
 };
 constexpr int kXFloats = 32 * 41 + 64 * (47 + 51 + 59 + 53);   // 14752
-constexpr int kDLd = 36;
-constexpr int kDFloats = 64 * kDLd;
+constexpr int kDLd = 40;                                      // 40 = 8 (mod 32): conflict-free mma A fragments
+constexpr int kDFloats = 64 * kDLd + 8;                       // + slack: the last m-tile reads 12 rows past kTT
 constexpr int kUS = 40;                                       // pitch of a feature plane row (u index)
 constexpr int kFeatFloats = 3 * kNumChannels * kUS;           // 4800 >= 64*64 staged 1x1 weights
-constexpr int kWBFloats = 64 * 64;                            // second staging buffer for the 1x1 weights
+constexpr int kWLdDev = 72;                                   // pitch of staged 1x1 weights (see mww_nn_mma.cuh)
+constexpr int kWBFloats = 64 * kWLdDev;                       // second staging buffer for the 1x1 weights
 constexpr int kNnSmemFloats = kXFloats + kDFloats + kFeatFloats + kWBFloats;
 constexpr int kNnSmemBytes = kNnSmemFloats * 4;               // 103.8 KB -> 2 CTAs / SM
-static_assert(kXFloats % 4 == 0 && kDFloats % 4 == 0 && kFeatFloats >= 64 * 64, "smem carve-up");
+static_assert(kXFloats % 4 == 0 && kDFloats % 4 == 0 && kFeatFloats >= 64 * 72, "smem carve-up");
 
 // per-stream state layout in HBM (floats), oldest row first, [row][channel] -- identical to the oracle
 constexpr int kStateOff[6] = {0, 80, 80 + 128, 80 + 128 + 640, 80 + 128 + 640 + 896, 80 + 128 + 640 + 896 + 1408};
@@ -136,81 +136,6 @@ MWW_HD void nn_load_features(int tid, float *sm, const NnInput &in, int step0, i
     }
 }
 
-// ---- phases: first conv (5x1, stride 3, 40 -> 32, no bias) + ReLU ----
-// thread tile 2 out-channels x 4 steps; threads [0,144) contract taps 0..2 (aligned float4 reads of the planes),
-// threads [144,288) taps 3..4 (plane index + 1: scalar reads) and park their partial sums in D.
-MWW_HD void nn_first_conv_a(int tid, float *sm, const NnWeightsF32 &W, float (&acc)[2][4]) {
-    const float *feat = sm + kXFloats + kDFloats;
-    const int half = tid >= 144, r = tid - 144 * half;
-    const int o0 = 2 * (r & 15), t0 = 4 * (r >> 4);
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
-    if (!half) {
-        // taps 0..2: plane j, u = t -> 16-byte aligned float4 of four consecutive steps
-#pragma unroll 1
-        for (int j = 0; j < 3; ++j) {
-            const float *plane = feat + j * kNumChannels * kUS + t0;
-            const float *w = W.w0 + j * kNumChannels * 32 + o0;
-#pragma unroll 8
-            for (int f = 0; f < kNumChannels; ++f) {
-#if defined(__CUDA_ARCH__)
-                const float2 ww = __ldg(reinterpret_cast<const float2 *>(w + f * 32));
-                const float4 xx = *reinterpret_cast<const float4 *>(plane + f * kUS);
-                const float w0 = ww.x, w1 = ww.y;
-                const float x[4] = {xx.x, xx.y, xx.z, xx.w};
-#else
-                const float w0 = w[f * 32], w1 = w[f * 32 + 1];
-                const float *x = plane + f * kUS;
-#endif
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { acc[0][q] = fmaf(w0, x[q], acc[0][q]); acc[1][q] = fmaf(w1, x[q], acc[1][q]); }
-            }
-        }
-    } else {
-        // taps 3, 4: plane j - 3, u = t + 1 -> unaligned, scalar reads
-#pragma unroll 1
-        for (int j = 3; j < 5; ++j) {
-            const float *plane = feat + (j - 3) * kNumChannels * kUS + t0 + 1;
-            const float *w = W.w0 + j * kNumChannels * 32 + o0;
-#pragma unroll 8
-            for (int f = 0; f < kNumChannels; ++f) {
-#if defined(__CUDA_ARCH__)
-                const float2 ww = __ldg(reinterpret_cast<const float2 *>(w + f * 32));
-                const float w0 = ww.x, w1 = ww.y;
-#else
-                const float w0 = w[f * 32], w1 = w[f * 32 + 1];
-#endif
-                const float *x = plane + f * kUS;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { acc[0][q] = fmaf(w0, x[q], acc[0][q]); acc[1][q] = fmaf(w1, x[q], acc[1][q]); }
-            }
-        }
-    }
-    if (half) {
-        float *part = sm + kXFloats;      // D region is idle until the first depthwise
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) part[(o0 + i) * kDLd + t0 + q] = acc[i][q];
-    }
-}
-MWW_HD void nn_first_conv_b(int tid, float *sm, const float (&acc)[2][4]) {
-    if (tid >= 144) return;
-    const int o0 = 2 * (tid & 15), t0 = 4 * (tid >> 4);
-    const float *part = sm + kXFloats;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        float *dst = sm + kGeom[0].off + (o0 + i) * kGeom[0].ld + kGeom[0].hp + t0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float v = acc[i][q] + part[(o0 + i) * kDLd + t0 + q];
-            dst[q] = v > 0.f ? v : 0.f;
-        }
-    }
-}
-
 // ---- phase helper: stage block L's 1x1 weights [cin][64] into shared memory ----
 // Two staging buffers alternate (even blocks: the feature-plane region, free once the first conv is done;
 // odd blocks: a dedicated buffer) so block L+1's weights stream in (cp.async, no register round trip)
@@ -224,11 +149,13 @@ MWW_HD void nn_stage_pw_weights(int tid, float *sm, const NnWeightsF32 &W) {
     float *wsm = nn_pw_weight_buffer<L>(sm);
     constexpr int n4 = kGeom[L].cin * 64 / 4;
     for (int e = tid; e < n4; e += kNnThreads) {
+        const int k = e >> 4, c4 = e & 15;             // row k of [cin][64], 16-byte chunk c4
+        float *dst = wsm + k * kWLdDev + 4 * c4;
 #if defined(__CUDA_ARCH__)
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(wsm + 4 * e);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(W.pw_w[L] + 4 * e));
+        const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(W.pw_w[L] + 4 * e));
 #else
-        for (int i = 0; i < 4; ++i) wsm[4 * e + i] = W.pw_w[L][4 * e + i];
+        for (int i = 0; i < 4; ++i) dst[i] = W.pw_w[L][4 * e + i];
 #endif
     }
 #if defined(__CUDA_ARCH__)
@@ -284,39 +211,6 @@ MWW_HD void nn_depthwise(int tid, float *sm, const NnWeightsF32 &W) {
         if (L == 1) { if (c < 32) nn_depthwise_k<L, 7, 9>(c, t0, sm, W); else nn_depthwise_k<L, 11, 9>(c, t0, sm, W); }
         else if (L == 2) { if (c < 32) nn_depthwise_k<L, 9, 9>(c, t0, sm, W); else nn_depthwise_k<L, 15, 9>(c, t0, sm, W); }
         else nn_depthwise_k<L, g.kmax, 9>(c, t0, sm, W);
-    }
-}
-
-// ---- phase: pointwise 1x1 (cin -> 64) + folded-BN bias + ReLU into the next ring buffer ----
-// thread tile: 4 output channels x 2 steps; 16 x 18 threads cover 64 x 36.
-template <int L>
-MWW_HD void nn_pointwise(int tid, float *sm, const NnWeightsF32 &W) {
-    constexpr int cin = kGeom[L].cin;
-    constexpr NnLayerGeom gn = kGeom[L + 1];
-    const int o0 = 4 * (tid & 15), t0 = 2 * (tid >> 4);
-    const float *wsm = nn_pw_weight_buffer<L>(sm) + o0;
-    const float *d = sm + kXFloats + t0;
-    float acc[4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
-#pragma unroll 8
-    for (int k = 0; k < cin; ++k) {
-        const float *w = wsm + k * 64;
-        const float *x = d + k * kDLd;
-        const float w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-        const float x0 = x[0], x1 = x[1];
-        acc[0][0] = fmaf(w0, x0, acc[0][0]); acc[0][1] = fmaf(w0, x1, acc[0][1]);
-        acc[1][0] = fmaf(w1, x0, acc[1][0]); acc[1][1] = fmaf(w1, x1, acc[1][1]);
-        acc[2][0] = fmaf(w2, x0, acc[2][0]); acc[2][1] = fmaf(w2, x1, acc[2][1]);
-        acc[3][0] = fmaf(w3, x0, acc[3][0]); acc[3][1] = fmaf(w3, x1, acc[3][1]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float bias = W.pw_b[L][o0 + i];
-        float *dst = sm + gn.off + (o0 + i) * gn.ld + gn.hp + t0;
-        const float v0 = acc[i][0] + bias, v1 = acc[i][1] + bias;
-        dst[0] = v0 > 0.f ? v0 : 0.f;
-        dst[1] = v1 > 0.f ? v1 : 0.f;
     }
 }
 

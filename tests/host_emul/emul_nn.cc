@@ -5,9 +5,97 @@
 
 #include <vector>
 
-#include "../../microwakeword_b200/csrc/mww_nn_dev.cuh"
+#include "../../microwakeword_b200/csrc/mww_nn_mma.cuh"
 
 using namespace mww;
+
+
+// ---- host model of mma.sync.m16n8k8.tf32 for one warp (fragment layouts from the PTX ISA) -------------
+namespace {
+float tf32_of(uint32_t bits) { bits &= 0xFFFFE000u; float f; memcpy(&f, &bits, 4); return f; }   // hardware ignores the low 13 bits
+
+void warp_mma_tf32(float (*c)[4], const uint32_t (*a)[4], const uint32_t (*b)[2]) {
+    float A[16][8], B[8][8], C[16][8];
+    for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, tig = lane & 3;
+        A[g][tig] = tf32_of(a[lane][0]); A[g + 8][tig] = tf32_of(a[lane][1]);
+        A[g][tig + 4] = tf32_of(a[lane][2]); A[g + 8][tig + 4] = tf32_of(a[lane][3]);
+        B[tig][g] = tf32_of(b[lane][0]); B[tig + 4][g] = tf32_of(b[lane][1]);
+        C[g][2 * tig] = c[lane][0]; C[g][2 * tig + 1] = c[lane][1];
+        C[g + 8][2 * tig] = c[lane][2]; C[g + 8][2 * tig + 1] = c[lane][3];
+    }
+    for (int m = 0; m < 16; ++m)
+        for (int n = 0; n < 8; ++n) {
+            float acc = C[m][n];
+            for (int k = 0; k < 8; ++k) acc += A[m][k] * B[k][n];
+            C[m][n] = acc;
+        }
+    for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, tig = lane & 3;
+        c[lane][0] = C[g][2 * tig]; c[lane][1] = C[g][2 * tig + 1];
+        c[lane][2] = C[g + 8][2 * tig]; c[lane][3] = C[g + 8][2 * tig + 1];
+    }
+}
+
+void warp_mma_3xtf32(float (*c)[4], const FragA *a, const FragB *b) {
+    uint32_t ah[32][4], al[32][4], bh[32][2], bl[32][2];
+    for (int l = 0; l < 32; ++l) {
+        for (int i = 0; i < 4; ++i) { ah[l][i] = a[l].hi[i]; al[l][i] = a[l].lo[i]; }
+        for (int i = 0; i < 2; ++i) { bh[l][i] = b[l].hi[i]; bl[l][i] = b[l].lo[i]; }
+    }
+    warp_mma_tf32(c, al, bh);
+    warp_mma_tf32(c, ah, bl);
+    warp_mma_tf32(c, ah, bh);
+}
+
+template <int L>
+void emul_pointwise_mma(float *sm, const NnWeightsF32 &W) {
+    constexpr int cin = kGeom[L].cin;
+    for (int warp = 0; warp < kNnThreads / 32; ++warp) {
+        const int t0 = 16 * pw_m_tile(warp), nt0 = pw_n_first(warp), ntc = pw_n_count(warp);
+        const float *d = sm + kXFloats;
+        const float *wsm = nn_pw_weight_buffer<L>(sm);
+        float c[3][32][4] = {};
+        for (int ks = 0; ks < cin / 8; ++ks) {
+            FragA a[32];
+            for (int lane = 0; lane < 32; ++lane) load_frag_a(d, kDLd, 8 * ks, t0, lane, a[lane]);
+            for (int i = 0; i < ntc; ++i) {
+                FragB b[32];
+                for (int lane = 0; lane < 32; ++lane) load_frag_b(wsm, kWLd, 8 * ks, 8 * (nt0 + i), lane, b[lane]);
+                warp_mma_3xtf32(c[i], a, b);
+            }
+        }
+        for (int i = 0; i < ntc; ++i)
+            for (int lane = 0; lane < 32; ++lane) pw_store_tile<L>(sm, W, t0, 8 * (nt0 + i), lane, c[i][lane]);
+    }
+}
+
+void emul_first_conv_mma(float *sm, const NnWeightsF32 &W) {
+    const float *feat = sm + kXFloats + kDFloats;
+    static float c[kNnThreads / 32][4][32][4];
+    memset(c, 0, sizeof c);
+    for (int warp = 0; warp < kNnThreads / 32; ++warp) {        // part a
+        const int t0 = 16 * fc_m_tile(warp);
+        for (int ks = fc_k_begin(warp); ks < fc_k_end(warp); ++ks) {
+            FragA a[32];
+            for (int lane = 0; lane < 32; ++lane) fc_load_frag_a(feat, ks, t0, lane, a[lane]);
+            for (int i = 0; i < 4; ++i) {
+                FragB b[32];
+                for (int lane = 0; lane < 32; ++lane) fc_load_frag_b(W.w0, ks, 8 * i, lane, b[lane]);
+                warp_mma_3xtf32(c[warp][i], a, b);
+            }
+        }
+        if (warp % 3 > 0)
+            for (int i = 0; i < 4; ++i)
+                for (int lane = 0; lane < 32; ++lane) fc_store_partial(sm, warp % 3, t0, 8 * i, lane, c[warp][i][lane]);
+    }
+    for (int warp = 0; warp < kNnThreads / 32; ++warp) {        // part b, after the barrier
+        if (warp % 3 != 0) continue;
+        for (int i = 0; i < 4; ++i)
+            for (int lane = 0; lane < 32; ++lane) fc_finish_tile(sm, 16 * fc_m_tile(warp), 8 * i, lane, c[warp][i][lane]);
+    }
+}
+}  // namespace
 
 extern "C" int emul_nn_f32(const float *const *wp /* w0, dw_w[4], dw_b[4], pw_w[4], pw_b[4], head_w, head_b */,
                            float *state, float *pend, int n_pend, const void *rows, int n_rows, int rows_are_f32,
@@ -35,16 +123,14 @@ extern "C" int emul_nn_f32(const float *const *wp /* w0, dw_w[4], dw_b[4], pw_w[
         for (int step0 = 0; step0 < n_steps; step0 += kTT) {
             const int n = n_steps - step0 < kTT ? n_steps - step0 : kTT;
             ALL(nn_load_features(tid, sm, in, step0, n));
-            std::vector<float> fc((size_t)kNnThreads * 8);
-            ALL(nn_first_conv_a(tid, sm, W, *reinterpret_cast<float(*)[2][4]>(&fc[(size_t)tid * 8])));
-            ALL(nn_first_conv_b(tid, sm, *reinterpret_cast<float(*)[2][4]>(&fc[(size_t)tid * 8])));
+            emul_first_conv_mma(sm, W);
             ALL(nn_stage_pw_weights<0>(tid, sm, W)); ALL(nn_stage_pw_weights<1>(tid, sm, W));
-            ALL(nn_depthwise<0>(tid, sm, W)); ALL(nn_pointwise<0>(tid, sm, W));
+            ALL(nn_depthwise<0>(tid, sm, W)); emul_pointwise_mma<0>(sm, W);
             ALL(nn_stage_pw_weights<2>(tid, sm, W));
-            ALL(nn_depthwise<1>(tid, sm, W)); ALL(nn_pointwise<1>(tid, sm, W));
+            ALL(nn_depthwise<1>(tid, sm, W)); emul_pointwise_mma<1>(sm, W);
             ALL(nn_stage_pw_weights<3>(tid, sm, W));
-            ALL(nn_depthwise<2>(tid, sm, W)); ALL(nn_pointwise<2>(tid, sm, W));
-            ALL(nn_depthwise<3>(tid, sm, W)); ALL(nn_pointwise<3>(tid, sm, W));
+            ALL(nn_depthwise<2>(tid, sm, W)); emul_pointwise_mma<2>(sm, W);
+            ALL(nn_depthwise<3>(tid, sm, W)); emul_pointwise_mma<3>(sm, W);
             ALL(nn_head_partial(tid, sm, W));
             ALL(nn_head_finish(tid, sm, W, n, probs + (size_t)s * max_probs + step0, logits ? logits + (size_t)s * max_probs + step0 : nullptr));
             std::vector<float> tmp((size_t)kNnThreads * 5 * kShiftPerThread);
