@@ -124,6 +124,20 @@ int mww_get_state(mww_t *h, int16_t *h_carry, uint32_t *h_estimate, void *h_nn, 
 int mww_set_state(mww_t *h, const int16_t *h_carry, int frontend_buffered, const uint32_t *h_estimate,
                   const void *h_nn, const void *h_pending, int pending_rows);
 
+/* ---- detection post-processing (microwakeword/test.py:337-341, :94-137, :364-373) -------------------------
+ * Tracks are ragged: track i is d_probs[d_offsets[i] .. d_offsets[i] + d_lengths[i]) (float32 probabilities as
+ * produced by mww_infer_features / mww_predict_clip).  All three are stateless and asynchronous on cu_stream.
+ *   mww_moving_average       out_i[j] = mean(probs_i[j .. j+window)), written at d_out[d_out_offsets[i] + j]
+ *   mww_false_accept_counts  d_counts[i][c] = detections of track i at cutoff c (float64 cutoffs) with the
+ *                            reference's cooldown rule, evaluated on the moving average
+ *   mww_positive_scores      d_scores[i] = max of the moving average of probs_i[ignore:], NaN if too short */
+int mww_moving_average(const float *d_probs, const long long *d_offsets, const int *d_lengths, int n_tracks, int max_length,
+                       int window, float *d_out, const long long *d_out_offsets, void *cu_stream);
+int mww_false_accept_counts(const float *d_probs, const long long *d_offsets, const int *d_lengths, int n_tracks, int window,
+                            const double *d_cutoffs, int n_cutoffs, int ignore_slices_after_accept, int *d_counts, void *cu_stream);
+int mww_positive_scores(const float *d_probs, const long long *d_offsets, const int *d_lengths, int n_tracks, int window,
+                        int ignore_slices_after_accept, float *d_scores, void *cu_stream);
+
 /* Per-kernel device timing for roofline reporting.  While enabled, every launch of the four kernel
  * classes is bracketed by CUDA events on the launching stream.  mww_profile_read synchronises the
  * device, adds the elapsed milliseconds into ms[4] and the launch counts into counts[4]

@@ -20,6 +20,7 @@ EXPORTS = (
     "mww_create", "mww_destroy", "mww_last_error", "mww_get_info", "mww_reset", "mww_reset_frontend",
     "mww_features", "mww_infer_features", "mww_predict_clip", "mww_predict_clip_host",
     "mww_get_state", "mww_set_state", "mww_launch_count", "mww_profile_enable", "mww_profile_read",
+    "mww_moving_average", "mww_false_accept_counts", "mww_positive_scores",
 )
 
 
@@ -81,6 +82,12 @@ def lib() -> ctypes.CDLL:
     L.mww_profile_enable.argtypes = [vp, i32]
     L.mww_profile_read.restype = i32
     L.mww_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
+    L.mww_moving_average.restype = i32
+    L.mww_moving_average.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    L.mww_false_accept_counts.restype = i32
+    L.mww_false_accept_counts.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, vp]
+    L.mww_positive_scores.restype = i32
+    L.mww_positive_scores.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     L.mww_launch_count.restype = ll
     L.mww_launch_count.argtypes = [vp]
     _lib = L

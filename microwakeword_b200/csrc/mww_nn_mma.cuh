@@ -66,7 +66,7 @@ MWW_HD void load_frag_b(const float *base, int ld, int k0, int n0, int lane, Fra
 
 #if defined(__CUDACC__)
 MWW_D void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
@@ -159,15 +159,18 @@ MWW_D void nn_pointwise_mma(int tid, float *sm, const NnWeightsF32 &W) {
 #pragma unroll 2
     for (int ks = 0; ks < cin / 8; ++ks) {
         FragA a;
+        FragB b[3];
         load_frag_a(d, kDLd, 8 * ks, t0, lane, a);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            if (i < ntc) {
-                FragB b;
-                load_frag_b(wsm, kWLd, 8 * ks, 8 * (nt0 + i), lane, b);
-                mma_3xtf32(c[i], a, b);
-            }
-        }
+        for (int i = 0; i < 3; ++i)
+            if (i < ntc) load_frag_b(wsm, kWLd, 8 * ks, 8 * (nt0 + i), lane, b[i]);
+        // three independent accumulator chains interleaved: a dependent HMMA never follows its predecessor directly
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (i < ntc) mma_tf32(c[i], a.lo, b[i].hi);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (i < ntc) mma_tf32(c[i], a.hi, b[i].lo);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (i < ntc) mma_tf32(c[i], a.hi, b[i].hi);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -183,15 +186,19 @@ MWW_D void nn_first_conv_mma_a(int tid, float *sm, const NnWeightsF32 &W, float 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int q = 0; q < 4; ++q) c[i][q] = 0.f;
+#pragma unroll 3
     for (int ks = fc_k_begin(warp); ks < fc_k_end(warp); ++ks) {
         FragA a;
+        FragB b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) fc_load_frag_b(W.w0, ks, 8 * i, lane, b[i]);     // L2-resident weights: issue first
         fc_load_frag_a(feat, ks, t0, lane, a);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            FragB b;
-            fc_load_frag_b(W.w0, ks, 8 * i, lane, b);
-            mma_3xtf32(c[i], a, b);
-        }
+        for (int i = 0; i < 4; ++i) mma_tf32(c[i], a.lo, b[i].hi);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mma_tf32(c[i], a.hi, b[i].lo);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mma_tf32(c[i], a.hi, b[i].hi);
     }
     const int kt = warp % 3;
     if (kt > 0) {
