@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--model", default="f32", choices=["f32", "int8"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scatter", action="store_true", help="skip the NCCL scatter/gather leg at N > 1")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -252,10 +253,10 @@ def run_gpu(args):
 
     # ---- device-resident timing: `value` ----
     eng.reset()
+    clocks = ClockSampler(local_rank) if rank == 0 else None           # samples every 100 ms from warm-up on
     for _ in range(max(args.warmup, 1)):
         eng.predict_clip(audio, out=probs)
     barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     l0 = eng.launch_count
     eng.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -320,6 +321,32 @@ def run_gpu(args):
                "checksum_matches_device_path": bool(abs(float(host_probs[:, :100].double().sum().item()) - checksum) < 1e-3 * max(1.0, abs(checksum)))}
         del host_audio, host_probs
 
+    # ---- N > 1: the north_star's ingest pattern -- audio scattered from rank 0, scores gathered back (NCCL) ----
+    scatter = None
+    if world > 1 and not args.no_scatter:
+        from microwakeword_b200.sharding import gather_probs, scatter_audio
+        total = S * world
+        full = audio.repeat(world, 1) if rank == 0 else None           # rank 0 holds every stream's audio
+        eng.reset()
+        for _ in range(2):
+            local = scatter_audio(full, total, SAMPLES_PER_STEP, src=0, device=device)
+            gather_probs(eng.predict_clip(local, out=probs), total, dst=0)
+        barrier()
+        sg_steps = 3
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s0.record()
+        for _ in range(sg_steps):
+            local = scatter_audio(full, total, SAMPLES_PER_STEP, src=0, device=device)
+            gathered = gather_probs(eng.predict_clip(local, out=probs), total, dst=0)
+        s1.record()
+        barrier()
+        sg_ms = max_over_ranks(s0.elapsed_time(s1)) / sg_steps
+        scatter = {"value": frames_per_step_all / (sg_ms / 1e3), "unit": UNIT, "ms_per_step": sg_ms, "steps": sg_steps,
+                   "nvlink_bytes_out_of_rank0_per_step": S * SAMPLES_PER_STEP * 2 * (world - 1),
+                   "note": "torch.distributed scatter of int16 audio from rank 0 + gather of float32 scores to rank 0 (NCCL), serialised with compute"}
+        del full
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -333,7 +360,8 @@ def run_gpu(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.model == "f32" else "int8", "data": "synthetic",
             "config": config_dict(args, world), "clocks": clock_info, "gpu_launches": int(launches),
-            "kernels": kernels, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "probs_checksum": checksum,
+            "kernels": kernels, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "scatter_gather": scatter, "probs_checksum": checksum,
+            "realtime_streams_capacity": value / 100.0,
         }
         print(json.dumps(line))
     if world > 1:
