@@ -292,7 +292,15 @@ def run_gpu(args):
                 "traffic_source": (tr or {}).get("source"),
                 "alg_bytes_per_frame": K1_ALG_BYTES_PER_FRAME, "frames_per_launch": frames_per_launch,
                 "share_of_step": k1_ms / max(sum(v[0] for v in prof.values()), 1e-9),
-                "note": "K1 is integer-ALU bound by construction (~25k integer ops per 320-byte frame); see DESIGN.md and profiles/ for issue-slot utilisation"}
+                "note": "K1 is integer-ALU bound by construction (~34k thread-instructions per 320-byte frame, ncu): the HBM fraction is low "
+                        "because the kernel is instruction-issue bound; see `issue` below, DESIGN.md and profiles/"}
+        tipf = (tr or {}).get("thread_instr_per_unit")
+        if tipf:
+            sm_hz = ((clock_info or {}).get("sm_mhz") or 1965.0) * 1e6
+            peak_issue = 148 * 4 * 32 * sm_hz            # 4 schedulers/SM x 1 warp-instruction/clk x 32 threads
+            ach = tipf * frames_per_launch / (k1_ms / k1_n / 1e3)
+            roof["issue"] = {"thread_instr_per_frame": tipf, "achieved_thread_instr_per_s": ach, "peak_thread_instr_per_s": peak_issue,
+                             "frac": ach / peak_issue, "source": "instructions per frame from the committed ncu capture; duration live from CUDA events"}
 
     # ---- e2e through the host-buffer C-ABI call ----
     e2e = None

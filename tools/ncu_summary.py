@@ -46,7 +46,7 @@ def main():
                   "dram bytes per unit: read %.1f  write %.1f  total %.1f" % (rd / frames, wr / frames, (rd + wr) / frames),
                   "thread-level instructions per unit (warp inst x 32): %.0f" % (inst * 32 / frames)]
         json.dump({"dram_bytes_per_launch": rd + wr, "units_in_launch": frames, "dram_bytes_per_unit": (rd + wr) / frames,
-                   "source": rep}, open(out.replace(".txt", ".json"), "w"))
+                   "thread_instr_per_unit": inst * 32 / frames, "source": rep}, open(out.replace(".txt", ".json"), "w"))
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
 
