@@ -65,3 +65,35 @@ def generate_features_for_clip(audio_samples: np.ndarray, step_ms: int = 20, use
     if use_c:
         return feat.astype(np.float32) * np.float32(FEATURE_SCALE)
     return feat
+
+
+def generate_features_for_clips(clips, use_c: bool = True, device: int = 0):
+    """Batched `generate_features_for_clip` for a list of clips of DIFFERENT lengths -- the call pattern of the
+    reference's dataset generator (microwakeword/audio/spectrograms.py:84-86 loops one clip at a time).
+
+    All clips go through one frontend launch: each clip is zero padded to the longest one (the frontend is
+    causal, so trailing padding cannot change earlier rows) and its own row count -- the strict-'<' chunk
+    accounting of audio_utils.py:56 for use_c=True, every full window for use_c=False -- is cut out afterwards.
+    Returns a list of float32 [T_i, 40] (use_c) or uint16 [T_i, 40] arrays.
+    """
+    import torch
+
+    from ..engine import StreamEngine
+
+    clips = [to_int16(np.asarray(c)).reshape(-1) for c in clips]
+    if not clips:
+        return []
+    fed = [clip_samples_fed(c.size) if use_c else c.size for c in clips]
+    rows = [max((n - 480) // 160 + 1, 0) if n >= 480 else 0 for n in fed]
+    n_max = max(max(fed), 1)
+    batch = np.zeros((len(clips), n_max), np.int16)
+    for i, (c, n) in enumerate(zip(clips, fed)):
+        batch[i, :n] = c[:n]
+    eng = StreamEngine(None, n_streams=len(clips), device=device)
+    feat = eng.features(torch.from_numpy(batch).to(eng._dev())).view(torch.int16).cpu().numpy().view(np.uint16)
+    eng.close()
+    out = []
+    for i, r in enumerate(rows):
+        f = feat[i, :r]
+        out.append(f.astype(np.float32) * np.float32(FEATURE_SCALE) if use_c else f.copy())
+    return out

@@ -142,6 +142,34 @@ class Model:
     def reset(self, stream_ids=None):
         self.engine.reset(stream_ids)
 
+    def predict_nonstreaming(self, spectrograms: np.ndarray) -> np.ndarray:
+        """Batched NON-streaming evaluation (what the reference's Keras model computes on
+        `[batch, spectrogram_length, 40]` windows in train.py:41-163 / data.py:301-311): one probability per window.
+
+        Every conv of the graph is 'valid', so the non-streaming output equals the streaming model's LAST step when the
+        rings hold real data (README.md:27-28).  The first conv's streaming windows start one row before a multiple of
+        the stride (stream.py:253-255), so one leading row is prepended; the window must be at least one receptive
+        field long (204 rows for okay_nabu, model_train_eval.py:64-88) for every ring to be filled with real data.
+        """
+        import torch
+        x = np.asarray(spectrograms)
+        if x.ndim != 3 or x.shape[2] != NUM_FEATURES:
+            raise ValueError("spectrograms must have shape [batch, T, 40]")
+        if self.is_quantized_model:
+            raise NotImplementedError("non-streaming evaluation is defined for the float model (the reference evaluates the Keras model)")
+        b, t = x.shape[0], x.shape[1]
+        if (t - 5) // 3 + 1 < 67:
+            raise ValueError("window shorter than the model's receptive field (204 rows)")
+        if x.dtype == np.uint16:
+            x = x.astype(np.float32) * np.float32(FEATURE_SCALE)
+        x = np.ascontiguousarray(x, np.float32)
+        rows = np.concatenate([np.zeros((b, 1, NUM_FEATURES), np.float32), x], 1)
+        eng = StreamEngine(self.engine._blob, n_streams=b, device=self.engine.device)
+        probs = eng.infer(torch.from_numpy(rows).to(eng._dev()))
+        out = probs[:, (t - 5) // 3 + 1].cpu().numpy()       # streaming step s covers non-streaming window s - 1
+        eng.close()
+        return out
+
     # ------------------------------------------------------------------ helpers
     def _single(self):
         if self.engine.n_streams != 1:

@@ -253,3 +253,37 @@ def test_full_size_properties(torch_cuda):
     a = eng.predict_clip(dev[:, :1760].contiguous())
     b = eng.predict_clip(dev[:, 1760:].contiguous())
     assert bool((torch.cat([a, b], 1) == got).all())
+
+
+def test_ragged_batch_feature_generation(torch_cuda):
+    """SURVEY.md 8 f-3 caller: many clips of different lengths through one frontend launch == one clip at a time."""
+    from microwakeword_b200.audio.audio_utils import generate_features_for_clips
+    lengths = [16000, 480, 479, 641, 24000, 8000, 16001, 0, 12345]
+    clips = [synth_audio(max(n, 1), 700 + i)[:n] for i, n in enumerate(lengths)]
+    got = generate_features_for_clips(clips)
+    assert len(got) == len(clips)
+    for c, g in zip(clips, got):
+        want = oracle.generate_features_for_clip(c)
+        assert g.dtype == np.float32 and g.shape == want.shape
+        assert np.array_equal(g, want.astype(np.float32) * np.float32(0.0390625))
+    got_tf = generate_features_for_clips(clips, use_c=False)
+    for c, g in zip(clips, got_tf):
+        fe = oracle.Frontend()
+        assert g.dtype == np.uint16 and np.array_equal(g, fe.stream(c))
+
+
+def test_nonstreaming_batch_equals_keras_nonstreaming_graph(torch_cuda):
+    """batched non-streaming evaluation through the clip kernel == the whole-clip 'valid' graph."""
+    from microwakeword_b200 import model_file as MF
+    from microwakeword_b200.inference import Model
+    from oracle import mixednet_ref as R
+    path = os.path.join(GOLDEN, "okay_nabu_synth_f32.mww")
+    m = Model(path)
+    feats = np.load(os.path.join(GOLDEN, "config0_features.npy"))
+    windows = np.stack([feats[s:s + 204] for s in (0, 37, 200, 555, 793)])          # [5, 204, 40] uint16
+    got = m.predict_nonstreaming(windows)
+    t = MF.load(path)
+    want = np.asarray([R._sigmoid(R.nonstreaming_logits(t, w.astype(np.float32) * R.FEATURE_SCALE)[-1]) for w in windows])
+    assert got.shape == (5,) and np.abs(got - want).max() <= F32_TOL
+    with pytest.raises(ValueError):
+        m.predict_nonstreaming(windows[:, :100])
