@@ -14,6 +14,7 @@
 
 #include "../../include/mww.h"
 #include "mww_kernels.h"
+#include "mww_nn_i8_prep.h"
 
 using namespace mww;
 
@@ -186,6 +187,15 @@ int run_nn_tile(mww_t *h, int first, int n, const void *d_rows, int row_type, lo
     }
     if (row_type == MWW_ROWS_I8) return fail(h, MWW_EINVAL, "int8 rows need a quantised model (inference.py:110)");
     const size_t rb = row_type == MWW_ROWS_F32 ? 4 : 2;
+    if (n_rows == 3 && !getenv("MWW_NO_LIVE")) {
+        // exactly one model step per stream: the stream-parallel live-step kernel (HBM-bound on the ring state)
+        CU(h, launch_nn_f32_live(h->W, static_cast<float *>(h->d_nn_state) + (size_t)first * kStateFloats,
+                                 static_cast<float *>(h->d_pend) + (size_t)first * 2 * kNumChannels, h->n_pend, d_rows,
+                                 rows_stream_stride_rows * kNumChannels * (long long)rb, row_type == MWW_ROWS_F32, d_probs, probs_stride, n,
+                                 h->sm_count, st));
+        h->launches += 1;
+        return MWW_OK;
+    }
     CU(h, launch_nn_f32(h->W, static_cast<float *>(h->d_nn_state) + (size_t)first * kStateFloats,
                         static_cast<float *>(h->d_pend) + (size_t)first * 2 * kNumChannels, h->n_pend, d_rows,
                         rows_stream_stride_rows * kNumChannels * (long long)rb, n_rows, row_type == MWW_ROWS_F32, d_probs, probs_stride,
@@ -296,6 +306,26 @@ int upload_weights(mww_t *h, const uint8_t *blob, size_t n) {
         memcpy(Q.zp, zp.data, sizeof Q.zp);
         Q.in_scale = scales[0];
         h->in_scale = scales[0]; h->in_zp = Q.zp[0];
+        // tensor-core operands: K-contiguous weight rows and zero-point-folded biases (mww_nn_i8_prep.h)
+        {
+            Tensor tw0, tb0, tpw[4], tpb[4];
+            bool ok = find_tensor(blob, n, "q/first_conv/w", &tw0) && find_tensor(blob, n, "q/first_conv/bias", &tb0);
+            const int8_t *pw_w[4]; const int32_t *pw_b[4];
+            for (int i = 0; i < 4 && ok; ++i) {
+                snprintf(name, sizeof name, "q/b%d/pw/w", i); ok = ok && find_tensor(blob, n, name, &tpw[i]);
+                snprintf(name, sizeof name, "q/b%d/pw/bias", i); ok = ok && find_tensor(blob, n, name, &tpb[i]);
+                pw_w[i] = reinterpret_cast<const int8_t *>(tpw[i].data); pw_b[i] = reinterpret_cast<const int32_t *>(tpb[i].data);
+            }
+            if (!ok) return fail(h, MWW_EMODEL, "model container: int8 weights missing");
+            I8MmaOperands ops;
+            build_i8_mma_operands(reinterpret_cast<const int8_t *>(tw0.data), reinterpret_cast<const int32_t *>(tb0.data), pw_w, pw_b, Q.zp, &ops);
+            bool up = upload(h->d_weights, cur, ops.w0t.data(), ops.w0t.size(), &Q.w0t, &e) &&
+                      upload(h->d_weights, cur, ops.b0f.data(), ops.b0f.size() * 4, &Q.b0f, &e);
+            for (int i = 0; i < 4 && up; ++i)
+                up = upload(h->d_weights, cur, ops.pwt[i].data(), ops.pwt[i].size(), &Q.pwt[i], &e) &&
+                     upload(h->d_weights, cur, ops.pw_bf[i].data(), ops.pw_bf[i].size() * 4, &Q.pw_bf[i], &e);
+            if (!up) return cuda_fail(h, e, "weight upload");
+        }
         h->out_scale = scales[11]; h->out_zp = 0;   // uint8 output tensor: zero point -128 + 128 (utils.py:338)
     }
     return MWW_OK;

@@ -32,3 +32,10 @@ cudaError_t launch_nn_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, int 
                          long long probs_stream_stride, int n_streams, cudaStream_t st);
 cudaError_t launch_fill_state_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, void *unused, int n_streams, cudaStream_t st);
 }  // namespace mww
+
+namespace mww {
+// live-step path (one model step for many streams per launch; mww_nn_live.cuh)
+cudaError_t launch_nn_f32_live(const NnWeightsF32 &W, float *state, float *pend, int n_pend, const void *rows,
+                               long long rows_stream_stride_bytes, int rows_are_f32, float *probs, long long probs_stride,
+                               int n_streams, int sm_count, cudaStream_t st);
+}  // namespace mww

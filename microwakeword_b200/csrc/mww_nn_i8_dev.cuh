@@ -26,27 +26,30 @@ struct NnWeightsI8 {
     int32_t head_bias, head_mult, head_shift;
     int32_t zp[12];          // [in, c0, d1, p1, d2, p2, d3, p3, d4, p4, fc, prob]
     float in_scale;
+    // tensor-core (IMMA) operands, built by mww_create from the tensors above:
+    const int8_t *w0t;        // [32 n][kW0Pitch]   first-conv weights, K-contiguous (k = tap*40 + feature), zero padded
+    const int8_t *pwt[4];     // [64 n][kPwPitch]   1x1 weights, K-contiguous
+    const int32_t *b0f;       // [32]  bias - zp_in * sum_k w   (the MMA runs on raw int8 activations)
+    const int32_t *pw_bf[4];  // [64]  bias - zp_d  * sum_k w
 };
 
 // zero point of the tensor buffered by ring L (0..3: block inputs, 4: head input)
 MWW_HD int32_t nnq_ring_zp(const NnWeightsI8 &W, int L) { return W.zp[1 + 2 * L]; }
 
-MWW_HD int32_t srdhm(int32_t a, int32_t b) {
-    if (a == INT32_MIN && b == INT32_MIN) return INT32_MAX;
-    const int64_t ab = (int64_t)a * (int64_t)b;
-    const int64_t t = ab + (ab >= 0 ? (1 << 30) : (1 - (1 << 30)));
-    // C++ division by 2^31 truncates toward zero
-    return (int32_t)(t >= 0 ? (t >> 31) : -((-t) >> 31));
-}
-MWW_HD int32_t rounding_divide_by_pot(int32_t x, int exponent) {
-    const int32_t mask = (int32_t)((1ll << exponent) - 1);
-    const int32_t rem = x & mask;
-    const int32_t thr = (mask >> 1) + (x < 0 ? 1 : 0);
-    return (x >> exponent) + (rem > thr ? 1 : 0);
-}
+// MultiplyByQuantizedMultiplier (TFLite, double-rounding variant) in closed form:
+//   SaturatingRoundingDoublingHighMul(a, b) = floor((a*b + 2^30) / 2^31)  for every sign of a*b: the reference's
+//     nudge (2^30 | 1 - 2^30) followed by a division that truncates toward zero is exactly "round half up", i.e. an
+//     ARITHMETIC 64-bit shift of (a*b + 2^30).  Its saturating case needs a == b == INT32_MIN; multipliers are >= 0.
+//   RoundingDivideByPOT(x, r) = (x + half + (x < 0 ? -1 : 0)) >> r  with half = 2^(r-1)   (round half away from zero; r = 0: x)
+// tests/test_host_emul.py fuzzes this against the literal restatement in oracle/mixednet.c.
 MWW_HD int32_t mbqm(int32_t x, int32_t mult, int32_t shift) {
-    const int left = shift > 0 ? shift : 0, right = shift > 0 ? 0 : -shift;
-    return rounding_divide_by_pot(srdhm((int32_t)((uint32_t)x << left), mult), right);
+    const int left = shift > 0 ? shift : 0, r = shift > 0 ? 0 : -shift;
+    const int32_t xs = (int32_t)((uint32_t)x << left);
+    const int64_t ab = (int64_t)xs * (int64_t)mult + (1ll << 30);
+    const int64_t p = ab >> 31;                               // |p| <= 2^31: keep 64 bits so p + half cannot wrap
+    const int64_t half = (int64_t)((1u << r) >> 1);
+    const int64_t fix = (p < 0 && r) ? -1 : 0;
+    return (int32_t)((p + half + fix) >> r);
 }
 // requantise an accumulator; returns (q_out - zp_out) so it can be stored pre-subtracted
 MWW_HD int32_t requant_rel(int32_t acc, int32_t mult, int32_t shift, int32_t zp_out, bool relu) {
@@ -101,64 +104,144 @@ MWW_HD void nnq_load_state(int tid, int32_t *sm, const int8_t *state, const NnWe
     nnq_load_state_l<3>(tid, sm, state, W); nnq_load_state_l<4>(tid, sm, state, W);
 }
 
-// de-interleave the chunk's rows into three planes of (q - zp_in) words (same indexing as the fp32 path)
+// ---- tensor-core formulation of the dense int8 layers (mma.sync.m16n8k32 s8: exact int32 accumulation) -------
+// M = time step, K = input channel (or tap*40 + feature), N = output channel.  Activations enter the MMA as RAW
+// int8 values packed four per word along K; sum_k (q - zp) w = sum_k q w - zp * sum_k w, and the second term is
+// folded into the bias on the host (b0f / pw_bf), so results equal the reference integer kernels bit for bit.
+// Fragments (PTX ISA), g = lane / 4, tig = lane % 4:
+//   A (16x32, row): a0 (g, 4tig..+3)  a1 (g+8, 4tig..)  a2 (g, 16+4tig..)  a3 (g+8, 16+4tig..)
+//   B (32x8,  col): b0 (k = 4tig..+3, n = g)            b1 (k = 16+4tig.., n = g)
+//   C (16x8)      : c0 (g, 2tig) c1 (g, 2tig+1) c2 (g+8, 2tig) c3 (g+8, 2tig+1)
+// Pitches of 80 / 240 bytes (20 / 60 words) put the 8 rows x 4 words of a fragment load on 32 distinct banks.
+constexpr int kPwPitch = 80;                          // bytes per row of D8 [t][k] and of the 1x1 weights [n][k]
+constexpr int kW0Pitch = 240;                         // bytes per row of the first-conv im2col A8 [t][k] and of w0t [n][k]
+constexpr int kMmaRows = 48;                          // 3 m-tiles of 16 steps (kTT = 36 valid)
+// byte offsets inside the int8 kernel's shared memory (after the int32 ring buffers)
+constexpr int kQOffD8 = kXFloats * 4;                               // packed depthwise output
+constexpr int kQOffA8 = kQOffD8 + kMmaRows * kPwPitch;              // first-conv im2col; later reused as the head's int32 partial sums
+constexpr int kQA8Bytes = (kMmaRows * kW0Pitch > kDFloats * 4) ? kMmaRows * kW0Pitch : kDFloats * 4;
+constexpr int kQOffW0 = kQOffA8 + kQA8Bytes;
+constexpr int kQOffPw = kQOffW0 + 32 * kW0Pitch;
+constexpr int kNnI8SmemBytes = kQOffPw + 4 * 64 * kPwPitch;        // 102.7 KB -> 2 CTAs / SM
+static_assert(kQOffD8 % 16 == 0 && kQOffA8 % 16 == 0 && kQOffW0 % 16 == 0 && kQOffPw % 16 == 0, "int8 smem carve-up");
+
+MWW_HD int8_t *nnq_bytes(int32_t *sm) { return reinterpret_cast<int8_t *>(sm); }
+MWW_HD int32_t *nnq_head_scratch(int32_t *sm) { return reinterpret_cast<int32_t *>(nnq_bytes(sm) + kQOffA8); }
+
+// all int8 MMA weights stay resident for the whole call (28 KB)
+MWW_HD void nnq_load_weights(int tid, int32_t *sm, const NnWeightsI8 &W) {
+    struct alignas(16) Vec16 { uint32_t v[4]; };      // 16-byte copies (both sides are 16-byte aligned)
+    int8_t *b = nnq_bytes(sm);
+    for (int e = tid; e < 32 * kW0Pitch / 16; e += kNnThreads)
+        reinterpret_cast<Vec16 *>(b + kQOffW0)[e] = reinterpret_cast<const Vec16 *>(W.w0t)[e];
+    for (int L = 0; L < 4; ++L)
+        for (int e = tid; e < 64 * kPwPitch / 16; e += kNnThreads)
+            reinterpret_cast<Vec16 *>(b + kQOffPw + L * 64 * kPwPitch)[e] = reinterpret_cast<const Vec16 *>(W.pwt[L])[e];
+}
+
+// im2col of the chunk's rows as raw int8: A8[t][tap*40 + f] = q(row 3(step0+t) + tap - 2, f)
 MWW_HD void nnq_load_features(int tid, int32_t *sm, const NnInputI8 &in, const NnWeightsI8 &W, int step0, int n) {
-    int32_t *feat = sm + kXFloats + kDFloats;
+    int8_t *a8 = nnq_bytes(sm) + kQOffA8;
     const int n_q = 3 * n + 2;
     for (int e = tid; e < n_q * kNumChannels; e += kNnThreads) {
         const int q = e / kNumChannels, f = e - q * kNumChannels;
-        feat[((q % 3) * kNumChannels + f) * kUS + q / 3] = nnq_virtual_row(in, W, 3 * step0 + q - 2, f);
+        const int8_t v = (int8_t)(nnq_virtual_row(in, W, 3 * step0 + q - 2, f) + W.zp[0]);
+        // chunk row q is tap j of step t for q = 3t + j: j = q % 3 and, when it exists, j + 3
+        const int j0 = q % 3, t0 = q / 3;
+        if (t0 < kMmaRows) a8[t0 * kW0Pitch + j0 * kNumChannels + f] = v;
+        if (j0 + 3 < 5 && t0 >= 1) a8[(t0 - 1) * kW0Pitch + (j0 + 3) * kNumChannels + f] = v;
     }
 }
 
-// first conv, K split over two thread groups (taps 0..2 | 3..4); integer partial sums meet in D
-MWW_HD void nnq_first_conv_a(int tid, int32_t *sm, const NnWeightsI8 &W, int32_t (&acc)[2][4]) {
-    const int32_t *feat = sm + kXFloats + kDFloats;
-    const int half = tid >= 144, r = tid - 144 * half;
-    const int o0 = 2 * (r & 15), t0 = 4 * (r >> 4);
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[i][q] = 0;
-    const int j_begin = half ? 3 : 0, j_end = half ? 5 : 3;
-    for (int j = j_begin; j < j_end; ++j) {
-        const int32_t *plane = feat + (j % 3) * kNumChannels * kUS + t0 + j / 3;
-        const int8_t *w = W.w0 + j * kNumChannels * 32 + o0;
-#pragma unroll 8
-        for (int f = 0; f < kNumChannels; ++f) {
-            const int32_t w0 = w[f * 32], w1 = w[f * 32 + 1];
-            const int32_t *x = plane + f * kUS;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { acc[0][q] += w0 * x[q]; acc[1][q] += w1 * x[q]; }
-        }
-    }
-    if (half) {
-        int32_t *part = sm + kXFloats;
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) part[(o0 + i) * kDLd + t0 + q] = acc[i][q];
-    }
+struct FragA8 { uint32_t r[4]; };
+struct FragB8 { uint32_t r[2]; };
+MWW_HD void load_frag_a8(const int8_t *base, int pitch, int k0, int t0, int lane, FragA8 &a) {
+    const int g = lane >> 2, tig = lane & 3;
+    const int8_t *p = base + (t0 + g) * pitch + k0 + 4 * tig;
+    a.r[0] = *reinterpret_cast<const uint32_t *>(p);
+    a.r[1] = *reinterpret_cast<const uint32_t *>(p + 8 * pitch);
+    a.r[2] = *reinterpret_cast<const uint32_t *>(p + 16);
+    a.r[3] = *reinterpret_cast<const uint32_t *>(p + 8 * pitch + 16);
 }
-MWW_HD void nnq_first_conv_b(int tid, int32_t *sm, const NnWeightsI8 &W, const int32_t (&acc)[2][4]) {
-    if (tid >= 144) return;
-    const int o0 = 2 * (tid & 15), t0 = 4 * (tid >> 4);
-    const int32_t *part = sm + kXFloats;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int32_t b = W.b0[o0 + i], m = W.m0[o0 + i], s = W.s0[o0 + i];
-        int32_t *dst = sm + kGeom[0].off + (o0 + i) * kGeom[0].ld + kGeom[0].hp + t0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = requant_rel(acc[i][q] + part[(o0 + i) * kDLd + t0 + q] + b, m, s, W.zp[1], true);
-    }
+MWW_HD void load_frag_b8(const int8_t *base, int pitch, int k0, int n0, int lane, FragB8 &b) {
+    const int g = lane >> 2, tig = lane & 3;
+    const int8_t *p = base + (n0 + g) * pitch + k0 + 4 * tig;
+    b.r[0] = *reinterpret_cast<const uint32_t *>(p);
+    b.r[1] = *reinterpret_cast<const uint32_t *>(p + 16);
 }
+#if defined(__CUDACC__)
+MWW_D void mma_s8(int32_t (&c)[4], const FragA8 &a, const FragB8 &b) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a.r[0]), "r"(a.r[1]), "r"(a.r[2]), "r"(a.r[3]), "r"(b.r[0]), "r"(b.r[1]));
+}
+#endif
 
+// first conv: warps 0..5 = (m-tile, pair of 8-channel tiles), 7 k-steps of 32 (K = 200 zero padded to 224)
+MWW_HD void nnq_fc_store_tile(int32_t *sm, const NnWeightsI8 &W, int t0, int n0, int lane, const int32_t (&c)[4]) {
+    const int g = lane >> 2, tig = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = t0 + g + ((i & 2) ? 8 : 0);
+        const int o = n0 + 2 * tig + (i & 1);
+        if (t < kTT) sm[kGeom[0].off + o * kGeom[0].ld + kGeom[0].hp + t] = requant_rel(c[i] + W.b0f[o], W.m0[o], W.s0[o], W.zp[1], true);
+    }
+}
 template <int L>
-MWW_HD void nnq_stage_pw_weights(int tid, int32_t *sm, const NnWeightsI8 &W) {
-    int32_t *wsm = sm + kXFloats + kDFloats;
-    constexpr int n = kGeom[L].cin * 64;
-    for (int e = tid; e < n; e += kNnThreads) wsm[e] = W.pw_w[L][e];
+MWW_HD void nnq_pw_store_tile(int32_t *sm, const NnWeightsI8 &W, int t0, int n0, int lane, const int32_t (&c)[4]) {
+    constexpr NnLayerGeom gn = kGeom[L + 1];
+    const int g = lane >> 2, tig = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = t0 + g + ((i & 2) ? 8 : 0);
+        const int o = n0 + 2 * tig + (i & 1);
+        if (t < kTT) sm[gn.off + o * gn.ld + gn.hp + t] = requant_rel(c[i] + W.pw_bf[L][o], W.pw_m[L][o], W.pw_s[L][o], W.zp[3 + 2 * L], true);
+    }
 }
+#if defined(__CUDACC__)
+MWW_D void nnq_first_conv_mma(int tid, int32_t *sm, const NnWeightsI8 &W) {
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp >= 6) return;
+    const int t0 = 16 * (warp >> 1), n0 = 16 * (warp & 1);
+    const int8_t *a8 = nnq_bytes(sm) + kQOffA8, *w0 = nnq_bytes(sm) + kQOffW0;
+    int32_t c[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll
+    for (int ks = 0; ks < 7; ++ks) {
+        FragA8 a;
+        FragB8 b0, b1;
+        load_frag_a8(a8, kW0Pitch, 32 * ks, t0, lane, a);
+        load_frag_b8(w0, kW0Pitch, 32 * ks, n0, lane, b0);
+        load_frag_b8(w0, kW0Pitch, 32 * ks, n0 + 8, lane, b1);
+        mma_s8(c[0], a, b0);
+        mma_s8(c[1], a, b1);
+    }
+    nnq_fc_store_tile(sm, W, t0, n0, lane, c[0]);
+    nnq_fc_store_tile(sm, W, t0, n0 + 8, lane, c[1]);
+}
+template <int L>
+MWW_D void nnq_pointwise_mma(int tid, int32_t *sm, const NnWeightsI8 &W) {
+    constexpr int cin = kGeom[L].cin;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int t0 = 16 * (warp / 3), nt0 = 3 * (warp % 3), ntc = (warp % 3) == 2 ? 2 : 3;
+    const int8_t *d8 = nnq_bytes(sm) + kQOffD8, *wt = nnq_bytes(sm) + kQOffPw + L * 64 * kPwPitch;
+    int32_t c[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll
+    for (int ks = 0; ks < cin / 32; ++ks) {
+        FragA8 a;
+        load_frag_a8(d8, kPwPitch, 32 * ks, t0, lane, a);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (i < ntc) {
+                FragB8 b;
+                load_frag_b8(wt, kPwPitch, 32 * ks, 8 * (nt0 + i), lane, b);
+                mma_s8(c[i], a, b);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        if (i < ntc) nnq_pw_store_tile<L>(sm, W, t0, 8 * (nt0 + i), lane, c[i]);
+}
+#endif
 
 template <int L, int K, int TN>
 MWW_HD void nnq_depthwise_k(int c, int t0, int32_t *sm, const NnWeightsI8 &W) {
@@ -180,9 +263,9 @@ MWW_HD void nnq_depthwise_k(int c, int t0, int32_t *sm, const NnWeightsI8 &W) {
         }
     }
     const int32_t b = W.dw_b[L][c], m = W.dw_m[L][c], s = W.dw_s[L][c];
-    int32_t *d = sm + kXFloats + c * kDLd + t0;
+    int8_t *d8 = nnq_bytes(sm) + kQOffD8 + t0 * kPwPitch + c;
 #pragma unroll
-    for (int i = 0; i < TN; ++i) d[i] = requant_rel(acc[i] + b, m, s, W.zp[2 + 2 * L], false);
+    for (int i = 0; i < TN; ++i) d8[i * kPwPitch] = (int8_t)(requant_rel(acc[i] + b, m, s, W.zp[2 + 2 * L], false) + W.zp[2 + 2 * L]);
 }
 
 template <int L>
@@ -196,33 +279,6 @@ MWW_HD void nnq_depthwise(int tid, int32_t *sm, const NnWeightsI8 &W) {
         if (L == 1) { if (c < 32) nnq_depthwise_k<L, 7, 9>(c, t0, sm, W); else nnq_depthwise_k<L, 11, 9>(c, t0, sm, W); }
         else if (L == 2) { if (c < 32) nnq_depthwise_k<L, 9, 9>(c, t0, sm, W); else nnq_depthwise_k<L, 15, 9>(c, t0, sm, W); }
         else nnq_depthwise_k<L, g.kmax, 9>(c, t0, sm, W);
-    }
-}
-
-template <int L>
-MWW_HD void nnq_pointwise(int tid, int32_t *sm, const NnWeightsI8 &W) {
-    constexpr int cin = kGeom[L].cin;
-    constexpr NnLayerGeom gn = kGeom[L + 1];
-    const int o0 = 4 * (tid & 15), t0 = 2 * (tid >> 4);
-    const int32_t *wsm = sm + kXFloats + kDFloats + o0;
-    const int32_t *d = sm + kXFloats + t0;
-    int32_t acc[4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { acc[i][0] = 0; acc[i][1] = 0; }
-#pragma unroll 8
-    for (int k = 0; k < cin; ++k) {
-        const int32_t *w = wsm + k * 64;
-        const int32_t *x = d + k * kDLd;
-        const int32_t x0 = x[0], x1 = x[1];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[i][0] += w[i] * x0; acc[i][1] += w[i] * x1; }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int32_t b = W.pw_b[L][o0 + i], m = W.pw_m[L][o0 + i], s = W.pw_s[L][o0 + i];
-        int32_t *dst = sm + gn.off + (o0 + i) * gn.ld + gn.hp + t0;
-        dst[0] = requant_rel(acc[i][0] + b, m, s, W.zp[3 + 2 * L], true);
-        dst[1] = requant_rel(acc[i][1] + b, m, s, W.zp[3 + 2 * L], true);
     }
 }
 
@@ -246,7 +302,7 @@ MWW_HD void nnq_head_partial(int tid, int32_t *sm, const NnWeightsI8 &W) {
             if (j >= 0 && j < 17) acc[tt] += w[j] * xv;
         }
     }
-    int32_t *d = sm + kXFloats + c * kDLd + t0;
+    int32_t *d = nnq_head_scratch(sm) + c * kDLd + t0;
 #pragma unroll
     for (int i = 0; i < 9; ++i) d[i] = acc[i];
 }
@@ -254,7 +310,7 @@ MWW_HD void nnq_head_partial(int tid, int32_t *sm, const NnWeightsI8 &W) {
 // FULLY_CONNECTED requant -> LOGISTIC LUT -> QUANTIZE to uint8 -> Model.dequantize_output_data (/255)
 MWW_HD void nnq_head_finish(int tid, int32_t *sm, const NnWeightsI8 &W, int n, float *probs_out) {
     if (tid >= kTT || tid >= n) return;
-    const int32_t *d = sm + kXFloats + tid;
+    const int32_t *d = nnq_head_scratch(sm) + tid;
     int32_t acc = 0;
     for (int c = 0; c < 64; ++c) acc += d[c * kDLd];
     const int32_t logit = requant_rel(acc + W.head_bias, W.head_mult, W.head_shift, W.zp[10], false) + W.zp[10];

@@ -25,24 +25,22 @@ nn_i8_clip_kernel(NnWeightsI8 W, int8_t *__restrict__ state, int8_t *__restrict_
     const int n_steps = n_virtual / 3;
 
     nnq_load_state(tid, smi, my_state, W);
+    nnq_load_weights(tid, smi, W);
     __syncthreads();
     for (int step0 = 0; step0 < n_steps; step0 += kTT) {
         const int n = min(kTT, n_steps - step0);
         nnq_load_features(tid, smi, in, W, step0, n);
         __syncthreads();
-        int32_t fc[2][4];
-        nnq_first_conv_a(tid, smi, W, fc);
+        nnq_first_conv_mma(tid, smi, W);
         __syncthreads();
-        nnq_first_conv_b(tid, smi, W, fc);
-        __syncthreads();
-        nnq_stage_pw_weights<0>(tid, smi, W); nnq_depthwise<0>(tid, smi, W); __syncthreads();
-        nnq_pointwise<0>(tid, smi, W); __syncthreads();
-        nnq_stage_pw_weights<1>(tid, smi, W); nnq_depthwise<1>(tid, smi, W); __syncthreads();
-        nnq_pointwise<1>(tid, smi, W); __syncthreads();
-        nnq_stage_pw_weights<2>(tid, smi, W); nnq_depthwise<2>(tid, smi, W); __syncthreads();
-        nnq_pointwise<2>(tid, smi, W); __syncthreads();
-        nnq_stage_pw_weights<3>(tid, smi, W); nnq_depthwise<3>(tid, smi, W); __syncthreads();
-        nnq_pointwise<3>(tid, smi, W); __syncthreads();
+        nnq_depthwise<0>(tid, smi, W); __syncthreads();
+        nnq_pointwise_mma<0>(tid, smi, W); __syncthreads();
+        nnq_depthwise<1>(tid, smi, W); __syncthreads();
+        nnq_pointwise_mma<1>(tid, smi, W); __syncthreads();
+        nnq_depthwise<2>(tid, smi, W); __syncthreads();
+        nnq_pointwise_mma<2>(tid, smi, W); __syncthreads();
+        nnq_depthwise<3>(tid, smi, W); __syncthreads();
+        nnq_pointwise_mma<3>(tid, smi, W); __syncthreads();
         nnq_head_partial(tid, smi, W);
         __syncthreads();
         nnq_head_finish(tid, smi, W, n, probs + s * probs_stream_stride + step0);
@@ -74,11 +72,11 @@ cudaError_t launch_nn_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, int 
     if (n_streams <= 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(nn_i8_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNnSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(nn_i8_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNnI8SmemBytes);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    nn_i8_clip_kernel<<<(unsigned)n_streams, kNnThreads, kNnSmemBytes, st>>>(W, state, pend, n_pend, rows, rows_stream_stride_bytes, n_rows,
+    nn_i8_clip_kernel<<<(unsigned)n_streams, kNnThreads, kNnI8SmemBytes, st>>>(W, state, pend, n_pend, rows, rows_stream_stride_bytes, n_rows,
                                                                             row_type, probs, probs_stream_stride);
     return cudaGetLastError();
 }

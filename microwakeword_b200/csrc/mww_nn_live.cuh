@@ -1,0 +1,242 @@
+// mww_nn_live.cuh -- fp32 MixedNet, LIVE-STEP formulation: one model step (three new 10 ms feature rows) for
+// many streams per launch -- the literal shape of the reference's hot loop (set_tensor / invoke / get_tensor once
+// per 30 ms, microwakeword/inference.py:109-123), batched over streams instead of repeated per stream.
+//
+// The clip kernels (mww_nn_dev.cuh) amortise the ring state over many steps of one stream; with one step per call
+// there is nothing to amortise, the ring state (4 176 floats per stream, stream.py:581-595) has to cross HBM once
+// per step and the kernel is HBM-bound (SURVEY.md 8d "live step": ~18.8 KB per stream-step algorithmic).  So here a
+// CTA owns 32 STREAMS: the stream index is the M dimension of the tensor-core contractions (first conv, 1x1
+// projections: same 3xTF32 mma path as the clip kernel), all 1x1 weights stay resident in shared memory, and the
+// depthwise / head stages stream each (stream, channel) ring column through registers: load R rows (coalesced
+// over channels), accumulate the taps, write the rows back shifted by one together with the new row -- the
+// concat(state, input)[-R:] update of stream.py:584-590 done in the same pass that consumes it.
+// The per-stream state layout in HBM is IDENTICAL to the clip kernels', so clip and live calls can be mixed.
+#pragma once
+
+#include "mww_nn_mma.cuh"
+
+namespace mww {
+
+constexpr int kLiveThreads = 256;
+constexpr int kLiveStreams = 32;                  // streams per CTA = two 16-row MMA tiles
+constexpr int kLivePitch = 40;                    // [k][stream] pitch: 40 = 8 (mod 32) -> conflict-free A fragments
+// shared memory (floats): 1x1 weights of the four blocks (pitch kWLd), A operand of the first conv [200][40],
+// H = new activation row of every stream [64][40], D = depthwise output [64][40]
+constexpr int kLiveOffPw0 = 0;
+constexpr int kLiveOffPw1 = kLiveOffPw0 + 32 * kWLd;
+constexpr int kLiveOffPw2 = kLiveOffPw1 + 64 * kWLd;
+constexpr int kLiveOffPw3 = kLiveOffPw2 + 64 * kWLd;
+constexpr int kLiveOffA = kLiveOffPw3 + 64 * kWLd;
+constexpr int kLiveOffH = kLiveOffA + 200 * kLivePitch;
+constexpr int kLiveOffD = kLiveOffH + 64 * kLivePitch;
+constexpr int kLiveSmemFloats = kLiveOffD + 64 * kLivePitch;
+constexpr int kLiveSmemBytes = kLiveSmemFloats * 4;           // 117 KB -> 1 CTA / SM (8 warps), persistent over stream groups
+
+template <int L>
+MWW_HD int live_pw_offset() { return L == 0 ? kLiveOffPw0 : (L == 1 ? kLiveOffPw1 : (L == 2 ? kLiveOffPw2 : kLiveOffPw3)); }
+
+// ---- once per CTA: stage all 1x1 weights ----
+MWW_HD void live_load_weights(int tid, float *sm, const NnWeightsF32 &W) {
+    for (int L = 0; L < 4; ++L) {
+        const int cin = L == 0 ? 32 : 64;
+        float *dst = sm + (L == 0 ? kLiveOffPw0 : (L == 1 ? kLiveOffPw1 : (L == 2 ? kLiveOffPw2 : kLiveOffPw3)));
+        for (int e = tid; e < cin * 64; e += kLiveThreads) dst[(e >> 6) * kWLd + (e & 63)] = W.pw_w[L][e];
+    }
+}
+
+// virtual feature row vr of one stream: pending rows first, then the three new rows (this call's input)
+struct LiveInput {
+    const float *state;        // [S][4176]
+    const float *pend;         // [S][2][40]
+    int n_pend;
+    const void *rows;          // [S][3][40] uint16 or float32
+    long long rows_stream_stride_bytes;
+    int rows_are_f32;
+};
+// Row w (0..6) of a stream's window: w = 0, 1 are the first-conv ring (virtual rows -2, -1), w >= 2 is virtual row
+// w - 2 (pending rows first, then this call's three rows).  All indices are kept NON-NEGATIVE and unsigned on purpose:
+// with a signed "virtual row - 2" formulation nvcc 12.9 re-associated (2 + vr) * 40 into a negative 32-bit term that
+// was then added to the 64-bit address without sign extension (a 16 GB stray access, caught by compute-sanitizer).
+MWW_HD float live_window_row(const LiveInput &in, long long s, unsigned w, unsigned f) {
+    const size_t su = (size_t)s;
+    if (w < 2u) return in.state[su * (size_t)kStateFloats + (size_t)(w * (unsigned)kNumChannels + f)];
+    const unsigned v = w - 2u;
+    if (v < (unsigned)in.n_pend) return in.pend[su * (size_t)(2 * kNumChannels) + (size_t)(v * (unsigned)kNumChannels + f)];
+    const char *base = static_cast<const char *>(in.rows) + su * (size_t)in.rows_stream_stride_bytes;
+    const unsigned e = (v - (unsigned)in.n_pend) * (unsigned)kNumChannels + f;
+    if (in.rows_are_f32) return reinterpret_cast<const float *>(base)[e];
+    return (float)reinterpret_cast<const uint16_t *>(base)[e] * kFeatureScale;
+}
+
+// ---- phase: A[k = tap*40 + f][stream] for the first conv; also capture the new first-conv ring / pending rows ----
+struct LiveTail { float v[2]; };      // per thread: up to 2 of the 32 x (80 + 80) tail values of the group
+MWW_HD void live_build_a(int tid, float *sm, const LiveInput &in, long long s0, int n_valid) {
+    float *a = sm + kLiveOffA;
+    for (int e = tid; e < 200 * kLiveStreams; e += kLiveThreads) {
+        const int sl = e / 200, k = e - 200 * sl;            // consecutive threads walk one stream's 200 window values
+        const int j = k / kNumChannels, f = k - j * kNumChannels;
+        a[k * kLivePitch + sl] = sl < n_valid ? live_window_row(in, s0 + sl, (unsigned)j, (unsigned)f) : 0.f;
+    }
+}
+// new first-conv ring = virtual rows 1, 2; new pending rows = virtual rows 3 .. 3 + n_pend - 1.  Values are read
+// (from the OLD state / pend / rows) here and written by live_write_tail after a barrier.
+MWW_HD void live_read_tail(int tid, const LiveInput &in, long long s0, int n_valid, float (&t)[2][10]) {
+    // 32 streams x 80 values = 2560 per kind; 10 per thread per kind
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+        const int e = tid + q * kLiveThreads;
+        const int sl = e / 80, i = e - 80 * sl, r = i / kNumChannels, f = i - r * kNumChannels;
+        t[0][q] = 0.f; t[1][q] = 0.f;
+        if (sl < n_valid) {
+            t[0][q] = live_window_row(in, s0 + sl, (unsigned)(3 + r), (unsigned)f);          // virtual rows 1, 2
+            t[1][q] = r < in.n_pend ? live_window_row(in, s0 + sl, (unsigned)(5 + r), (unsigned)f) : 0.f;   // virtual rows 3, 4
+        }
+    }
+}
+MWW_HD void live_write_tail(int tid, float *state, float *pend, long long s0, int n_valid, const float (&t)[2][10]) {
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+        const int e = tid + q * kLiveThreads;
+        const int sl = e / 80, i = e - 80 * sl;
+        if (sl < n_valid) {
+            state[(s0 + sl) * kStateFloats + i] = t[0][q];
+            pend[(s0 + sl) * 2 * kNumChannels + i] = t[1][q];
+        }
+    }
+}
+
+// ---- first conv epilogue: ReLU into H[o][stream] ----
+MWW_HD void live_fc_store_tile(float *sm, int r0, int n0, int lane, const float (&c)[4]) {
+    const int g = lane >> 2, tig = lane & 3;
+    float *h = sm + kLiveOffH;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = r0 + g + ((i & 2) ? 8 : 0), o = n0 + 2 * tig + (i & 1);
+        h[o * kLivePitch + row] = c[i] > 0.f ? c[i] : 0.f;
+    }
+}
+template <int L>
+MWW_HD void live_pw_store_tile(float *sm, const NnWeightsF32 &W, int r0, int n0, int lane, const float (&c)[4]) {
+    const int g = lane >> 2, tig = lane & 3;
+    float *h = sm + kLiveOffH;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = r0 + g + ((i & 2) ? 8 : 0), o = n0 + 2 * tig + (i & 1);
+        const float v = c[i] + W.pw_b[L][o];
+        h[o * kLivePitch + row] = v > 0.f ? v : 0.f;
+    }
+}
+
+// ---- depthwise of block L for (stream, channel) columns: ring rows stream through registers ----
+// thread -> channel c = tid % cin, stream subgroup = tid / cin; each thread walks kLiveStreams * cin / 256 streams.
+template <int L>
+MWW_HD void live_depthwise(int tid, float *sm, const NnWeightsF32 &W, float *state, long long s0, int n_valid) {
+    constexpr NnLayerGeom g = kGeom[L];
+    constexpr int R = g.ring;
+    constexpr int per = kLiveStreams * g.cin / kLiveThreads;     // streams per thread: 4 (cin 32) or 8 (cin 64)
+    const int c = tid % g.cin, sub = tid / g.cin;
+    float w[g.kmax];
+#pragma unroll
+    for (int j = 0; j < g.kmax; ++j) w[j] = W.dw_w[L][j * g.cin + c];      // zero padded at the front for short MixConv kernels
+    const float bias = W.dw_b[L][c];
+    const float *h = sm + kLiveOffH + c * kLivePitch;
+    float *d = sm + kLiveOffD + c * kLivePitch;
+    for (int i = 0; i < per; ++i) {
+        const int sl = sub * per + i;
+        if (sl >= n_valid) { d[sl] = 0.f; continue; }
+        float *ring = state + (s0 + sl) * kStateFloats + kStateOff[L + 1] + c;
+        float x[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = ring[r * g.cin];
+        const float xn = h[sl];
+        float acc = bias;
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc = fmaf(w[r], x[r], acc);
+        acc = fmaf(w[R], xn, acc);
+        d[sl] = acc;
+#pragma unroll
+        for (int r = 0; r + 1 < R; ++r) ring[r * g.cin] = x[r + 1];
+        ring[(R - 1) * g.cin] = xn;
+    }
+}
+
+// ---- head: 17-tap dot per (stream, channel) into D, ring shifted; then reduce over channels ----
+MWW_HD void live_head_partial(int tid, float *sm, const NnWeightsF32 &W, float *state, long long s0, int n_valid) {
+    constexpr int per = kLiveStreams * 64 / kLiveThreads;        // 8
+    const int c = tid & 63, sub = tid >> 6;
+    float w[17];
+#pragma unroll
+    for (int j = 0; j < 17; ++j) w[j] = W.head_w[j * 64 + c];
+    const float *h = sm + kLiveOffH + c * kLivePitch;
+    float *d = sm + kLiveOffD + c * kLivePitch;
+    for (int i = 0; i < per; ++i) {
+        const int sl = sub * per + i;
+        if (sl >= n_valid) { d[sl] = 0.f; continue; }
+        float *ring = state + (s0 + sl) * kStateFloats + kStateOff[5] + c;
+        float x[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = ring[r * 64];
+        const float xn = h[sl];
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc = fmaf(w[r], x[r], acc);
+        acc = fmaf(w[16], xn, acc);
+        d[sl] = acc;
+#pragma unroll
+        for (int r = 0; r + 1 < 16; ++r) ring[r * 64] = x[r + 1];
+        ring[15 * 64] = xn;
+    }
+}
+MWW_HD void live_head_finish(int tid, const float *sm, const NnWeightsF32 &W, long long s0, int n_valid, float *probs, long long probs_stride) {
+    if (tid >= kLiveStreams || tid >= n_valid) return;
+    const float *d = sm + kLiveOffD + tid;
+    float acc = 0.f;
+    for (int c = 0; c < 64; ++c) acc += d[c * kLivePitch];
+    probs[(s0 + tid) * probs_stride] = nn_sigmoid(acc + W.head_b[0]);
+}
+
+#if defined(__CUDACC__)
+// first conv on tensor cores: 8 warps = 2 stream tiles x 4 channel tiles, K = 200 (25 k-steps), B fragments from L2
+MWW_D void live_first_conv_mma(int tid, float *sm, const NnWeightsF32 &W) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int r0 = 16 * (warp >> 2), n0 = 8 * (warp & 3);
+    const float *a_base = sm + kLiveOffA;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 5
+    for (int ks = 0; ks < 25; ++ks) {
+        FragA a;
+        FragB b;
+        load_frag_b(W.w0, 32, 8 * ks, n0, lane, b);
+        load_frag_a(a_base, kLivePitch, 8 * ks, r0, lane, a);
+        mma_tf32(c, a.lo, b.hi);
+        mma_tf32(c, a.hi, b.lo);
+        mma_tf32(c, a.hi, b.hi);
+    }
+    live_fc_store_tile(sm, r0, n0, lane, c);
+}
+// 1x1 of block L: 8 warps = 2 stream tiles x 4 pairs of channel tiles
+template <int L>
+MWW_D void live_pointwise_mma(int tid, float *sm, const NnWeightsF32 &W) {
+    constexpr int cin = kGeom[L].cin;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int r0 = 16 * (warp >> 2), n0 = 16 * (warp & 3);
+    const float *d = sm + kLiveOffD;
+    const float *wsm = sm + live_pw_offset<L>();
+    float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 2
+    for (int ks = 0; ks < cin / 8; ++ks) {
+        FragA a;
+        FragB b0, b1;
+        load_frag_a(d, kLivePitch, 8 * ks, r0, lane, a);
+        load_frag_b(wsm, kWLd, 8 * ks, n0, lane, b0);
+        load_frag_b(wsm, kWLd, 8 * ks, n0 + 8, lane, b1);
+        mma_tf32(c[0], a.lo, b0.hi); mma_tf32(c[1], a.lo, b1.hi);
+        mma_tf32(c[0], a.hi, b0.lo); mma_tf32(c[1], a.hi, b1.lo);
+        mma_tf32(c[0], a.hi, b0.hi); mma_tf32(c[1], a.hi, b1.hi);
+    }
+    live_pw_store_tile<L>(sm, W, r0, n0, lane, c[0]);
+    live_pw_store_tile<L>(sm, W, r0, n0 + 8, lane, c[1]);
+}
+#endif
+
+}  // namespace mww

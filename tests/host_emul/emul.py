@@ -29,6 +29,7 @@ def lib():
         L.emul_features.restype = ctypes.c_int
         L.emul_nn_f32.restype = ctypes.c_int
         L.emul_nn_i8.restype = ctypes.c_int
+        L.emul_nn_f32_live.restype = ctypes.c_int
         L.emul_isqrt64_round.restype = ctypes.c_uint32
         L.emul_isqrt64_round.argtypes = [ctypes.c_uint64]
         _lib = L
@@ -87,6 +88,18 @@ class NnF32:
                               _p(probs), probs.shape[1], None)
         self.n_pend = (self.n_pend + n_rows) % 3
         return probs[:, :n]
+
+
+class NnF32Live(NnF32):
+    """Same weights / state / pending layout as NnF32, stepped with the live-step kernel's phase functions (3 rows per call)."""
+
+    def step(self, rows3):
+        rows3 = np.ascontiguousarray(rows3)
+        S = rows3.shape[0]
+        assert rows3.shape[1:] == (3, 40)
+        probs = np.zeros((S, 1), np.float32)
+        lib().emul_nn_f32_live(self.wp, _p(self.state), _p(self.pend), self.n_pend, _p(rows3), int(rows3.dtype == np.float32), S, _p(probs), 1)
+        return probs[:, 0]
 
 
 def i8_names():

@@ -5,7 +5,7 @@
 
 #include <vector>
 
-#include "../../microwakeword_b200/csrc/mww_nn_mma.cuh"
+#include "../../microwakeword_b200/csrc/mww_nn_live.cuh"
 
 using namespace mww;
 
@@ -146,7 +146,70 @@ extern "C" int emul_nn_f32(const float *const *wp /* w0, dw_w[4], dw_b[4], pw_w[
 }
 
 // ---- int8 path --------------------------------------------------------------------------------
-#include "../../microwakeword_b200/csrc/mww_nn_i8_dev.cuh"
+#include "../../microwakeword_b200/csrc/mww_nn_i8_prep.h"
+
+
+// ---- host model of mma.sync.m16n8k32.s8 for one warp ------------------------------------------------------
+namespace {
+void warp_mma_s8(int32_t (*c)[4], const FragA8 *a, const FragB8 *b) {
+    int32_t A[16][32], B[32][8], C[16][8];
+    for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, tig = lane & 3;
+        for (int i = 0; i < 4; ++i) {
+            A[g][4 * tig + i] = (int8_t)(a[lane].r[0] >> (8 * i)); A[g + 8][4 * tig + i] = (int8_t)(a[lane].r[1] >> (8 * i));
+            A[g][16 + 4 * tig + i] = (int8_t)(a[lane].r[2] >> (8 * i)); A[g + 8][16 + 4 * tig + i] = (int8_t)(a[lane].r[3] >> (8 * i));
+            B[4 * tig + i][g] = (int8_t)(b[lane].r[0] >> (8 * i)); B[16 + 4 * tig + i][g] = (int8_t)(b[lane].r[1] >> (8 * i));
+        }
+        C[g][2 * tig] = c[lane][0]; C[g][2 * tig + 1] = c[lane][1]; C[g + 8][2 * tig] = c[lane][2]; C[g + 8][2 * tig + 1] = c[lane][3];
+    }
+    for (int m = 0; m < 16; ++m)
+        for (int n = 0; n < 8; ++n) { int32_t acc = C[m][n]; for (int k = 0; k < 32; ++k) acc += A[m][k] * B[k][n]; C[m][n] = acc; }
+    for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, tig = lane & 3;
+        c[lane][0] = C[g][2 * tig]; c[lane][1] = C[g][2 * tig + 1]; c[lane][2] = C[g + 8][2 * tig]; c[lane][3] = C[g + 8][2 * tig + 1];
+    }
+}
+
+void emul_q_first_conv_mma(int32_t *sm, const NnWeightsI8 &W) {
+    const int8_t *a8 = nnq_bytes(sm) + kQOffA8, *w0 = nnq_bytes(sm) + kQOffW0;
+    for (int warp = 0; warp < 6; ++warp) {
+        const int t0 = 16 * (warp >> 1), n0 = 16 * (warp & 1);
+        int32_t c[2][32][4] = {};
+        for (int ks = 0; ks < 7; ++ks) {
+            FragA8 a[32]; FragB8 b0[32], b1[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                load_frag_a8(a8, kW0Pitch, 32 * ks, t0, lane, a[lane]);
+                load_frag_b8(w0, kW0Pitch, 32 * ks, n0, lane, b0[lane]);
+                load_frag_b8(w0, kW0Pitch, 32 * ks, n0 + 8, lane, b1[lane]);
+            }
+            warp_mma_s8(c[0], a, b0);
+            warp_mma_s8(c[1], a, b1);
+        }
+        for (int lane = 0; lane < 32; ++lane) { nnq_fc_store_tile(sm, W, t0, n0, lane, c[0][lane]); nnq_fc_store_tile(sm, W, t0, n0 + 8, lane, c[1][lane]); }
+    }
+}
+
+template <int L>
+void emul_q_pointwise_mma(int32_t *sm, const NnWeightsI8 &W) {
+    constexpr int cin = kGeom[L].cin;
+    const int8_t *d8 = nnq_bytes(sm) + kQOffD8, *wt = nnq_bytes(sm) + kQOffPw + L * 64 * kPwPitch;
+    for (int warp = 0; warp < kNnThreads / 32; ++warp) {
+        const int t0 = 16 * (warp / 3), nt0 = 3 * (warp % 3), ntc = (warp % 3) == 2 ? 2 : 3;
+        int32_t c[3][32][4] = {};
+        for (int ks = 0; ks < cin / 32; ++ks) {
+            FragA8 a[32];
+            for (int lane = 0; lane < 32; ++lane) load_frag_a8(d8, kPwPitch, 32 * ks, t0, lane, a[lane]);
+            for (int i = 0; i < ntc; ++i) {
+                FragB8 b[32];
+                for (int lane = 0; lane < 32; ++lane) load_frag_b8(wt, kPwPitch, 32 * ks, 8 * (nt0 + i), lane, b[lane]);
+                warp_mma_s8(c[i], a, b);
+            }
+        }
+        for (int i = 0; i < ntc; ++i)
+            for (int lane = 0; lane < 32; ++lane) nnq_pw_store_tile<L>(sm, W, t0, 8 * (nt0 + i), lane, c[i][lane]);
+    }
+}
+}  // namespace
 
 extern "C" int emul_nn_i8(const void *const *wp /* see order below */, const int32_t *zp12, const int32_t *head3, float in_scale,
                           int8_t *state, int8_t *pend, int n_pend, const void *rows, int n_rows, int row_type,
@@ -162,10 +225,14 @@ extern "C" int emul_nn_i8(const void *const *wp /* see order below */, const int
     W.head_bias = head3[0]; W.head_mult = head3[1]; W.head_shift = head3[2];
     memcpy(W.zp, zp12, sizeof W.zp);
     W.in_scale = in_scale;
+    I8MmaOperands ops;
+    build_i8_mma_operands(W.w0, W.b0, W.pw_w, W.pw_b, W.zp, &ops);
+    W.w0t = ops.w0t.data(); W.b0f = ops.b0f.data();
+    for (int i = 0; i < 4; ++i) { W.pwt[i] = ops.pwt[i].data(); W.pw_bf[i] = ops.pw_bf[i].data(); }
     const int n_virtual = n_pend + n_rows;
     const int n_steps = n_virtual / 3;
     const size_t row_bytes = (size_t)kNumChannels * (row_type == 1 ? 4 : (row_type == 0 ? 2 : 1));
-    std::vector<int32_t> smv(kNnSmemFloats);
+    std::vector<int32_t> smv(kNnI8SmemBytes / 4 + 4);
     int32_t *sm = smv.data();
     for (int s = 0; s < n_streams; ++s) {
         for (auto &v : smv) v = 0x5A5A5A5A;
@@ -177,16 +244,15 @@ extern "C" int emul_nn_i8(const void *const *wp /* see order below */, const int
         in.n_rows = n_rows; in.row_type = row_type;
 #define ALL(stmt) for (int tid = 0; tid < kNnThreads; ++tid) { stmt; }
         ALL(nnq_load_state(tid, sm, my_state, W));
+        ALL(nnq_load_weights(tid, sm, W));
         for (int step0 = 0; step0 < n_steps; step0 += kTT) {
             const int n = n_steps - step0 < kTT ? n_steps - step0 : kTT;
             ALL(nnq_load_features(tid, sm, in, W, step0, n));
-            std::vector<int32_t> fc((size_t)kNnThreads * 8);
-            ALL(nnq_first_conv_a(tid, sm, W, *reinterpret_cast<int32_t(*)[2][4]>(&fc[(size_t)tid * 8])));
-            ALL(nnq_first_conv_b(tid, sm, W, *reinterpret_cast<int32_t(*)[2][4]>(&fc[(size_t)tid * 8])));
-            ALL(nnq_stage_pw_weights<0>(tid, sm, W)); ALL(nnq_depthwise<0>(tid, sm, W)); ALL(nnq_pointwise<0>(tid, sm, W));
-            ALL(nnq_stage_pw_weights<1>(tid, sm, W)); ALL(nnq_depthwise<1>(tid, sm, W)); ALL(nnq_pointwise<1>(tid, sm, W));
-            ALL(nnq_stage_pw_weights<2>(tid, sm, W)); ALL(nnq_depthwise<2>(tid, sm, W)); ALL(nnq_pointwise<2>(tid, sm, W));
-            ALL(nnq_stage_pw_weights<3>(tid, sm, W)); ALL(nnq_depthwise<3>(tid, sm, W)); ALL(nnq_pointwise<3>(tid, sm, W));
+            emul_q_first_conv_mma(sm, W);
+            ALL(nnq_depthwise<0>(tid, sm, W)); emul_q_pointwise_mma<0>(sm, W);
+            ALL(nnq_depthwise<1>(tid, sm, W)); emul_q_pointwise_mma<1>(sm, W);
+            ALL(nnq_depthwise<2>(tid, sm, W)); emul_q_pointwise_mma<2>(sm, W);
+            ALL(nnq_depthwise<3>(tid, sm, W)); emul_q_pointwise_mma<3>(sm, W);
             ALL(nnq_head_partial(tid, sm, W));
             ALL(nnq_head_finish(tid, sm, W, n, probs + (size_t)s * max_probs + step0));
             std::vector<float> tmp((size_t)kNnThreads * 5 * kShiftPerThread);
@@ -208,4 +274,77 @@ extern "C" void emul_fill_state_i8(const int32_t *zp12, int8_t *state, int8_t *p
         for (int e = 0; e < kStateFloats; ++e) state[(size_t)s * kStateFloats + e] = nnq_reset_value(W, e);
         for (int e = 0; e < 2 * kNumChannels; ++e) pend[(size_t)s * 2 * kNumChannels + e] = (int8_t)W.zp[0];
     }
+}
+
+extern "C" int32_t emul_mbqm(int32_t x, int32_t mult, int32_t shift) { return mbqm(x, mult, shift); }
+
+
+// ---- live-step fp32 kernel (mww_nn_live.cuh) ---------------------------------------------------------------
+namespace {
+void emul_live_first_conv(float *sm, const NnWeightsF32 &W) {
+    for (int warp = 0; warp < kLiveThreads / 32; ++warp) {
+        const int r0 = 16 * (warp >> 2), n0 = 8 * (warp & 3);
+        float c[32][4] = {};
+        for (int ks = 0; ks < 25; ++ks) {
+            FragA a[32]; FragB b[32];
+            for (int lane = 0; lane < 32; ++lane) { load_frag_b(W.w0, 32, 8 * ks, n0, lane, b[lane]); load_frag_a(sm + kLiveOffA, kLivePitch, 8 * ks, r0, lane, a[lane]); }
+            warp_mma_3xtf32(c, a, b);
+        }
+        for (int lane = 0; lane < 32; ++lane) live_fc_store_tile(sm, r0, n0, lane, c[lane]);
+    }
+}
+template <int L>
+void emul_live_pointwise(float *sm, const NnWeightsF32 &W) {
+    constexpr int cin = kGeom[L].cin;
+    for (int warp = 0; warp < kLiveThreads / 32; ++warp) {
+        const int r0 = 16 * (warp >> 2), n0 = 16 * (warp & 3);
+        float c[2][32][4] = {};
+        for (int ks = 0; ks < cin / 8; ++ks) {
+            FragA a[32]; FragB b0[32], b1[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                load_frag_a(sm + kLiveOffD, kLivePitch, 8 * ks, r0, lane, a[lane]);
+                load_frag_b(sm + live_pw_offset<L>(), kWLd, 8 * ks, n0, lane, b0[lane]);
+                load_frag_b(sm + live_pw_offset<L>(), kWLd, 8 * ks, n0 + 8, lane, b1[lane]);
+            }
+            warp_mma_3xtf32(c[0], a, b0);
+            warp_mma_3xtf32(c[1], a, b1);
+        }
+        for (int lane = 0; lane < 32; ++lane) { live_pw_store_tile<L>(sm, W, r0, n0, lane, c[0][lane]); live_pw_store_tile<L>(sm, W, r0, n0 + 8, lane, c[1][lane]); }
+    }
+}
+}  // namespace
+
+extern "C" int emul_nn_f32_live(const float *const *wp, float *state, float *pend, int n_pend, const void *rows, int rows_are_f32,
+                                int n_streams, float *probs, int probs_stride) {
+    NnWeightsF32 W;
+    W.w0 = wp[0];
+    for (int i = 0; i < 4; ++i) { W.dw_w[i] = wp[1 + i]; W.dw_b[i] = wp[5 + i]; W.pw_w[i] = wp[9 + i]; W.pw_b[i] = wp[13 + i]; }
+    W.head_w = wp[17]; W.head_b = wp[18];
+    LiveInput in;
+    in.state = state; in.pend = pend; in.n_pend = n_pend; in.rows = rows;
+    in.rows_stream_stride_bytes = 3 * kNumChannels * (rows_are_f32 ? 4 : 2); in.rows_are_f32 = rows_are_f32;
+    std::vector<float> smv(kLiveSmemFloats, -777.f);
+    float *sm = smv.data();
+#define ALLL(stmt) for (int tid = 0; tid < kLiveThreads; ++tid) { stmt; }
+    ALLL(live_load_weights(tid, sm, W));
+    const int n_groups = (n_streams + kLiveStreams - 1) / kLiveStreams;
+    for (int g = 0; g < n_groups; ++g) {
+        const long long s0 = (long long)g * kLiveStreams;
+        const int n_valid = n_streams - (int)s0 < kLiveStreams ? n_streams - (int)s0 : kLiveStreams;
+        std::vector<float> tails((size_t)kLiveThreads * 20);
+#define TL(tid) (*reinterpret_cast<float(*)[2][10]>(&tails[(size_t)(tid) * 20]))
+        ALLL(live_build_a(tid, sm, in, s0, n_valid));
+        ALLL(live_read_tail(tid, in, s0, n_valid, TL(tid)));
+        ALLL(live_write_tail(tid, state, pend, s0, n_valid, TL(tid)));
+#undef TL
+        emul_live_first_conv(sm, W);
+        ALLL(live_depthwise<0>(tid, sm, W, state, s0, n_valid)); emul_live_pointwise<0>(sm, W);
+        ALLL(live_depthwise<1>(tid, sm, W, state, s0, n_valid)); emul_live_pointwise<1>(sm, W);
+        ALLL(live_depthwise<2>(tid, sm, W, state, s0, n_valid)); emul_live_pointwise<2>(sm, W);
+        ALLL(live_depthwise<3>(tid, sm, W, state, s0, n_valid)); emul_live_pointwise<3>(sm, W);
+        ALLL(live_head_partial(tid, sm, W, state, s0, n_valid));
+        ALLL(live_head_finish(tid, sm, W, s0, n_valid, probs, probs_stride));
+    }
+#undef ALLL
+    return 1;
 }

@@ -181,7 +181,10 @@ def test_batch_pipeline_device_and_host_paths(torch_cuda, kind):
     parts = [eng3.step(dev[:, i:i + 480].contiguous()) for i in range(0, audio.shape[1] - 479, 480)]
     got3 = torch.cat(parts, 1).cpu().numpy()
     n = got3.shape[1]
-    assert n >= want.shape[1] - 1 and np.array_equal(got3, got[:, :n])
+    assert n >= want.shape[1] - 1
+    # int8: one integer kernel either way -> identical; fp32: the 3-row calls take the stream-parallel live-step kernel,
+    # whose summation order differs from the clip kernel's
+    assert np.array_equal(got3, got[:, :n]) if kind == "int8" else np.abs(got3 - want[:, :n]).max() <= F32_TOL
 
 
 def test_golden_batch_fixture(torch_cuda):

@@ -97,3 +97,44 @@ def test_nn_int8_phases_bit_exact():
     nn = emul.NnI8(q, 1)
     parts = [nn.infer(f0[None, a:b]) for a, b in ((0, 2), (2, 300), (300, 301), (301, 997))]
     assert np.array_equal(np.concatenate(parts, 1)[0], np.load(os.path.join(GOLDEN, "config0_probs_int8.npy")))
+
+
+def test_closed_form_requantisation_equals_tflite_reference():
+    """The kernels' MultiplyByQuantizedMultiplier (arithmetic-shift closed form) == the literal SRDHM + RoundingDivideByPOT."""
+    from oracle import mixednet_ref as R
+    L = emul.lib()
+    L.emul_mbqm.restype = __import__("ctypes").c_int32
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.integers(-(1 << 31), 1 << 31, 3000), rng.integers(-70000, 70000, 3000),
+                         np.array([0, 1, -1, (1 << 31) - 1, -(1 << 31), 1 << 30, -(1 << 30), 3 << 29, -(3 << 29)])]).astype(np.int64)
+    cases = [(R.quantize_multiplier(m)) for m in (0.75, 0.5, 0.4999999, 0.0123, 0.00071, 0.999999, 1.0, 1.7, 3.2e-6)] + [(1 << 30, 0), ((1 << 31) - 1, 0), (1 << 30, -31), (0, 0)]
+    for mult, shift in cases:
+        if shift > 0:
+            use = xs[np.abs(xs) < (1 << (30 - shift))]       # the reference's x * 2^left is int32 arithmetic; stay clear of overflow
+        else:
+            use = xs
+        want = R.mbqm(use, mult, shift)
+        got = np.array([L.emul_mbqm(int(x), int(mult), int(shift)) for x in use], np.int64)
+        assert np.array_equal(got, np.asarray(want, np.int64)), (mult, shift)
+
+
+def test_live_step_kernel_phases_match_oracle_and_interleave_with_clip():
+    """Stream-parallel live-step kernel (one model step per call for many streams) == the oracle, for every pending-row
+    phase (0, 1, 2), for a ragged last group (70 streams = 32 + 32 + 6), and it shares its state with the clip kernel."""
+    t = MF.load(os.path.join(GOLDEN, "okay_nabu_synth_f32.mww"))
+    S = 70
+    audio = np.stack([synth_audio(9600, 900 + i) for i in range(S)])
+    feats, want = oracle.run_pipeline(MF.write_container(t), audio)            # 58 rows -> 19 probabilities
+    for n_first in (3, 4, 5):                                                   # first call leaves 0 / 1 / 2 rows pending
+        nn = emul.NnF32Live(t, S)
+        got = [nn.infer(feats[:, :n_first])]                                   # clip-kernel phases: 1 step (+ pending)
+        pos = n_first
+        while pos + 3 <= feats.shape[1]:
+            got.append(nn.step(feats[:, pos:pos + 3])[:, None])                # live-step phases
+            pos += 3
+        got = np.concatenate(got, 1)
+        assert np.abs(got - want[:, :got.shape[1]]).max() <= 1e-5, n_first
+        # hand the state back to the clip kernel for the remaining rows: still the same chain
+        rest = nn.infer(feats[:, pos:])
+        tail = want[:, got.shape[1]:got.shape[1] + rest.shape[1]]
+        assert rest.shape == tail.shape and (rest.size == 0 or np.abs(rest - tail).max() <= 1e-5)
