@@ -342,14 +342,24 @@ def run_gpu(args):
             eng.predict_clip(c, out=probs)
         barrier()
         l0e, l1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.profile(True)
         l0e.record()
         for i in range(calls):
             eng.predict_clip(chunks[i % len(chunks)], out=probs)
         l1e.record()
         barrier()
         live_ms = max_over_ranks(l0e.elapsed_time(l1e))
+        lp = eng.profile_read()
+        eng.profile(False)
         frames = S * world * calls * (n_live // 160)
-        live = {"samples_per_call": n_live, "calls": calls, "value": frames / (live_ms / 1e3), "unit": UNIT, "ms_per_call": live_ms / calls}
+        # live-step NN: ring state (4 176 floats) is read and written back shifted once per stream-step
+        nn_ms = lp["mixednet"][0] / max(lp["mixednet"][1], 1)
+        nn_bytes = S * (2 * 4176 * 4 + 3 * 80 + 4)
+        live = {"samples_per_call": n_live, "calls": calls, "value": frames / (live_ms / 1e3), "unit": UNIT, "ms_per_call": live_ms / calls,
+                "kernels_ms_per_call": {k: v[0] / calls for k, v in lp.items()},
+                "nn_live_hbm": {"bytes_per_stream_step": 2 * 4176 * 4 + 3 * 80 + 4, "achieved_gbs": nn_bytes / (nn_ms / 1e3) / 1e9 if nn_ms else None,
+                                "frac_of_measured_hbm": (nn_bytes / (nn_ms / 1e3) / 1e9) / measured_peaks()[0] if nn_ms else None},
+                "realtime_streams_capacity": S * world * (n_live / 16.0) / (live_ms / calls)}
 
     # ---- N > 1: the north_star's ingest pattern -- audio scattered from rank 0, scores gathered back (NCCL) ----
     scatter = None

@@ -61,7 +61,7 @@ k1_spectral_kernel(FrontendParams P, int fb_coef_len, const int16_t *__restrict_
         }
         const int f0 = g * kFramesPerGroup;
         K1Pass1Ctx ctx;
-        k1_window_fft1<2>(tid, sm, buf, P, ctx);
+        k1_window_fft1<2>(tid, sm, buf, (kHop / 2) * (tid >> 4), P, ctx);
         __syncthreads();
         k1_fft_pass2(tid, sm, lane);
         __syncthreads();
@@ -72,6 +72,33 @@ k1_spectral_kernel(FrontendParams P, int fb_coef_len, const int16_t *__restrict_
         // hazards: the next iteration's top barrier orders filterbank's reads of B/shift before the next
         // window_fft1 rewrites them; A is rewritten only after two more barriers
     }
+}
+
+// K1 for short calls (n_frames <= 8, e.g. the three frames of a 30 ms live step): one CTA = `spc` streams x `fps`
+// frames, so the 16 frame slots stay (almost) full instead of serving 3 of 16.
+__global__ void __launch_bounds__(kK1Threads, 3)
+k1_spectral_packed_kernel(FrontendParams P, int fb_coef_len, const int16_t *__restrict__ carry, int used,
+                          const int16_t *__restrict__ audio, long long audio_stride, int n_samples, int n_streams, int fps, int spc,
+                          uint32_t *__restrict__ vout) {
+    __shared__ __align__(16) K1Smem sm;
+    const int tid = threadIdx.x;
+    const long long s0 = (long long)blockIdx.x * spc;
+    K1Lane lane;
+    k1_lane_init(tid, P, lane);
+    for (int i = tid; i < fb_coef_len; i += kK1Threads) sm.fb_coef[i] = P.fb_coef[i];
+    k1_packed_load_audio(tid, sm, carry, used, audio, audio_stride, n_samples, s0, n_streams, spc, fps);
+    __syncthreads();
+    const int fl = tid >> 4;
+    K1Pass1Ctx ctx;
+    k1_window_fft1<2>(tid, sm, 0, k1_packed_pair_base(fl < spc * fps ? fl : 0, fps), P, ctx);
+    __syncthreads();
+    k1_fft_pass2(tid, sm, lane);
+    __syncthreads();
+    k1_real_energy(tid, sm, P);
+    __syncthreads();
+    const long long s = s0 + fl / fps;
+    const bool active = fl < spc * fps && s < n_streams;
+    k1_filterbank(tid, sm, P, active ? vout + (s * fps + fl % fps) * kNumChannels : nullptr);
 }
 
 // K2: one thread per (stream, channel); frames are scanned in order, noise estimate kept in a register.
@@ -136,6 +163,12 @@ cudaError_t launch_k1(const FrontendParams &P, int fb_coef_len, const int16_t *c
                       long long audio_stride, int n_samples, int n_streams, int n_frames, uint32_t *vout, int sm_count,
                       cudaStream_t st) {
     if (n_frames <= 0 || n_streams <= 0) return cudaSuccess;
+    if (n_frames <= 8 && n_streams >= 2) {
+        const int spc = k1_packed_streams(n_frames);
+        const unsigned grid = (unsigned)((n_streams + spc - 1) / spc);
+        k1_spectral_packed_kernel<<<grid, kK1Threads, 0, st>>>(P, fb_coef_len, carry, used, audio, audio_stride, n_samples, n_streams, n_frames, spc, vout);
+        return cudaGetLastError();
+    }
     const int n_groups = (n_frames + kFramesPerGroup - 1) / kFramesPerGroup;
     // enough CTAs to fill the chip a few times over, but keep per-CTA setup amortised when streams abound
     int chunks = 1;

@@ -154,14 +154,16 @@ MWW_HD void k1_load_audio(int tid, K1Smem &sm, int buf, const int16_t *carry, in
 // of lane maxima through shared memory sits between them); PART 2 is the device version.
 struct K1Pass1Ctx { int32_t xr[16], xi[16]; };
 
+// `pair_base` = word offset of the frame's first sample pair inside sm.audio[buf] (80 * slot when the 16 slots are
+// consecutive frames of one stream; see k1_packed_* for the several-streams-per-CTA mapping of short calls).
 template <int PART>
-MWW_HD void k1_window_fft1(int tid, K1Smem &sm, int buf, const FrontendParams &P, K1Pass1Ctx &ctx) {
+MWW_HD void k1_window_fft1(int tid, K1Smem &sm, int buf, int pair_base, const FrontendParams &P, K1Pass1Ctx &ctx) {
     const int fl = tid >> 4, a = tid & 15;
     const int c = (a >> 2) + 4 * (a & 3);     // complex sample index modulo 16 owned by this lane
     int32_t (&xr)[16] = ctx.xr;
     int32_t (&xi)[16] = ctx.xi;
     if (PART != 1) {
-        const uint32_t *pairs = reinterpret_cast<const uint32_t *>(sm.audio[buf]) + (kHop / 2) * fl;
+        const uint32_t *pairs = reinterpret_cast<const uint32_t *>(sm.audio[buf]) + pair_base;
         // max |v| as max(mx, -mn); a windowed value of -32768 (only reachable where the Q12 coefficient is
         // exactly 4096: samples 238..241 = pairs 119, 120 = the j == 7 column) must not win, because the
         // library's int16 negate leaves it negative.
@@ -231,6 +233,30 @@ MWW_HD void k1_window_fft1(int tid, K1Smem &sm, int buf, const FrontendParams &P
 #pragma unroll
     for (int b = 0; b < 16; ++b) sm.B[fl][17 * a + b] = pack16(xr[b], xi[b]);
 }
+
+// ---- packed mapping for short calls (live mode): n_frames <= 8 frames per stream, several streams per CTA ----
+// slot fl -> (stream_local = fl / fps, frame = fl % fps); every stream's span of (fps + 2) hops sits back to back in
+// the (flat) audio staging area.
+MWW_HD int k1_packed_streams(int fps) {
+    const int by_slots = kFramesPerGroup / fps;
+    const int by_smem = (2 * kGroupSamples) / ((fps + 2) * kHop);
+    return by_slots < by_smem ? by_slots : by_smem;
+}
+MWW_HD void k1_packed_load_audio(int tid, K1Smem &sm, const int16_t *carry, int used, const int16_t *audio, long long audio_stride,
+                                 int n_samples, long long s0, int n_streams, int spc, int fps) {
+    const int span = (fps + 2) * kHop;
+    int16_t *dst = &sm.audio[0][0];
+    for (int i = tid; i < spc * span; i += kK1Threads) {
+        const int sl = i / span, vi = i - sl * span;
+        int16_t v = 0;
+        if (s0 + sl < n_streams) {
+            if (vi < used) v = carry[(s0 + sl) * kWindow + vi];
+            else if (vi - used < n_samples) v = audio[(s0 + sl) * audio_stride + (vi - used)];
+        }
+        dst[i] = v;
+    }
+}
+MWW_HD int k1_packed_pair_base(int fl, int fps) { return (fl / fps) * ((fps + 2) * (kHop / 2)) + (kHop / 2) * (fl % fps); }
 
 // P3: transpose (lane b gathers position b of every 16-point block), FFT stages 3 and 4
 MWW_HD void k1_fft_pass2(int tid, K1Smem &sm, const K1Lane &L) {

@@ -41,7 +41,7 @@ MWW_HD int32_t nnq_ring_zp(const NnWeightsI8 &W, int L) { return W.zp[1 + 2 * L]
 //     nudge (2^30 | 1 - 2^30) followed by a division that truncates toward zero is exactly "round half up", i.e. an
 //     ARITHMETIC 64-bit shift of (a*b + 2^30).  Its saturating case needs a == b == INT32_MIN; multipliers are >= 0.
 //   RoundingDivideByPOT(x, r) = (x + half + (x < 0 ? -1 : 0)) >> r  with half = 2^(r-1)   (round half away from zero; r = 0: x)
-// tests/test_host_emul.py fuzzes this against the literal restatement in oracle/mixednet.c.
+// tests/test_host_emul.py fuzzes this against the literal SRDHM + RoundingDivideByPOT restatement of the CPU checker.
 MWW_HD int32_t mbqm(int32_t x, int32_t mult, int32_t shift) {
     const int left = shift > 0 ? shift : 0, r = shift > 0 ? 0 : -shift;
     const int32_t xs = (int32_t)((uint32_t)x << left);

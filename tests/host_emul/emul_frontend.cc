@@ -69,6 +69,30 @@ int emul_features(const int16_t *audio, int n_streams, int n_samples, int16_t *c
     K1Smem *sm = new K1Smem;
     std::vector<K1Lane> lanes(kK1Threads);
     const int n_groups = (n_frames + kFramesPerGroup - 1) / kFramesPerGroup;
+    if (n_frames > 0 && n_frames <= 8 && n_streams >= 2) {
+        // packed mapping (mirrors launch_k1): several streams per CTA
+        const int fps = n_frames, spc = k1_packed_streams(fps);
+        for (long long s0 = 0; s0 < n_streams; s0 += spc) {
+            memset(sm, 0xA5, sizeof *sm);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_lane_init(tid, g_params, lanes[tid]);
+            for (size_t i = 0; i < g_tables.fb_coef.size(); ++i) sm->fb_coef[i] = g_tables.fb_coef[i];
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_packed_load_audio(tid, *sm, carry, used, audio, n_samples, n_samples, s0, n_streams, spc, fps);
+            std::vector<K1Pass1Ctx> ctx(kK1Threads);
+            for (int part = 0; part < 2; ++part)
+                for (int tid = 0; tid < kK1Threads; ++tid) {
+                    const int fl = tid >> 4, pb = k1_packed_pair_base(fl < spc * fps ? fl : 0, fps);
+                    if (part == 0) k1_window_fft1<0>(tid, *sm, 0, pb, g_params, ctx[tid]); else k1_window_fft1<1>(tid, *sm, 0, pb, g_params, ctx[tid]);
+                }
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_fft_pass2(tid, *sm, lanes[tid]);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_real_energy(tid, *sm, g_params);
+            for (int tid = 0; tid < kK1Threads; ++tid) {
+                const int fl = tid >> 4;
+                const long long s = s0 + fl / fps;
+                const bool active = fl < spc * fps && s < n_streams;
+                k1_filterbank(tid, *sm, g_params, active ? &v[((size_t)s * fps + fl % fps) * kNumChannels] : nullptr);
+            }
+        }
+    } else
     for (int s = 0; s < n_streams; ++s) {
         memset(sm, 0xA5, sizeof *sm);   // poison: phases must not depend on stale shared memory
         for (int tid = 0; tid < kK1Threads; ++tid) k1_lane_init(tid, g_params, lanes[tid]);
@@ -80,8 +104,8 @@ int emul_features(const int16_t *audio, int n_streams, int n_samples, int16_t *c
             const int buf = g & 1;
             for (int tid = 0; tid < kK1Threads; ++tid) k1_load_audio(tid, *sm, buf, my_carry, used, my_audio, n_samples, f0);
             std::vector<K1Pass1Ctx> ctx(kK1Threads);
-            for (int tid = 0; tid < kK1Threads; ++tid) k1_window_fft1<0>(tid, *sm, buf, g_params, ctx[tid]);   // half-warp exchange between
-            for (int tid = 0; tid < kK1Threads; ++tid) k1_window_fft1<1>(tid, *sm, buf, g_params, ctx[tid]);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_window_fft1<0>(tid, *sm, buf, (kHop / 2) * (tid >> 4), g_params, ctx[tid]);   // half-warp exchange between
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_window_fft1<1>(tid, *sm, buf, (kHop / 2) * (tid >> 4), g_params, ctx[tid]);
             for (int tid = 0; tid < kK1Threads; ++tid) k1_fft_pass2(tid, *sm, lanes[tid]);
             for (int tid = 0; tid < kK1Threads; ++tid) k1_real_energy(tid, *sm, g_params);
             for (int tid = 0; tid < kK1Threads; ++tid) {
