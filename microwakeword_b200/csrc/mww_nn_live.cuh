@@ -128,63 +128,84 @@ MWW_HD void live_pw_store_tile(float *sm, const NnWeightsF32 &W, int r0, int n0,
 }
 
 // ---- depthwise of block L for (stream, channel) columns: ring rows stream through registers ----
-// thread -> channel c = tid % cin, stream subgroup = tid / cin; each thread walks kLiveStreams * cin / 256 streams.
+// thread -> channel c = tid % cin, stream subgroup = tid / cin; each thread walks kLiveStreams * cin / 256 streams,
+// U at a time: the kernel is bound by HBM latency (one 8-warp CTA per SM), so U ring columns (U * R independent
+// loads) are put in flight before any of them is consumed.
+template <int R, int CIN, int U>
+MWW_HD void live_ring_pass(float *const (&ring)[U], const bool (&ok)[U], const float (&w)[R + 1], const float (&xn)[U], float bias, float (&out)[U]) {
+    float x[U][R];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[u][r] = ok[u] ? ring[u][r * CIN] : 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        float acc = bias;
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc = fmaf(w[r], x[u][r], acc);
+        out[u] = fmaf(w[R], xn[u], acc);
+        if (ok[u]) {
+#pragma unroll
+            for (int r = 0; r + 1 < R; ++r) ring[u][r * CIN] = x[u][r + 1];
+            ring[u][(R - 1) * CIN] = xn[u];
+        }
+    }
+}
+
 template <int L>
 MWW_HD void live_depthwise(int tid, float *sm, const NnWeightsF32 &W, float *state, long long s0, int n_valid) {
     constexpr NnLayerGeom g = kGeom[L];
     constexpr int R = g.ring;
     constexpr int per = kLiveStreams * g.cin / kLiveThreads;     // streams per thread: 4 (cin 32) or 8 (cin 64)
+    constexpr int U = L == 3 ? 2 : 4;
+    constexpr int ring_off = kStateOff[L + 1];
     const int c = tid % g.cin, sub = tid / g.cin;
-    float w[g.kmax];
+    float w[R + 1];
 #pragma unroll
-    for (int j = 0; j < g.kmax; ++j) w[j] = W.dw_w[L][j * g.cin + c];      // zero padded at the front for short MixConv kernels
+    for (int j = 0; j <= R; ++j) w[j] = W.dw_w[L][j * g.cin + c];         // kmax = R + 1; zero padded at the front for short MixConv kernels
     const float bias = W.dw_b[L][c];
     const float *h = sm + kLiveOffH + c * kLivePitch;
     float *d = sm + kLiveOffD + c * kLivePitch;
-    for (int i = 0; i < per; ++i) {
-        const int sl = sub * per + i;
-        if (sl >= n_valid) { d[sl] = 0.f; continue; }
-        float *ring = state + (s0 + sl) * kStateFloats + kStateOff[L + 1] + c;
-        float x[R];
+#pragma unroll 1
+    for (int i = 0; i < per; i += U) {
+        float *ring[U]; bool ok[U]; float xn[U], out[U];
 #pragma unroll
-        for (int r = 0; r < R; ++r) x[r] = ring[r * g.cin];
-        const float xn = h[sl];
-        float acc = bias;
+        for (int u = 0; u < U; ++u) {
+            const int sl = sub * per + i + u;
+            ok[u] = sl < n_valid;
+            ring[u] = state + (size_t)(s0 + (ok[u] ? sl : 0)) * kStateFloats + ring_off + c;
+            xn[u] = h[sl];
+        }
+        live_ring_pass<R, g.cin, U>(ring, ok, w, xn, bias, out);
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc = fmaf(w[r], x[r], acc);
-        acc = fmaf(w[R], xn, acc);
-        d[sl] = acc;
-#pragma unroll
-        for (int r = 0; r + 1 < R; ++r) ring[r * g.cin] = x[r + 1];
-        ring[(R - 1) * g.cin] = xn;
+        for (int u = 0; u < U; ++u) d[sub * per + i + u] = ok[u] ? out[u] : 0.f;
     }
 }
 
 // ---- head: 17-tap dot per (stream, channel) into D, ring shifted; then reduce over channels ----
 MWW_HD void live_head_partial(int tid, float *sm, const NnWeightsF32 &W, float *state, long long s0, int n_valid) {
     constexpr int per = kLiveStreams * 64 / kLiveThreads;        // 8
+    constexpr int U = 4;
+    constexpr int ring_off = kStateOff[5];
     const int c = tid & 63, sub = tid >> 6;
     float w[17];
 #pragma unroll
     for (int j = 0; j < 17; ++j) w[j] = W.head_w[j * 64 + c];
     const float *h = sm + kLiveOffH + c * kLivePitch;
     float *d = sm + kLiveOffD + c * kLivePitch;
-    for (int i = 0; i < per; ++i) {
-        const int sl = sub * per + i;
-        if (sl >= n_valid) { d[sl] = 0.f; continue; }
-        float *ring = state + (s0 + sl) * kStateFloats + kStateOff[5] + c;
-        float x[16];
+#pragma unroll 1
+    for (int i = 0; i < per; i += U) {
+        float *ring[U]; bool ok[U]; float xn[U], out[U];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) x[r] = ring[r * 64];
-        const float xn = h[sl];
-        float acc = 0.f;
+        for (int u = 0; u < U; ++u) {
+            const int sl = sub * per + i + u;
+            ok[u] = sl < n_valid;
+            ring[u] = state + (size_t)(s0 + (ok[u] ? sl : 0)) * kStateFloats + ring_off + c;
+            xn[u] = h[sl];
+        }
+        live_ring_pass<16, 64, U>(ring, ok, w, xn, 0.f, out);
 #pragma unroll
-        for (int r = 0; r < 16; ++r) acc = fmaf(w[r], x[r], acc);
-        acc = fmaf(w[16], xn, acc);
-        d[sl] = acc;
-#pragma unroll
-        for (int r = 0; r + 1 < 16; ++r) ring[r * 64] = x[r + 1];
-        ring[15 * 64] = xn;
+        for (int u = 0; u < U; ++u) d[sub * per + i + u] = ok[u] ? out[u] : 0.f;
     }
 }
 MWW_HD void live_head_finish(int tid, const float *sm, const NnWeightsF32 &W, long long s0, int n_valid, float *probs, long long probs_stride) {
