@@ -10,7 +10,7 @@
 namespace mww {
 
 // persistent CTAs: each walks groups of 32 streams; 1x1 weights are staged once per CTA
-__global__ void __launch_bounds__(kLiveThreads, 1)
+__global__ void __launch_bounds__(kLiveThreads, 2)
 nn_f32_live_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict__ pend, int n_pend, const void *__restrict__ rows,
                    long long rows_stream_stride_bytes, int rows_are_f32, float *__restrict__ probs, long long probs_stride,
                    int n_streams) {
@@ -58,7 +58,7 @@ cudaError_t launch_nn_f32_live(const NnWeightsF32 &W, float *state, float *pend,
         attr_set = true;
     }
     const int n_groups = (n_streams + kLiveStreams - 1) / kLiveStreams;
-    const int grid = std::min(n_groups, sm_count);
+    const int grid = std::min(n_groups, 2 * sm_count);
     nn_f32_live_kernel<<<grid, kLiveThreads, kLiveSmemBytes, st>>>(W, state, pend, n_pend, rows, rows_stream_stride_bytes, rows_are_f32, probs,
                                                                    probs_stride, n_streams);
     return cudaGetLastError();

@@ -22,25 +22,24 @@ constexpr int kLiveStreams = 32;                  // streams per CTA = two 16-ro
 constexpr int kLivePitch = 40;                    // [k][stream] pitch: 40 = 8 (mod 32) -> conflict-free A fragments
 // shared memory (floats): 1x1 weights of the four blocks (pitch kWLd), A operand of the first conv [200][40],
 // H = new activation row of every stream [64][40], D = depthwise output [64][40]
-constexpr int kLiveOffPw0 = 0;
-constexpr int kLiveOffPw1 = kLiveOffPw0 + 32 * kWLd;
+constexpr int kLiveOffPw0 = 0;                    // block 0's 32x64 weights are NOT staged (read from L2): keeps 2 CTAs / SM
+constexpr int kLiveOffPw1 = 0;
 constexpr int kLiveOffPw2 = kLiveOffPw1 + 64 * kWLd;
 constexpr int kLiveOffPw3 = kLiveOffPw2 + 64 * kWLd;
 constexpr int kLiveOffA = kLiveOffPw3 + 64 * kWLd;
 constexpr int kLiveOffH = kLiveOffA + 200 * kLivePitch;
 constexpr int kLiveOffD = kLiveOffH + 64 * kLivePitch;
 constexpr int kLiveSmemFloats = kLiveOffD + 64 * kLivePitch;
-constexpr int kLiveSmemBytes = kLiveSmemFloats * 4;           // 117 KB -> 1 CTA / SM (8 warps), persistent over stream groups
+constexpr int kLiveSmemBytes = kLiveSmemFloats * 4;           // 107.8 KB -> 2 CTAs / SM (16 warps), persistent over stream groups
 
 template <int L>
 MWW_HD int live_pw_offset() { return L == 0 ? kLiveOffPw0 : (L == 1 ? kLiveOffPw1 : (L == 2 ? kLiveOffPw2 : kLiveOffPw3)); }
 
 // ---- once per CTA: stage all 1x1 weights ----
 MWW_HD void live_load_weights(int tid, float *sm, const NnWeightsF32 &W) {
-    for (int L = 0; L < 4; ++L) {
-        const int cin = L == 0 ? 32 : 64;
-        float *dst = sm + (L == 0 ? kLiveOffPw0 : (L == 1 ? kLiveOffPw1 : (L == 2 ? kLiveOffPw2 : kLiveOffPw3)));
-        for (int e = tid; e < cin * 64; e += kLiveThreads) dst[(e >> 6) * kWLd + (e & 63)] = W.pw_w[L][e];
+    for (int L = 1; L < 4; ++L) {
+        float *dst = sm + (L == 1 ? kLiveOffPw1 : (L == 2 ? kLiveOffPw2 : kLiveOffPw3));
+        for (int e = tid; e < 64 * 64; e += kLiveThreads) dst[(e >> 6) * kWLd + (e & 63)] = W.pw_w[L][e];
     }
 }
 
@@ -242,15 +241,16 @@ MWW_D void live_pointwise_mma(int tid, float *sm, const NnWeightsF32 &W) {
     const int warp = tid >> 5, lane = tid & 31;
     const int r0 = 16 * (warp >> 2), n0 = 16 * (warp & 3);
     const float *d = sm + kLiveOffD;
-    const float *wsm = sm + live_pw_offset<L>();
+    const float *wsm = L == 0 ? W.pw_w[0] : sm + live_pw_offset<L>();       // block 0: B fragments straight from L2
+    constexpr int wld = L == 0 ? 64 : kWLd;
     float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll 2
     for (int ks = 0; ks < cin / 8; ++ks) {
         FragA a;
         FragB b0, b1;
         load_frag_a(d, kLivePitch, 8 * ks, r0, lane, a);
-        load_frag_b(wsm, kWLd, 8 * ks, n0, lane, b0);
-        load_frag_b(wsm, kWLd, 8 * ks, n0 + 8, lane, b1);
+        load_frag_b(wsm, wld, 8 * ks, n0, lane, b0);
+        load_frag_b(wsm, wld, 8 * ks, n0 + 8, lane, b1);
         mma_tf32(c[0], a.lo, b0.hi); mma_tf32(c[1], a.lo, b1.hi);
         mma_tf32(c[0], a.hi, b0.lo); mma_tf32(c[1], a.hi, b1.lo);
         mma_tf32(c[0], a.hi, b0.hi); mma_tf32(c[1], a.hi, b1.hi);

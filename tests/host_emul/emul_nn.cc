@@ -303,8 +303,10 @@ void emul_live_pointwise(float *sm, const NnWeightsF32 &W) {
             FragA a[32]; FragB b0[32], b1[32];
             for (int lane = 0; lane < 32; ++lane) {
                 load_frag_a(sm + kLiveOffD, kLivePitch, 8 * ks, r0, lane, a[lane]);
-                load_frag_b(sm + live_pw_offset<L>(), kWLd, 8 * ks, n0, lane, b0[lane]);
-                load_frag_b(sm + live_pw_offset<L>(), kWLd, 8 * ks, n0 + 8, lane, b1[lane]);
+                const float *wsm = L == 0 ? W.pw_w[0] : sm + live_pw_offset<L>();
+                const int wld = L == 0 ? 64 : kWLd;
+                load_frag_b(wsm, wld, 8 * ks, n0, lane, b0[lane]);
+                load_frag_b(wsm, wld, 8 * ks, n0 + 8, lane, b1[lane]);
             }
             warp_mma_3xtf32(c[0], a, b0);
             warp_mma_3xtf32(c[1], a, b1);
