@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--no-scatter", action="store_true", help="skip the NCCL scatter/gather leg at N > 1")
     ap.add_argument("--live", type=int, default=0, metavar="SAMPLES",
                     help="also time live mode: step() calls with SAMPLES new samples per stream (e.g. 480 = one 30 ms model step)")
+    ap.add_argument("--features", action="store_true",
+                    help="also time BASELINE.json configs[3]: the feature extractor alone on 1 M 30 ms windows (streaming and stateless)")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -137,7 +139,7 @@ def synth_audio_device(torch, n_streams, n_samples, seed, device):
     g.manual_seed(seed)
     out = torch.empty((n_streams, n_samples), dtype=torch.int16, device=device)
     t = torch.arange(n_samples, device=device, dtype=torch.float32)
-    chunk = 4096
+    chunk = 4096 if n_samples > 4096 else 1 << 18
     for s0 in range(0, n_streams, chunk):
         n = min(chunk, n_streams - s0)
         sigma = torch.exp(torch.empty(n, 1, device=device).uniform_(np.log(50.0), np.log(8000.0), generator=g))
@@ -145,7 +147,7 @@ def synth_audio_device(torch, n_streams, n_samples, seed, device):
         for _ in range(2):
             f = torch.empty(n, 1, device=device).uniform_(200.0, 4000.0, generator=g)
             a = torch.empty(n, 1, device=device).uniform_(500.0, 12000.0, generator=g)
-            start = torch.empty(n, 1, device=device).uniform_(0, n_samples - 8000, generator=g)
+            start = torch.empty(n, 1, device=device).uniform_(0, max(n_samples - 8000, 1), generator=g)
             length = torch.empty(n, 1, device=device).uniform_(1600, 8000, generator=g)
             mask = (t[None, :] >= start) & (t[None, :] < start + length)
             x += mask * a * torch.sin(2 * np.pi * f * t[None, :] / 16000.0)
@@ -361,6 +363,34 @@ def run_gpu(args):
                                 "frac_of_measured_hbm": (nn_bytes / (nn_ms / 1e3) / 1e9) / measured_peaks()[0] if nn_ms else None},
                 "realtime_streams_capacity": S * world * (n_live / 16.0) / (live_ms / calls)}
 
+    # ---- optional: BASELINE.json configs[3], feature extractor only ----
+    feat = None
+    if args.features:
+        feat = {}
+        for name, fs, fn in (("streaming_4096x256", 4096, 160 * 256 + 320), ("stateless_1048576x480", 1 << 20, 480)):
+            fe = StreamEngine(None, n_streams=fs, device=local_rank)
+            fa = synth_audio_device(torch, fs, fn, 99 + rank, device)
+            n_fr = (fn - 480) // 160 + 1
+            fo = torch.empty((fs, n_fr, 40), dtype=torch.uint16, device=device)
+            for _ in range(3):
+                fe.reset()
+                fe.features(fa, out=fo)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            f0.record()
+            for _ in range(reps):
+                fe.reset()                                   # every pass starts from the reset frontend state, like a new clip
+                fe.features(fa, out=fo)
+            f1.record()
+            barrier()
+            f_ms = max_over_ranks(f0.elapsed_time(f1)) / reps
+            windows = fs * n_fr * world
+            feat[name] = {"windows": windows, "ms": f_ms, "windows_per_s": windows / (f_ms / 1e3),
+                          "alg_bytes_per_window": (fn * 2 + n_fr * 80) / n_fr,
+                          "achieved_gbs": fs * (fn * 2 + n_fr * 80) / (f_ms / 1e3) / 1e9}
+            del fe, fa, fo
+
     # ---- N > 1: the north_star's ingest pattern -- audio scattered from rank 0, scores gathered back (NCCL) ----
     scatter = None
     if world > 1 and not args.no_scatter:
@@ -400,7 +430,7 @@ def run_gpu(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.model == "f32" else "int8", "data": "synthetic",
             "config": config_dict(args, world), "clocks": clock_info, "gpu_launches": int(launches),
-            "kernels": kernels, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "scatter_gather": scatter, "live": live, "probs_checksum": checksum,
+            "kernels": kernels, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "scatter_gather": scatter, "live": live, "features_only": feat, "probs_checksum": checksum,
             "realtime_streams_capacity": value / 100.0,
         }
         print(json.dumps(line))

@@ -28,7 +28,8 @@ def _torch():
 
 
 class StreamEngine:
-    """`model`: path to an MWW container, its bytes, or None for a frontend-only engine."""
+    """`model`: path to (or bytes of) an MWW container or a streaming ``.tflite`` flatbuffer (recognised and converted by
+    ``tflite_file``, inference.py:36-45), or None for a frontend-only engine."""
 
     def __init__(self, model, n_streams: int = 1, device: int = 0):
         if isinstance(model, (bytes, bytearray, memoryview)):
@@ -38,6 +39,10 @@ class StreamEngine:
         else:
             with open(model, "rb") as f:
                 blob = f.read()
+        if blob is not None:
+            from . import tflite_file
+            if tflite_file.is_tflite(blob):
+                blob = tflite_file.container_from_tflite(blob)      # raises TfliteError for graphs outside the hot path
         self._L = _lib.lib()
         self._h = ctypes.c_void_p()
         self._blob = blob  # keep alive during create
@@ -106,14 +111,18 @@ class StreamEngine:
     def reset_frontend(self):
         _lib.check(self._h, self._L.mww_reset_frontend(self._h, self._cu_stream()))
 
-    def features(self, audio):
-        """int16 CUDA tensor [S, N] -> uint16 CUDA tensor [S, rows, 40] (rows may be 0)."""
+    def features(self, audio, out=None):
+        """int16 CUDA tensor [S, N] -> uint16 CUDA tensor [S, rows, 40] (rows may be 0); `out` reuses a caller buffer."""
         torch = _torch()
         n, stride = self._check_audio(audio)
         rows = max((self.frontend_buffered + n - WINDOW) // HOP + 1, 0) if self.frontend_buffered + n >= WINDOW else 0
-        out = torch.empty((self.n_streams, max(rows, 1), NUM_FEATURES), dtype=torch.uint16, device=self._dev())
+        if out is None:
+            out = torch.empty((self.n_streams, max(rows, 1), NUM_FEATURES), dtype=torch.uint16, device=self._dev())
+        elif (out.dtype != torch.uint16 or not out.is_cuda or not out.is_contiguous() or out.dim() != 3 or out.shape[0] != self.n_streams
+              or out.shape[1] < max(rows, 1) or out.shape[2] != NUM_FEATURES):
+            raise ValueError("out must be a contiguous CUDA uint16 tensor [n_streams, >= rows, 40]")
         got = ctypes.c_int(0)
-        _lib.check(self._h, self._L.mww_features(self._h, audio.data_ptr(), n, max(stride, n), out.data_ptr(), max(rows, 1),
+        _lib.check(self._h, self._L.mww_features(self._h, audio.data_ptr(), n, max(stride, n), out.data_ptr(), out.shape[1],
                                                  ctypes.byref(got), self._cu_stream()))
         return out[:, :got.value]
 

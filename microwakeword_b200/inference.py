@@ -28,17 +28,14 @@ class Model:
     Class for loading and running microwakeword streaming models on a B200
 
     Args:
-        tflite_model_path (str | bytes): Path to (or bytes of) an MWW model container.
+        tflite_model_path (str | bytes): Path to (or bytes of) a streaming ``.tflite`` model (microwakeword_b200/tflite_file.py)
+            or an MWW model container (microwakeword_b200/model_file.py).
         stride (int | None, optional): Time dimension's stride. If None, then the stride is the input tensor's time dimension. Defaults to None.
         batch (int): number of independent streams carried by this object (extension; default 1).
         device (int): CUDA device index (extension; default 0).
     """
 
     def __init__(self, tflite_model_path, stride: int | None = None, *, batch: int = 1, device: int = 0):
-        if isinstance(tflite_model_path, str) and tflite_model_path.endswith(".tflite"):
-            raise NotImplementedError(
-                "this build loads MWW containers (see microwakeword_b200/model_file.py); a .tflite flatbuffer reader "
-                "is a documented 'next' item (SURVEY.md 8f-2) that cannot be validated without TensorFlow or a sample model")
         self.engine = StreamEngine(tflite_model_path, n_streams=batch, device=device)
         info = self.engine.info
         self.is_quantized_model = bool(info.is_quantized)                       # inference.py:44

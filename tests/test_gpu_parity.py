@@ -258,6 +258,39 @@ def test_full_size_properties(torch_cuda):
     assert bool((torch.cat([a, b], 1) == got).all())
 
 
+def test_feature_extractor_only_config3(torch_cuda):
+    """BASELINE.json configs[3]: 1 M 30 ms windows through the frontend alone, both layouts SURVEY.md 8(d) names --
+    4 096 streams x 256 frames with carried state, and 1 048 576 stateless windows of 480 samples (the packed short-call
+    kernel).  Distinct content is replicated so that full size is checked through replica equality + an oracle sample."""
+    from microwakeword_b200.engine import StreamEngine
+    torch = torch_cuda
+    # streaming layout
+    S, F = 4096, 256
+    N = 160 * F + 320
+    base = np.stack([synth_audio(N, 900 + i) for i in range(32)])
+    dev = torch.from_numpy(base).cuda().repeat(S // 32, 1)
+    eng = StreamEngine(None, n_streams=S)
+    got = eng.features(dev)
+    assert got.shape == (S, F, 40)
+    g = got.view(torch.int16).view(S // 32, 32, F, 40)
+    assert bool((g == g[0:1]).all())
+    for i in (0, 7, 31):
+        assert np.array_equal(g[0, i].cpu().numpy().view(np.uint16), oracle.Frontend().stream(base[i]))
+    del eng, dev, got, g
+    # stateless layout: every 480-sample window from the reset state -> exactly one row each
+    W = 1 << 20
+    wins = np.stack([synth_audio(480, 2000 + i) for i in range(1020)] + list(edge_case_audio(480)[:4]))    # 1024 distinct windows
+    devw = torch.from_numpy(wins).cuda().repeat(W // 1024, 1)
+    engw = StreamEngine(None, n_streams=W)
+    out = torch.empty((W, 1, 40), dtype=torch.uint16, device="cuda")
+    gw = engw.features(devw, out=out)
+    assert gw.shape == (W, 1, 40) and gw.data_ptr() == out.data_ptr()
+    gv = gw.view(torch.int16).view(W // 1024, 1024, 40)
+    assert bool((gv == gv[0:1]).all())
+    want = np.stack([oracle.Frontend().stream(w)[0] for w in wins])
+    assert np.array_equal(gv[0].cpu().numpy().view(np.uint16), want)
+
+
 def test_ragged_batch_feature_generation(torch_cuda):
     """SURVEY.md 8 f-3 caller: many clips of different lengths through one frontend launch == one clip at a time."""
     from microwakeword_b200.audio.audio_utils import generate_features_for_clips

@@ -1,0 +1,162 @@
+"""the `.tflite` loader.
+
+Three independent readings of the same TFL3 bytes must agree:
+  (1) the recogniser (product, `microwakeword_b200/tflite_file.py`) -> MWW tensors,
+  (2) the op-by-op interpreter (`oracle/tflite_interp.py`) executing the graph as written,
+  (3) the oracle's streaming MixedNet run on the recognised tensors.
+The files come from `tests/tflite_writer.py` (no TensorFlow exists here: PARITY UNPINNED for this row).
+"""
+
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from microwakeword_b200 import model_file as MF
+from microwakeword_b200 import tflite_file as TF
+from oracle import mixednet_ref as R
+from oracle.tflite_interp import Interpreter
+import tflite_writer as W
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _tensors(kind):
+    return MF.load(os.path.join(GOLDEN, "okay_nabu_synth_%s.mww" % kind))
+
+
+@pytest.mark.parametrize("kind", ["f32", "int8"])
+def test_round_trip_is_exact(kind):
+    t = _tensors(kind)
+    blob = W.write_streaming_mixednet(t)
+    assert TF.is_tflite(blob) and not TF.is_tflite(MF.write_container(t))
+    got = TF.tensors_from_tflite(blob)
+    assert sorted(got) == sorted(t)
+    for k in t:
+        assert got[k].dtype == t[k].dtype and got[k].shape == t[k].shape and np.array_equal(got[k], t[k]), k
+    assert MF.Arch.decode(got["arch"]) == MF.OKAY_NABU
+    # and the container bytes the C-ABI would receive parse back
+    assert sorted(MF.read_container(TF.container_from_tflite(blob))) == sorted(t)
+
+
+@pytest.mark.parametrize("kind", ["f32", "int8"])
+def test_interpreter_equals_oracle_on_recognised_tensors(kind):
+    t = _tensors(kind)
+    blob = W.write_streaming_mixednet(t)
+    got = TF.tensors_from_tflite(blob)
+    feats = np.load(os.path.join(GOLDEN, "config0_features.npy"))[:150]           # uint16 [150, 40]
+    it = Interpreter(blob)
+    if kind == "int8":
+        model = R.StreamingInt8(got)
+        x = R.quantize_input(feats.astype(np.float32) * R.FEATURE_SCALE, model.input_scale, model.input_zero_point)
+        for s in range(50):
+            a = int(it.invoke(x[3 * s:3 * s + 3]).reshape(-1)[0])
+            assert a == model.step(x[3 * s:3 * s + 3]), s
+    else:
+        model = R.FoldedStreamingF32(got)
+        x = feats.astype(np.float32) * R.FEATURE_SCALE
+        for s in range(50):
+            a = float(it.invoke(x[3 * s:3 * s + 3]).reshape(-1)[0])
+            assert abs(a - float(model.step(x[3 * s:3 * s + 3]))) <= 2e-6, s
+    # reset re-runs the CALL_ONCE initialiser
+    it.reset()
+    first = it.invoke(x[0:3]).reshape(-1)[0]
+    it2 = Interpreter(blob)
+    assert first == it2.invoke(x[0:3]).reshape(-1)[0]
+
+
+def test_unsupported_graphs_fail_loudly():
+    t = _tensors("f32")
+    # 1. not a flatbuffer / wrong identifier
+    with pytest.raises(TF.TfliteError):
+        TF.tensors_from_tflite(b"\0" * 64)
+    blob = bytearray(W.write_streaming_mixednet(t))
+    bad = bytes(blob[:4]) + b"TFL2" + bytes(blob[8:])
+    with pytest.raises(TF.TfliteError):
+        TF.tensors_from_tflite(bad)
+    # 2. truncated file
+    with pytest.raises((TF.TfliteError, struct.error, ValueError)):
+        TF.tensors_from_tflite(bytes(blob[:len(blob) // 2]))
+    # 3. structurally different graphs, produced by patching the writer
+    class NoWriteBack(W.GraphWriter):
+        def op(self, name, inputs, outputs, **options):
+            if name == "ASSIGN_VARIABLE" and len(self.ops) > 40:          # drop a late state update
+                return
+            super().op(name, inputs, outputs, **options)
+
+    saved = W.GraphWriter
+    try:
+        W.GraphWriter = NoWriteBack
+        with pytest.raises(TF.TfliteError, match="never written back"):
+            TF.tensors_from_tflite(W.write_streaming_mixednet(t))
+
+        class ReluLess(saved):
+            def op(self, name, inputs, outputs, **options):
+                if name == "CONV_2D" and options.get("stride_h", 1) == 1:
+                    options["act"] = 0
+                super().op(name, inputs, outputs, **options)
+        W.GraphWriter = ReluLess
+        with pytest.raises(TF.TfliteError, match="without ReLU"):
+            TF.tensors_from_tflite(W.write_streaming_mixednet(t))
+
+        class WrongKeep(saved):
+            def tensor(self, name, shape, dtype, data=None, **kw):
+                if name.endswith("keep_0/begin"):
+                    data = np.asarray([0, 0, 0, 0], np.int32)              # keeps the FIRST rows instead of the last
+                return super().tensor(name, shape, dtype, data=data, **kw)
+        W.GraphWriter = WrongKeep
+        with pytest.raises(TF.TfliteError, match="StridedKeep"):
+            TF.tensors_from_tflite(W.write_streaming_mixednet(t))
+    finally:
+        W.GraphWriter = saved
+    # 4. an initial ring state that is not zero cannot be represented by the engine's reset
+    tq = _tensors("int8")
+
+    blob_q = bytearray(W.write_streaming_mixednet(tq))
+    g = TF.Graph(bytes(blob_q))
+    tensors1, ops1, _, _ = g.subgraphs[1]
+    victim = [op for op in ops1 if op.code == TF.OP_ASSIGN_VARIABLE][0]
+    raw = g.buffers[tensors1[victim.inputs[1]].buffer]
+    off = bytes(blob_q).find(raw.tobytes())
+    assert off > 0
+    blob_q[off] = (blob_q[off] + 1) & 0xFF
+    with pytest.raises(TF.TfliteError, match="initialiser"):
+        TF.tensors_from_tflite(bytes(blob_q))
+
+
+def test_flatbuffer_reader_handles_defaults_and_vtables():
+    """fields omitted because they equal the schema default read back as the default"""
+    t = _tensors("f32")
+    g = TF.Graph(W.write_streaming_mixednet(t))
+    convs = [op for op in g.ops if op.code == TF.OP_CONV_2D]
+    assert convs[0].opt(2, "i", 1) == 3 and convs[1].opt(2, "i", 1) == 1           # stride_h; absent -> default 1
+    assert g.tensors[g.inputs[0]].shape == (1, 3, 40) and g.tensors[g.outputs[0]].shape == (1, 1)
+    assert sum(op.code == TF.OP_READ_VARIABLE for op in g.ops) == 6
+    assert len(g.subgraphs) == 2 and g.version == 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["f32", "int8"])
+def test_model_loads_tflite_and_matches_container(kind, tmp_path, torch_cuda):
+    """`Model("x.tflite")` (inference.py:34-45) == `Model("x.mww")` on the GPU, probability for probability."""
+    from microwakeword.inference import Model
+    t = _tensors(kind)
+    p = tmp_path / ("okay_nabu_synth_%s.tflite" % kind)
+    p.write_bytes(W.write_streaming_mixednet(t))
+    feats = np.load(os.path.join(GOLDEN, "config0_features.npy"))
+    a = Model(str(p)).predict_spectrogram(feats)
+    b = Model(os.path.join(GOLDEN, "okay_nabu_synth_%s.mww" % kind)).predict_spectrogram(feats)
+    assert len(a) == len(b) == 332 and np.array_equal(np.asarray(a), np.asarray(b))
+    m = Model(str(p))
+    assert m.is_quantized_model == (kind == "int8") and m.input_feature_slices == 3
+    # and against the interpreter executing the file itself (first 40 steps)
+    it = Interpreter(p.read_bytes())
+    if kind == "int8":
+        x = R.quantize_input(feats.astype(np.float32) * R.FEATURE_SCALE, m.input_details[0]["quantization"][0], m.input_details[0]["quantization"][1])
+        want = [np.float32(int(it.invoke(x[3 * s:3 * s + 3]).reshape(-1)[0])) / np.float32(255.0) for s in range(40)]
+        assert np.array_equal(np.asarray(a[:40], np.float32), np.asarray(want, np.float32))
+    else:
+        x = feats.astype(np.float32) * R.FEATURE_SCALE
+        want = [float(it.invoke(x[3 * s:3 * s + 3]).reshape(-1)[0]) for s in range(40)]
+        assert np.abs(np.asarray(a[:40]) - np.asarray(want)).max() <= 1e-5
