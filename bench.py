@@ -354,13 +354,15 @@ def run_gpu(args):
         lp = eng.profile_read()
         eng.profile(False)
         frames = S * world * calls * (n_live // 160)
-        # live-step NN: ring state (4 176 floats) is read and written back shifted once per stream-step
+        # live-step NN, algorithmic bytes per stream-step: every ring row read once (4 176 floats), one new
+        # row per ring + the 2-row first-conv ring written (368 floats), 3 uint16 feature rows in, one probability out
         nn_ms = lp["mixednet"][0] / max(lp["mixednet"][1], 1)
-        nn_bytes = S * (2 * 4176 * 4 + 3 * 80 + 4)
+        step_bytes = 4176 * 4 + 368 * 4 + 3 * 80 + 4
+        nn_gbs = S * step_bytes / (nn_ms / 1e3) / 1e9 if nn_ms else None
         live = {"samples_per_call": n_live, "calls": calls, "value": frames / (live_ms / 1e3), "unit": UNIT, "ms_per_call": live_ms / calls,
                 "kernels_ms_per_call": {k: v[0] / calls for k, v in lp.items()},
-                "nn_live_hbm": {"bytes_per_stream_step": 2 * 4176 * 4 + 3 * 80 + 4, "achieved_gbs": nn_bytes / (nn_ms / 1e3) / 1e9 if nn_ms else None,
-                                "frac_of_measured_hbm": (nn_bytes / (nn_ms / 1e3) / 1e9) / measured_peaks()[0] if nn_ms else None},
+                "nn_live_hbm": {"bytes_per_stream_step": step_bytes, "achieved_gbs": nn_gbs,
+                                "frac_of_measured_hbm": nn_gbs / measured_peaks()[0] if nn_gbs else None},
                 "realtime_streams_capacity": S * world * (n_live / 16.0) / (live_ms / calls)}
 
     # ---- optional: BASELINE.json configs[3], feature extractor only ----

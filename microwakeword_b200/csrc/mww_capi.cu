@@ -81,6 +81,9 @@ struct mww_handle {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     int16_t *d_audio_tile[2] = {nullptr, nullptr}; size_t audio_tile_bytes = 0;
     float *d_probs_tile[2] = {nullptr, nullptr}; size_t probs_tile_bytes = 0;
+    // live-step path: rings stay rotated between live calls (mww_nn_live.cuh); all streams advance in lockstep
+    LiveHeads live_heads{};
+    bool no_live = false;
     long long launches = 0;
     // optional per-kernel timing (mww_profile_*)
     bool profiling = false;
@@ -171,6 +174,25 @@ int run_carry_tile(mww_t *h, int first, int n, const int16_t *d_audio, long long
     return MWW_OK;
 }
 
+bool use_live(const mww_t *h, int n_rows) { return h->has_nn && !h->quantized && n_rows == 3 && !h->no_live; }
+
+// rotate every ring back to the canonical layout before anything that assumes it (clip kernels, mww_get_state)
+int canonicalise_rings(mww_t *h, cudaStream_t st) {
+    bool any = false;
+    for (int i = 0; i < 5; ++i) any = any || h->live_heads.h[i] != 0;
+    if (!any || !h->has_nn || h->quantized) return MWW_OK;
+    CU(h, launch_nn_live_canonicalise(static_cast<float *>(h->d_nn_state), h->n_streams, h->live_heads, st));
+    h->launches += 1;
+    h->live_heads = LiveHeads{};
+    return MWW_OK;
+}
+// once per API call, around the tile loop
+int begin_nn_call(mww_t *h, int n_rows, cudaStream_t st) { return use_live(h, n_rows) ? MWW_OK : canonicalise_rings(h, st); }
+void end_nn_call(mww_t *h, int n_rows) {
+    if (!use_live(h, n_rows)) return;
+    for (int i = 0; i < 5; ++i) h->live_heads.h[i] = (h->live_heads.h[i] + 1) % kLiveRingRows[i];
+}
+
 int run_nn_tile(mww_t *h, int first, int n, const void *d_rows, int row_type, long long rows_stream_stride_rows, int n_rows,
                 float *d_probs, long long probs_stride, cudaStream_t st) {
     ProfScope p(h, 2, st);
@@ -187,12 +209,12 @@ int run_nn_tile(mww_t *h, int first, int n, const void *d_rows, int row_type, lo
     }
     if (row_type == MWW_ROWS_I8) return fail(h, MWW_EINVAL, "int8 rows need a quantised model (inference.py:110)");
     const size_t rb = row_type == MWW_ROWS_F32 ? 4 : 2;
-    if (n_rows == 3 && !getenv("MWW_NO_LIVE")) {
+    if (use_live(h, n_rows)) {
         // exactly one model step per stream: the stream-parallel live-step kernel (HBM-bound on the ring state)
         CU(h, launch_nn_f32_live(h->W, static_cast<float *>(h->d_nn_state) + (size_t)first * kStateFloats,
                                  static_cast<float *>(h->d_pend) + (size_t)first * 2 * kNumChannels, h->n_pend, d_rows,
                                  rows_stream_stride_rows * kNumChannels * (long long)rb, row_type == MWW_ROWS_F32, d_probs, probs_stride, n,
-                                 h->sm_count, st));
+                                 h->live_heads, h->sm_count, st));
         h->launches += 1;
         return MWW_OK;
     }
@@ -345,6 +367,7 @@ int zero_state(mww_t *h, cudaStream_t st) {
         CU(h, cudaMemsetAsync(h->d_nn_state, 0, S * kStateFloats * 4, st));
         CU(h, cudaMemsetAsync(h->d_pend, 0, S * 2 * kNumChannels * 4, st));
     }
+    h->live_heads = LiveHeads{};
     h->used = 0;
     h->n_pend = 0;
     return MWW_OK;
@@ -386,6 +409,7 @@ int mww_create(const void *model_blob, size_t n_bytes, int device, int n_streams
     h->device = device;
     h->n_streams = n_streams;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    h->no_live = getenv("MWW_NO_LIVE") != nullptr;
     if (const char *mb = getenv("MWW_SCRATCH_MB")) { const long v = atol(mb); if (v > 0) h->scratch_budget = (size_t)v << 20; }
     h->has_nn = model_blob != nullptr;
     int rc = upload_tables(h);
@@ -515,7 +539,10 @@ int mww_infer_features(mww_t *h, const void *d_rows, int row_type, int n_rows, l
     CU(h, cudaSetDevice(h->device));
     const int n_steps = (h->n_pend + n_rows) / 3;
     if (n_steps > max_probs || (n_steps > 0 && !d_probs)) return fail(h, MWW_EINVAL, "mww_infer_features: probability buffer too small");
-    int rc = run_nn_tile(h, 0, h->n_streams, d_rows, row_type, rows_stride, n_rows, d_probs, max_probs, static_cast<cudaStream_t>(cu_stream));
+    int rc = begin_nn_call(h, n_rows, static_cast<cudaStream_t>(cu_stream));
+    if (rc) return rc;
+    rc = run_nn_tile(h, 0, h->n_streams, d_rows, row_type, rows_stride, n_rows, d_probs, max_probs, static_cast<cudaStream_t>(cu_stream));
+    if (rc == MWW_OK) end_nn_call(h, n_rows);
     if (rc) return rc;
     h->n_pend = (h->n_pend + n_rows) % 3;
     if (h_probs_out) *h_probs_out = n_steps;
@@ -535,6 +562,8 @@ int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long 
     const int tile = tile_streams(h, n_frames, true);
     int rc = ensure_scratch(h, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 2);
     if (rc) return rc;
+    rc = begin_nn_call(h, n_frames, st);
+    if (rc) return rc;
     for (int first = 0; first < h->n_streams; first += tile) {
         const int n = std::min(tile, h->n_streams - first);
         rc = run_frontend_tile(h, first, n, d_audio + (size_t)first * audio_stride, audio_stride, n_samples, n_frames, h->d_feat,
@@ -543,6 +572,7 @@ int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long 
         rc = run_nn_tile(h, first, n, h->d_feat, MWW_ROWS_U16, n_frames, n_frames, d_probs + (size_t)first * max_probs, max_probs, st);
         if (rc) return rc;
     }
+    end_nn_call(h, n_frames);
     if (n_samples > 0) {
         rc = run_carry_tile(h, 0, h->n_streams, d_audio, audio_stride, n_samples, n_frames, st);
         if (rc) return rc;
@@ -592,6 +622,8 @@ int mww_predict_clip_host(mww_t *h, const int16_t *h_audio, int n_samples, long 
         }
         h->audio_tile_bytes = a_bytes; h->probs_tile_bytes = p_bytes;
     }
+    rc = begin_nn_call(h, n_frames, h->st_compute);
+    if (rc) return rc;
     int it = 0;
     for (int first = 0; first < h->n_streams; first += tile, ++it) {
         const int n = std::min(tile, h->n_streams - first);
@@ -621,6 +653,7 @@ int mww_predict_clip_host(mww_t *h, const int16_t *h_audio, int n_samples, long 
     }
     CU(h, cudaStreamSynchronize(h->st_d2h));
     CU(h, cudaStreamSynchronize(h->st_compute));
+    end_nn_call(h, n_frames);
     h->used = h->used + n_samples - n_frames * kHop;
     h->n_pend = (h->n_pend + n_frames) % 3;
     if (h_probs_out) *h_probs_out = n_steps;
@@ -631,6 +664,11 @@ int mww_get_state(mww_t *h, int16_t *h_carry, uint32_t *h_estimate, void *h_nn, 
     if (!h) return MWW_EINVAL;
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaDeviceSynchronize());
+    if (h_nn) {                                    // the exported layout is always the canonical oldest-first one
+        const int rc = canonicalise_rings(h, nullptr);
+        if (rc) return rc;
+        CU(h, cudaDeviceSynchronize());
+    }
     const size_t S = (size_t)h->n_streams;
     if (h_carry) CU(h, cudaMemcpy(h_carry, h->d_carry, S * kWindow * 2, cudaMemcpyDeviceToHost));
     if (h_estimate) CU(h, cudaMemcpy(h_estimate, h->d_estimate, S * kNumChannels * 4, cudaMemcpyDeviceToHost));
@@ -651,7 +689,10 @@ int mww_set_state(mww_t *h, const int16_t *h_carry, int frontend_buffered, const
     if (h_carry) CU(h, cudaMemcpy(h->d_carry, h_carry, S * kWindow * 2, cudaMemcpyHostToDevice));
     if (h_estimate) CU(h, cudaMemcpy(h->d_estimate, h_estimate, S * kNumChannels * 4, cudaMemcpyHostToDevice));
     if ((h_nn || h_pending) && !h->has_nn) return fail(h, MWW_EINVAL, "frontend-only handle has no NN state");
-    if (h_nn) CU(h, cudaMemcpy(h->d_nn_state, h_nn, S * kStateFloats * elem_size(h), cudaMemcpyHostToDevice));
+    if (h_nn) {
+        CU(h, cudaMemcpy(h->d_nn_state, h_nn, S * kStateFloats * elem_size(h), cudaMemcpyHostToDevice));
+        h->live_heads = LiveHeads{};
+    }
     if (h_pending) CU(h, cudaMemcpy(h->d_pend, h_pending, S * 2 * kNumChannels * elem_size(h), cudaMemcpyHostToDevice));
     h->used = frontend_buffered;
     h->n_pend = pending_rows;

@@ -33,9 +33,13 @@ cudaError_t launch_nn_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, int 
 cudaError_t launch_fill_state_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, void *unused, int n_streams, cudaStream_t st);
 }  // namespace mww
 
+#include "mww_nn_live.cuh"
 namespace mww {
-// live-step path (one model step for many streams per launch; mww_nn_live.cuh)
+// live-step path (one model step for many streams per launch; mww_nn_live.cuh).  `heads` = current rotation of the rings;
+// the caller advances every head by one (mod its ring length) after the launch.
 cudaError_t launch_nn_f32_live(const NnWeightsF32 &W, float *state, float *pend, int n_pend, const void *rows,
                                long long rows_stream_stride_bytes, int rows_are_f32, float *probs, long long probs_stride,
-                               int n_streams, int sm_count, cudaStream_t st);
+                               int n_streams, const LiveHeads &heads, int sm_count, cudaStream_t st);
+// rotate every ring of every stream back to the canonical oldest-first layout (no-op rings with head 0 are skipped)
+cudaError_t launch_nn_live_canonicalise(float *state, int n_streams, const LiveHeads &heads, cudaStream_t st);
 }  // namespace mww

@@ -13,7 +13,7 @@ namespace mww {
 __global__ void __launch_bounds__(kLiveThreads, 2)
 nn_f32_live_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict__ pend, int n_pend, const void *__restrict__ rows,
                    long long rows_stream_stride_bytes, int rows_are_f32, float *__restrict__ probs, long long probs_stride,
-                   int n_streams) {
+                   int n_streams, LiveHeads heads) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x;
     LiveInput in;
@@ -32,15 +32,15 @@ nn_f32_live_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
         live_write_tail(tid, state, pend, s0, n_valid, tail);
         live_first_conv_mma(tid, sm, W);
         __syncthreads();
-        live_depthwise<0>(tid, sm, W, state, s0, n_valid); __syncthreads();
+        live_depthwise<0>(tid, sm, W, state, s0, n_valid, heads.h[0]); __syncthreads();
         live_pointwise_mma<0>(tid, sm, W); __syncthreads();
-        live_depthwise<1>(tid, sm, W, state, s0, n_valid); __syncthreads();
+        live_depthwise<1>(tid, sm, W, state, s0, n_valid, heads.h[1]); __syncthreads();
         live_pointwise_mma<1>(tid, sm, W); __syncthreads();
-        live_depthwise<2>(tid, sm, W, state, s0, n_valid); __syncthreads();
+        live_depthwise<2>(tid, sm, W, state, s0, n_valid, heads.h[2]); __syncthreads();
         live_pointwise_mma<2>(tid, sm, W); __syncthreads();
-        live_depthwise<3>(tid, sm, W, state, s0, n_valid); __syncthreads();
+        live_depthwise<3>(tid, sm, W, state, s0, n_valid, heads.h[3]); __syncthreads();
         live_pointwise_mma<3>(tid, sm, W); __syncthreads();
-        live_head_partial(tid, sm, W, state, s0, n_valid);
+        live_head_partial(tid, sm, W, state, s0, n_valid, heads.h[4]);
         __syncthreads();
         live_head_finish(tid, sm, W, s0, n_valid, probs, probs_stride);
         // the next group's D / H writes are separated from these reads by the barriers at its top
@@ -49,7 +49,7 @@ nn_f32_live_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
 
 cudaError_t launch_nn_f32_live(const NnWeightsF32 &W, float *state, float *pend, int n_pend, const void *rows,
                                long long rows_stream_stride_bytes, int rows_are_f32, float *probs, long long probs_stride,
-                               int n_streams, int sm_count, cudaStream_t st) {
+                               int n_streams, const LiveHeads &heads, int sm_count, cudaStream_t st) {
     if (n_streams <= 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
@@ -60,7 +60,20 @@ cudaError_t launch_nn_f32_live(const NnWeightsF32 &W, float *state, float *pend,
     const int n_groups = (n_streams + kLiveStreams - 1) / kLiveStreams;
     const int grid = std::min(n_groups, 2 * sm_count);
     nn_f32_live_kernel<<<grid, kLiveThreads, kLiveSmemBytes, st>>>(W, state, pend, n_pend, rows, rows_stream_stride_bytes, rows_are_f32, probs,
-                                                                   probs_stride, n_streams);
+                                                                   probs_stride, n_streams, heads);
+    return cudaGetLastError();
+}
+
+__global__ void nn_live_canonicalise_kernel(float *__restrict__ state, int n_streams, LiveHeads heads) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n_streams * 288) return;
+    live_canonicalise_column(state, e / 288, (int)(e % 288), heads);
+}
+
+cudaError_t launch_nn_live_canonicalise(float *state, int n_streams, const LiveHeads &heads, cudaStream_t st) {
+    if (n_streams <= 0) return cudaSuccess;
+    const long long total = (long long)n_streams * 288;
+    nn_live_canonicalise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(state, n_streams, heads);
     return cudaGetLastError();
 }
 

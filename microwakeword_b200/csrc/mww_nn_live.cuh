@@ -8,14 +8,24 @@
 // CTA owns 32 STREAMS: the stream index is the M dimension of the tensor-core contractions (first conv, 1x1
 // projections: same 3xTF32 mma path as the clip kernel), all 1x1 weights stay resident in shared memory, and the
 // depthwise / head stages stream each (stream, channel) ring column through registers: load R rows (coalesced
-// over channels), accumulate the taps, write the rows back shifted by one together with the new row -- the
-// concat(state, input)[-R:] update of stream.py:584-590 done in the same pass that consumes it.
-// The per-stream state layout in HBM is IDENTICAL to the clip kernels', so clip and live calls can be mixed.
+// over channels), accumulate the taps, and write ONLY the new row over the oldest one: between live calls every ring is
+// kept ROTATED (LiveHeads: the physical row that holds the oldest logical row; all streams of a handle advance in
+// lockstep so one head per ring serves every stream), which is the concat(state, input)[-R:] update of
+// stream.py:584-590 without moving R - 1 rows through HBM.  Per stream-step that is the SURVEY.md 8d algorithmic
+// traffic: the ring read once (16.7 KB) + one new row per ring written (1.5 KB), not 2 x 16.7 KB.
+// Rings are rotated back to the canonical (oldest-first) layout of the clip kernels by live_canonicalise_column
+// whenever a clip call, mww_get_state or a mode switch needs it, so clip and live calls can still be mixed.
 #pragma once
 
 #include "mww_nn_mma.cuh"
 
 namespace mww {
+
+// physical row of the oldest logical row of each rotating ring: MixConv blocks 0..3, then the head ring
+struct LiveHeads { int h[5]; };
+constexpr int kLiveRingRows[5] = {4, 10, 14, 22, 16};      // host-side copy (device code uses the functions below)
+MWW_HD constexpr int live_ring_rows(int i) { return i == 0 ? 4 : (i == 1 ? 10 : (i == 2 ? 14 : (i == 3 ? 22 : 16))); }
+MWW_HD constexpr int live_ring_cols(int i) { return i == 0 ? 32 : 64; }
 
 constexpr int kLiveThreads = 256;
 constexpr int kLiveStreams = 32;                  // streams per CTA = two 16-row MMA tiles
@@ -130,8 +140,10 @@ MWW_HD void live_pw_store_tile(float *sm, const NnWeightsF32 &W, int r0, int n0,
 // thread -> channel c = tid % cin, stream subgroup = tid / cin; each thread walks kLiveStreams * cin / 256 streams,
 // U at a time: the kernel is bound by HBM latency (one 8-warp CTA per SM), so U ring columns (U * R independent
 // loads) are put in flight before any of them is consumed.
+// w[p] must already be the tap of PHYSICAL row p (i.e. of logical row (p - head) mod R); w[R] is the new row's tap.
 template <int R, int CIN, int U>
-MWW_HD void live_ring_pass(float *const (&ring)[U], const bool (&ok)[U], const float (&w)[R + 1], const float (&xn)[U], float bias, float (&out)[U]) {
+MWW_HD void live_ring_pass(float *const (&ring)[U], const bool (&ok)[U], const float (&w)[R + 1], const float (&xn)[U], float bias, int head,
+                           float (&out)[U]) {
     float x[U][R];
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -143,16 +155,12 @@ MWW_HD void live_ring_pass(float *const (&ring)[U], const bool (&ok)[U], const f
 #pragma unroll
         for (int r = 0; r < R; ++r) acc = fmaf(w[r], x[u][r], acc);
         out[u] = fmaf(w[R], xn[u], acc);
-        if (ok[u]) {
-#pragma unroll
-            for (int r = 0; r + 1 < R; ++r) ring[u][r * CIN] = x[u][r + 1];
-            ring[u][(R - 1) * CIN] = xn[u];
-        }
+        if (ok[u]) ring[u][head * CIN] = xn[u];          // overwrite the oldest row; the caller advances the head
     }
 }
 
 template <int L>
-MWW_HD void live_depthwise(int tid, float *sm, const NnWeightsF32 &W, float *state, long long s0, int n_valid) {
+MWW_HD void live_depthwise(int tid, float *sm, const NnWeightsF32 &W, float *state, long long s0, int n_valid, int head) {
     constexpr NnLayerGeom g = kGeom[L];
     constexpr int R = g.ring;
     constexpr int per = kLiveStreams * g.cin / kLiveThreads;     // streams per thread: 4 (cin 32) or 8 (cin 64)
@@ -161,7 +169,10 @@ MWW_HD void live_depthwise(int tid, float *sm, const NnWeightsF32 &W, float *sta
     const int c = tid % g.cin, sub = tid / g.cin;
     float w[R + 1];
 #pragma unroll
-    for (int j = 0; j <= R; ++j) w[j] = W.dw_w[L][j * g.cin + c];         // kmax = R + 1; zero padded at the front for short MixConv kernels
+    for (int p = 0; p <= R; ++p) {                                        // kmax = R + 1; zero padded at the front for short MixConv kernels
+        const int j = p == R ? R : (p - head < 0 ? p - head + R : p - head);
+        w[p] = W.dw_w[L][j * g.cin + c];
+    }
     const float bias = W.dw_b[L][c];
     const float *h = sm + kLiveOffH + c * kLivePitch;
     float *d = sm + kLiveOffD + c * kLivePitch;
@@ -175,21 +186,24 @@ MWW_HD void live_depthwise(int tid, float *sm, const NnWeightsF32 &W, float *sta
             ring[u] = state + (size_t)(s0 + (ok[u] ? sl : 0)) * kStateFloats + ring_off + c;
             xn[u] = h[sl];
         }
-        live_ring_pass<R, g.cin, U>(ring, ok, w, xn, bias, out);
+        live_ring_pass<R, g.cin, U>(ring, ok, w, xn, bias, head, out);
 #pragma unroll
         for (int u = 0; u < U; ++u) d[sub * per + i + u] = ok[u] ? out[u] : 0.f;
     }
 }
 
 // ---- head: 17-tap dot per (stream, channel) into D, ring shifted; then reduce over channels ----
-MWW_HD void live_head_partial(int tid, float *sm, const NnWeightsF32 &W, float *state, long long s0, int n_valid) {
+MWW_HD void live_head_partial(int tid, float *sm, const NnWeightsF32 &W, float *state, long long s0, int n_valid, int head) {
     constexpr int per = kLiveStreams * 64 / kLiveThreads;        // 8
     constexpr int U = 4;
     constexpr int ring_off = kStateOff[5];
     const int c = tid & 63, sub = tid >> 6;
     float w[17];
 #pragma unroll
-    for (int j = 0; j < 17; ++j) w[j] = W.head_w[j * 64 + c];
+    for (int p = 0; p < 17; ++p) {
+        const int j = p == 16 ? 16 : (p - head < 0 ? p - head + 16 : p - head);
+        w[p] = W.head_w[j * 64 + c];
+    }
     const float *h = sm + kLiveOffH + c * kLivePitch;
     float *d = sm + kLiveOffD + c * kLivePitch;
 #pragma unroll 1
@@ -202,7 +216,7 @@ MWW_HD void live_head_partial(int tid, float *sm, const NnWeightsF32 &W, float *
             ring[u] = state + (size_t)(s0 + (ok[u] ? sl : 0)) * kStateFloats + ring_off + c;
             xn[u] = h[sl];
         }
-        live_ring_pass<16, 64, U>(ring, ok, w, xn, 0.f, out);
+        live_ring_pass<16, 64, U>(ring, ok, w, xn, 0.f, head, out);
 #pragma unroll
         for (int u = 0; u < U; ++u) d[sub * per + i + u] = ok[u] ? out[u] : 0.f;
     }
@@ -213,6 +227,21 @@ MWW_HD void live_head_finish(int tid, const float *sm, const NnWeightsF32 &W, lo
     float acc = 0.f;
     for (int c = 0; c < 64; ++c) acc += d[c * kLivePitch];
     probs[(s0 + tid) * probs_stride] = nn_sigmoid(acc + W.head_b[0]);
+}
+
+// ---- back to the canonical layout: one (stream, ring, channel) column per call ----
+// col in [0, 288): ring i owns kLiveRingCols[i] consecutive columns.
+MWW_HD void live_canonicalise_column(float *state, long long s, int col, const LiveHeads &heads) {
+    int i = 0, c = col;
+    while (c >= live_ring_cols(i)) { c -= live_ring_cols(i); ++i; }
+    const int R = live_ring_rows(i), C = live_ring_cols(i), h = heads.h[i];
+    if (h == 0) return;
+    int off = 2 * kNumChannels;
+    for (int k = 0; k < i; ++k) off += live_ring_rows(k) * live_ring_cols(k);
+    float *ring = state + (size_t)s * kStateFloats + off + c;
+    float tmp[22];
+    for (int j = 0; j < R; ++j) { const int p = h + j >= R ? h + j - R : h + j; tmp[j] = ring[p * C]; }
+    for (int j = 0; j < R; ++j) ring[j * C] = tmp[j];
 }
 
 #if defined(__CUDACC__)

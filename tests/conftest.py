@@ -21,3 +21,10 @@ from microwakeword_b200.synth_audio import edge_case_audio, synth_audio  # noqa:
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch

@@ -30,6 +30,7 @@ def lib():
         L.emul_nn_f32.restype = ctypes.c_int
         L.emul_nn_i8.restype = ctypes.c_int
         L.emul_nn_f32_live.restype = ctypes.c_int
+        L.emul_nn_live_canonicalise.restype = None
         L.emul_isqrt64_round.restype = ctypes.c_uint32
         L.emul_isqrt64_round.argtypes = [ctypes.c_uint64]
         _lib = L
@@ -91,15 +92,33 @@ class NnF32:
 
 
 class NnF32Live(NnF32):
-    """Same weights / state / pending layout as NnF32, stepped with the live-step kernel's phase functions (3 rows per call)."""
+    """Same weights / state / pending layout as NnF32, stepped with the live-step kernel's phase functions (3 rows per call).
+    Between live steps the rings are ROTATED (heads); `canonicalise` restores the clip kernels' layout, exactly as
+    mww_capi.cu does before a clip call or mww_get_state."""
+
+    RING_ROWS = (4, 10, 14, 22, 16)
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.heads = np.zeros(5, np.int32)
 
     def step(self, rows3):
         rows3 = np.ascontiguousarray(rows3)
         S = rows3.shape[0]
         assert rows3.shape[1:] == (3, 40)
         probs = np.zeros((S, 1), np.float32)
-        lib().emul_nn_f32_live(self.wp, _p(self.state), _p(self.pend), self.n_pend, _p(rows3), int(rows3.dtype == np.float32), S, _p(probs), 1)
+        lib().emul_nn_f32_live(self.wp, _p(self.state), _p(self.pend), self.n_pend, _p(rows3), int(rows3.dtype == np.float32), S, _p(probs), 1,
+                               _p(self.heads))
+        self.heads = ((self.heads + 1) % np.asarray(self.RING_ROWS, np.int32)).astype(np.int32)
         return probs[:, 0]
+
+    def canonicalise(self):
+        lib().emul_nn_live_canonicalise(_p(self.state), self.state.shape[0], _p(self.heads))
+        self.heads[:] = 0
+
+    def infer(self, rows):
+        self.canonicalise()
+        return super().infer(rows)
 
 
 def i8_names():

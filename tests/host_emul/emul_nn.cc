@@ -317,11 +317,13 @@ void emul_live_pointwise(float *sm, const NnWeightsF32 &W) {
 }  // namespace
 
 extern "C" int emul_nn_f32_live(const float *const *wp, float *state, float *pend, int n_pend, const void *rows, int rows_are_f32,
-                                int n_streams, float *probs, int probs_stride) {
+                                int n_streams, float *probs, int probs_stride, const int *heads5) {
     NnWeightsF32 W;
     W.w0 = wp[0];
     for (int i = 0; i < 4; ++i) { W.dw_w[i] = wp[1 + i]; W.dw_b[i] = wp[5 + i]; W.pw_w[i] = wp[9 + i]; W.pw_b[i] = wp[13 + i]; }
     W.head_w = wp[17]; W.head_b = wp[18];
+    LiveHeads heads;
+    for (int i = 0; i < 5; ++i) heads.h[i] = heads5[i];
     LiveInput in;
     in.state = state; in.pend = pend; in.n_pend = n_pend; in.rows = rows;
     in.rows_stream_stride_bytes = 3 * kNumChannels * (rows_are_f32 ? 4 : 2); in.rows_are_f32 = rows_are_f32;
@@ -340,13 +342,20 @@ extern "C" int emul_nn_f32_live(const float *const *wp, float *state, float *pen
         ALLL(live_write_tail(tid, state, pend, s0, n_valid, TL(tid)));
 #undef TL
         emul_live_first_conv(sm, W);
-        ALLL(live_depthwise<0>(tid, sm, W, state, s0, n_valid)); emul_live_pointwise<0>(sm, W);
-        ALLL(live_depthwise<1>(tid, sm, W, state, s0, n_valid)); emul_live_pointwise<1>(sm, W);
-        ALLL(live_depthwise<2>(tid, sm, W, state, s0, n_valid)); emul_live_pointwise<2>(sm, W);
-        ALLL(live_depthwise<3>(tid, sm, W, state, s0, n_valid)); emul_live_pointwise<3>(sm, W);
-        ALLL(live_head_partial(tid, sm, W, state, s0, n_valid));
+        ALLL(live_depthwise<0>(tid, sm, W, state, s0, n_valid, heads.h[0])); emul_live_pointwise<0>(sm, W);
+        ALLL(live_depthwise<1>(tid, sm, W, state, s0, n_valid, heads.h[1])); emul_live_pointwise<1>(sm, W);
+        ALLL(live_depthwise<2>(tid, sm, W, state, s0, n_valid, heads.h[2])); emul_live_pointwise<2>(sm, W);
+        ALLL(live_depthwise<3>(tid, sm, W, state, s0, n_valid, heads.h[3])); emul_live_pointwise<3>(sm, W);
+        ALLL(live_head_partial(tid, sm, W, state, s0, n_valid, heads.h[4]));
         ALLL(live_head_finish(tid, sm, W, s0, n_valid, probs, probs_stride));
     }
 #undef ALLL
     return 1;
+}
+
+extern "C" void emul_nn_live_canonicalise(float *state, int n_streams, const int *heads5) {
+    LiveHeads heads;
+    for (int i = 0; i < 5; ++i) heads.h[i] = heads5[i];
+    for (long long s = 0; s < n_streams; ++s)
+        for (int col = 0; col < 288; ++col) live_canonicalise_column(state, s, col, heads);
 }

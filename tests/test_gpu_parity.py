@@ -18,13 +18,6 @@ pytestmark = pytest.mark.gpu
 F32_TOL = 1e-5
 
 
-@pytest.fixture(scope="module")
-def torch_cuda():
-    import torch
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    return torch
-
-
 def _blob(name):
     with open(os.path.join(GOLDEN, name), "rb") as f:
         return f.read()
@@ -219,6 +212,49 @@ def test_nn_state_roundtrip_and_reset_ids(torch_cuda):
     a.reset([2])
     st = a.state_dict()
     assert not st["nn"][2].any() and not st["estimate"][2].any() and st["nn"][1].any()
+
+
+def test_live_rings_rotate_and_canonicalise(torch_cuda):
+    """Live calls keep the NN rings rotated (only the new row is written); a snapshot, a clip call or a mode switch
+    rotates them back.  Every hand-over must continue the same probability chain as the oracle."""
+    from microwakeword_b200.engine import StreamEngine
+    torch = torch_cuda
+    blob = _blob("okay_nabu_synth_f32.mww")
+    S = 70                                                       # 2 full groups of 32 streams + a ragged one
+    audio = np.stack([synth_audio(48000, 1200 + i) for i in range(S)])
+    _, whole = oracle.run_pipeline(blob, audio, want_features=False, threads=8)
+    dev = torch.from_numpy(audio).cuda()
+    live = StreamEngine(blob, n_streams=S)
+    clip = StreamEngine(blob, n_streams=S)
+    got, pos = [], 0
+    for n_live in (23, 1, 40):                                   # 23, 24 and 64 live steps: every ring wraps at least once (rows 4..22)
+        for _ in range(n_live):
+            got.append(live.step(dev[:, pos:pos + 480].contiguous()))
+            pos += 480
+        # (a) snapshot == state of an engine that only ever ran the clip kernel over the same samples
+        clip.reset()
+        clip.predict_clip(dev[:, :pos].contiguous())
+        a, b = live.state_dict(), clip.state_dict()
+        assert np.abs(a["nn"] - b["nn"]).max() <= 1e-4 and np.array_equal(a["pending"], b["pending"]) and np.array_equal(a["carry"], b["carry"])
+        # (b) a longer call goes through the clip kernel, then live again
+        got.append(live.predict_clip(dev[:, pos:pos + 2000].contiguous()))
+        pos += 2000
+    # (c) per-stream reset while the rings are rotated, then keep stepping: stream 3 restarts from silence
+    for _ in range(5):
+        got.append(live.step(dev[:, pos:pos + 480].contiguous()))
+        pos += 480
+    got = torch.cat(got, 1).cpu().numpy()
+    assert np.abs(got - whole[:, :got.shape[1]]).max() <= F32_TOL
+    live.reset([3])
+    st = live.state_dict()
+    assert not st["nn"][3].any() and st["nn"][4].any()
+    # (d) loading a snapshot into a rotated engine resets the rotation
+    live.step(dev[:, :480].contiguous())
+    live.load_state_dict(clip.state_dict())
+    x = live.step(dev[:, pos:pos + 480].contiguous())
+    clip2 = StreamEngine(blob, n_streams=S)
+    clip2.load_state_dict(clip.state_dict())
+    assert np.abs((x - clip2.step(dev[:, pos:pos + 480].contiguous())).cpu().numpy()).max() <= 1e-5
 
 
 def test_errors_are_loud(torch_cuda):

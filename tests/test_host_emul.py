@@ -134,6 +134,12 @@ def test_live_step_kernel_phases_match_oracle_and_interleave_with_clip():
             pos += 3
         got = np.concatenate(got, 1)
         assert np.abs(got - want[:, :got.shape[1]]).max() <= 1e-5, n_first
+        # live calls keep the rings rotated; rotated back they are the clip kernel's state after the same rows
+        assert nn.heads.any()
+        ref = emul.NnF32(t, S)
+        ref.infer(feats[:, :pos])
+        nn.canonicalise()
+        assert not nn.heads.any() and np.abs(nn.state - ref.state).max() <= 1e-5 and np.array_equal(nn.pend, ref.pend)
         # hand the state back to the clip kernel for the remaining rows: still the same chain
         rest = nn.infer(feats[:, pos:])
         tail = want[:, got.shape[1]:got.shape[1] + rest.shape[1]]

@@ -154,8 +154,8 @@ def test_model_loads_tflite_and_matches_container(kind, tmp_path, torch_cuda):
     it = Interpreter(p.read_bytes())
     if kind == "int8":
         x = R.quantize_input(feats.astype(np.float32) * R.FEATURE_SCALE, m.input_details[0]["quantization"][0], m.input_details[0]["quantization"][1])
-        want = [np.float32(int(it.invoke(x[3 * s:3 * s + 3]).reshape(-1)[0])) / np.float32(255.0) for s in range(40)]
-        assert np.array_equal(np.asarray(a[:40], np.float32), np.asarray(want, np.float32))
+        want = [int(it.invoke(x[3 * s:3 * s + 3]).reshape(-1)[0]) for s in range(40)]                 # uint8 output of the graph
+        assert np.array_equal(np.round(np.asarray(a[:40], np.float64) * 255.0).astype(np.int64), np.asarray(want, np.int64))
     else:
         x = feats.astype(np.float32) * R.FEATURE_SCALE
         want = [float(it.invoke(x[3 * s:3 * s + 3]).reshape(-1)[0]) for s in range(40)]
