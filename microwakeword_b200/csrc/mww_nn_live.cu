@@ -25,11 +25,10 @@ nn_f32_live_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const long long s0 = (long long)g * kLiveStreams;
         const int n_valid = min(kLiveStreams, n_streams - (int)s0);
-        float tail[2][10];
-        live_build_a(tid, sm, in, s0, n_valid);
-        live_read_tail(tid, in, s0, n_valid, tail);
+        float keep[4][kLiveKeep];
+        live_build_a(tid, sm, in, s0, n_valid, keep);
         __syncthreads();
-        live_write_tail(tid, state, pend, s0, n_valid, tail);
+        live_write_tail(tid, state, pend, s0, n_valid, keep);
         live_first_conv_mma(tid, sm, W);
         __syncthreads();
         live_depthwise<0>(tid, sm, W, state, s0, n_valid, heads.h[0]); __syncthreads();

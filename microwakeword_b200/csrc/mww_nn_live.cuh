@@ -62,54 +62,87 @@ struct LiveInput {
     long long rows_stream_stride_bytes;
     int rows_are_f32;
 };
-// Row w (0..6) of a stream's window: w = 0, 1 are the first-conv ring (virtual rows -2, -1), w >= 2 is virtual row
-// w - 2 (pending rows first, then this call's three rows).  All indices are kept NON-NEGATIVE and unsigned on purpose:
-// with a signed "virtual row - 2" formulation nvcc 12.9 re-associated (2 + vr) * 40 into a negative 32-bit term that
-// was then added to the 64-bit address without sign extension (a 16 GB stray access, caught by compute-sanitizer).
-MWW_HD float live_window_row(const LiveInput &in, long long s, unsigned w, unsigned f) {
-    const size_t su = (size_t)s;
-    if (w < 2u) return in.state[su * (size_t)kStateFloats + (size_t)(w * (unsigned)kNumChannels + f)];
-    const unsigned v = w - 2u;
-    if (v < (unsigned)in.n_pend) return in.pend[su * (size_t)(2 * kNumChannels) + (size_t)(v * (unsigned)kNumChannels + f)];
+// One stream's first-conv window is a plain concatenation of three contiguous arrays:
+//     window[0:200] = state[0:80] (the 2-row first-conv ring) ++ pend[0:40 p] ++ rows[0:40 (3 - p)],     p = n_pend
+// and the call leaves   new ring = window[120:200]   and   new pend = rows[40 (3 - p) : 120]  (p rows).
+// All indices are kept NON-NEGATIVE and unsigned on purpose: with a signed "virtual row - 2" formulation nvcc 12.9
+// re-associated (2 + vr) * 40 into a negative 32-bit term that was then added to the 64-bit address without sign
+// extension (a 16 GB stray access, caught by compute-sanitizer).
+MWW_HD float live_row_value(const LiveInput &in, size_t su, unsigned e) {
     const char *base = static_cast<const char *>(in.rows) + su * (size_t)in.rows_stream_stride_bytes;
-    const unsigned e = (v - (unsigned)in.n_pend) * (unsigned)kNumChannels + f;
     if (in.rows_are_f32) return reinterpret_cast<const float *>(base)[e];
     return (float)reinterpret_cast<const uint16_t *>(base)[e] * kFeatureScale;
 }
 
-// ---- phase: A[k = tap*40 + f][stream] for the first conv; also capture the new first-conv ring / pending rows ----
-struct LiveTail { float v[2]; };      // per thread: up to 2 of the 32 x (80 + 80) tail values of the group
-MWW_HD void live_build_a(int tid, float *sm, const LiveInput &in, long long s0, int n_valid) {
+// ---- phase: A[k = tap*40 + f][stream] for the first conv.  A warp owns 4 of the group's 32 streams; lane l reads
+// window elements l, l + 32, ... (coalesced, 7 independent loads per stream) and keeps them: after the barrier the
+// holders of window[120:200] write the new first-conv ring, and 3 more values per lane become the new pending rows.
+constexpr int kLiveKeep = 10;         // per thread and stream: 7 window values + 3 new-pending values
+// Every load below is UNCONDITIONAL on a clamped, always-valid address and the value is selected afterwards: with
+// conditional loads the compiler emitted one branch per element and the 40 loads of a thread serialised into 40
+// dependent DRAM round trips (measured: +11 % kernel time).
+template <bool F32ROWS>
+MWW_HD void live_build_a_t(int tid, float *sm, const LiveInput &in, long long s0, int n_valid, float (&keep)[4][kLiveKeep]) {
+    const int warp = tid >> 5;
+    const unsigned lane = (unsigned)(tid & 31), np40 = (unsigned)in.n_pend * (unsigned)kNumChannels;
     float *a = sm + kLiveOffA;
-    for (int e = tid; e < 200 * kLiveStreams; e += kLiveThreads) {
-        const int sl = e / 200, k = e - 200 * sl;            // consecutive threads walk one stream's 200 window values
-        const int j = k / kNumChannels, f = k - j * kNumChannels;
-        a[k * kLivePitch + sl] = sl < n_valid ? live_window_row(in, s0 + sl, (unsigned)j, (unsigned)f) : 0.f;
-    }
-}
-// new first-conv ring = virtual rows 1, 2; new pending rows = virtual rows 3 .. 3 + n_pend - 1.  Values are read
-// (from the OLD state / pend / rows) here and written by live_write_tail after a barrier.
-MWW_HD void live_read_tail(int tid, const LiveInput &in, long long s0, int n_valid, float (&t)[2][10]) {
-    // 32 streams x 80 values = 2560 per kind; 10 per thread per kind
 #pragma unroll
-    for (int q = 0; q < 10; ++q) {
-        const int e = tid + q * kLiveThreads;
-        const int sl = e / 80, i = e - 80 * sl, r = i / kNumChannels, f = i - r * kNumChannels;
-        t[0][q] = 0.f; t[1][q] = 0.f;
-        if (sl < n_valid) {
-            t[0][q] = live_window_row(in, s0 + sl, (unsigned)(3 + r), (unsigned)f);          // virtual rows 1, 2
-            t[1][q] = r < in.n_pend ? live_window_row(in, s0 + sl, (unsigned)(5 + r), (unsigned)f) : 0.f;   // virtual rows 3, 4
+    for (int q = 0; q < 4; ++q) {
+        const int sl = warp * 4 + q;
+        const bool ok = sl < n_valid;
+        const size_t su = (size_t)(s0 + (ok ? sl : 0));
+        const float *st = in.state + su * (size_t)kStateFloats;
+        const float *pd = in.pend + su * (size_t)(2 * kNumChannels);
+        const char *rb = static_cast<const char *>(in.rows) + su * (size_t)in.rows_stream_stride_bytes;
+        const float *rf = reinterpret_cast<const float *>(rb);
+        const uint16_t *r16 = reinterpret_cast<const uint16_t *>(rb);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const unsigned k = lane + 32u * (unsigned)i, kk = k < 199u ? k : 199u;
+            const bool in_ring = kk < 80u, in_pend = !in_ring && kk < 80u + np40, is_row = !in_ring && !in_pend;
+            const unsigned e = is_row ? kk - 80u - np40 : 0u;
+            const float *fp = in_ring ? st + kk : (in_pend ? pd + (kk - 80u) : (F32ROWS ? rf + e : st));
+            float v = *fp;
+            if (!F32ROWS) {
+                const float u = (float)r16[e] * kFeatureScale;
+                v = is_row ? u : v;
+            }
+            v = (ok && k < 200u) ? v : 0.f;
+            keep[q][i] = v;
+            if (k < 200u) a[k * (unsigned)kLivePitch + (unsigned)sl] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const unsigned e2 = lane + 32u * (unsigned)i;
+            const bool live = ok && e2 < np40;
+            const unsigned idx = live ? 3u * (unsigned)kNumChannels - np40 + e2 : 0u;
+            const float v = F32ROWS ? rf[idx] : (float)r16[idx] * kFeatureScale;
+            keep[q][7 + i] = live ? v : 0.f;
         }
     }
 }
-MWW_HD void live_write_tail(int tid, float *state, float *pend, long long s0, int n_valid, const float (&t)[2][10]) {
+MWW_HD void live_build_a(int tid, float *sm, const LiveInput &in, long long s0, int n_valid, float (&keep)[4][kLiveKeep]) {
+    if (in.rows_are_f32) live_build_a_t<true>(tid, sm, in, s0, n_valid, keep);
+    else live_build_a_t<false>(tid, sm, in, s0, n_valid, keep);
+}
+// after a barrier (every read of the old ring / pending rows is done): new ring = window[120:200], new pending rows
+MWW_HD void live_write_tail(int tid, float *state, float *pend, long long s0, int n_valid, const float (&keep)[4][kLiveKeep]) {
+    const int warp = tid >> 5;
+    const unsigned lane = (unsigned)(tid & 31);
 #pragma unroll
-    for (int q = 0; q < 10; ++q) {
-        const int e = tid + q * kLiveThreads;
-        const int sl = e / 80, i = e - 80 * sl;
-        if (sl < n_valid) {
-            state[(s0 + sl) * kStateFloats + i] = t[0][q];
-            pend[(s0 + sl) * 2 * kNumChannels + i] = t[1][q];
+    for (int q = 0; q < 4; ++q) {
+        const int sl = warp * 4 + q;
+        if (sl >= n_valid) continue;
+        const size_t su = (size_t)(s0 + sl);
+#pragma unroll
+        for (int i = 3; i < 7; ++i) {
+            const unsigned k = lane + 32u * (unsigned)i;
+            if (k >= 120u && k < 200u) state[su * (size_t)kStateFloats + (k - 120u)] = keep[q][i];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const unsigned e = lane + 32u * (unsigned)i;
+            if (e < 80u) pend[su * (size_t)(2 * kNumChannels) + e] = keep[q][7 + i];
         }
     }
 }

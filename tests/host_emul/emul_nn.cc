@@ -335,12 +335,11 @@ extern "C" int emul_nn_f32_live(const float *const *wp, float *state, float *pen
     for (int g = 0; g < n_groups; ++g) {
         const long long s0 = (long long)g * kLiveStreams;
         const int n_valid = n_streams - (int)s0 < kLiveStreams ? n_streams - (int)s0 : kLiveStreams;
-        std::vector<float> tails((size_t)kLiveThreads * 20);
-#define TL(tid) (*reinterpret_cast<float(*)[2][10]>(&tails[(size_t)(tid) * 20]))
-        ALLL(live_build_a(tid, sm, in, s0, n_valid));
-        ALLL(live_read_tail(tid, in, s0, n_valid, TL(tid)));
-        ALLL(live_write_tail(tid, state, pend, s0, n_valid, TL(tid)));
-#undef TL
+        std::vector<float> keeps((size_t)kLiveThreads * 4 * kLiveKeep);
+#define KP(tid) (*reinterpret_cast<float(*)[4][kLiveKeep]>(&keeps[(size_t)(tid) * 4 * kLiveKeep]))
+        ALLL(live_build_a(tid, sm, in, s0, n_valid, KP(tid)));
+        ALLL(live_write_tail(tid, state, pend, s0, n_valid, KP(tid)));
+#undef KP
         emul_live_first_conv(sm, W);
         ALLL(live_depthwise<0>(tid, sm, W, state, s0, n_valid, heads.h[0])); emul_live_pointwise<0>(sm, W);
         ALLL(live_depthwise<1>(tid, sm, W, state, s0, n_valid, heads.h[1])); emul_live_pointwise<1>(sm, W);
