@@ -357,7 +357,8 @@ def run_gpu(args):
         # live-step NN, algorithmic bytes per stream-step: every ring row read once (4 176 floats), one new
         # row per ring + the 2-row first-conv ring written (368 floats), 3 uint16 feature rows in, one probability out
         nn_ms = lp["mixednet"][0] / max(lp["mixednet"][1], 1)
-        step_bytes = 4176 * 4 + 368 * 4 + 3 * 80 + 4
+        eb = 4 if args.model == "f32" else 1                                        # ring element size
+        step_bytes = 4176 * eb + 368 * eb + 3 * 80 + 4
         nn_gbs = S * step_bytes / (nn_ms / 1e3) / 1e9 if nn_ms else None
         live = {"samples_per_call": n_live, "calls": calls, "value": frames / (live_ms / 1e3), "unit": UNIT, "ms_per_call": live_ms / calls,
                 "kernels_ms_per_call": {k: v[0] / calls for k, v in lp.items()},

@@ -174,14 +174,16 @@ int run_carry_tile(mww_t *h, int first, int n, const int16_t *d_audio, long long
     return MWW_OK;
 }
 
-bool use_live(const mww_t *h, int n_rows) { return h->has_nn && !h->quantized && n_rows == 3 && !h->no_live; }
+// one model step per stream -> the stream-parallel live-step kernels (fp32: mww_nn_live.cuh, int8: mww_nn_i8_live.cuh)
+bool use_live(const mww_t *h, int n_rows) { return h->has_nn && n_rows == 3 && !h->no_live; }
 
 // rotate every ring back to the canonical layout before anything that assumes it (clip kernels, mww_get_state)
 int canonicalise_rings(mww_t *h, cudaStream_t st) {
     bool any = false;
     for (int i = 0; i < 5; ++i) any = any || h->live_heads.h[i] != 0;
-    if (!any || !h->has_nn || h->quantized) return MWW_OK;
-    CU(h, launch_nn_live_canonicalise(static_cast<float *>(h->d_nn_state), h->n_streams, h->live_heads, st));
+    if (!any || !h->has_nn) return MWW_OK;
+    if (h->quantized) CU(h, launch_nn_i8_live_canonicalise(static_cast<int8_t *>(h->d_nn_state), h->n_streams, h->live_heads, st));
+    else CU(h, launch_nn_live_canonicalise(static_cast<float *>(h->d_nn_state), h->n_streams, h->live_heads, st));
     h->launches += 1;
     h->live_heads = LiveHeads{};
     return MWW_OK;
@@ -199,6 +201,16 @@ int run_nn_tile(mww_t *h, int first, int n, const void *d_rows, int row_type, lo
     if (h->quantized) {
         if (row_type == MWW_ROWS_F32 || row_type == MWW_ROWS_U16 || row_type == MWW_ROWS_I8) {
             const size_t rb = row_type == MWW_ROWS_F32 ? 4 : (row_type == MWW_ROWS_U16 ? 2 : 1);
+            if (use_live(h, n_rows)) {
+                if (reinterpret_cast<uintptr_t>(d_rows) % 16 != 0)
+                    return fail(h, MWW_EINVAL, "feature rows of a one-step call on an int8 model must be 16-byte aligned");
+                CU(h, launch_nn_i8_live(h->Wq, static_cast<int8_t *>(h->d_nn_state) + (size_t)first * kStateFloats,
+                                        static_cast<int8_t *>(h->d_pend) + (size_t)first * 2 * kNumChannels, h->n_pend, d_rows,
+                                        rows_stream_stride_rows * kNumChannels * (long long)rb, row_type, d_probs, probs_stride, n,
+                                        h->live_heads, h->sm_count, st));
+                h->launches += 1;
+                return MWW_OK;
+            }
             CU(h, launch_nn_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state) + (size_t)first * kStateFloats,
                                static_cast<int8_t *>(h->d_pend) + (size_t)first * 2 * kNumChannels, h->n_pend, d_rows,
                                rows_stream_stride_rows * kNumChannels * (long long)rb, n_rows, row_type, d_probs, probs_stride, n, st));

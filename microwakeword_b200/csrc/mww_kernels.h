@@ -42,4 +42,9 @@ cudaError_t launch_nn_f32_live(const NnWeightsF32 &W, float *state, float *pend,
                                int n_streams, const LiveHeads &heads, int sm_count, cudaStream_t st);
 // rotate every ring of every stream back to the canonical oldest-first layout (no-op rings with head 0 are skipped)
 cudaError_t launch_nn_live_canonicalise(float *state, int n_streams, const LiveHeads &heads, cudaStream_t st);
+// int8 live-step path (mww_nn_i8_live.cuh); rows must be 16-byte aligned with a 16-byte-multiple stream stride
+cudaError_t launch_nn_i8_live(const NnWeightsI8 &W, int8_t *state, int8_t *pend, int n_pend, const void *rows,
+                              long long rows_stream_stride_bytes, int row_type, float *probs, long long probs_stride, int n_streams,
+                              const LiveHeads &heads, int sm_count, cudaStream_t st);
+cudaError_t launch_nn_i8_live_canonicalise(int8_t *state, int n_streams, const LiveHeads &heads, cudaStream_t st);
 }  // namespace mww

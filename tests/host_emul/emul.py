@@ -31,6 +31,8 @@ def lib():
         L.emul_nn_i8.restype = ctypes.c_int
         L.emul_nn_f32_live.restype = ctypes.c_int
         L.emul_nn_live_canonicalise.restype = None
+        L.emul_nn_i8_live.restype = ctypes.c_int
+        L.emul_nn_i8_live_canonicalise.restype = None
         L.emul_isqrt64_round.restype = ctypes.c_uint32
         L.emul_isqrt64_round.argtypes = [ctypes.c_uint64]
         _lib = L
@@ -153,3 +155,33 @@ class NnI8:
                              _p(rows), n_rows, rt, S, _p(probs), probs.shape[1])
         self.n_pend = (self.n_pend + n_rows) % 3
         return probs[:, :n]
+
+
+class NnI8Live(NnI8):
+    """NnI8 stepped with the int8 live-step kernel's phase functions (3 rows per call); rings stay rotated between
+    live steps and are canonicalised before a clip-kernel call, as mww_capi.cu does."""
+
+    RING_ROWS = (4, 10, 14, 22, 16)
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.heads = np.zeros(5, np.int32)
+
+    def step(self, rows3):
+        rows3 = np.ascontiguousarray(rows3)
+        S = rows3.shape[0]
+        assert rows3.shape[1:] == (3, 40)
+        rt = {np.dtype(np.uint16): 0, np.dtype(np.float32): 1, np.dtype(np.int8): 2}[rows3.dtype]
+        probs = np.zeros((S, 1), np.float32)
+        lib().emul_nn_i8_live(self.wp, _p(self.zp), _p(self.head3), ctypes.c_float(self.in_scale), _p(self.state), _p(self.pend), self.n_pend,
+                              _p(rows3), rt, S, _p(probs), 1, _p(self.heads))
+        self.heads = ((self.heads + 1) % np.asarray(self.RING_ROWS, np.int32)).astype(np.int32)
+        return probs[:, 0]
+
+    def canonicalise(self):
+        lib().emul_nn_i8_live_canonicalise(_p(self.state), self.state.shape[0], _p(self.heads))
+        self.heads[:] = 0
+
+    def infer(self, rows):
+        self.canonicalise()
+        return super().infer(rows)

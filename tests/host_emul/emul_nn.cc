@@ -211,6 +211,10 @@ void emul_q_pointwise_mma(int32_t *sm, const NnWeightsI8 &W) {
 }
 }  // namespace
 
+namespace {
+void unpack_i8_weights(const void *const *wp, const int32_t *zp12, const int32_t *head3, float in_scale, NnWeightsI8 &W, I8MmaOperands &ops);
+}
+
 extern "C" int emul_nn_i8(const void *const *wp /* see order below */, const int32_t *zp12, const int32_t *head3, float in_scale,
                           int8_t *state, int8_t *pend, int n_pend, const void *rows, int n_rows, int row_type,
                           int n_streams, float *probs, int max_probs) {
@@ -357,4 +361,102 @@ extern "C" void emul_nn_live_canonicalise(float *state, int n_streams, const int
     for (int i = 0; i < 5; ++i) heads.h[i] = heads5[i];
     for (long long s = 0; s < n_streams; ++s)
         for (int col = 0; col < 288; ++col) live_canonicalise_column(state, s, col, heads);
+}
+
+
+// ---- live-step int8 kernel (mww_nn_i8_live.cuh) -------------------------------------------------------------
+#include "../../microwakeword_b200/csrc/mww_nn_i8_live.cuh"
+namespace {
+void unpack_i8_weights(const void *const *wp, const int32_t *zp12, const int32_t *head3, float in_scale, NnWeightsI8 &W, I8MmaOperands &ops) {
+    int k = 0;
+    W.w0 = (const int8_t *)wp[k++]; W.b0 = (const int32_t *)wp[k++]; W.m0 = (const int32_t *)wp[k++]; W.s0 = (const int32_t *)wp[k++];
+    for (int i = 0; i < 4; ++i) {
+        W.dw_w[i] = (const int8_t *)wp[k++]; W.dw_b[i] = (const int32_t *)wp[k++]; W.dw_m[i] = (const int32_t *)wp[k++]; W.dw_s[i] = (const int32_t *)wp[k++];
+        W.pw_w[i] = (const int8_t *)wp[k++]; W.pw_b[i] = (const int32_t *)wp[k++]; W.pw_m[i] = (const int32_t *)wp[k++]; W.pw_s[i] = (const int32_t *)wp[k++];
+    }
+    W.head_w = (const int8_t *)wp[k++]; W.lut = (const int8_t *)wp[k++];
+    W.head_bias = head3[0]; W.head_mult = head3[1]; W.head_shift = head3[2];
+    memcpy(W.zp, zp12, sizeof W.zp);
+    W.in_scale = in_scale;
+    build_i8_mma_operands(W.w0, W.b0, W.pw_w, W.pw_b, W.zp, &ops);
+    W.w0t = ops.w0t.data(); W.b0f = ops.b0f.data();
+    for (int i = 0; i < 4; ++i) { W.pwt[i] = ops.pwt[i].data(); W.pw_bf[i] = ops.pw_bf[i].data(); }
+}
+
+void emul_livq_first_conv(uint8_t *smb, const NnWeightsI8 &W) {
+    const int8_t *a8 = reinterpret_cast<const int8_t *>(smb + kLqOffA), *w0 = reinterpret_cast<const int8_t *>(smb + kLqOffW0);
+    for (int warp = 0; warp < 8; ++warp) {
+        const int r0 = 16 * (warp >> 2), n0 = 8 * (warp & 3);
+        int32_t c[32][4] = {};
+        for (int ks = 0; ks < 7; ++ks) {
+            FragA8 a[32]; FragB8 b[32];
+            for (int lane = 0; lane < 32; ++lane) { load_frag_a8(a8, kW0Pitch, 32 * ks, r0, lane, a[lane]); load_frag_b8(w0, kW0Pitch, 32 * ks, n0, lane, b[lane]); }
+            warp_mma_s8(c, a, b);
+        }
+        for (int lane = 0; lane < 32; ++lane) livq_fc_store_tile(smb, W, r0, n0, lane, c[lane]);
+    }
+}
+template <int L>
+void emul_livq_pointwise(uint8_t *smb, const NnWeightsI8 &W) {
+    constexpr int cin = kGeom[L].cin;
+    const int8_t *d8 = reinterpret_cast<const int8_t *>(smb + kLqOffD), *wt = reinterpret_cast<const int8_t *>(smb + kLqOffPw + L * 64 * kPwPitch);
+    for (int warp = 0; warp < 8; ++warp) {
+        const int r0 = 16 * (warp >> 2), n0 = 16 * (warp & 3);
+        int32_t c[2][32][4] = {};
+        for (int ks = 0; ks < cin / 32; ++ks) {
+            FragA8 a[32]; FragB8 b0[32], b1[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                load_frag_a8(d8, kPwPitch, 32 * ks, r0, lane, a[lane]);
+                load_frag_b8(wt, kPwPitch, 32 * ks, n0, lane, b0[lane]);
+                load_frag_b8(wt, kPwPitch, 32 * ks, n0 + 8, lane, b1[lane]);
+            }
+            warp_mma_s8(c[0], a, b0);
+            warp_mma_s8(c[1], a, b1);
+        }
+        for (int lane = 0; lane < 32; ++lane) { livq_pw_store_tile<L>(smb, W, r0, n0, lane, c[0][lane]); livq_pw_store_tile<L>(smb, W, r0, n0 + 8, lane, c[1][lane]); }
+    }
+}
+}  // namespace
+
+extern "C" int emul_nn_i8_live(const void *const *wp, const int32_t *zp12, const int32_t *head3, float in_scale, int8_t *state, int8_t *pend,
+                               int n_pend, const void *rows, int row_type, int n_streams, float *probs, int probs_stride, const int *heads5) {
+    NnWeightsI8 W;
+    I8MmaOperands ops;
+    unpack_i8_weights(wp, zp12, head3, in_scale, W, ops);
+    LiveHeads heads;
+    for (int i = 0; i < 5; ++i) heads.h[i] = heads5[i];
+    LiveInputI8 in;
+    in.state = state; in.pend = pend; in.n_pend = n_pend; in.rows = rows;
+    in.rows_stream_stride_bytes = 3 * kNumChannels * (row_type == 1 ? 4 : (row_type == 0 ? 2 : 1)); in.row_type = row_type;
+    std::vector<uint8_t> smv(kLiveQSmemBytes + 16, 0xA5);
+    uint8_t *smb = smv.data();
+    smb += (16 - reinterpret_cast<uintptr_t>(smb) % 16) % 16;
+#define ALLQ(stmt) for (int tid = 0; tid < kLiveQThreads; ++tid) { stmt; }
+    ALLQ(livq_load_weights(tid, smb, W));
+    const int n_groups = (n_streams + kLiveStreams - 1) / kLiveStreams;
+    for (int g = 0; g < n_groups; ++g) {
+        const long long s0 = (long long)g * kLiveStreams;
+        const int n_valid = n_streams - (int)s0 < kLiveStreams ? n_streams - (int)s0 : kLiveStreams;
+        std::vector<uint32_t> keeps((size_t)kLiveQThreads * 4 * kLqKeep);
+#define KQ(tid) (*reinterpret_cast<uint32_t(*)[4][kLqKeep]>(&keeps[(size_t)(tid) * 4 * kLqKeep]))
+        ALLQ(livq_build_a(tid, smb, in, W, s0, n_valid, KQ(tid)));
+        ALLQ(livq_write_tail(tid, state, pend, s0, n_valid, KQ(tid)));
+#undef KQ
+        emul_livq_first_conv(smb, W);
+        ALLQ(livq_depthwise<0>(tid, smb, W, state, s0, n_valid, heads.h[0])); emul_livq_pointwise<0>(smb, W);
+        ALLQ(livq_depthwise<1>(tid, smb, W, state, s0, n_valid, heads.h[1])); emul_livq_pointwise<1>(smb, W);
+        ALLQ(livq_depthwise<2>(tid, smb, W, state, s0, n_valid, heads.h[2])); emul_livq_pointwise<2>(smb, W);
+        ALLQ(livq_depthwise<3>(tid, smb, W, state, s0, n_valid, heads.h[3])); emul_livq_pointwise<3>(smb, W);
+        ALLQ(livq_head_partial(tid, smb, W, state, s0, n_valid, heads.h[4]));
+        ALLQ(livq_head_finish(tid, smb, W, s0, n_valid, probs, probs_stride));
+    }
+#undef ALLQ
+    return 1;
+}
+
+extern "C" void emul_nn_i8_live_canonicalise(int8_t *state, int n_streams, const int *heads5) {
+    LiveHeads heads;
+    for (int i = 0; i < 5; ++i) heads.h[i] = heads5[i];
+    for (long long s = 0; s < n_streams; ++s)
+        for (int col = 0; col < 288; ++col) livq_canonicalise_column(state, s, col, heads);
 }

@@ -144,3 +144,32 @@ def test_live_step_kernel_phases_match_oracle_and_interleave_with_clip():
         rest = nn.infer(feats[:, pos:])
         tail = want[:, got.shape[1]:got.shape[1] + rest.shape[1]]
         assert rest.shape == tail.shape and (rest.size == 0 or np.abs(rest - tail).max() <= 1e-5)
+
+
+def test_int8_live_step_kernel_phases_are_bit_exact():
+    """int8 live-step kernel (IMMA, rotated int8 rings) == the integer oracle bit for bit: every pending-row phase, a
+    ragged last group (70 streams), all three row dtypes, and a hand-over of the state to and from the clip kernel."""
+    q = MF.load(os.path.join(GOLDEN, "okay_nabu_synth_int8.mww"))
+    S = 70
+    audio = np.concatenate([np.stack([synth_audio(9600, 950 + i) for i in range(S - 4)]), edge_case_audio(9600)[:4]])
+    feats, want = oracle.run_pipeline(MF.write_container(q), audio)            # uint16 [70, 58, 40] -> 19 probabilities
+    assert feats.dtype == np.uint16
+    from oracle import mixednet_ref as R
+    as_f32 = feats.astype(np.float32) * np.float32(0.0390625)
+    as_i8 = R.quantize_input(as_f32, q["q/scales"][0], q["q/zps"][0])
+    for rows, n_first in ((feats, 3), (feats, 4), (feats, 5), (as_f32, 4), (as_i8, 5)):
+        nn = emul.NnI8Live(q, S)
+        got = [nn.infer(rows[:, :n_first])]                                    # clip-kernel phases first (leaves 0 / 1 / 2 rows pending)
+        pos = n_first
+        while pos + 3 <= rows.shape[1]:
+            got.append(nn.step(rows[:, pos:pos + 3])[:, None])                 # live-step phases
+            pos += 3
+        got = np.concatenate(got, 1)
+        assert np.array_equal(got, want[:, :got.shape[1]]), (rows.dtype, n_first)
+        assert nn.heads.any()
+        ref = emul.NnI8(q, S)
+        ref.infer(rows[:, :pos])
+        nn.canonicalise()
+        assert np.array_equal(nn.state, ref.state) and np.array_equal(nn.pend, ref.pend)
+        rest = nn.infer(rows[:, pos:])
+        assert np.array_equal(rest, want[:, got.shape[1]:got.shape[1] + rest.shape[1]])
