@@ -83,7 +83,7 @@ struct mww_handle {
     float *d_probs_tile[2] = {nullptr, nullptr}; size_t probs_tile_bytes = 0;
     // live-step path: rings stay rotated between live calls (mww_nn_live.cuh); all streams advance in lockstep
     LiveHeads live_heads{};
-    bool no_live = false;
+    bool no_live = false, no_fuse = false;
     long long launches = 0;
     // optional per-kernel timing (mww_profile_*)
     bool profiling = false;
@@ -151,6 +151,14 @@ int tile_streams(const mww_t *h, int n_frames, bool need_feat) {
 int run_frontend_tile(mww_t *h, int first, int n, const int16_t *d_audio, long long audio_stride, int n_samples,
                       int n_frames, uint16_t *d_feat, long long feat_stream_stride, cudaStream_t st) {
     if (n_frames <= 0) return MWW_OK;
+    if (!h->no_fuse && frontend_fusable(h->used, n_samples, n_frames)) {
+        // short call: K1 + K2 + carry update in one launch (run_carry_tile sees the same predicate and does nothing)
+        ProfScope p(h, 0, st);
+        CU(h, launch_frontend_fused(h->P, h->fb_coef_len, h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n,
+                                    n_frames, h->d_estimate + (size_t)first * kNumChannels, d_feat, feat_stream_stride, st));
+        h->launches += 1;
+        return MWW_OK;
+    }
     {
         ProfScope p(h, 0, st);
         CU(h, launch_k1(h->P, h->fb_coef_len, h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n,
@@ -168,6 +176,7 @@ int run_carry_tile(mww_t *h, int first, int n, const int16_t *d_audio, long long
                    cudaStream_t st) {
     const int consumed = n_frames * kHop;
     const int new_used = h->used + n_samples - consumed;
+    if (!h->no_fuse && n_frames > 0 && frontend_fusable(h->used, n_samples, n_frames)) return MWW_OK;     // done by the fused frontend kernel
     ProfScope p(h, 3, st);
     CU(h, launch_carry_update(h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n, consumed, new_used, st));
     h->launches += 1;
@@ -422,6 +431,7 @@ int mww_create(const void *model_blob, size_t n_bytes, int device, int n_streams
     h->n_streams = n_streams;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     h->no_live = getenv("MWW_NO_LIVE") != nullptr;
+    h->no_fuse = getenv("MWW_NO_FUSE") != nullptr;
     if (const char *mb = getenv("MWW_SCRATCH_MB")) { const long v = atol(mb); if (v > 0) h->scratch_budget = (size_t)v << 20; }
     h->has_nn = model_blob != nullptr;
     int rc = upload_tables(h);

@@ -122,6 +122,69 @@ k1_spectral_packed_kernel(FrontendParams P, int fb_coef_len, const int16_t *__re
     k1_filterbank(tid, sm, P, active ? vout + (s * fps + fl % fps) * kNumChannels : nullptr);
 }
 
+// Whole frontend of a short call in ONE launch: packed K1, then -- all frames of a CTA's streams being resident -- the
+// K2 temporal chain (noise reduction -> PCAN -> log) straight from shared memory, then the carry update from the staged
+// audio.  Saves the V round trip through HBM and two launches per live step.  Requires new_used <= 2 hops (the staged
+// span ends 2 hops after the last frame's start) -- the launcher checks.
+__global__ void __launch_bounds__(kK1Threads, 3)
+k1k2_packed_kernel(FrontendParams P, int fb_coef_len, int16_t *__restrict__ carry, int used, const int16_t *__restrict__ audio,
+                   long long audio_stride, int n_samples, int n_streams, int fps, int spc, int vec_ok, uint32_t *__restrict__ estimate,
+                   uint16_t *__restrict__ feat, long long feat_stream_stride, int new_used) {
+    __shared__ __align__(16) K1Smem sm;
+    const int tid = threadIdx.x;
+    const long long s0 = (long long)blockIdx.x * spc;
+    K1Lane lane;
+    k1_lane_init(tid, P, lane);
+    for (int i = tid; i < fb_coef_len; i += kK1Threads) sm.fb_coef[i] = P.fb_coef[i];
+    if (vec_ok) {
+        k1_packed_load_audio_async(tid, sm, carry, used, audio, audio_stride, n_samples, s0, n_streams, spc, fps);
+        cp_async_commit_and_wait_all();
+    } else {
+        k1_packed_load_audio(tid, sm, carry, used, audio, audio_stride, n_samples, s0, n_streams, spc, fps);
+    }
+    __syncthreads();
+    const int fl = tid >> 4;
+    K1Pass1Ctx ctx;
+    k1_window_fft1<2>(tid, sm, 0, k1_packed_pair_base(fl < spc * fps ? fl : 0, fps), P, ctx);
+    __syncthreads();
+    k1_fft_pass2(tid, sm, lane);
+    __syncthreads();
+    k1_real_energy(tid, sm, P);
+    __syncthreads();
+    // sm.A is free from here on: row fl receives the frame's 40 channel energies
+    k1_filterbank(tid, sm, P, fl < spc * fps ? &sm.A[fl][0] : nullptr);
+    __syncthreads();
+    for (int t = tid; t < spc * kNumChannels; t += kK1Threads) {        // up to 12 streams x 40 channels per CTA
+        const int sl = t / kNumChannels, ch = t - sl * kNumChannels;
+        const long long s = s0 + sl;
+        if (s < n_streams) {
+            const uint32_t smoothing = (ch & 1) ? kOddSmoothing : kEvenSmoothing;
+            uint32_t est = estimate[s * kNumChannels + ch];
+            uint16_t *out = feat + s * feat_stream_stride + ch;
+            for (int f = 0; f < fps; ++f) out[(long long)f * kNumChannels] = k2_channel_step(sm.A[sl * fps + f][ch], est, smoothing, P.gain_lut, P.log_lut);
+            estimate[s * kNumChannels + ch] = est;
+        }
+    }
+    // carry: samples [consumed, consumed + new_used) of (old carry ++ audio) are staged at span offset `consumed`
+    const int span = (fps + 2) * kHop, consumed = fps * kHop;
+    const int16_t *staged = &sm.audio[0][0];
+    if (vec_ok) {
+        for (int i = tid; i < spc * (kWindow / 8); i += kK1Threads) {
+            const int sl = i / (kWindow / 8), v8 = i - sl * (kWindow / 8);
+            if (s0 + sl >= n_streams) continue;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (8 * v8 < new_used) v = *reinterpret_cast<const uint4 *>(staged + sl * span + consumed + 8 * v8);
+            *reinterpret_cast<uint4 *>(carry + (s0 + sl) * kWindow + 8 * v8) = v;
+        }
+    } else {
+        for (int i = tid; i < spc * kWindow; i += kK1Threads) {
+            const int sl = i / kWindow, k = i - sl * kWindow;
+            if (s0 + sl >= n_streams) continue;
+            carry[(s0 + sl) * kWindow + k] = k < new_used ? staged[sl * span + consumed + k] : (int16_t)0;
+        }
+    }
+}
+
 // K2: one thread per (stream, channel); frames are scanned in order, noise estimate kept in a register.
 __global__ void __launch_bounds__(256)
 k2_temporal_kernel(FrontendParams P, const uint32_t *__restrict__ vin, int n_streams, int n_frames,
@@ -201,6 +264,24 @@ cudaError_t launch_k1(const FrontendParams &P, int fb_coef_len, const int16_t *c
     chunks = (n_groups + gpb - 1) / gpb;
     dim3 grid((unsigned)n_streams, (unsigned)chunks);
     k1_spectral_kernel<<<grid, kK1Threads, 0, st>>>(P, fb_coef_len, carry, used, audio, audio_stride, n_samples, n_frames, gpb, vec_ok, vout);
+    return cudaGetLastError();
+}
+
+bool frontend_fusable(int used, int n_samples, int n_frames) {
+    const int new_used = used + n_samples - n_frames * kHop;
+    return n_frames >= 1 && n_frames <= 8 && new_used >= 0 && new_used <= 2 * kHop;
+}
+
+cudaError_t launch_frontend_fused(const FrontendParams &P, int fb_coef_len, int16_t *carry, int used, const int16_t *audio,
+                                  long long audio_stride, int n_samples, int n_streams, int n_frames, uint32_t *estimate, uint16_t *feat,
+                                  long long feat_stream_stride, cudaStream_t st) {
+    if (n_streams <= 0) return cudaSuccess;
+    const int vec_ok = (used % 8 == 0) && (n_samples % 8 == 0) && (audio_stride % 8 == 0) &&
+                       (reinterpret_cast<uintptr_t>(audio) % 16 == 0) && (reinterpret_cast<uintptr_t>(carry) % 16 == 0);
+    const int spc = k1_packed_streams(n_frames);
+    const unsigned grid = (unsigned)((n_streams + spc - 1) / spc);
+    k1k2_packed_kernel<<<grid, kK1Threads, 0, st>>>(P, fb_coef_len, carry, used, audio, audio_stride, n_samples, n_streams, n_frames, spc, vec_ok,
+                                                    estimate, feat, feat_stream_stride, used + n_samples - n_frames * kHop);
     return cudaGetLastError();
 }
 

@@ -11,6 +11,11 @@ namespace mww {
 cudaError_t launch_k1(const FrontendParams &P, int fb_coef_len, const int16_t *carry, int used, const int16_t *audio,
                       long long audio_stride, int n_samples, int n_streams, int n_frames, uint32_t *vout, int sm_count,
                       cudaStream_t st);
+// short calls (<= 8 frames per stream, <= 2 hops left over): K1 + K2 + carry update in one launch
+bool frontend_fusable(int used, int n_samples, int n_frames);
+cudaError_t launch_frontend_fused(const FrontendParams &P, int fb_coef_len, int16_t *carry, int used, const int16_t *audio,
+                                  long long audio_stride, int n_samples, int n_streams, int n_frames, uint32_t *estimate, uint16_t *feat,
+                                  long long feat_stream_stride, cudaStream_t st);
 cudaError_t launch_k2(const FrontendParams &P, const uint32_t *vin, int n_streams, int n_frames, uint32_t *estimate,
                       uint16_t *feat, long long feat_stream_stride, cudaStream_t st);
 cudaError_t launch_carry_update(int16_t *carry, int used, const int16_t *audio, long long audio_stride, int n_samples,

@@ -93,6 +93,45 @@ def test_features_chunking_invariance_and_state(torch_cuda):
     assert np.array_equal(st["estimate"][3], est)
 
 
+def test_fused_short_call_frontend(torch_cuda):
+    """Hop-aligned short calls (1..8 frames, exactly 2 hops left over) take the fused K1+K2+carry kernel: every frames-per-call
+    count, stream counts that do not fill the last CTA, aligned and unaligned audio views, against the oracle and against the
+    same engine with the fusion switched off."""
+    from microwakeword_b200.engine import StreamEngine
+    torch = torch_cuda
+    S = 37
+    calls = [480] + [160 * k for k in (1, 2, 3, 4, 5, 6, 7, 8, 3, 3, 1, 8)] + [2000, 160, 480]      # 2000: not hop aligned -> unfused, then re-aligns? no: stays off the grid
+    total = sum(calls) + 160 * 4
+    audio = np.concatenate([np.stack([synth_audio(total, 1500 + i) for i in range(S - 3)]), edge_case_audio(total)[:3]])
+    whole, _ = oracle.run_pipeline(None, audio, want_probs=False)
+    dev = torch.from_numpy(audio).cuda()
+    pad = torch.zeros((S, total + 3), dtype=torch.int16, device="cuda")
+    pad[:, 3:] = dev                                                       # rows start 6 bytes off 16-byte alignment -> scalar staging path
+    os.environ["MWW_NO_FUSE"] = "1"
+    try:
+        plain = StreamEngine(None, n_streams=S)
+    finally:
+        del os.environ["MWW_NO_FUSE"]
+    for name, src, off in (("aligned", dev, 0), ("unaligned", pad, 3)):
+        eng = StreamEngine(None, n_streams=S)
+        plain.reset()
+        pos, parts, launches = 0, [], []
+        for n in calls:
+            l0 = eng.launch_count
+            view = src[:, off + pos:off + pos + n]
+            a = eng.features(view if name == "unaligned" else view.contiguous())
+            b = plain.features(dev[:, pos:pos + n].contiguous())
+            assert bool((a.view(torch.int16) == b.view(torch.int16)).all()), (name, n)
+            parts.append(_u16(a))
+            launches.append(eng.launch_count - l0)
+            pos += n
+        got = np.concatenate(parts, 1)
+        assert np.array_equal(got, whole[:, :got.shape[1]]), name
+        assert launches[:13] == [1] * 13 and launches[13] == 3, launches           # one fused launch per aligned call; K1 + K2 + carry otherwise
+        sa, sb = eng.state_dict(), plain.state_dict()
+        assert np.array_equal(sa["carry"], sb["carry"]) and np.array_equal(sa["estimate"], sb["estimate"])
+
+
 @pytest.mark.parametrize("kind", ["f32", "int8"])
 def test_model_golden_config0(torch_cuda, kind):
     from microwakeword.inference import Model               # the reference's import path
