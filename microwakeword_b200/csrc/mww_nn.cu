@@ -1,6 +1,7 @@
 // mww_nn.cu -- sm_100a kernel + launcher for the fp32 streaming MixedNet in clip formulation
 // (phase functions and reference citations: mww_nn_dev.cuh).
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #include "mww_kernels.h"
 #include "mww_nn_mma.cuh"
@@ -72,12 +73,14 @@ cudaError_t launch_nn_f32(const NnWeightsF32 &W, float *state, float *pend, int 
                           long long probs_stream_stride, float *logits, int n_streams, cudaStream_t st) {
     if (n_streams <= 0) return cudaSuccess;
     static bool attr_set = false;
+    static int pad = 0;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(nn_f32_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNnSmemBytes);
+        if (const char *e = getenv("MWW_NN_SMEM_PAD")) pad = atoi(e);       // experiment: force 1 CTA / SM
+        cudaError_t e = cudaFuncSetAttribute(nn_f32_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNnSmemBytes + pad);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    nn_f32_clip_kernel<<<(unsigned)n_streams, kNnThreads, kNnSmemBytes, st>>>(W, state, pend, n_pend, rows, rows_stream_stride_bytes,
+    nn_f32_clip_kernel<<<(unsigned)n_streams, kNnThreads, kNnSmemBytes + pad, st>>>(W, state, pend, n_pend, rows, rows_stream_stride_bytes,
                                                                              n_rows, rows_are_f32, probs, probs_stream_stride, logits);
     return cudaGetLastError();
 }

@@ -48,6 +48,11 @@ constexpr NnLayerGeom kGeom[5] = {
 constexpr int kXFloats = 32 * 41 + 64 * (47 + 51 + 59 + 53);   // 14752
 constexpr int kDLd = 40;                                      // 40 = 8 (mod 32): conflict-free mma A fragments
 constexpr int kDFloats = 64 * kDLd + 8;                       // + slack: the last m-tile reads 12 rows past kTT
+// D[c][t] is WRITTEN with lanes = channels (bank = 8 c + t: 4 banks, 8-way replays) and READ as mma A fragments with
+// lanes = (4 channels x 8 steps).  XOR-ing the step with bits 2..4 of the channel keeps a fragment's 8 steps inside
+// their aligned 8-block (reads stay conflict-free) and spreads 32 consecutive channels over all 32 banks on the write.
+MWW_HD int nn_d_swz(int c) { return (c >> 2) & 7; }
+MWW_HD int nn_d_index(int c, int t) { return c * kDLd + (t ^ nn_d_swz(c)); }
 constexpr int kUS = 40;                                       // pitch of a feature plane row (u index)
 constexpr int kFeatFloats = 3 * kNumChannels * kUS;           // 4800 >= 64*64 staged 1x1 weights
 constexpr int kWLdDev = 72;                                   // pitch of staged 1x1 weights (see mww_nn_mma.cuh)
@@ -109,12 +114,17 @@ MWW_HD void nn_load_state(int tid, float *sm, const float *state) {
 // previous chunk's last two rows); plane[q % 3][f][q / 3].  Step t, tap j reads q = 3t + j.
 MWW_HD void nn_load_features(int tid, float *sm, const NnInput &in, int step0, int n) {
     float *feat = sm + kXFloats + kDFloats;
-    const int n_q = 3 * n + 2;
-    // one thread handles 8 consecutive features of one row: a single 16-byte load on the uint16 fast path
-    for (int e = tid; e < n_q * 5; e += kNnThreads) {
-        const int q = e / 5, f0 = 8 * (e - 5 * q);
+    const int n_q = 3 * n + 2, U = n + 1;          // plane column u = q / 3 <= n
+    // one thread handles 8 consecutive features of one row: a single 16-byte load on the uint16 fast path.
+    // thread -> (8-feature group, plane j, u) with u FASTEST: consecutive lanes store consecutive words of a plane row
+    // (row-major thread order put the 32 lanes of a store on 2-3 banks: 93 % of this phase's wavefronts were
+    // conflict replays, ncu).  The 16-byte global loads of neighbouring lanes are then 3 rows apart and meet in L1.
+    for (int e = tid; e < 15 * U; e += kNnThreads) {
+        const int u = e % U, jf = e / U, j = jf % 3, f0 = 8 * (jf / 3);
+        const int q = 3 * u + j;
+        if (q >= n_q) continue;
         const int vr = 3 * step0 + q - 2;
-        float *dst = feat + ((q % 3) * kNumChannels + f0) * kUS + q / 3;
+        float *dst = feat + (j * kNumChannels + f0) * kUS + u;
         const int r = vr - in.n_pend;
         if (vr >= in.n_pend && !in.rows_are_f32) {
             const uint16_t *src = static_cast<const uint16_t *>(in.rows) + (long long)r * kNumChannels + f0;
@@ -195,9 +205,9 @@ MWW_HD void nn_depthwise_k(int c, int t0, float *sm, const NnWeightsF32 &W) {
             if (j >= 0 && j < K) acc[tt] = fmaf(w[j], xv, acc[tt]);
         }
     }
-    float *d = sm + kXFloats + c * kDLd + t0;
+    float *d = sm + kXFloats;
 #pragma unroll
-    for (int i = 0; i < TN; ++i) d[i] = acc[i] + bias;
+    for (int i = 0; i < TN; ++i) d[nn_d_index(c, t0 + i)] = acc[i] + bias;
 }
 
 template <int L>
@@ -235,9 +245,9 @@ MWW_HD void nn_head_partial(int tid, float *sm, const NnWeightsF32 &W) {
             if (j >= 0 && j < 17) acc[tt] = fmaf(w[j], xv, acc[tt]);
         }
     }
-    float *d = sm + kXFloats + c * kDLd + t0;
+    float *d = sm + kXFloats;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) d[i] = acc[i];
+    for (int i = 0; i < 9; ++i) d[nn_d_index(c, t0 + i)] = acc[i];
 }
 
 MWW_HD float nn_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -245,9 +255,9 @@ MWW_HD float nn_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 // ---- phase: head, part 2: reduce over channels, bias, sigmoid ----
 MWW_HD void nn_head_finish(int tid, float *sm, const NnWeightsF32 &W, int n, float *probs_out /* step0-relative */, float *logits_out) {
     if (tid >= kTT || tid >= n) return;
-    const float *d = sm + kXFloats + tid;
+    const float *d = sm + kXFloats;
     float acc = 0.f;
-    for (int c = 0; c < 64; ++c) acc += d[c * kDLd];
+    for (int c = 0; c < 64; ++c) acc += d[nn_d_index(c, tid)];
     const float logit = acc + W.head_b[0];
     if (logits_out) logits_out[tid] = logit;
     probs_out[tid] = nn_sigmoid(logit);

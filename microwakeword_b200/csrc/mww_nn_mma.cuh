@@ -56,6 +56,17 @@ MWW_HD void load_frag_a(const float *base, int ld, int k0, int t0, int lane, Fra
     split_tf32(p[4 * ld], a.hi[2], a.lo[2]);
     split_tf32(p[4 * ld + 8], a.hi[3], a.lo[3]);
 }
+// A fragment from the swizzled depthwise output D (nn_d_index): k0 is a multiple of 8, so the swizzle is one constant
+// per fragment half
+MWW_HD void load_frag_a_d(const float *d, int k0, int t0, int lane, FragA &a) {
+    const int g = lane >> 2, tig = lane & 3;
+    const int s0 = ((k0 >> 2) & 7), s1 = (((k0 >> 2) + 1) & 7);
+    const float *p0 = d + (k0 + tig) * kDLd, *p1 = p0 + 4 * kDLd;
+    split_tf32(p0[(t0 + g) ^ s0], a.hi[0], a.lo[0]);
+    split_tf32(p0[(t0 + g + 8) ^ s0], a.hi[1], a.lo[1]);
+    split_tf32(p1[(t0 + g) ^ s1], a.hi[2], a.lo[2]);
+    split_tf32(p1[(t0 + g + 8) ^ s1], a.hi[3], a.lo[3]);
+}
 // B fragment from a [k][n] array with pitch `ld` (output channel contiguous)
 MWW_HD void load_frag_b(const float *base, int ld, int k0, int n0, int lane, FragB &b) {
     const int g = lane >> 2, tig = lane & 3;
@@ -160,7 +171,7 @@ MWW_D void nn_pointwise_mma(int tid, float *sm, const NnWeightsF32 &W) {
     for (int ks = 0; ks < cin / 8; ++ks) {
         FragA a;
         FragB b[3];
-        load_frag_a(d, kDLd, 8 * ks, t0, lane, a);
+        load_frag_a_d(d, 8 * ks, t0, lane, a);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
             if (i < ntc) load_frag_b(wsm, kWLd, 8 * ks, 8 * (nt0 + i), lane, b[i]);

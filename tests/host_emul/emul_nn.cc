@@ -58,7 +58,7 @@ void emul_pointwise_mma(float *sm, const NnWeightsF32 &W) {
         float c[3][32][4] = {};
         for (int ks = 0; ks < cin / 8; ++ks) {
             FragA a[32];
-            for (int lane = 0; lane < 32; ++lane) load_frag_a(d, kDLd, 8 * ks, t0, lane, a[lane]);
+            for (int lane = 0; lane < 32; ++lane) load_frag_a_d(d, 8 * ks, t0, lane, a[lane]);
             for (int i = 0; i < ntc; ++i) {
                 FragB b[32];
                 for (int lane = 0; lane < 32; ++lane) load_frag_b(wsm, kWLd, 8 * ks, 8 * (nt0 + i), lane, b[lane]);
