@@ -29,8 +29,8 @@ nn_f32_clip_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
     const int n_virtual = n_pend + n_rows;
     const int n_steps = n_virtual / 3;
 
-    nn_load_state(tid, sm, my_state);
-    __syncthreads();
+    nn_load_state(tid, sm, my_state);                 // cp.async group 0: lands while the first chunk's features load
+    nn_commit_group();
     for (int step0 = 0; step0 < n_steps; step0 += kTT) {
         const int n = min(kTT, n_steps - step0);
         nn_load_features(tid, sm, in, step0, n);
@@ -41,6 +41,7 @@ nn_f32_clip_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
         nn_first_conv_mma_b(tid, sm, fc);
         nn_stage_pw_weights<0>(tid, sm, W);          // feature planes are dead: block 0's weights land there
         nn_stage_pw_weights<1>(tid, sm, W);
+        nn_wait_weights<2>();                         // first chunk: the ring-state group is complete (only the two weight groups may be in flight)
         __syncthreads();
         nn_depthwise<0>(tid, sm, W); nn_wait_weights<1>(); __syncthreads();
         nn_pointwise_mma<0>(tid, sm, W); __syncthreads();
@@ -64,6 +65,7 @@ nn_f32_clip_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
     }
     NnTail tail;
     nn_tail_read(tid, in, n_steps, n_virtual, tail);
+    nn_wait_weights<0>();                             // a call without a full step still has the ring-state copy in flight
     __syncthreads();
     nn_tail_write(tid, sm, my_state, my_pend, tail);
 }

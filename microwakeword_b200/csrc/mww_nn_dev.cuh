@@ -99,9 +99,16 @@ template <int L>
 MWW_HD void nn_load_state_l(int tid, float *sm, const float *state) {
     constexpr NnLayerGeom g = kGeom[L];
     const float *src = state + kStateOff[L + 1];
+    // 4-byte cp.async (LDGSTS): the ~15 transposing copies a thread issues are all in flight at once instead of one
+    // load -> store round trip after the other (this phase held 9 % of the kernel's stall samples, all long-scoreboard)
     for (int e = tid; e < g.ring * g.cin; e += kNnThreads) {
         const int r = e / g.cin, c = e - r * g.cin;
-        sm[g.off + c * g.ld + (g.hp - g.ring) + r] = src[e];
+        float *dst = sm + g.off + c * g.ld + (g.hp - g.ring) + r;
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src + e));
+#else
+        *dst = src[e];
+#endif
     }
 }
 MWW_HD void nn_load_state(int tid, float *sm, const float *state) {
@@ -168,6 +175,11 @@ MWW_HD void nn_stage_pw_weights(int tid, float *sm, const NnWeightsF32 &W) {
         for (int i = 0; i < 4; ++i) dst[i] = W.pw_w[L][4 * e + i];
 #endif
     }
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+MWW_HD void nn_commit_group() {
 #if defined(__CUDA_ARCH__)
     asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
