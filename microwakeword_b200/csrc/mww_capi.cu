@@ -210,9 +210,9 @@ int run_nn_tile(mww_t *h, int first, int n, const void *d_rows, int row_type, lo
     if (h->quantized) {
         if (row_type == MWW_ROWS_F32 || row_type == MWW_ROWS_U16 || row_type == MWW_ROWS_I8) {
             const size_t rb = row_type == MWW_ROWS_F32 ? 4 : (row_type == MWW_ROWS_U16 ? 2 : 1);
+            if (reinterpret_cast<uintptr_t>(d_rows) % 16 != 0)          // the integer kernels read rows 8 / 16 bytes at a time
+                return fail(h, MWW_EINVAL, "feature rows for an int8 model must be 16-byte aligned");
             if (use_live(h, n_rows)) {
-                if (reinterpret_cast<uintptr_t>(d_rows) % 16 != 0)
-                    return fail(h, MWW_EINVAL, "feature rows of a one-step call on an int8 model must be 16-byte aligned");
                 CU(h, launch_nn_i8_live(h->Wq, static_cast<int8_t *>(h->d_nn_state) + (size_t)first * kStateFloats,
                                         static_cast<int8_t *>(h->d_pend) + (size_t)first * 2 * kNumChannels, h->n_pend, d_rows,
                                         rows_stream_stride_rows * kNumChannels * (long long)rb, row_type, d_probs, probs_stride, n,

@@ -140,16 +140,48 @@ MWW_HD void nnq_load_weights(int tid, int32_t *sm, const NnWeightsI8 &W) {
 }
 
 // im2col of the chunk's rows as raw int8: A8[t][tap*40 + f] = q(row 3(step0+t) + tap - 2, f)
+// One thread handles 8 consecutive features of one row: a single 8 / 16 / 2 x 16-byte load (int8 / uint16 / float32
+// rows), eight quantisations (Model.quantize_input_data, inference.py:127-147) and one 8-byte store per im2col copy.
+// The first version walked single elements -- one dependent 2-byte load, a division and two byte stores each -- and
+// held 47 % of this kernel's stall samples (profiles/r01_nn_i8_stalls.txt).
+struct alignas(8) NnQ8 { uint32_t lo, hi; };
+MWW_HD NnQ8 nnq_row_octet(const NnInputI8 &in, const NnWeightsI8 &W, int vr, int f0) {
+    if (vr < 0) return *reinterpret_cast<const NnQ8 *>(in.ring0 + (2 + vr) * kNumChannels + f0);
+    if (vr < in.n_pend) return *reinterpret_cast<const NnQ8 *>(in.pend + vr * kNumChannels + f0);
+    const long long e = (long long)(vr - in.n_pend) * kNumChannels + f0;
+    if (in.row_type == 2) return *reinterpret_cast<const NnQ8 *>(static_cast<const int8_t *>(in.rows) + e);
+    float x[8];
+    if (in.row_type == 1) {
+        struct alignas(16) F4 { float v[4]; };
+        const F4 a = *reinterpret_cast<const F4 *>(static_cast<const float *>(in.rows) + e);
+        const F4 b = *reinterpret_cast<const F4 *>(static_cast<const float *>(in.rows) + e + 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { x[i] = a.v[i]; x[4 + i] = b.v[i]; }
+    } else {
+        struct alignas(16) U8 { uint16_t v[8]; };
+        const U8 u = *reinterpret_cast<const U8 *>(static_cast<const uint16_t *>(in.rows) + e);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = (float)u.v[i] * kFeatureScale;
+    }
+    uint32_t w[2] = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i >> 2] |= (uint32_t)(nnq_quantize(x[i], W.in_scale, W.zp[0]) & 0xFF) << (8 * (i & 3));
+    NnQ8 r;
+    r.lo = w[0]; r.hi = w[1];
+    return r;
+}
 MWW_HD void nnq_load_features(int tid, int32_t *sm, const NnInputI8 &in, const NnWeightsI8 &W, int step0, int n) {
     int8_t *a8 = nnq_bytes(sm) + kQOffA8;
-    const int n_q = 3 * n + 2;
-    for (int e = tid; e < n_q * kNumChannels; e += kNnThreads) {
-        const int q = e / kNumChannels, f = e - q * kNumChannels;
-        const int8_t v = (int8_t)(nnq_virtual_row(in, W, 3 * step0 + q - 2, f) + W.zp[0]);
-        // chunk row q is tap j of step t for q = 3t + j: j = q % 3 and, when it exists, j + 3
-        const int j0 = q % 3, t0 = q / 3;
-        if (t0 < kMmaRows) a8[t0 * kW0Pitch + j0 * kNumChannels + f] = v;
-        if (j0 + 3 < 5 && t0 >= 1) a8[(t0 - 1) * kW0Pitch + (j0 + 3) * kNumChannels + f] = v;
+    const int n_q = 3 * n + 2, U = n + 1;
+    // thread -> (8-feature group, tap phase j, u) with u fastest; chunk row q = 3u + j is tap j of step u and, for
+    // j < 2, tap j + 3 of step u - 1
+    for (int e = tid; e < 15 * U; e += kNnThreads) {
+        const int u = e % U, jf = e / U, j = jf % 3, f0 = 8 * (jf / 3);
+        const int q = 3 * u + j;
+        if (q >= n_q) continue;
+        const NnQ8 v = nnq_row_octet(in, W, 3 * step0 + q - 2, f0);
+        if (u < kMmaRows) *reinterpret_cast<NnQ8 *>(a8 + u * kW0Pitch + j * kNumChannels + f0) = v;
+        if (j + 3 < 5 && u >= 1) *reinterpret_cast<NnQ8 *>(a8 + (u - 1) * kW0Pitch + (j + 3) * kNumChannels + f0) = v;
     }
 }
 
