@@ -1,9 +1,10 @@
 """oracle/ -- CPU restatement of the reference's streaming-inference path (TEST INFRASTRUCTURE).
 
-*** PARITY UNPINNED ***: the reference's arithmetic for this path lives in pymicro-features /
-TensorFlow-Lite native code that is absent from /root/reference and not installable here, and
-the reference ships no golden vectors.  The oracle is pinned only by closed-form
-known-answer tests.
+*** PARITY ***: the reference's arithmetic for this path lives in pymicro-features / TensorFlow-Lite
+native code that is absent from /root/reference and not installable here, and the reference ships no
+golden vectors.  Micro-frontend: pinned to the upstream library's own unit-test vectors
+(tests/test_upstream_kat.py - all nine stages + consecutive frames reproduced exactly) and closed-form
+known answers.  MixedNet / TFLite int8 kernels: UNPINNED (closed-form known answers only).
 
 Import rules: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import
 this package.  The product package (microwakeword_b200/) never does.
@@ -45,6 +46,10 @@ def lib():
         L = ctypes.CDLL(_SO)
         vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
         L.mwwo_frontend_create.restype = vp
+        L.mwwo_frontend_create_cfg.restype = vp
+        L.mwwo_frontend_create_cfg.argtypes = [i32, i32, i32, i32, ctypes.c_float, ctypes.c_float]
+        L.mwwo_frontend_config.argtypes = [vp, vp]
+        L.mwwo_frontend_window_tap.argtypes = [vp, vp, vp]
         L.mwwo_frontend_free.argtypes = [vp]
         L.mwwo_frontend_reset.argtypes = [vp]
         L.mwwo_frontend_process.restype = i32
@@ -93,11 +98,17 @@ def _ptr(a):
 class Frontend:
     """Stateful micro-frontend, one stream (pymicro_features.MicroFrontend stand-in)."""
 
-    def __init__(self):
+    def __init__(self, config=None):
+        """config=None: the okay_nabu configuration (audio_utils.py:71-78); otherwise a tuple
+        (sample_rate, window_ms, step_ms, num_channels, lower_hz, upper_hz) -- used to run the upstream
+        micro-frontend library's own unit-test configuration through the same code (tests/test_upstream_kat.py)."""
         self._L = lib()
-        self._h = self._L.mwwo_frontend_create()
+        self._h = self._L.mwwo_frontend_create() if config is None else self._L.mwwo_frontend_create_cfg(*config)
         if not self._h:
             raise RuntimeError("oracle frontend: table construction failed")
+        cfg = np.zeros(8, np.int32)
+        self._L.mwwo_frontend_config(self._h, cfg.ctypes.data)
+        self.sample_rate, self.window, self.step, self.fft_size, self.num_channels, self.start_index, self.end_index = (int(v) for v in cfg[:7])
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -113,21 +124,28 @@ class Frontend:
         out = np.zeros(NUM_CHANNELS, np.uint16)
         n_read = ctypes.c_size_t(0)
         got = self._L.mwwo_frontend_process(self._h, samples.ctypes.data, samples.size, ctypes.byref(n_read), out.ctypes.data)
-        return (out if got else None), n_read.value
+        return (out[:self.num_channels] if got else None), n_read.value
 
     def stream(self, audio: np.ndarray) -> np.ndarray:
         audio = np.ascontiguousarray(audio, np.int16)
-        out = np.zeros((audio.size // 160 + 1, NUM_CHANNELS), np.uint16)
+        out = np.zeros((audio.size // self.step + 1, self.num_channels), np.uint16)
         n = self._L.mwwo_frontend_stream(self._h, audio.ctypes.data, audio.size, out.ctypes.data, out.shape[0])
         return out[:n]
 
     def tables(self) -> dict:
-        t = dict(window=np.zeros(480, np.int16), bin_channel=np.zeros(257, np.int16), bin_weight=np.zeros(257, np.int16),
+        t = dict(window=np.zeros(512, np.int16), bin_channel=np.zeros(257, np.int16), bin_weight=np.zeros(257, np.int16),
                  bin_unweight=np.zeros(257, np.int16), chan_start=np.zeros(42, np.int16), gain_lut=np.zeros(125, np.int16),
                  log_lut=np.zeros(129, np.uint16), twiddles=np.zeros((256, 2), np.int16), super_twiddles=np.zeros((128, 2), np.int16),
                  scalars=np.zeros(8, np.int32))
         self._L.mwwo_frontend_tables(self._h, *[_ptr(t[k]) for k in ("window", "bin_channel", "bin_weight", "bin_unweight", "chan_start",
                                                                       "gain_lut", "log_lut", "twiddles", "super_twiddles", "scalars")])
+        nb, nc = self.fft_size // 2 + 1, self.num_channels
+        t["window"] = t["window"][:self.window]
+        for k in ("bin_channel", "bin_weight", "bin_unweight"):
+            t[k] = t[k][:nb]
+        t["chan_start"] = t["chan_start"][:nc + 2]
+        t["twiddles"] = t["twiddles"][:self.fft_size // 2]
+        t["super_twiddles"] = t["super_twiddles"][:self.fft_size // 4]
         return t
 
     def taps(self) -> dict:
@@ -135,18 +153,29 @@ class Frontend:
                  energy=np.zeros(257, np.uint32), work=np.zeros(41, np.uint64), sqrt=np.zeros(40, np.uint32),
                  nr=np.zeros(40, np.uint32), pcan=np.zeros(40, np.uint32), estimate=np.zeros(40, np.uint32))
         self._L.mwwo_frontend_taps(self._h, *[_ptr(t[k]) for k in ("shift", "fft_in", "fft_out", "energy", "work", "sqrt", "nr", "pcan", "estimate")])
+        nb, nc = self.fft_size // 2 + 1, self.num_channels
+        t["fft_in"] = t["fft_in"][:self.fft_size]
+        t["fft_out"], t["energy"] = t["fft_out"][:nb], t["energy"][:nb]
+        t["work"] = t["work"][:nc + 1]
+        for k in ("sqrt", "nr", "pcan", "estimate"):
+            t[k] = t[k][:nc]
+        win = np.zeros(512, np.int16)
+        mx = np.zeros(1, np.int32)
+        self._L.mwwo_frontend_window_tap(self._h, win.ctypes.data, mx.ctypes.data)
+        t["window_out"], t["max_abs"] = win[:self.window], int(mx[0])
         return t
 
     def state(self):
-        buf, used, est = np.zeros(480, np.int16), np.zeros(1, np.int32), np.zeros(40, np.uint32)
+        buf, used, est = np.zeros(512, np.int16), np.zeros(1, np.int32), np.zeros(40, np.uint32)
         self._L.mwwo_frontend_get_state(self._h, buf.ctypes.data, used.ctypes.data, est.ctypes.data)
-        return buf, int(used[0]), est
+        return buf[:self.window], int(used[0]), est[:self.num_channels]
 
     def fftr(self, x512: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x512, np.int16)
+        assert x.size == self.fft_size
         out = np.zeros((257, 2), np.int16)
         self._L.mwwo_fftr(self._h, x.ctypes.data, out.ctypes.data)
-        return out
+        return out[:self.fft_size // 2 + 1]
 
     def wdf(self, x: int) -> int:
         return self._L.mwwo_wdf(self._h, x)

@@ -10,11 +10,17 @@
  * /root/reference and from this image, so this file restates the PUBLISHED
  * algorithm from knowledge of the upstream sources.
  *
- *      *** PARITY UNPINNED ***
- * The reference holds no golden vectors / tests for this path and the
- * real library cannot run here, so this oracle is checked only against closed-form
- * known answers (tests/test_oracle_frontend.py).  Every GPU parity claim in this repo
- * is relative to this file.
+ *      *** PARITY: pinned to the upstream library's unit-test vectors; not to the reference ***
+ * The reference itself holds no golden vectors / tests for this path and the real
+ * library cannot run here.  What pins this file: the upstream micro-frontend library's OWN published
+ * unit tests (window_test.cc, fft_test.cc, filterbank_test.cc, noise_reduction_test.cc,
+ * pcan_gain_control_test.cc, log_scale_test.cc, frontend_test.cc: 1 kHz / 25 ms / 2 channels) -- this
+ * code, constructed with that FrontendConfig (mwwo_frontend_create_cfg), reproduces every expected value
+ * of all nine stages and the consecutive-frame case exactly (tests/test_upstream_kat.py; the vectors were
+ * written down from knowledge of those files, which are not fetchable here, and are cross-checked for
+ * mutual consistency), plus closed-form known answers (tests/test_oracle_frontend.py).  The 16 kHz /
+ * 40-channel tables are built by the same code.  Every GPU parity claim in this repo is relative to
+ * this file.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this code.  The product (microwakeword_b200/) never links it.
@@ -67,11 +73,12 @@ static cpx kf_cmul(cpx a, cpx b) {
 static cpx kf_add(cpx a, cpx b) { cpx c = { (int16_t)(a.r + b.r), (int16_t)(a.i + b.i) }; return c; }
 static cpx kf_sub(cpx a, cpx b) { cpx c = { (int16_t)(a.r - b.r), (int16_t)(a.i - b.i) }; return c; }
 
-#define NCFFT 256 /* complex length of the packed real FFT */
+#define NCFFT_MAX 256 /* complex length of the packed real FFT: 256 for the 512-point okay_nabu frame */
 
 struct kf_state {
-    cpx tw[NCFFT];          /* exp(-2*pi*i*k/256), Q15, floor(.5 + 32767*x) */
-    cpx super[NCFFT / 2];   /* real post-pass twiddles */
+    int ncfft;                  /* runtime length (fft_size / 2), as kiss_fftr_alloc(nfft) stores it */
+    cpx tw[NCFFT_MAX];          /* exp(-2*pi*i*k/ncfft), Q15, floor(.5 + 32767*x) */
+    cpx super[NCFFT_MAX / 2];   /* real post-pass twiddles */
     int factors[16];
 };
 
@@ -93,7 +100,9 @@ static void kf_factor(int n, int *fac) {
     } while (n > 1);
 }
 
-static void kf_init(struct kf_state *st) {
+static void kf_init(struct kf_state *st, int ncfft) {
+    const int NCFFT = ncfft;
+    st->ncfft = ncfft;
     const double pi = 3.141592653589793238462643383279502884197169399375105820974944;
     for (int i = 0; i < NCFFT; ++i) {
         double phase = -2.0 * pi * i / NCFFT;
@@ -161,13 +170,14 @@ static void kf_work(cpx *Fout, const cpx *f, size_t fstride, const int *factors,
     switch (p) {
         case 2: kf_bfly2(Fout, fstride, st, m); break;
         case 4: kf_bfly4(Fout, fstride, st, (size_t)m); break;
-        default: abort(); /* 256 = 4*4*4*4; other radices never occur for this configuration */
+        default: abort(); /* power-of-two lengths only (256 = 4*4*4*4, 16 = 4*4): radix 3/5/generic never occur */
     }
 }
 
-/* kiss_fftr: 512 real int16 -> 257 complex int16 */
+/* kiss_fftr: 2*ncfft real int16 -> ncfft+1 complex int16 (512 -> 257 for okay_nabu) */
 static void kf_fftr(const struct kf_state *st, const int16_t *timedata, cpx *freq) {
-    cpx tmp[NCFFT];
+    const int NCFFT = st->ncfft;
+    cpx tmp[NCFFT_MAX];
     kf_work(tmp, (const cpx *)timedata, 1, st->factors, st);
 
     cpx tdc = tmp[0];
@@ -194,10 +204,9 @@ static void kf_fftr(const struct kf_state *st, const int16_t *timedata, cpx *fre
 /* ------------------------------------------------------------------------- */
 /* frontend state                                                            */
 
-#define WIN 480
-#define STEP 160
-#define FFT_N 512
-#define NCH MWWO_NUM_CHANNELS
+#define WIN_MAX 512
+#define FFT_MAX 512
+#define NCH_MAX MWWO_NUM_CHANNELS
 #define WINDOW_BITS 12
 #define FB_BITS 12
 #define NR_BITS 14
@@ -210,25 +219,29 @@ static void kf_fftr(const struct kf_state *st, const int16_t *timedata, cpx *fre
 #define LOG_COEFF 45426
 
 struct mwwo_frontend {
+    /* configuration (upstream FrontendConfig): runtime values so that the upstream library's own unit-test
+     * configuration (1 kHz, 25 ms window, 2 channels) runs through exactly the code the okay_nabu one does */
+    int sample_rate, win, step, fft_n, nch;
+    float lower_hz, upper_hz;
     /* window */
-    int16_t coef[WIN];
-    int16_t input[WIN];
+    int16_t coef[WIN_MAX];
+    int16_t input[WIN_MAX];
     size_t input_used;
-    int16_t win_out[WIN];
+    int16_t win_out[WIN_MAX];
     int16_t max_abs;
     /* fft */
     struct kf_state kf;
-    int16_t fft_in[FFT_N];
-    cpx fft_out[FFT_N / 2 + 1];
+    int16_t fft_in[FFT_MAX];
+    cpx fft_out[FFT_MAX / 2 + 1];
     /* filterbank (kept in "logical" form: per-bin weight + owning channel) */
     int start_index, end_index;
-    int16_t bin_channel[FFT_N / 2 + 1];   /* channel (0..40) whose range the bin falls in, -1 outside */
-    int16_t bin_weight[FFT_N / 2 + 1];
-    int16_t bin_unweight[FFT_N / 2 + 1];
-    int16_t chan_start[NCH + 2];          /* first bin of each of the 41 ranges, + sentinel */
-    uint64_t work[NCH + 1];
+    int16_t bin_channel[FFT_MAX / 2 + 1];   /* channel (0..nch) whose range the bin falls in, -1 outside */
+    int16_t bin_weight[FFT_MAX / 2 + 1];
+    int16_t bin_unweight[FFT_MAX / 2 + 1];
+    int16_t chan_start[NCH_MAX + 2];        /* first bin of each of the nch+1 ranges, + sentinel */
+    uint64_t work[NCH_MAX + 1];
     /* noise reduction */
-    uint32_t estimate[NCH];
+    uint32_t estimate[NCH_MAX];
     uint16_t even_smoothing, odd_smoothing, min_signal_remaining;
     int smoothing_bits;
     /* pcan */
@@ -240,16 +253,17 @@ struct mwwo_frontend {
     int correction_bits;
     /* taps for stage-level tests */
     int last_shift;
-    uint32_t last_energy[FFT_N / 2 + 1];
-    uint64_t last_work[NCH + 1];
-    uint32_t last_sqrt[NCH];
-    uint32_t last_nr[NCH];
-    uint32_t last_pcan[NCH];
+    uint32_t last_energy[FFT_MAX / 2 + 1];
+    uint64_t last_work[NCH_MAX + 1];
+    uint32_t last_sqrt[NCH_MAX];
+    uint32_t last_nr[NCH_MAX];
+    uint32_t last_pcan[NCH_MAX];
 };
 
 static float freq_to_mel(float freq) { return 1127.0 * log1p(freq / 700.0); }
 
 static void build_window(struct mwwo_frontend *s) {
+    const int WIN = s->win;
     const float arg = M_PI * 2.0 / ((float)WIN);
     for (int i = 0; i < WIN; ++i) {
         float v = 0.5 - (0.5 * cos(arg * (i + 0.5)));
@@ -258,17 +272,17 @@ static void build_window(struct mwwo_frontend *s) {
 }
 
 static int build_filterbank(struct mwwo_frontend *s) {
-    const int nch1 = NCH + 1;
-    const int spectrum = FFT_N / 2 + 1;
-    float center[NCH + 1];
-    const float lower = 125.0f, upper = 7500.0f;
+    const int nch1 = s->nch + 1;
+    const int spectrum = s->fft_n / 2 + 1;
+    float center[NCH_MAX + 1];
+    const float lower = s->lower_hz, upper = s->upper_hz;
     const float mel_low = freq_to_mel(lower);
     const float mel_hi = freq_to_mel(upper);
     const float mel_span = mel_hi - mel_low;
     const float mel_spacing = mel_span / ((float)nch1);
     for (int i = 0; i < nch1; ++i) center[i] = mel_low + (mel_spacing * (i + 1));
 
-    const float hz_per_sbin = 0.5 * 16000 / ((float)spectrum - 1);
+    const float hz_per_sbin = 0.5 * s->sample_rate / ((float)spectrum - 1);
     s->start_index = 1.5 + lower / hz_per_sbin;
     s->end_index = 0;
     for (int b = 0; b < spectrum; ++b) { s->bin_channel[b] = -1; s->bin_weight[b] = s->bin_unweight[b] = 0; }
@@ -276,7 +290,7 @@ static int build_filterbank(struct mwwo_frontend *s) {
     int freq_start = s->start_index;
     for (int ch = 0; ch < nch1; ++ch) {
         int f = freq_start;
-        while (freq_to_mel(f * hz_per_sbin) <= center[ch]) ++f;
+        while (f < spectrum && freq_to_mel(f * hz_per_sbin) <= center[ch]) ++f;
         s->chan_start[ch] = (int16_t)freq_start;
         const float denom = (ch == 0) ? mel_low : center[ch - 1];
         for (int b = freq_start; b < f; ++b) {
@@ -302,7 +316,7 @@ static int16_t pcan_gain_fn(int32_t input_bits, uint32_t x) {
 }
 
 static void build_pcan(struct mwwo_frontend *s) {
-    const int input_correction_bits = msb32(FFT_N) - 1 - (FB_BITS / 2);   /* 3 */
+    const int input_correction_bits = msb32((uint32_t)s->fft_n) - 1 - (FB_BITS / 2);   /* 3 for 512 */
     s->snr_shift = 21 - input_correction_bits - PCAN_SNR_BITS;            /* 6 */
     const int32_t input_bits = s->smoothing_bits - input_correction_bits; /* 7 */
     s->gain_lut[0] = pcan_gain_fn(input_bits, 0);
@@ -332,10 +346,25 @@ static void build_log_lut(struct mwwo_frontend *s) {
 }
 
 mwwo_frontend *mwwo_frontend_create(void) {
+    /* audio_utils.py:71-78: 16 kHz, 30 ms window, 10 ms step, 40 channels, 125..7500 Hz */
+    return mwwo_frontend_create_cfg(16000, 30, 10, MWWO_NUM_CHANNELS, 125.0f, 7500.0f);
+}
+
+mwwo_frontend *mwwo_frontend_create_cfg(int sample_rate, int window_ms, int step_ms, int num_channels,
+                                        float lower_hz, float upper_hz) {
     mwwo_frontend *s = (mwwo_frontend *)calloc(1, sizeof *s);
     if (!s) return NULL;
+    s->sample_rate = sample_rate;
+    s->win = window_ms * sample_rate / 1000;      /* upstream WindowPopulateState */
+    s->step = step_ms * sample_rate / 1000;
+    s->nch = num_channels;
+    s->lower_hz = lower_hz; s->upper_hz = upper_hz;
+    s->fft_n = 1;
+    while (s->fft_n < s->win) s->fft_n <<= 1;     /* upstream FftPopulateState: next power of two */
+    if (s->win < 2 || s->win > WIN_MAX || s->step < 1 || s->step > s->win || s->fft_n > FFT_MAX || s->fft_n < 8 ||
+        num_channels < 1 || num_channels > NCH_MAX) { free(s); return NULL; }
     build_window(s);
-    kf_init(&s->kf);
+    kf_init(&s->kf, s->fft_n / 2);
     if (!build_filterbank(s)) { free(s); return NULL; }
     s->smoothing_bits = 10;
     s->even_smoothing = (uint16_t)(0.025f * (1 << NR_BITS));
@@ -365,6 +394,7 @@ void mwwo_frontend_reset(mwwo_frontend *s) {
 /* per-frame stages                                                          */
 
 static int window_process(struct mwwo_frontend *s, const int16_t *samples, size_t n, size_t *n_read) {
+    const size_t WIN = (size_t)s->win, STEP = (size_t)s->step;
     size_t take = WIN - s->input_used;
     if (take > n) take = n;
     memcpy(s->input + s->input_used, samples, take * sizeof(int16_t));
@@ -373,7 +403,7 @@ static int window_process(struct mwwo_frontend *s, const int16_t *samples, size_
     if (s->input_used < WIN) return 0;
 
     int16_t max_abs = 0;
-    for (int i = 0; i < WIN; ++i) {
+    for (size_t i = 0; i < WIN; ++i) {
         int16_t v = (int16_t)((((int32_t)s->input[i]) * s->coef[i]) >> WINDOW_BITS);
         s->win_out[i] = v;
         if (v < 0) v = (int16_t)(-v);  /* -(-32768) wraps back to -32768 like upstream */
@@ -466,8 +496,9 @@ int mwwo_frontend_process(mwwo_frontend *s, const int16_t *samples, size_t n, si
     const int shift = 15 - msb32((uint32_t)s->max_abs);
     s->last_shift = shift;
     int i;
-    for (i = 0; i < WIN; ++i) s->fft_in[i] = (int16_t)(uint16_t)(((uint16_t)s->win_out[i]) << shift);
-    for (; i < FFT_N; ++i) s->fft_in[i] = 0;
+    const int NCH = s->nch;
+    for (i = 0; i < s->win; ++i) s->fft_in[i] = (int16_t)(uint16_t)(((uint16_t)s->win_out[i]) << shift);
+    for (; i < s->fft_n; ++i) s->fft_in[i] = 0;
     kf_fftr(&s->kf, s->fft_in, s->fft_out);
 
     /* energy of the bins the filterbank touches */
@@ -492,7 +523,7 @@ int mwwo_frontend_process(mwwo_frontend *s, const int16_t *samples, size_t n, si
     }
     memcpy(s->last_work, s->work, sizeof s->work);
 
-    uint32_t sig[NCH];
+    uint32_t sig[NCH_MAX];
     for (int ch = 0; ch < NCH; ++ch) {
         sig[ch] = sqrt64(s->work[ch + 1]) >> shift;
         s->last_sqrt[ch] = sig[ch];
@@ -539,13 +570,14 @@ size_t mwwo_generate_features(const int16_t *audio, size_t n_samples, uint16_t *
     size_t rows = 0;
     size_t idx = 0;                       /* byte index, as in the reference loop */
     const size_t n_bytes = n_samples * 2;
-    uint16_t feat[NCH];
+    const size_t NCH = (size_t)s->nch;
+    uint16_t feat[NCH_MAX];
     while (idx + 160 * 2 < n_bytes) {     /* strict '<' : audio_utils.py:56 */
         size_t n_read = 0;
         int got = mwwo_frontend_process(s, audio + idx / 2, 160, &n_read, feat);
         idx += n_read * 2;
         if (got) {
-            if (rows < max_rows) memcpy(out + rows * NCH, feat, sizeof feat);
+            if (rows < max_rows) memcpy(out + rows * NCH, feat, NCH * sizeof(uint16_t));
             ++rows;
         }
     }
@@ -556,14 +588,15 @@ size_t mwwo_generate_features(const int16_t *audio, size_t n_samples, uint16_t *
 /* stream variant: state persists in `s`; audio fed in 160-sample hops (any remainder is fed too) */
 size_t mwwo_frontend_stream(mwwo_frontend *s, const int16_t *audio, size_t n_samples, uint16_t *out, size_t max_rows) {
     size_t rows = 0, pos = 0;
-    uint16_t feat[NCH];
+    const size_t NCH = (size_t)s->nch, HOP = (size_t)s->step;
+    uint16_t feat[NCH_MAX];
     while (pos < n_samples) {
-        size_t n = n_samples - pos; if (n > 160) n = 160;
+        size_t n = n_samples - pos; if (n > HOP) n = HOP;
         size_t n_read = 0;
         int got = mwwo_frontend_process(s, audio + pos, n, &n_read, feat);
         pos += n_read;
         if (got) {
-            if (rows < max_rows) memcpy(out + rows * NCH, feat, sizeof feat);
+            if (rows < max_rows) memcpy(out + rows * NCH, feat, NCH * sizeof(uint16_t));
             ++rows;
         }
     }
@@ -606,6 +639,17 @@ void mwwo_frontend_taps(const mwwo_frontend *s, int32_t *shift, int16_t *fft_in5
     if (nr40) memcpy(nr40, s->last_nr, sizeof s->last_nr);
     if (pcan40) memcpy(pcan40, s->last_pcan, sizeof s->last_pcan);
     if (estimate40) memcpy(estimate40, s->estimate, sizeof s->estimate);
+}
+
+/* runtime sizes: {sample_rate, window, step, fft_size, num_channels, start_index, end_index, 0} */
+void mwwo_frontend_config(const mwwo_frontend *s, int32_t *cfg8) {
+    cfg8[0] = s->sample_rate; cfg8[1] = s->win; cfg8[2] = s->step; cfg8[3] = s->fft_n;
+    cfg8[4] = s->nch; cfg8[5] = s->start_index; cfg8[6] = s->end_index; cfg8[7] = 0;
+}
+/* windowed frame of the last produced row (upstream WindowState.output) and its max |value| */
+void mwwo_frontend_window_tap(const mwwo_frontend *s, int16_t *win_out512, int32_t *max_abs) {
+    if (win_out512) memcpy(win_out512, s->win_out, sizeof s->win_out);
+    if (max_abs) *max_abs = s->max_abs;
 }
 
 void mwwo_frontend_get_state(const mwwo_frontend *s, int16_t *input480, int32_t *input_used, uint32_t *estimate40) {

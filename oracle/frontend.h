@@ -13,7 +13,12 @@ extern "C" {
 
 typedef struct mwwo_frontend mwwo_frontend;
 
-mwwo_frontend *mwwo_frontend_create(void);
+mwwo_frontend *mwwo_frontend_create(void);   /* the okay_nabu configuration, audio_utils.py:71-78 */
+/* any upstream FrontendConfig the static buffers can hold (window <= 512 samples, <= 40 channels); the noise
+ * reduction / PCAN / log parameters stay the ones audio_utils.py and pymicro-features use.  Exists so the upstream
+ * library's own unit-test configuration (1 kHz, 25 ms / 10 ms, 2 channels, 8..450 Hz) can pin this restatement. */
+mwwo_frontend *mwwo_frontend_create_cfg(int sample_rate, int window_ms, int step_ms, int num_channels,
+                                        float lower_hz, float upper_hz);
 void mwwo_frontend_free(mwwo_frontend *s);
 void mwwo_frontend_reset(mwwo_frontend *s);
 
@@ -34,6 +39,8 @@ void mwwo_frontend_tables(const mwwo_frontend *s, int16_t *window480, int16_t *b
 void mwwo_frontend_taps(const mwwo_frontend *s, int32_t *shift, int16_t *fft_in512, int16_t *fft_out514,
                         uint32_t *energy257, uint64_t *work41, uint32_t *sqrt40, uint32_t *nr40,
                         uint32_t *pcan40, uint32_t *estimate40);
+void mwwo_frontend_config(const mwwo_frontend *s, int32_t *cfg8);
+void mwwo_frontend_window_tap(const mwwo_frontend *s, int16_t *win_out512, int32_t *max_abs);
 void mwwo_frontend_get_state(const mwwo_frontend *s, int16_t *input480, int32_t *input_used, uint32_t *estimate40);
 
 uint32_t mwwo_sqrt64(uint64_t x);
