@@ -261,13 +261,14 @@ MWW_D void nnq_pointwise_mma(int tid, int32_t *sm, const NnWeightsI8 &W) {
     for (int ks = 0; ks < cin / 32; ++ks) {
         FragA8 a;
         load_frag_a8(d8, kPwPitch, 32 * ks, t0, lane, a);
+        // uniform three tiles per warp (the two-tile warps recompute tile 7 into a dead accumulator): no mma.sync behind
+        // a warp-dependent branch, hence no WARPSYNC / NOP wrappers (same reasoning as nn_pointwise_mma)
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
-            if (i < ntc) {
-                FragB8 b;
-                load_frag_b8(wt, kPwPitch, 32 * ks, 8 * (nt0 + i), lane, b);
-                mma_s8(c[i], a, b);
-            }
+        for (int i = 0; i < 3; ++i) {
+            FragB8 b;
+            load_frag_b8(wt, kPwPitch, 32 * ks, 8 * (nt0 + i < 8 ? nt0 + i : 7), lane, b);
+            mma_s8(c[i], a, b);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i)

@@ -26,18 +26,26 @@ nn_f32_live_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
         const long long s0 = (long long)g * kLiveStreams;
         const int n_valid = min(kLiveStreams, n_streams - (int)s0);
         float keep[4][kLiveKeep];
+        // every ring is requested from L2 two to three stages before its register loads (mww_nn_live.cuh, "L2 prefetch");
+        // at most ~9.7 KB per stream are requested-but-unread at any point of the chain
+        live_prefetch_rings<1, 2>(tid, state, s0, n_valid);
         live_build_a(tid, sm, in, s0, n_valid, keep);
         __syncthreads();
+        live_prefetch_rings<3, 3>(tid, state, s0, n_valid);
         live_write_tail(tid, state, pend, s0, n_valid, keep);
         live_first_conv_mma(tid, sm, W);
         __syncthreads();
         live_depthwise<0>(tid, sm, W, state, s0, n_valid, heads.h[0]); __syncthreads();
         live_pointwise_mma<0>(tid, sm, W); __syncthreads();
         live_depthwise<1>(tid, sm, W, state, s0, n_valid, heads.h[1]); __syncthreads();
+        live_prefetch_rings<4, 4>(tid, state, s0, n_valid);
         live_pointwise_mma<1>(tid, sm, W); __syncthreads();
         live_depthwise<2>(tid, sm, W, state, s0, n_valid, heads.h[2]); __syncthreads();
+        live_prefetch_rings<5, 5>(tid, state, s0, n_valid);
         live_pointwise_mma<2>(tid, sm, W); __syncthreads();
         live_depthwise<3>(tid, sm, W, state, s0, n_valid, heads.h[3]); __syncthreads();
+        live_prefetch_next_window(tid, state, pend, rows, rows_stream_stride_bytes, rows_are_f32 ? 480u : 240u,
+                                  (long long)(g + gridDim.x) * kLiveStreams, n_streams);
         live_pointwise_mma<3>(tid, sm, W); __syncthreads();
         live_head_partial(tid, sm, W, state, s0, n_valid, heads.h[4]);
         __syncthreads();

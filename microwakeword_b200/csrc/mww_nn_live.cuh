@@ -278,6 +278,44 @@ MWW_HD void live_canonicalise_column(float *state, long long s, int col, const L
 }
 
 #if defined(__CUDACC__)
+// ---- L2 prefetch of ring data one stage ahead (cp.async.bulk.prefetch.L2: no registers, no shared memory, no barrier) ----
+// The layer chain is serial (ring read -> depthwise -> barrier -> MMA -> barrier -> next ring read), so a CTA's ring loads
+// only ever cover one stage and their DRAM latency is exposed once per stage; with two CTAs per SM that left the kernel
+// bound by bytes in flight (NN live step).  One thread per stream asks the L2 for the NEXT stage's ring
+// (<= 5.6 KB per stream, contiguous) while the current stage computes; the later register loads hit in L2.  Look-ahead is
+// a single stage on purpose: 32 streams x 5.6 KB x 296 CTAs = 53 MB stays inside the 126 MB L2, a whole group ahead would not.
+// Addresses and sizes are multiples of 16 by construction (ring offsets 320/832/3392/6976/12608 B, stream pitch 16 704 B).
+MWW_D void l2_prefetch(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+MWW_D int live_prefetch_slot(int tid) { return (tid & 31) < 4 ? (tid >> 5) * 4 + (tid & 31) : -1; }   // 256 threads -> 32 streams
+// rings FIRST..LAST of the state (0 = first-conv ring, 1..4 = MixConv blocks, 5 = head) of this CTA's stream group;
+// T = float (fp32 model) or int8_t (int8 model: offsets 80/208/848/1744/3152 B, pitch 4 176 B -- still multiples of 16)
+template <int FIRST, int LAST, typename T>
+MWW_D void live_prefetch_rings(int tid, const T *state, long long s0, int n_valid) {
+    constexpr int lo = kStateOff[FIRST], hi = LAST == 5 ? kStateFloats : kStateOff[LAST + 1];
+    static_assert((lo * sizeof(T)) % 16 == 0 && ((hi - lo) * sizeof(T)) % 16 == 0 && (kStateFloats * sizeof(T)) % 16 == 0,
+                  "bulk prefetch granularity");
+    // UBLKPF takes its address from the uniform datapath, so the compiler serialises the active lanes (R2UR loop): four
+    // lanes of each of the 8 warps issue one request each instead of 32 lanes of one warp
+    const int sl = live_prefetch_slot(tid);
+    if (sl >= 0 && sl < n_valid) l2_prefetch(state + (size_t)(s0 + sl) * kStateFloats + lo, (unsigned)((hi - lo) * sizeof(T)));
+}
+// the next group's first-conv window: first-conv ring + block-0 ring (contiguous), pending rows, feature rows
+template <typename T>
+MWW_D void live_prefetch_next_window(int tid, const T *state, const T *pend, const void *rows, long long rows_stream_stride_bytes,
+                                     unsigned row_bytes, long long s0n, int n_streams) {
+    const int sl = live_prefetch_slot(tid);
+    if (sl < 0 || s0n + sl >= n_streams) return;
+    const size_t su = (size_t)(s0n + sl);
+    constexpr unsigned window_bytes = (unsigned)(kStateOff[2] * sizeof(T));        // first-conv ring + block-0 ring
+    static_assert(window_bytes % 16 == 0 && (2 * kNumChannels * sizeof(T)) % 16 == 0, "bulk prefetch granularity");
+    l2_prefetch(state + su * kStateFloats, window_bytes);
+    l2_prefetch(pend + su * (2 * kNumChannels), (unsigned)(2 * kNumChannels * sizeof(T)));
+    const char *rb = static_cast<const char *>(rows) + su * (size_t)rows_stream_stride_bytes;
+    if ((reinterpret_cast<uintptr_t>(rb) & 15) == 0) l2_prefetch(rb, row_bytes & ~15u);
+}
+
 // first conv on tensor cores: 8 warps = 2 stream tiles x 4 channel tiles, K = 200 (25 k-steps), B fragments from L2
 MWW_D void live_first_conv_mma(int tid, float *sm, const NnWeightsF32 &W) {
     const int warp = tid >> 5, lane = tid & 31;

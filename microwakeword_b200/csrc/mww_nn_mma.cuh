@@ -167,21 +167,26 @@ MWW_D void nn_pointwise_mma(int tid, float *sm, const NnWeightsF32 &W) {
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int q = 0; q < 4; ++q) c[i][q] = 0.f;
+    // Every warp issues THREE tiles' worth of MMAs: the warps that own only two n-tiles recompute tile 7 into a dead
+    // accumulator.  A warp-dependent tile count put each mma.sync behind a branch the compiler cannot prove uniform, and
+    // every one of them was wrapped in WARPSYNC + NOP (20 % of the instructions of this phase, ncu source view).
+    int nb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) nb[i] = 8 * (nt0 + i < 8 ? nt0 + i : 7);
 #pragma unroll 2
     for (int ks = 0; ks < cin / 8; ++ks) {
         FragA a;
         FragB b[3];
         load_frag_a_d(d, 8 * ks, t0, lane, a);
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
-            if (i < ntc) load_frag_b(wsm, kWLd, 8 * ks, 8 * (nt0 + i), lane, b[i]);
+        for (int i = 0; i < 3; ++i) load_frag_b(wsm, kWLd, 8 * ks, nb[i], lane, b[i]);
         // three independent accumulator chains interleaved: a dependent HMMA never follows its predecessor directly
 #pragma unroll
-        for (int i = 0; i < 3; ++i) if (i < ntc) mma_tf32(c[i], a.lo, b[i].hi);
+        for (int i = 0; i < 3; ++i) mma_tf32(c[i], a.lo, b[i].hi);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) if (i < ntc) mma_tf32(c[i], a.hi, b[i].lo);
+        for (int i = 0; i < 3; ++i) mma_tf32(c[i], a.hi, b[i].lo);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) if (i < ntc) mma_tf32(c[i], a.hi, b[i].hi);
+        for (int i = 0; i < 3; ++i) mma_tf32(c[i], a.hi, b[i].hi);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i)

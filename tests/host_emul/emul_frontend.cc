@@ -56,6 +56,12 @@ int emul_tables(int16_t *window480, int16_t *bin_weight257, int16_t *bin_unweigh
 }
 
 uint32_t emul_isqrt64_round(uint64_t x) { return isqrt64_round(x); }
+uint32_t emul_isqrt64_round_fast(uint64_t x) { return isqrt64_round_fast(x); }
+// first index where the FP64 fast path and the integer routine disagree, -1 if none (bulk fuzz without ctypes overhead)
+long long emul_isqrt_fast_mismatch(const uint64_t *x, long long n) {
+    for (long long i = 0; i < n; ++i) if (isqrt64_round_fast(x[i]) != isqrt64_round(x[i])) return i;
+    return -1;
+}
 
 // Mirrors mww_features(): streams advance in lockstep; returns the number of feature rows per stream.
 int emul_features(const int16_t *audio, int n_streams, int n_samples, int16_t *carry, int used, uint32_t *estimate,

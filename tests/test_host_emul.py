@@ -32,6 +32,25 @@ def test_isqrt_matches_library_rule():
     vals += [int(r) * int(r) + int(r) + int(d) for r, d in zip(rng.integers(1, 1 << 31, 5000), rng.integers(-2, 3, 5000))]
     for v in vals:
         assert L.emul_isqrt64_round(v) == O.mwwo_sqrt64(v), v
+        assert L.emul_isqrt64_round_fast(v) == O.mwwo_sqrt64(v), v
+
+
+def test_isqrt_fp64_fast_path_is_exact_below_2_48():
+    """K1 takes one IEEE double sqrt for accumulators < 2^48 (mww_frontend_dev.cuh::isqrt64_round_fast).  The only
+    inputs that could break trunc(RN(sqrt x) + 0.5) sit next to a half-integer root: x = n^2 - n and n^2 - n + 1;
+    sweep them densely up to n = 2^24 together with squares, the 32/64-bit seam of the library and random values."""
+    L, O = emul.lib(), oracle.lib()
+    rng = np.random.default_rng(1)
+    n = np.concatenate([np.arange(1, 1 << 16, dtype=np.uint64), rng.integers(1 << 16, 1 << 24, 1 << 20).astype(np.uint64),
+                        np.arange((1 << 24) - 4096, 1 << 24, dtype=np.uint64)])
+    cand = np.concatenate([n * n - n, n * n - n + 1, n * n, n * n + n, n * n + n + 1, n * n - 1,
+                           rng.integers(0, 1 << 48, 1 << 20).astype(np.uint64), rng.integers(0, 1 << 33, 1 << 18).astype(np.uint64),
+                           np.arange((1 << 32) - 70000, (1 << 32) + 70000, dtype=np.uint64),
+                           (np.uint64(1) << np.uint64(48)) - np.arange(1, 4096, dtype=np.uint64)])
+    cand = np.ascontiguousarray(cand[cand < (1 << 48)])
+    assert L.emul_isqrt_fast_mismatch(cand.ctypes.data, cand.size) == -1
+    for v in (0, 1, 2, 65535 ** 2 + 65535, 65535 ** 2 + 65536, (1 << 32) - 1, 1 << 32, (1 << 48) - 1, 1 << 48, (1 << 64) - 1):
+        assert L.emul_isqrt64_round_fast(v) == O.mwwo_sqrt64(v), v
 
 
 def test_frontend_phases_bit_exact_random_edge_and_adversarial():

@@ -104,6 +104,18 @@ def test_tflite_integer_primitives():
     assert list(q) == [-128, -127, 127, -90]     # -127.51 truncates toward zero; 166 wraps to -90
 
 
+def test_upstream_quantize_multiplier_vectors():
+    """Expected pairs of TFLite's own kernels/internal/quantization_util_test.cc
+    (QuantizeMultiplierSmallerThanOneExp / QuantizeMultiplierGreaterThanOne); upstream sources are absent here,
+    the pairs are restated from knowledge of that file and each is re-derivable as round(frexp(x) * 2^31)."""
+    want = {0.25: (1073741824, -1), 0.50 - 5e-9: (2147483627, -1), 0.50 - 1e-10: (1073741824, 0),
+            0.50: (1073741824, 0), 0.75: (1610612736, 0), 1 - 1e-9: (2147483646, 0),
+            1 + 1e-9: (1073741825, 1), 1.5: (1610612736, 1), 2.0: (1073741824, 2), 3.0: (1610612736, 2),
+            4.0: (1073741824, 3), 5.0: (1342177280, 3)}
+    for real, pair in want.items():
+        assert tuple(int(v) for v in R.quantize_multiplier(real)) == pair, real
+
+
 def test_int8_reset_state_is_zero_point(q8):
     m = R.StreamingInt8(q8)
     assert np.all(m.st_first == m.zp["in"]) and np.all(m.st_head == m.zp["p4"])
