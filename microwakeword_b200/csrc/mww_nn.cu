@@ -36,23 +36,23 @@ nn_f32_clip_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
         nn_load_features(tid, sm, in, step0, n);
         __syncthreads();
         float fc[4][4];
-        nn_first_conv_mma_a(tid, sm, W, fc);
+        nn_first_conv_mma_a(tid, sm, W, fc, n);
         __syncthreads();
-        nn_first_conv_mma_b(tid, sm, fc);
+        nn_first_conv_mma_b(tid, sm, fc, n);
         nn_stage_pw_weights<0>(tid, sm, W);          // feature planes are dead: block 0's weights land there
         nn_stage_pw_weights<1>(tid, sm, W);
         nn_wait_weights<2>();                         // first chunk: the ring-state group is complete (only the two weight groups may be in flight)
         __syncthreads();
         nn_depthwise<0>(tid, sm, W); nn_wait_weights<1>(); __syncthreads();
-        nn_pointwise_mma<0>(tid, sm, W); __syncthreads();
+        nn_pointwise_mma<0>(tid, sm, W, n); __syncthreads();
         nn_stage_pw_weights<2>(tid, sm, W);          // buffer of block 0 is free again
         nn_depthwise<1>(tid, sm, W); nn_wait_weights<1>(); __syncthreads();
-        nn_pointwise_mma<1>(tid, sm, W); __syncthreads();
+        nn_pointwise_mma<1>(tid, sm, W, n); __syncthreads();
         nn_stage_pw_weights<3>(tid, sm, W);
         nn_depthwise<2>(tid, sm, W); nn_wait_weights<1>(); __syncthreads();
-        nn_pointwise_mma<2>(tid, sm, W); __syncthreads();
+        nn_pointwise_mma<2>(tid, sm, W, n); __syncthreads();
         nn_depthwise<3>(tid, sm, W); nn_wait_weights<0>(); __syncthreads();
-        nn_pointwise_mma<3>(tid, sm, W); __syncthreads();
+        nn_pointwise_mma<3>(tid, sm, W, n); __syncthreads();
         nn_head_partial(tid, sm, W);
         __syncthreads();
         nn_head_finish(tid, sm, W, n, probs + s * probs_stream_stride + step0,

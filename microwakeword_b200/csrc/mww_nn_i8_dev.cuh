@@ -231,10 +231,11 @@ MWW_HD void nnq_pw_store_tile(int32_t *sm, const NnWeightsI8 &W, int t0, int n0,
     }
 }
 #if defined(__CUDACC__)
-MWW_D void nnq_first_conv_mma(int tid, int32_t *sm, const NnWeightsI8 &W) {
+MWW_D void nnq_first_conv_mma(int tid, int32_t *sm, const NnWeightsI8 &W, int n) {     // n: steps in this chunk (m-tiles beyond it are skipped)
     const int warp = tid >> 5, lane = tid & 31;
     if (warp >= 6) return;
     const int t0 = 16 * (warp >> 1), n0 = 16 * (warp & 1);
+    if (t0 >= n) return;
     const int8_t *a8 = nnq_bytes(sm) + kQOffA8, *w0 = nnq_bytes(sm) + kQOffW0;
     int32_t c[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
 #pragma unroll
@@ -251,10 +252,11 @@ MWW_D void nnq_first_conv_mma(int tid, int32_t *sm, const NnWeightsI8 &W) {
     nnq_fc_store_tile(sm, W, t0, n0 + 8, lane, c[1]);
 }
 template <int L>
-MWW_D void nnq_pointwise_mma(int tid, int32_t *sm, const NnWeightsI8 &W) {
+MWW_D void nnq_pointwise_mma(int tid, int32_t *sm, const NnWeightsI8 &W, int n) {
     constexpr int cin = kGeom[L].cin;
     const int warp = tid >> 5, lane = tid & 31;
     const int t0 = 16 * (warp / 3), nt0 = 3 * (warp % 3), ntc = (warp % 3) == 2 ? 2 : 3;
+    if (t0 >= n) return;
     const int8_t *d8 = nnq_bytes(sm) + kQOffD8, *wt = nnq_bytes(sm) + kQOffPw + L * 64 * kPwPitch;
     int32_t c[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
 #pragma unroll

@@ -31,16 +31,16 @@ nn_i8_clip_kernel(NnWeightsI8 W, int8_t *__restrict__ state, int8_t *__restrict_
         const int n = min(kTT, n_steps - step0);
         nnq_load_features(tid, smi, in, W, step0, n);
         __syncthreads();
-        nnq_first_conv_mma(tid, smi, W);
+        nnq_first_conv_mma(tid, smi, W, n);
         __syncthreads();
         nnq_depthwise<0>(tid, smi, W); __syncthreads();
-        nnq_pointwise_mma<0>(tid, smi, W); __syncthreads();
+        nnq_pointwise_mma<0>(tid, smi, W, n); __syncthreads();
         nnq_depthwise<1>(tid, smi, W); __syncthreads();
-        nnq_pointwise_mma<1>(tid, smi, W); __syncthreads();
+        nnq_pointwise_mma<1>(tid, smi, W, n); __syncthreads();
         nnq_depthwise<2>(tid, smi, W); __syncthreads();
-        nnq_pointwise_mma<2>(tid, smi, W); __syncthreads();
+        nnq_pointwise_mma<2>(tid, smi, W, n); __syncthreads();
         nnq_depthwise<3>(tid, smi, W); __syncthreads();
-        nnq_pointwise_mma<3>(tid, smi, W); __syncthreads();
+        nnq_pointwise_mma<3>(tid, smi, W, n); __syncthreads();
         nnq_head_partial(tid, smi, W);
         __syncthreads();
         nnq_head_finish(tid, smi, W, n, probs + s * probs_stream_stride + step0);

@@ -155,11 +155,14 @@ MWW_HD void fc_finish_tile(float *sm, int t0, int n0, int lane, const float (&c)
 // ---- device phases -----------------------------------------------------------------------------
 
 // block L's 1x1 conv on tensor cores; D[k][t] (pitch kDLd) is A, the staged weights [k][o] (pitch kWLd) are B
+// `n` = model steps in this chunk: an m-tile whose 16 rows all lie beyond n is skipped by its three warps (the last chunk
+// of a 100-step call has 28 steps: two m-tiles instead of three; the MMA phases are tensor-pipe bound, ncu math_pipe_throttle)
 template <int L>
-MWW_D void nn_pointwise_mma(int tid, float *sm, const NnWeightsF32 &W) {
+MWW_D void nn_pointwise_mma(int tid, float *sm, const NnWeightsF32 &W, int n) {
     constexpr int cin = kGeom[L].cin;
     const int warp = tid >> 5, lane = tid & 31;
     const int t0 = 16 * pw_m_tile(warp), nt0 = pw_n_first(warp), ntc = pw_n_count(warp);
+    if (t0 >= n) return;
     const float *d = sm + kXFloats;
     const float *wsm = nn_pw_weight_buffer<L>(sm);
     float c[3][4];
@@ -194,7 +197,7 @@ MWW_D void nn_pointwise_mma(int tid, float *sm, const NnWeightsF32 &W) {
 }
 
 // first conv, part a: every warp contracts its k-third for all four 8-channel tiles of its m-tile
-MWW_D void nn_first_conv_mma_a(int tid, float *sm, const NnWeightsF32 &W, float (&c)[4][4]) {
+MWW_D void nn_first_conv_mma_a(int tid, float *sm, const NnWeightsF32 &W, float (&c)[4][4], int n) {
     const int warp = tid >> 5, lane = tid & 31;
     const int t0 = 16 * fc_m_tile(warp);
     const float *feat = sm + kXFloats + kDFloats;
@@ -202,6 +205,7 @@ MWW_D void nn_first_conv_mma_a(int tid, float *sm, const NnWeightsF32 &W, float 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int q = 0; q < 4; ++q) c[i][q] = 0.f;
+    if (t0 >= n) return;
 #pragma unroll 3
     for (int ks = fc_k_begin(warp); ks < fc_k_end(warp); ++ks) {
         FragA a;
@@ -223,10 +227,11 @@ MWW_D void nn_first_conv_mma_a(int tid, float *sm, const NnWeightsF32 &W, float 
     }
 }
 // part b (after a barrier): the k-third-0 warps add the parked partial sums, ReLU, write block 0's ring buffer
-MWW_D void nn_first_conv_mma_b(int tid, float *sm, const float (&c)[4][4]) {
+MWW_D void nn_first_conv_mma_b(int tid, float *sm, const float (&c)[4][4], int n) {
     const int warp = tid >> 5, lane = tid & 31;
     if (warp % 3 != 0) return;
     const int t0 = 16 * fc_m_tile(warp);
+    if (t0 >= n) return;
 #pragma unroll
     for (int i = 0; i < 4; ++i) fc_finish_tile(sm, t0, 8 * i, lane, c[i]);
 }

@@ -24,6 +24,20 @@ def test_partition_is_contiguous_and_balanced():
         partition(4, 0)
 
 
+def test_tile_blocks_cover_every_rank_block_in_order():
+    from microwakeword_b200.sharding import tile_blocks
+    for n, w, t in ((524288, 8, 8), (11, 2, 3), (12, 2, 4), (7, 3, 2), (5, 2, 1)):
+        blocks = tile_blocks(n, w, t)
+        assert len(blocks) == t and all(len(b) == w for b in blocks)
+        for r, (start, count) in enumerate(partition(n, w)):
+            pos = start
+            for tb in blocks:                       # a rank's tiles are contiguous, in order, and tile its block exactly
+                assert tb[r][0] == pos
+                pos += tb[r][1]
+            assert pos == start + count
+    assert tile_blocks(524288, 8, 8)[3][5] == (5 * 65536 + 3 * 8192, 8192)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -32,12 +46,12 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_streams, q):
+def _worker(rank, world, port, n_streams, q, tiles=0):
     import torch
     import torch.distributed as dist
 
     import oracle
-    from microwakeword_b200.sharding import gather_probs, scatter_audio
+    from microwakeword_b200.sharding import gather_probs, scatter_audio, scatter_compute_gather
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -45,6 +59,23 @@ def _worker(rank, world, port, n_streams, q):
         audio = np.load(os.path.join(GOLDEN, "batch_audio.npy"))[:n_streams]
         blob = open(os.path.join(GOLDEN, "okay_nabu_synth_int8.mww"), "rb").read()
         full = torch.from_numpy(audio) if rank == 0 else None
+        if tiles:
+            # the pipelined ingest: tile scatters issued up front, the oracle standing in for each tile's GPU engine
+            seen = []
+
+            def compute(t, local):
+                seen.append((t, local.shape[0]))
+                _, p = oracle.run_pipeline(blob, local.numpy(), want_features=False)
+                return torch.from_numpy(p)
+
+            out = scatter_compute_gather(full, n_streams, audio.shape[1], compute, tiles=tiles, src=0)
+            start, count = partition(n_streams, world)[rank]
+            assert [t for t, _ in seen] == list(range(tiles)) and sum(c for _, c in seen) == count
+            if rank == 0:
+                q.put(out.numpy())
+            else:
+                assert out is None
+            return
         local = scatter_audio(full, n_streams, audio.shape[1], src=0)
         start, count = partition(n_streams, world)[rank]
         assert local.shape == (count, audio.shape[1]) and np.array_equal(local.numpy(), audio[start:start + count])
@@ -58,13 +89,14 @@ def _worker(rank, world, port, n_streams, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_streams", [12, 11])
-def test_two_rank_scatter_compute_gather_equals_single_process(n_streams):
+@pytest.mark.parametrize("n_streams,tiles", [(12, 0), (11, 0), (12, 3), (11, 2)])
+def test_two_rank_scatter_compute_gather_equals_single_process(n_streams, tiles):
+    """tiles = 0: one scatter, compute, gather; tiles > 0: the pipelined ingest (equal and ragged tile sizes)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_streams, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_streams, q, tiles)) for r in range(2)]
     for p in procs:
         p.start()
     got = q.get(timeout=120)
