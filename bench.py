@@ -440,7 +440,32 @@ def run_gpu(args):
         barrier()
         pp_ms = max_over_ranks(p0.elapsed_time(p1)) / sg_steps
         scatter["pipelined"] = {"value": frames_per_step_all / (pp_ms / 1e3), "unit": UNIT, "ms_per_step": pp_ms, "tiles_per_rank": sh.tiles,
-                                "note": "scatter of tile t+1 overlaps the kernels of tile t; one gather of the scores at the end"}
+                                "note": "NCCL scatter of tile t+1 overlaps the kernels of tile t; one gather of the scores at the end"}
+        # third variant: every rank pulls its tiles from rank 0's buffer with copy-engine DMA over NVLink peer access
+        # (CUDA IPC), no communication kernels; scores still come back through one NCCL gather
+        try:
+            from microwakeword_b200.sharding import PeerAudio
+            peer = PeerAudio(full, total, SAMPLES_PER_STEP, src=0, device=device)
+            for _ in range(2):
+                sh.reset()
+                gathered_q = sh.predict_clip_pulled(peer)
+            if rank == 0:
+                scatter["pulled_equals_serial"] = bool(torch.equal(gathered_q, gathered))
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            q0.record()
+            for _ in range(sg_steps):
+                sh.predict_clip_pulled(peer)
+            q1.record()
+            barrier()
+            pl_ms = max_over_ranks(q0.elapsed_time(q1)) / sg_steps
+            scatter["pulled"] = {"value": frames_per_step_all / (pl_ms / 1e3), "unit": UNIT, "ms_per_step": pl_ms, "tiles_per_rank": sh.tiles,
+                                 "note": "ranks pull their tiles from rank 0 over NVLink peer access (copy engines, CUDA IPC) while earlier tiles compute; "
+                                         "NCCL only for the per-step barrier and the gather of the scores"}
+            del peer
+        except Exception as exc:                       # CUDA IPC / peer access unavailable in this container: report, do not hide
+            scatter["pulled"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
         del full, sh
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----

@@ -105,6 +105,88 @@ def scatter_audio_tiles(audio, n_streams: int, n_samples: int, tiles: int, src: 
     return locals_, works
 
 
+class PeerAudio:
+    """The ingest rank's audio buffer mapped into every rank's address space (CUDA IPC over NVLink peer access), so that
+    a rank PULLS its tiles with copy-engine DMA (cudaMemcpyPeerAsync): no communication kernel occupies SMs on either
+    side and no send/recv rendezvous has to be co-scheduled with the compute kernels -- which is what made the NCCL
+    tile pipeline slower than the serial exchange.  One box only (the north_star's 8 x B200).
+
+        peer = PeerAudio(full_audio_or_None, n_streams, n_samples, src=0)     # once per buffer (collective)
+        probs = peer.pull_compute_gather(compute, tiles=8)                     # every step (collective)
+
+    Ordering per step: a barrier makes the ingest rank's writes to the buffer (stream-ordered before its barrier) visible
+    before any peer's copies start; the final gather of the scores is what tells the ingest rank that every peer has
+    finished reading, so it may refill the buffer after pull_compute_gather() returns on its stream."""
+
+    def __init__(self, audio_on_src, n_streams: int, n_samples: int, src: int = 0, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        self.group, self.src = group, src
+        self.n_streams, self.n_samples = n_streams, n_samples
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.rank == src:
+            if tuple(audio_on_src.shape) != (n_streams, n_samples) or audio_on_src.dtype != torch.int16 or not audio_on_src.is_cuda \
+                    or not audio_on_src.is_contiguous():
+                raise ValueError("PeerAudio: the ingest rank must pass a contiguous CUDA int16 [%d, %d]" % (n_streams, n_samples))
+            torch.cuda.current_stream().synchronize()          # the IPC handle carries no stream ordering of earlier writes
+        box = [reduce_tensor(audio_on_src) if self.rank == src else None]
+        dist.broadcast_object_list(box, src=src, group=group)
+        err = None
+        try:
+            if self.rank == src:
+                self.remote = audio_on_src
+            else:
+                rebuild, args = box[0]
+                self.remote = rebuild(*args)                    # a tensor on the ingest rank's device, readable from here
+                probe = torch.empty(16, dtype=torch.int16, device=self.device)
+                probe.copy_(self.remote.view(-1)[:16])          # peer access really works from this process
+                torch.cuda.synchronize(self.device)
+        except Exception as exc:                                # noqa: BLE001 -- reported on every rank below
+            err = exc
+        # agree on the outcome (also: nobody drops the handle before everybody has opened it)
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            raise RuntimeError("PeerAudio: CUDA IPC / peer access to the ingest rank's buffer is unavailable (%s)" % (err or "on another rank"))
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+
+    def pull_tiles(self, tiles: int):
+        """Start the DMA of this rank's tiles (in order, on a side stream); returns (locals, events)."""
+        import torch
+        import torch.distributed as dist
+
+        dist.barrier(group=self.group)                          # the buffer is complete on the ingest rank (see class docstring)
+        blocks = tile_blocks(self.n_streams, self.world, tiles)
+        cur = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_stream(cur)
+        locals_, events = [], []
+        for blk in blocks:
+            s, c = blk[self.rank]
+            local = torch.empty((c, self.n_samples), dtype=torch.int16, device=self.device)
+            with torch.cuda.stream(self.copy_stream):
+                local.copy_(self.remote[s:s + c], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            local.record_stream(self.copy_stream)
+            locals_.append(local)
+            events.append(ev)
+        return locals_, events
+
+    def pull_compute_gather(self, compute, tiles: int = 8):
+        import torch
+
+        locals_, events = self.pull_tiles(tiles)
+        cur = torch.cuda.current_stream(self.device)
+        outs = []
+        for t, (local, ev) in enumerate(zip(locals_, events)):
+            cur.wait_event(ev)
+            outs.append(compute(t, local))
+        return gather_probs(torch.cat(outs, 0), self.n_streams, dst=self.src, group=self.group)
+
+
 def scatter_compute_gather(audio_on_src, n_streams: int, n_samples: int, compute, tiles: int = 8, src: int = 0, group=None, device=None):
     """BASELINE.json configs[4] ingest pattern with the exchange hidden behind the compute: audio lives on `src`, every
     rank's block is cut into `tiles` sub-blocks, all tile scatters are issued up front and `compute(t, local_audio)`
@@ -177,3 +259,7 @@ class ShardedEngine:
 
         return scatter_compute_gather(audio_on_src, self.n_total, n_samples, lambda t, local: self.engines[t].predict_clip(local),
                                       tiles=self.tiles, src=src, group=self.group, device=torch.device("cuda", self.engine.device))
+
+    def predict_clip_pulled(self, peer: "PeerAudio"):
+        """Same result with the audio pulled over NVLink by copy engines (PeerAudio) instead of NCCL send/recv kernels."""
+        return peer.pull_compute_gather(lambda t, local: self.engines[t].predict_clip(local), tiles=self.tiles)
