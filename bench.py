@@ -460,6 +460,25 @@ def run_gpu(args):
             q1.record()
             barrier()
             pl_ms = max_over_ranks(q0.elapsed_time(q1)) / sg_steps
+            # where the time goes: the tile engines alone on resident audio, and the pull alone
+            def timed(fn, reps=3):
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    fn()
+                b.record()
+                barrier()
+                return max_over_ranks(a.elapsed_time(b)) / reps
+            tile_audio = [audio[s0_:s0_ + c_] for s0_, c_ in sh.tile_parts]
+            tiles_ms = timed(lambda: [e.predict_clip(a_) for e, a_ in zip(sh.engines, tile_audio)])
+            def pull_only():
+                loc, evs = peer.pull_tiles(sh.tiles)
+                for ev in evs:
+                    torch.cuda.current_stream().wait_event(ev)
+            pull_ms = timed(pull_only)
+            scatter["pulled_breakdown"] = {"tile_engines_compute_only_ms": tiles_ms, "pull_only_ms": pull_ms,
+                                           "pull_gbs_into_each_peer": S * SAMPLES_PER_STEP * 2 / (pull_ms / 1e3) / 1e9}
             scatter["pulled"] = {"value": frames_per_step_all / (pl_ms / 1e3), "unit": UNIT, "ms_per_step": pl_ms, "tiles_per_rank": sh.tiles,
                                  "note": "ranks pull their tiles from rank 0 over NVLink peer access (copy engines, CUDA IPC) while earlier tiles compute; "
                                          "NCCL only for the per-step barrier and the gather of the scores"}

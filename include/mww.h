@@ -148,6 +148,14 @@ int mww_profile_read(mww_t *h, double *ms4, long long *counts4);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 long long mww_launch_count(const mww_t *h);
 
+/* Stream-ordered device copy issued on the CALLER'S stream: cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, cu_stream).
+ * Used by the multi-GPU ingest (microwakeword_b200/sharding.py::PeerAudio; the north_star's "scatter stream batches"):
+ * `src` may be peer memory of another GPU of the box mapped through CUDA IPC, and because the stream belongs to the
+ * DESTINATION device the transfer is a copy-engine pull inside the caller's own context -- no communication kernel and
+ * no work in a second context on the source GPU.  The reference has no counterpart (it is single-process).
+ * Returns 0 or a negative MWW_ECUDA; no handle is involved (the message goes to mww_last_error(NULL)). */
+int mww_copy_async(void *d_dst, const void *d_src, size_t bytes, void *cu_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ EXPORTS = (
     "mww_create", "mww_destroy", "mww_last_error", "mww_get_info", "mww_reset", "mww_reset_frontend",
     "mww_features", "mww_infer_features", "mww_predict_clip", "mww_predict_clip_host",
     "mww_get_state", "mww_set_state", "mww_launch_count", "mww_profile_enable", "mww_profile_read",
-    "mww_moving_average", "mww_false_accept_counts", "mww_positive_scores",
+    "mww_moving_average", "mww_false_accept_counts", "mww_positive_scores", "mww_copy_async",
 )
 
 
@@ -90,6 +90,8 @@ def lib() -> ctypes.CDLL:
     L.mww_positive_scores.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     L.mww_launch_count.restype = ll
     L.mww_launch_count.argtypes = [vp]
+    L.mww_copy_async.restype = i32
+    L.mww_copy_async.argtypes = [vp, vp, sz, vp]
     _lib = L
     return L
 

@@ -457,6 +457,14 @@ const char *mww_last_error(const mww_t *h) { return h ? h->err.c_str() : g_creat
 
 long long mww_launch_count(const mww_t *h) { return h ? h->launches : 0; }
 
+int mww_copy_async(void *d_dst, const void *d_src, size_t bytes, void *cu_stream) {
+    if (bytes == 0) return MWW_OK;
+    if (!d_dst || !d_src) { g_create_error = "mww_copy_async: null pointer"; return MWW_EINVAL; }
+    const cudaError_t e = cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(cu_stream));
+    if (e != cudaSuccess) { g_create_error = std::string("mww_copy_async: ") + cudaGetErrorString(e); return MWW_ECUDA; }
+    return MWW_OK;
+}
+
 int mww_profile_enable(mww_t *h, int on) {
     if (!h) return MWW_EINVAL;
     h->profiling = on != 0;

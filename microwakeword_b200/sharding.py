@@ -13,6 +13,10 @@ tests that run without a GPU).
 
 from __future__ import annotations
 
+import ctypes
+
+from . import _lib
+
 
 def partition(n_streams: int, world: int):
     """Contiguous, balanced blocks: [(start, count)] * world; the first n % world ranks get one extra."""
@@ -166,10 +170,14 @@ class PeerAudio:
         for blk in blocks:
             s, c = blk[self.rank]
             local = torch.empty((c, self.n_samples), dtype=torch.int16, device=self.device)
-            with torch.cuda.stream(self.copy_stream):
-                local.copy_(self.remote[s:s + c], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.copy_stream)
+            # torch's Tensor.copy_ would issue a cross-device copy on the SOURCE device's stream, i.e. in a second context
+            # of this process on the ingest GPU, where it is time-sliced against the ingest rank's own kernels (measured:
+            # no overlap at all).  The C-ABI copy runs on this rank's stream: a pull by this GPU's copy engine.
+            if c:
+                _lib.check(None, _lib.lib().mww_copy_async(local.data_ptr(), self.remote.data_ptr() + s * self.n_samples * 2,
+                                                          c * self.n_samples * 2, ctypes.c_void_p(self.copy_stream.cuda_stream)))
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
             local.record_stream(self.copy_stream)
             locals_.append(local)
             events.append(ev)
