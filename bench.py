@@ -418,31 +418,16 @@ def run_gpu(args):
         scatter = {"value": frames_per_step_all / (sg_ms / 1e3), "unit": UNIT, "ms_per_step": sg_ms, "steps": sg_steps,
                    "nvlink_bytes_out_of_rank0_per_step": S * SAMPLES_PER_STEP * 2 * (world - 1),
                    "note": "torch.distributed scatter of int16 audio from rank 0 + gather of float32 scores to rank 0 (NCCL), serialised with compute"}
-        # the same exchange hidden behind the compute: every rank's block cut into 8 tiles (one engine each), all tile
-        # scatters issued up front, tile t computes while tiles t+1.. are still on NVLink (sharding.scatter_compute_gather)
+        # the same exchange hidden behind the compute: every rank's block is cut into 8 tiles (one engine each) and the rank
+        # PULLS tile t+1 from rank 0's buffer with copy-engine DMA over NVLink peer access (CUDA IPC) while tile t computes;
+        # no communication kernels, the scores come back through one NCCL gather.  (Pipelining the NCCL scatter itself over
+        # the same tiles was measured too: 52 - 215 ms per step at N = 2, slower than the serial exchange -- its send/recv
+        # kernels have to be co-scheduled with saturating compute grids on both GPUs)
         from microwakeword_b200.sharding import ShardedEngine
         eng.reset()                                     # one serial pass from the reset state as the comparison value
         local = scatter_audio(full, total, SAMPLES_PER_STEP, src=0, device=device)
         gathered = gather_probs(eng.predict_clip(local, out=probs), total, dst=0)
         sh = ShardedEngine(model_blob(args.model), total, local_rank, tiles=8)
-        for _ in range(2):
-            sh.reset()
-            gathered_p = sh.predict_clip_scattered(full, SAMPLES_PER_STEP, src=0)
-        if rank == 0:                                   # pipelined ingest == serial ingest, bit for bit
-            scatter["pipelined_equals_serial"] = bool(torch.equal(gathered_p, gathered))
-        barrier()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        p0.record()
-        for _ in range(sg_steps):
-            sh.predict_clip_scattered(full, SAMPLES_PER_STEP, src=0)
-        p1.record()
-        barrier()
-        pp_ms = max_over_ranks(p0.elapsed_time(p1)) / sg_steps
-        scatter["pipelined"] = {"value": frames_per_step_all / (pp_ms / 1e3), "unit": UNIT, "ms_per_step": pp_ms, "tiles_per_rank": sh.tiles,
-                                "note": "NCCL scatter of tile t+1 overlaps the kernels of tile t; one gather of the scores at the end"}
-        # third variant: every rank pulls its tiles from rank 0's buffer with copy-engine DMA over NVLink peer access
-        # (CUDA IPC), no communication kernels; scores still come back through one NCCL gather
         try:
             from microwakeword_b200.sharding import PeerAudio
             peer = PeerAudio(full, total, SAMPLES_PER_STEP, src=0, device=device)

@@ -402,3 +402,35 @@ def test_nonstreaming_batch_equals_keras_nonstreaming_graph(torch_cuda):
     assert got.shape == (5,) and np.abs(got - want).max() <= F32_TOL
     with pytest.raises(ValueError):
         m.predict_nonstreaming(windows[:, :100])
+
+
+def test_tiled_ingest_pull_equals_one_engine(torch_cuda):
+    """The multi-GPU ingest path on one GPU (world size 1, NCCL): a rank's block cut into tiles, each tile pulled through
+    mww_copy_async on a side stream while the previous tile computes, scores gathered -- identical to one engine over the
+    whole block, across two consecutive calls (every tile engine carries its own streaming state)."""
+    import socket
+
+    import torch.distributed as dist
+
+    from microwakeword_b200.engine import StreamEngine
+    from microwakeword_b200.sharding import PeerAudio, ShardedEngine
+    torch = torch_cuda
+    blob = _blob("okay_nabu_synth_int8.mww")
+    audio = np.stack([synth_audio(9600, 900 + i) for i in range(13)])          # 13 streams -> ragged tiles 4,3,3,3
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        dev = torch.from_numpy(audio).cuda()
+        one = StreamEngine(blob, n_streams=13)
+        sh = ShardedEngine(blob, 13, 0, tiles=4)
+        assert [c for _, c in sh.tile_parts] == [4, 3, 3, 3]
+        peer = PeerAudio(dev, 13, 9600, src=0)
+        for _ in range(2):
+            want = one.predict_clip(dev)
+            got = sh.predict_clip_pulled(peer)
+            assert got.shape == want.shape and torch.equal(got, want)
+    finally:
+        dist.destroy_process_group()
