@@ -117,34 +117,25 @@ MWW_HD uint32_t isqrt64_round(uint64_t x) {
     return x == 0 ? 0u : r;
 }
 
-// The filterbank's accumulators are far below 2^48 (<= 28 bins x 12-bit weights x 31-bit energies), where the library's
-// rule ("round up iff remainder > root") is simply round-to-nearest of sqrt x, and a double holds x exactly.  Branch-free:
-// MUFU.RSQ64H seed (2^-22), two Newton steps on the FMA residual (the FP64 pipe is otherwise idle in K1), r = trunc(s + 0.5),
-// then ONE exact integer check makes the result independent of how well the double root was rounded:
-//     t = x - r^2;   t > r  -> r + 1;   t <= -r  -> r - 1        (R is the rounded root  <=>  R^2 - R < x <= R^2 + R)
-// which also maps x = 0 (seeded as 1) to 0.  No branches, so the three roots a lane computes per frame overlap; the
-// integer routine above needed ~70 dependent instructions per root, IEEE sqrt() a slow-path branch per call.
-MWW_HD uint32_t isqrt48_round(uint64_t x) {
+// The filterbank's accumulators are far below 2^48 (<= 28 bins x 12-bit weights x 31-bit energies), where the whole
+// rule collapses into one IEEE double square root: x is exact in a double, s = RN(sqrt x) is within 2^-30 of the
+// real root (s < 2^24), and the library's "round up iff remainder > root" is round-to-nearest of sqrt x, which never
+// ties and never comes closer than 2^-27 to a half-integer (sqrt(n^2 - n) = n - 1/2 - 1/(8n) ...), so
+// trunc(s + 0.5) is exact.  ~22 instructions (MUFU.RSQ64H + 10 FP64 ops) instead of ~70 integer ones; the FP64
+// pipe is otherwise idle in K1 (K1 23.7 -> 22.0 ms per step).  Measured and rejected: a branch-free variant (hand-written
+// RSQ64H seed + two Newton steps + an exact integer check, all of a lane's roots in one block) -- 22.9 ms: the extra
+// instructions cost more than the slow-path branch of sqrt() and the serial FP64 chains.  x >= 2^48 -- only reachable through the library's int32 view of an energy of
+// exactly 2^31 -- takes the integer routine above.
+MWW_HD uint32_t isqrt64_round_fast(uint64_t x) {
+    if (x >> 48) return isqrt64_round(x);
 #if defined(__CUDA_ARCH__)
-    const double d = fmax(__ull2double_rn(x), 1.0);
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double s = d * r;
-    const double h = 0.5 * r;
-    s = fma(fma(-s, s, d), h, s);
-    s = fma(fma(-s, s, d), h, s);
-    const uint32_t r0 = __double2uint_rz(s + 0.5);
+    const uint32_t r = __double2uint_rz(sqrt(__ull2double_rn(x)) + 0.5);
 #else
-    const uint32_t r0 = (uint32_t)(sqrt(x ? (double)x : 1.0) + 0.5);
+    const uint32_t r = (uint32_t)(sqrt((double)x) + 0.5);
 #endif
-    const int64_t t = (int64_t)x - (int64_t)((uint64_t)r0 * r0);
-    uint32_t rr = r0 + (t > (int64_t)r0 ? 1u : 0u) - (t <= -(int64_t)r0 ? 1u : 0u);
     const uint32_t cap = (x >> 32) == 0 ? 0xFFFFu : 0xFFFFFFFFu;      // the library's 32-bit fast path saturates at 0xFFFF
-    return rr > cap ? cap : rr;
+    return r > cap ? cap : r;
 }
-// any x: values >= 2^48 -- only reachable through the library's int32 view of an energy of exactly 2^31 -- take the
-// integer routine
-MWW_HD uint32_t isqrt64_round_fast(uint64_t x) { return (x >> 48) ? isqrt64_round(x) : isqrt48_round(x); }
 
 // ---------------------------------------------------------------------------------------------
 // K1 phases
@@ -356,11 +347,8 @@ MWW_HD void k1_real_energy(int tid, K1Smem &sm, const FrontendParams &P) {
 MWW_HD void k1_filterbank(int tid, K1Smem &sm, const FrontendParams &P, uint32_t *vout_frame /* [40] or nullptr */) {
     const int fl = tid >> 4, l = tid & 15;
     const int sh = sm.shift[fl];
-    uint64_t acc_s[kFbSlots];
-    int ch_s[kFbSlots];
 #pragma unroll
     for (int s = 0; s < kFbSlots; ++s) {
-        acc_s[s] = 0; ch_s[s] = -1;
         if (fb_len(s) == 0) continue;
         const FbSlot slot = P.fb_slots[l * kFbSlots + s];
         int64_t acc = 0;
@@ -373,24 +361,8 @@ MWW_HD void k1_filterbank(int tid, K1Smem &sm, const FrontendParams &P, uint32_t
             acc = mad_wide_s32((int32_t)e[2 * j], unpack_lo(cw), acc);
             acc = mad_wide_s32((int32_t)e[2 * j + 1], unpack_hi(cw), acc);
         }
-        acc_s[s] = (uint64_t)acc; ch_s[s] = slot.ch;
+        if (slot.ch >= 0 && vout_frame) vout_frame[slot.ch] = isqrt64_round_fast((uint64_t)acc) >> sh;
     }
-    // all of the lane's roots in one straight-line block (independent FP64 chains overlap); the >= 2^48 case is one
-    // never-taken branch for the whole lane instead of one per root
-    uint64_t any = 0;
-#pragma unroll
-    for (int s = 0; s < kFbSlots; ++s) any |= acc_s[s];
-    uint32_t root[kFbSlots];
-    if (any >> 48) {
-#pragma unroll
-        for (int s = 0; s < kFbSlots; ++s) root[s] = isqrt64_round(acc_s[s]);
-    } else {
-#pragma unroll
-        for (int s = 0; s < kFbSlots; ++s) root[s] = fb_len(s) ? isqrt48_round(acc_s[s]) : 0u;
-    }
-#pragma unroll
-    for (int s = 0; s < kFbSlots; ++s)
-        if (fb_len(s) && ch_s[s] >= 0 && vout_frame) vout_frame[ch_s[s]] = root[s] >> sh;
 }
 
 // ---------------------------------------------------------------------------------------------

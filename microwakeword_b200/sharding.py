@@ -136,8 +136,9 @@ class PeerAudio:
                     or not audio_on_src.is_contiguous():
                 raise ValueError("PeerAudio: the ingest rank must pass a contiguous CUDA int16 [%d, %d]" % (n_streams, n_samples))
             torch.cuda.current_stream().synchronize()          # the IPC handle carries no stream ordering of earlier writes
-        box = [reduce_tensor(audio_on_src) if self.rank == src else None]
-        dist.broadcast_object_list(box, src=src, group=group)
+        box = [reduce_tensor(audio_on_src) if self.rank == src and self.world > 1 else None]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=src, group=group)
         err = None
         try:
             if self.rank == src:

@@ -37,8 +37,6 @@ def lib():
         L.emul_isqrt64_round.argtypes = [ctypes.c_uint64]
         L.emul_isqrt64_round_fast.restype = ctypes.c_uint32
         L.emul_isqrt64_round_fast.argtypes = [ctypes.c_uint64]
-        L.emul_isqrt_fix.restype = ctypes.c_uint32
-        L.emul_isqrt_fix.argtypes = [ctypes.c_uint64, ctypes.c_uint32]
         L.emul_isqrt_fast_mismatch.restype = ctypes.c_longlong
         L.emul_isqrt_fast_mismatch.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
         _lib = L

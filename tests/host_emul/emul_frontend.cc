@@ -57,11 +57,6 @@ int emul_tables(int16_t *window480, int16_t *bin_weight257, int16_t *bin_unweigh
 
 uint32_t emul_isqrt64_round(uint64_t x) { return isqrt64_round(x); }
 uint32_t emul_isqrt64_round_fast(uint64_t x) { return isqrt64_round_fast(x); }
-// the integer verification step alone, fed a deliberately wrong (+-1) candidate: returns the corrected root
-uint32_t emul_isqrt_fix(uint64_t x, uint32_t r0) {
-    const int64_t t = (int64_t)x - (int64_t)((uint64_t)r0 * r0);
-    return r0 + (t > (int64_t)r0 ? 1u : 0u) - (t <= -(int64_t)r0 ? 1u : 0u);
-}
 // first index where the FP64 fast path and the integer routine disagree, -1 if none (bulk fuzz without ctypes overhead)
 long long emul_isqrt_fast_mismatch(const uint64_t *x, long long n) {
     for (long long i = 0; i < n; ++i) if (isqrt64_round_fast(x[i]) != isqrt64_round(x[i])) return i;
