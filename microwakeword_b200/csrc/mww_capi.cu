@@ -632,9 +632,11 @@ int mww_predict_clip_host(mww_t *h, const int16_t *h_audio, int n_samples, long 
             CU(h, cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming));
         }
     }
-    // tile so that copies and kernels of neighbouring tiles overlap: at least 8 tiles when there are enough streams
+    // tile so that copies and kernels of neighbouring tiles overlap: at least 16 tiles when there are enough streams (the
+    // last tile's kernels are the only part of the compute the host->device stream cannot hide), but never fewer than
+    // 2 048 streams per tile so that every launch still fills the GPU
     int tile = tile_streams(h, n_frames, true);
-    tile = std::max(1, std::min(tile, (h->n_streams + 7) / 8));
+    tile = std::max(1, std::min(tile, std::max((h->n_streams + 15) / 16, std::min(h->n_streams, 2048))));
     int rc = ensure_scratch(h, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 2);
     if (rc) return rc;
     const size_t a_bytes = (size_t)tile * std::max(n_samples, 1) * sizeof(int16_t);
