@@ -69,9 +69,18 @@ struct mww_handle {
     // per-stream state
     int16_t *d_carry = nullptr;
     uint32_t *d_estimate = nullptr;
-    void *d_nn_state = nullptr;     // float or int8 [S][4176]
-    void *d_pend = nullptr;         // float or int8 [S][2][40]
+    void *d_nn_state = nullptr;     // float or int8 [S][state_elems]   (4176 for okay_nabu)
+    void *d_pend = nullptr;         // float or int8 [S][pend_cap][40]  (2 rows for stride 3)
     int used = 0, n_pend = 0;
+    // geometry: the compiled-in okay_nabu kernels, or the run-time-geometry path (mww_nn_generic.cuh) for any other arch
+    bool generic = false;
+    GenArch G{};
+    GenWeightsF32 GW{};
+    GenWeightsI8 GQ{};
+    int stride = 3;                 // feature rows per model step
+    int pend_cap = 2;               // rows of the pending buffer
+    int state_elems = kStateFloats; // ring-state elements per stream
+    long long macs_per_step = 24800;
     // scratch
     uint32_t *d_v = nullptr; size_t v_bytes = 0;
     uint16_t *d_feat = nullptr; size_t feat_bytes = 0;
@@ -184,7 +193,7 @@ int run_carry_tile(mww_t *h, int first, int n, const int16_t *d_audio, long long
 }
 
 // one model step per stream -> the stream-parallel live-step kernels (fp32: mww_nn_live.cuh, int8: mww_nn_i8_live.cuh)
-bool use_live(const mww_t *h, int n_rows) { return h->has_nn && n_rows == 3 && !h->no_live; }
+bool use_live(const mww_t *h, int n_rows) { return h->has_nn && !h->generic && n_rows == 3 && !h->no_live; }
 
 // rotate every ring back to the canonical layout before anything that assumes it (clip kernels, mww_get_state)
 int canonicalise_rings(mww_t *h, cudaStream_t st) {
@@ -207,21 +216,38 @@ void end_nn_call(mww_t *h, int n_rows) {
 int run_nn_tile(mww_t *h, int first, int n, const void *d_rows, int row_type, long long rows_stream_stride_rows, int n_rows,
                 float *d_probs, long long probs_stride, cudaStream_t st) {
     ProfScope p(h, 2, st);
+    if (h->generic) {
+        // any architecture other than the compiled-in one: run-time-geometry kernels (mww_nn_generic.cuh)
+        if (row_type != MWW_ROWS_F32 && row_type != MWW_ROWS_U16 && row_type != MWW_ROWS_I8) return fail(h, MWW_EINVAL, "unknown row_type");
+        if (row_type == MWW_ROWS_I8 && !h->quantized) return fail(h, MWW_EINVAL, "int8 rows need a quantised model (inference.py:110)");
+        const size_t rb = row_type == MWW_ROWS_F32 ? 4 : (row_type == MWW_ROWS_U16 ? 2 : 1);
+        const int rt = row_type == MWW_ROWS_U16 ? 0 : (row_type == MWW_ROWS_F32 ? 1 : 2);
+        if (h->quantized)
+            CU(h, launch_nn_generic_i8(h->G, h->GQ, static_cast<int8_t *>(h->d_nn_state) + (size_t)first * h->state_elems,
+                                       static_cast<int8_t *>(h->d_pend) + (size_t)first * h->pend_cap * kNumChannels, h->n_pend, d_rows,
+                                       rows_stream_stride_rows * kNumChannels * (long long)rb, n_rows, rt, d_probs, probs_stride, n, st));
+        else
+            CU(h, launch_nn_generic_f32(h->G, h->GW, static_cast<float *>(h->d_nn_state) + (size_t)first * h->state_elems,
+                                        static_cast<float *>(h->d_pend) + (size_t)first * h->pend_cap * kNumChannels, h->n_pend, d_rows,
+                                        rows_stream_stride_rows * kNumChannels * (long long)rb, n_rows, rt, d_probs, probs_stride, n, st));
+        h->launches += 1;
+        return MWW_OK;
+    }
     if (h->quantized) {
         if (row_type == MWW_ROWS_F32 || row_type == MWW_ROWS_U16 || row_type == MWW_ROWS_I8) {
             const size_t rb = row_type == MWW_ROWS_F32 ? 4 : (row_type == MWW_ROWS_U16 ? 2 : 1);
             if (reinterpret_cast<uintptr_t>(d_rows) % 16 != 0)          // the integer kernels read rows 8 / 16 bytes at a time
                 return fail(h, MWW_EINVAL, "feature rows for an int8 model must be 16-byte aligned");
             if (use_live(h, n_rows)) {
-                CU(h, launch_nn_i8_live(h->Wq, static_cast<int8_t *>(h->d_nn_state) + (size_t)first * kStateFloats,
-                                        static_cast<int8_t *>(h->d_pend) + (size_t)first * 2 * kNumChannels, h->n_pend, d_rows,
+                CU(h, launch_nn_i8_live(h->Wq, static_cast<int8_t *>(h->d_nn_state) + (size_t)first * h->state_elems,
+                                        static_cast<int8_t *>(h->d_pend) + (size_t)first * h->pend_cap * kNumChannels, h->n_pend, d_rows,
                                         rows_stream_stride_rows * kNumChannels * (long long)rb, row_type, d_probs, probs_stride, n,
                                         h->live_heads, h->sm_count, st));
                 h->launches += 1;
                 return MWW_OK;
             }
-            CU(h, launch_nn_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state) + (size_t)first * kStateFloats,
-                               static_cast<int8_t *>(h->d_pend) + (size_t)first * 2 * kNumChannels, h->n_pend, d_rows,
+            CU(h, launch_nn_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state) + (size_t)first * h->state_elems,
+                               static_cast<int8_t *>(h->d_pend) + (size_t)first * h->pend_cap * kNumChannels, h->n_pend, d_rows,
                                rows_stream_stride_rows * kNumChannels * (long long)rb, n_rows, row_type, d_probs, probs_stride, n, st));
             h->launches += 1;
             return MWW_OK;
@@ -232,15 +258,15 @@ int run_nn_tile(mww_t *h, int first, int n, const void *d_rows, int row_type, lo
     const size_t rb = row_type == MWW_ROWS_F32 ? 4 : 2;
     if (use_live(h, n_rows)) {
         // exactly one model step per stream: the stream-parallel live-step kernel (HBM-bound on the ring state)
-        CU(h, launch_nn_f32_live(h->W, static_cast<float *>(h->d_nn_state) + (size_t)first * kStateFloats,
-                                 static_cast<float *>(h->d_pend) + (size_t)first * 2 * kNumChannels, h->n_pend, d_rows,
+        CU(h, launch_nn_f32_live(h->W, static_cast<float *>(h->d_nn_state) + (size_t)first * h->state_elems,
+                                 static_cast<float *>(h->d_pend) + (size_t)first * h->pend_cap * kNumChannels, h->n_pend, d_rows,
                                  rows_stream_stride_rows * kNumChannels * (long long)rb, row_type == MWW_ROWS_F32, d_probs, probs_stride, n,
                                  h->live_heads, h->sm_count, st));
         h->launches += 1;
         return MWW_OK;
     }
-    CU(h, launch_nn_f32(h->W, static_cast<float *>(h->d_nn_state) + (size_t)first * kStateFloats,
-                        static_cast<float *>(h->d_pend) + (size_t)first * 2 * kNumChannels, h->n_pend, d_rows,
+    CU(h, launch_nn_f32(h->W, static_cast<float *>(h->d_nn_state) + (size_t)first * h->state_elems,
+                        static_cast<float *>(h->d_pend) + (size_t)first * h->pend_cap * kNumChannels, h->n_pend, d_rows,
                         rows_stream_stride_rows * kNumChannels * (long long)rb, n_rows, row_type == MWW_ROWS_F32, d_probs, probs_stride,
                         nullptr, n, st));
     h->launches += 1;
@@ -282,13 +308,98 @@ int upload_tables(mww_t *h) {
 
 struct Need { const char *name; uint32_t dtype; size_t count; };
 
+// weights of an architecture other than the compiled-in one (tensor names and layouts: microwakeword_b200/model_file.py,
+// the same names the CPU checker reads)
+int upload_weights_generic(mww_t *h, const uint8_t *blob, size_t n, const Tensor &arch) {
+    GenArch &G = h->G;
+    const int rc_arch = gen_arch_from_tensor(reinterpret_cast<const int32_t *>(arch.data), (int)(arch.nbytes / 4), &G);
+    if (rc_arch == -1) return fail(h, MWW_EMODEL, "model container: malformed 'arch' tensor");
+    if (rc_arch != 0 || (size_t)G.sm_elems * 4 > 200 * 1024)
+        return fail(h, MWW_EUNSUPPORTED, "model container: architecture outside the supported range (first_conv_kernel_size >= stride, <= 8 blocks, "
+                                         "<= 512 channels, kernels <= 64 taps, ring buffers of one stream within 200 KB)");
+    Tensor probe;
+    h->quantized = find_tensor(blob, n, "q/scales", &probe);
+    h->generic = true;
+    h->stride = G.stride; h->pend_cap = G.pend_cap; h->state_elems = G.state_elems; h->macs_per_step = G.macs_per_step;
+    size_t total = 1 << 16;                          // room for alignment padding; tensors are added below
+    {
+        uint32_t hdr[4];
+        memcpy(hdr, blob + 8, 16);
+        total += n + (size_t)hdr[1] * 256;
+    }
+    CU(h, cudaMalloc(&h->d_weights, total));
+    size_t cur = 0;
+    cudaError_t e = cudaSuccess;
+    char name[64];
+    auto get = [&](const char *nm, uint32_t dtype, size_t count, const void **dev) -> int {
+        Tensor t;
+        static const size_t esz[6] = {4, 1, 4, 1, 2, 2};
+        if (!find_tensor(blob, n, nm, &t)) return fail(h, MWW_EMODEL, std::string("model container: missing tensor ") + nm);
+        if (t.dtype != dtype || t.nbytes != count * esz[dtype]) return fail(h, MWW_EMODEL, std::string("model container: wrong dtype/size for ") + nm);
+        if (cur + t.nbytes + 256 > total) return fail(h, MWW_EMODEL, "model container: tensors larger than the container");
+        if (!upload(h->d_weights, cur, t.data, (size_t)t.nbytes, reinterpret_cast<const uint8_t **>(dev), &e)) return cuda_fail(h, e, "weight upload");
+        return MWW_OK;
+    };
+    auto scalar = [&](const char *nm, int32_t *out) -> int {
+        Tensor t;
+        if (!find_tensor(blob, n, nm, &t) || t.nbytes != 4) return fail(h, MWW_EMODEL, std::string("model container: ") + nm);
+        memcpy(out, t.data, 4);
+        return MWW_OK;
+    };
+    int rc;
+    const size_t k0f = (size_t)G.k0 * kNumChannels * G.c0;
+    if (!h->quantized) {
+        GenWeightsF32 &W = h->GW;
+        if ((rc = get("first_conv/w", 0, k0f, (const void **)&W.w0))) return rc;
+        for (int i = 0; i < G.n_blocks; ++i) {
+            snprintf(name, sizeof name, "b%d/dw/w", i); if ((rc = get(name, 0, (size_t)G.kmax[i] * G.cin[i], (const void **)&W.dw_w[i]))) return rc;
+            snprintf(name, sizeof name, "b%d/dw/b", i); if ((rc = get(name, 0, G.cin[i], (const void **)&W.dw_b[i]))) return rc;
+            snprintf(name, sizeof name, "b%d/pw/w", i); if ((rc = get(name, 0, (size_t)G.cin[i] * G.cout[i], (const void **)&W.pw_w[i]))) return rc;
+            snprintf(name, sizeof name, "b%d/pw/b", i); if ((rc = get(name, 0, G.cout[i], (const void **)&W.pw_b[i]))) return rc;
+        }
+        if ((rc = get("head/w", 0, (size_t)G.head_rows * G.c_last, (const void **)&W.head_w))) return rc;
+        if ((rc = get("head/b", 0, 1, (const void **)&W.head_b))) return rc;
+        return MWW_OK;
+    }
+    GenWeightsI8 &Q = h->GQ;
+    if ((rc = get("q/first_conv/w", 1, k0f, (const void **)&Q.w0))) return rc;
+    if ((rc = get("q/first_conv/bias", 2, G.c0, (const void **)&Q.b0))) return rc;
+    if ((rc = get("q/first_conv/mult", 2, G.c0, (const void **)&Q.m0))) return rc;
+    if ((rc = get("q/first_conv/shift", 2, G.c0, (const void **)&Q.s0))) return rc;
+    for (int i = 0; i < G.n_blocks; ++i) {
+        snprintf(name, sizeof name, "q/b%d/dw/w", i); if ((rc = get(name, 1, (size_t)G.kmax[i] * G.cin[i], (const void **)&Q.dw_w[i]))) return rc;
+        snprintf(name, sizeof name, "q/b%d/dw/bias", i); if ((rc = get(name, 2, G.cin[i], (const void **)&Q.dw_b[i]))) return rc;
+        snprintf(name, sizeof name, "q/b%d/dw/mult", i); if ((rc = get(name, 2, G.cin[i], (const void **)&Q.dw_m[i]))) return rc;
+        snprintf(name, sizeof name, "q/b%d/dw/shift", i); if ((rc = get(name, 2, G.cin[i], (const void **)&Q.dw_s[i]))) return rc;
+        snprintf(name, sizeof name, "q/b%d/pw/w", i); if ((rc = get(name, 1, (size_t)G.cin[i] * G.cout[i], (const void **)&Q.pw_w[i]))) return rc;
+        snprintf(name, sizeof name, "q/b%d/pw/bias", i); if ((rc = get(name, 2, G.cout[i], (const void **)&Q.pw_b[i]))) return rc;
+        snprintf(name, sizeof name, "q/b%d/pw/mult", i); if ((rc = get(name, 2, G.cout[i], (const void **)&Q.pw_m[i]))) return rc;
+        snprintf(name, sizeof name, "q/b%d/pw/shift", i); if ((rc = get(name, 2, G.cout[i], (const void **)&Q.pw_s[i]))) return rc;
+    }
+    if ((rc = get("q/head/w", 1, (size_t)G.head_rows * G.c_last, (const void **)&Q.head_w))) return rc;
+    if ((rc = get("q/logistic_lut", 1, 256, (const void **)&Q.lut))) return rc;
+    if ((rc = scalar("q/head/bias", &Q.head_bias)) || (rc = scalar("q/head/mult", &Q.head_mult)) || (rc = scalar("q/head/shift", &Q.head_shift))) return rc;
+    const size_t n_q = 4 + 2 * (size_t)G.n_blocks;       // in, first conv, (depthwise, pointwise) per block, logit, prob
+    Tensor sc, zp;
+    if (!find_tensor(blob, n, "q/scales", &sc) || sc.nbytes != n_q * 4 || !find_tensor(blob, n, "q/zps", &zp) || zp.nbytes != n_q * 4)
+        return fail(h, MWW_EMODEL, "model container: q/scales / q/zps must hold 4 + 2 * n_blocks entries");
+    std::vector<float> scales(n_q);
+    memcpy(scales.data(), sc.data, n_q * 4);
+    memcpy(Q.zp, zp.data, n_q * 4);
+    Q.in_scale = scales[0];
+    h->in_scale = scales[0]; h->in_zp = Q.zp[0];
+    h->out_scale = scales[n_q - 1]; h->out_zp = 0;      // uint8 output tensor: zero point -128 + 128 (utils.py:338)
+    return MWW_OK;
+}
+
 int upload_weights(mww_t *h, const uint8_t *blob, size_t n) {
     Tensor arch;
     if (!find_tensor(blob, n, "arch", &arch) || arch.dtype != 2) return fail(h, MWW_EMODEL, "model container: missing 'arch' tensor or bad magic/version");
-    if (arch.nbytes != sizeof kOkayNabuArch || memcmp(arch.data, kOkayNabuArch, sizeof kOkayNabuArch) != 0)
-        return fail(h, MWW_EUNSUPPORTED,
-                    "this build is compiled for the okay_nabu MixedNet (first conv 32x5 stride 3; MixConv [5],[7,11],[9,15],[23]; "
-                    "pointwise 64x4; 17-row head); the container describes another architecture");
+    // the tensor-core kernels are compiled for the okay_nabu MixedNet (first conv 32x5 stride 3; MixConv [5],[7,11],[9,15],[23];
+    // pointwise 64x4; 17-row head); every other architecture takes the run-time-geometry path.  MWW_FORCE_GENERIC=1 sends
+    // okay_nabu through it as well (tests compare the two paths).
+    if (arch.nbytes != sizeof kOkayNabuArch || memcmp(arch.data, kOkayNabuArch, sizeof kOkayNabuArch) != 0 || getenv("MWW_FORCE_GENERIC") != nullptr)
+        return upload_weights_generic(h, blob, n, arch);
     Tensor probe;
     h->quantized = find_tensor(blob, n, "q/scales", &probe);
     const size_t total = 1 << 20;
@@ -381,12 +492,15 @@ int zero_state(mww_t *h, cudaStream_t st) {
     h->used = 0;
     h->n_pend = 0;
     if (!h->has_nn) return MWW_OK;
-    if (h->quantized) {
+    if (h->quantized && h->generic) {
+        CU(h, launch_gen_fill_state_i8(h->G, h->GQ, static_cast<int8_t *>(h->d_nn_state), static_cast<int8_t *>(h->d_pend), h->n_streams, st));
+        h->launches += 1;
+    } else if (h->quantized) {
         CU(h, launch_fill_state_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state), static_cast<int8_t *>(h->d_pend), nullptr, h->n_streams, st));
         h->launches += 1;
     } else {
-        CU(h, cudaMemsetAsync(h->d_nn_state, 0, S * kStateFloats * 4, st));
-        CU(h, cudaMemsetAsync(h->d_pend, 0, S * 2 * kNumChannels * 4, st));
+        CU(h, cudaMemsetAsync(h->d_nn_state, 0, S * h->state_elems * 4, st));
+        CU(h, cudaMemsetAsync(h->d_pend, 0, S * h->pend_cap * kNumChannels * 4, st));
     }
     h->live_heads = LiveHeads{};
     h->used = 0;
@@ -440,8 +554,8 @@ int mww_create(const void *model_blob, size_t n_bytes, int device, int n_streams
         const size_t S = (size_t)n_streams;
         cudaError_t a = cudaMalloc(&h->d_carry, S * kWindow * sizeof(int16_t));
         if (a == cudaSuccess) a = cudaMalloc(&h->d_estimate, S * kNumChannels * sizeof(uint32_t));
-        if (a == cudaSuccess && h->has_nn) a = cudaMalloc(&h->d_nn_state, S * kStateFloats * elem_size(h));
-        if (a == cudaSuccess && h->has_nn) a = cudaMalloc(&h->d_pend, S * 2 * kNumChannels * elem_size(h));
+        if (a == cudaSuccess && h->has_nn) a = cudaMalloc(&h->d_nn_state, S * h->state_elems * elem_size(h));
+        if (a == cudaSuccess && h->has_nn) a = cudaMalloc(&h->d_pend, S * h->pend_cap * kNumChannels * elem_size(h));
         if (a != cudaSuccess) rc = fail(h, a == cudaErrorMemoryAllocation ? MWW_ENOMEM : MWW_ECUDA, std::string("state allocation: ") + cudaGetErrorString(a));
     }
     if (rc == MWW_OK) rc = zero_state(h, nullptr);
@@ -491,12 +605,12 @@ int mww_get_info(const mww_t *h, mww_info *o) {
     if (!h || !o) return MWW_EINVAL;
     memset(o, 0, sizeof *o);
     o->n_streams = h->n_streams; o->device = h->device; o->is_quantized = h->quantized;
-    o->input_feature_slices = 3; o->num_features = kNumChannels;
+    o->input_feature_slices = h->stride; o->num_features = kNumChannels;
     o->input_scale = h->in_scale; o->input_zero_point = h->in_zp;
     o->output_scale = h->out_scale; o->output_zero_point = h->out_zp;
-    o->state_bytes_per_stream = (int)(kStateFloats * elem_size(h));
+    o->state_bytes_per_stream = (int)(h->state_elems * elem_size(h));
     o->frontend_buffered = h->used; o->pending_rows = h->n_pend;
-    o->sm_count = h->sm_count; o->macs_per_step = 24800;
+    o->sm_count = h->sm_count; o->macs_per_step = (int)h->macs_per_step;
     return MWW_OK;
 }
 
@@ -511,13 +625,17 @@ int mww_reset(mww_t *h, const int32_t *h_ids, int n, void *cu_stream) {
         CU(h, cudaMemsetAsync(h->d_carry + (size_t)id * kWindow, 0, kWindow * sizeof(int16_t), st));
         CU(h, cudaMemsetAsync(h->d_estimate + (size_t)id * kNumChannels, 0, kNumChannels * sizeof(uint32_t), st));
         if (!h->has_nn) continue;
-        if (h->quantized) {
-            CU(h, launch_fill_state_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state) + (size_t)id * kStateFloats,
-                                       static_cast<int8_t *>(h->d_pend) + (size_t)id * 2 * kNumChannels, nullptr, 1, st));
+        if (h->quantized && h->generic) {
+            CU(h, launch_gen_fill_state_i8(h->G, h->GQ, static_cast<int8_t *>(h->d_nn_state) + (size_t)id * h->state_elems,
+                                           static_cast<int8_t *>(h->d_pend) + (size_t)id * h->pend_cap * kNumChannels, 1, st));
+            h->launches += 1;
+        } else if (h->quantized) {
+            CU(h, launch_fill_state_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state) + (size_t)id * h->state_elems,
+                                       static_cast<int8_t *>(h->d_pend) + (size_t)id * h->pend_cap * kNumChannels, nullptr, 1, st));
             h->launches += 1;
         } else {
-            CU(h, cudaMemsetAsync(static_cast<float *>(h->d_nn_state) + (size_t)id * kStateFloats, 0, kStateFloats * 4, st));
-            CU(h, cudaMemsetAsync(static_cast<float *>(h->d_pend) + (size_t)id * 2 * kNumChannels, 0, 2 * kNumChannels * 4, st));
+            CU(h, cudaMemsetAsync(static_cast<float *>(h->d_nn_state) + (size_t)id * h->state_elems, 0, (size_t)h->state_elems * 4, st));
+            CU(h, cudaMemsetAsync(static_cast<float *>(h->d_pend) + (size_t)id * h->pend_cap * kNumChannels, 0, (size_t)h->pend_cap * kNumChannels * 4, st));
         }
     }
     return MWW_OK;
@@ -567,14 +685,14 @@ int mww_infer_features(mww_t *h, const void *d_rows, int row_type, int n_rows, l
     if (row_type < 0 || row_type > 2) return fail(h, MWW_EINVAL, "mww_infer_features: unknown row_type");
     if (!h->has_nn) return fail(h, MWW_EINVAL, "mww_infer_features: frontend-only handle (created without a model)");
     CU(h, cudaSetDevice(h->device));
-    const int n_steps = (h->n_pend + n_rows) / 3;
+    const int n_steps = (h->n_pend + n_rows) / h->stride;
     if (n_steps > max_probs || (n_steps > 0 && !d_probs)) return fail(h, MWW_EINVAL, "mww_infer_features: probability buffer too small");
     int rc = begin_nn_call(h, n_rows, static_cast<cudaStream_t>(cu_stream));
     if (rc) return rc;
     rc = run_nn_tile(h, 0, h->n_streams, d_rows, row_type, rows_stride, n_rows, d_probs, max_probs, static_cast<cudaStream_t>(cu_stream));
     if (rc == MWW_OK) end_nn_call(h, n_rows);
     if (rc) return rc;
-    h->n_pend = (h->n_pend + n_rows) % 3;
+    h->n_pend = (h->n_pend + n_rows) % h->stride;
     if (h_probs_out) *h_probs_out = n_steps;
     return MWW_OK;
 }
@@ -587,7 +705,7 @@ int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long 
     CU(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(cu_stream);
     const int n_frames = frames_for(h->used, n_samples);
-    const int n_steps = (h->n_pend + n_frames) / 3;
+    const int n_steps = (h->n_pend + n_frames) / h->stride;
     if (n_steps > max_probs || (n_steps > 0 && !d_probs)) return fail(h, MWW_EINVAL, "mww_predict_clip: probability buffer too small");
     const int tile = tile_streams(h, n_frames, true);
     int rc = ensure_scratch(h, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 2);
@@ -608,7 +726,7 @@ int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long 
         if (rc) return rc;
     }
     h->used = h->used + n_samples - n_frames * kHop;
-    h->n_pend = (h->n_pend + n_frames) % 3;
+    h->n_pend = (h->n_pend + n_frames) % h->stride;
     if (h_probs_out) *h_probs_out = n_steps;
     return MWW_OK;
 }
@@ -620,7 +738,7 @@ int mww_predict_clip_host(mww_t *h, const int16_t *h_audio, int n_samples, long 
     if (!h->has_nn) return fail(h, MWW_EINVAL, "mww_predict_clip_host: frontend-only handle (created without a model)");
     CU(h, cudaSetDevice(h->device));
     const int n_frames = frames_for(h->used, n_samples);
-    const int n_steps = (h->n_pend + n_frames) / 3;
+    const int n_steps = (h->n_pend + n_frames) / h->stride;
     if (n_steps > max_probs || (n_steps > 0 && !h_probs)) return fail(h, MWW_EINVAL, "mww_predict_clip_host: probability buffer too small");
     if (!h->st_compute) {
         CU(h, cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
@@ -687,7 +805,7 @@ int mww_predict_clip_host(mww_t *h, const int16_t *h_audio, int n_samples, long 
     CU(h, cudaStreamSynchronize(h->st_compute));
     end_nn_call(h, n_frames);
     h->used = h->used + n_samples - n_frames * kHop;
-    h->n_pend = (h->n_pend + n_frames) % 3;
+    h->n_pend = (h->n_pend + n_frames) % h->stride;
     if (h_probs_out) *h_probs_out = n_steps;
     return MWW_OK;
 }
@@ -705,15 +823,15 @@ int mww_get_state(mww_t *h, int16_t *h_carry, uint32_t *h_estimate, void *h_nn, 
     if (h_carry) CU(h, cudaMemcpy(h_carry, h->d_carry, S * kWindow * 2, cudaMemcpyDeviceToHost));
     if (h_estimate) CU(h, cudaMemcpy(h_estimate, h->d_estimate, S * kNumChannels * 4, cudaMemcpyDeviceToHost));
     if ((h_nn || h_pending) && !h->has_nn) return fail(h, MWW_EINVAL, "frontend-only handle has no NN state");
-    if (h_nn) CU(h, cudaMemcpy(h_nn, h->d_nn_state, S * kStateFloats * elem_size(h), cudaMemcpyDeviceToHost));
-    if (h_pending) CU(h, cudaMemcpy(h_pending, h->d_pend, S * 2 * kNumChannels * elem_size(h), cudaMemcpyDeviceToHost));
+    if (h_nn) CU(h, cudaMemcpy(h_nn, h->d_nn_state, S * h->state_elems * elem_size(h), cudaMemcpyDeviceToHost));
+    if (h_pending) CU(h, cudaMemcpy(h_pending, h->d_pend, S * h->pend_cap * kNumChannels * elem_size(h), cudaMemcpyDeviceToHost));
     return MWW_OK;
 }
 
 int mww_set_state(mww_t *h, const int16_t *h_carry, int frontend_buffered, const uint32_t *h_estimate, const void *h_nn,
                   const void *h_pending, int pending_rows) {
     if (!h) return MWW_EINVAL;
-    if (frontend_buffered < 0 || frontend_buffered >= kWindow || pending_rows < 0 || pending_rows > 2)
+    if (frontend_buffered < 0 || frontend_buffered >= kWindow || pending_rows < 0 || pending_rows > h->stride - 1)
         return fail(h, MWW_EINVAL, "mww_set_state: counters out of range");
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaDeviceSynchronize());
@@ -722,10 +840,10 @@ int mww_set_state(mww_t *h, const int16_t *h_carry, int frontend_buffered, const
     if (h_estimate) CU(h, cudaMemcpy(h->d_estimate, h_estimate, S * kNumChannels * 4, cudaMemcpyHostToDevice));
     if ((h_nn || h_pending) && !h->has_nn) return fail(h, MWW_EINVAL, "frontend-only handle has no NN state");
     if (h_nn) {
-        CU(h, cudaMemcpy(h->d_nn_state, h_nn, S * kStateFloats * elem_size(h), cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->d_nn_state, h_nn, S * h->state_elems * elem_size(h), cudaMemcpyHostToDevice));
         h->live_heads = LiveHeads{};
     }
-    if (h_pending) CU(h, cudaMemcpy(h->d_pend, h_pending, S * 2 * kNumChannels * elem_size(h), cudaMemcpyHostToDevice));
+    if (h_pending) CU(h, cudaMemcpy(h->d_pend, h_pending, S * h->pend_cap * kNumChannels * elem_size(h), cudaMemcpyHostToDevice));
     h->used = frontend_buffered;
     h->n_pend = pending_rows;
     return MWW_OK;

@@ -53,3 +53,15 @@ cudaError_t launch_nn_i8_live(const NnWeightsI8 &W, int8_t *state, int8_t *pend,
                               const LiveHeads &heads, int sm_count, cudaStream_t st);
 cudaError_t launch_nn_i8_live_canonicalise(int8_t *state, int n_streams, const LiveHeads &heads, cudaStream_t st);
 }  // namespace mww
+
+#include "mww_nn_generic.cuh"
+namespace mww {
+// run-time-geometry MixedNet (any architecture other than the compiled-in okay_nabu one; mww_nn_generic.cuh)
+cudaError_t launch_nn_generic_f32(const GenArch &A, const GenWeightsF32 &W, float *state, float *pend, int n_pend, const void *rows,
+                                  long long rows_stream_stride_bytes, int n_rows, int row_type, float *probs, long long probs_stream_stride,
+                                  int n_streams, cudaStream_t st);
+cudaError_t launch_nn_generic_i8(const GenArch &A, const GenWeightsI8 &W, int8_t *state, int8_t *pend, int n_pend, const void *rows,
+                                 long long rows_stream_stride_bytes, int n_rows, int row_type, float *probs, long long probs_stream_stride,
+                                 int n_streams, cudaStream_t st);
+cudaError_t launch_gen_fill_state_i8(const GenArch &A, const GenWeightsI8 &W, int8_t *state, int8_t *pend, int n_streams, cudaStream_t st);
+}  // namespace mww

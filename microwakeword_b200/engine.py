@@ -19,7 +19,7 @@ from .model_file import NUM_FEATURES
 
 HOP = 160
 WINDOW = 480
-STATE_ELEMENTS = 4176
+STATE_ELEMENTS = 4176      # okay_nabu; other architectures: StreamEngine.state_elements
 
 
 def _torch():
@@ -54,6 +54,9 @@ class StreamEngine:
         self.device = int(device)
         self.info = self._info()
         self.is_quantized = bool(self.info.is_quantized)
+        # geometry of the loaded model (mww_get_info): feature rows per model step, ring-state elements per stream
+        self.stride = max(int(self.info.input_feature_slices), 1)
+        self.state_elements = int(self.info.state_bytes_per_stream) // (1 if self.is_quantized else 4) if blob is not None else 0
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -134,7 +137,7 @@ class StreamEngine:
             raise ValueError("rows must be a CUDA uint16/float32/int8 tensor of shape [n_streams, R, 40]")
         rows = rows.contiguous()
         r = rows.shape[1]
-        steps = (self.pending_rows + r) // 3
+        steps = (self.pending_rows + r) // self.stride
         probs = torch.empty((self.n_streams, max(steps, 1)), dtype=torch.float32, device=self._dev())
         got = ctypes.c_int(0)
         _lib.check(self._h, self._L.mww_infer_features(self._h, rows.data_ptr(), kinds[rows.dtype], r, max(r, 0), probs.data_ptr(),
@@ -147,7 +150,7 @@ class StreamEngine:
         n, stride = self._check_audio(audio)
         buffered = self.frontend_buffered
         rows = (buffered + n - WINDOW) // HOP + 1 if buffered + n >= WINDOW else 0
-        steps = (self.pending_rows + rows) // 3
+        steps = (self.pending_rows + rows) // self.stride
         if out is None:
             out = torch.empty((self.n_streams, max(steps, 1)), dtype=torch.float32, device=self._dev())
         got = ctypes.c_int(0)
@@ -166,7 +169,7 @@ class StreamEngine:
         n = audio.shape[1]
         buffered = self.frontend_buffered
         rows = (buffered + n - WINDOW) // HOP + 1 if buffered + n >= WINDOW else 0
-        steps = (self.pending_rows + rows) // 3
+        steps = (self.pending_rows + rows) // self.stride
         if out is None:
             out = np.empty((self.n_streams, max(steps, 1)), np.float32)
         got = ctypes.c_int(0)
@@ -193,8 +196,8 @@ class StreamEngine:
         nn_dtype = np.int8 if self.is_quantized else np.float32
         d = dict(carry=np.zeros((S, WINDOW), np.int16), estimate=np.zeros((S, NUM_FEATURES), np.uint32))
         if self._blob is not None:
-            d["nn"] = np.zeros((S, STATE_ELEMENTS), nn_dtype)
-            d["pending"] = np.zeros((S, 2, NUM_FEATURES), nn_dtype)
+            d["nn"] = np.zeros((S, self.state_elements), nn_dtype)
+            d["pending"] = np.zeros((S, max(self.stride - 1, 1), NUM_FEATURES), nn_dtype)
         _lib.check(self._h, self._L.mww_get_state(self._h, d["carry"].ctypes.data, d["estimate"].ctypes.data,
                                                   d["nn"].ctypes.data if "nn" in d else None,
                                                   d["pending"].ctypes.data if "pending" in d else None))

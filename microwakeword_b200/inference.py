@@ -155,6 +155,8 @@ class Model:
         if self.is_quantized_model:
             raise NotImplementedError("non-streaming evaluation is defined for the float model (the reference evaluates the Keras model)")
         b, t = x.shape[0], x.shape[1]
+        if self.engine.state_elements != 4176 or self.engine.stride != 3:
+            raise NotImplementedError("non-streaming evaluation is implemented for the okay_nabu geometry (its receptive field is hard-wired below)")
         if (t - 5) // 3 + 1 < 67:
             raise ValueError("window shorter than the model's receptive field (204 rows)")
         if x.dtype == np.uint16:

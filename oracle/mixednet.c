@@ -203,8 +203,10 @@ float mwwo_mixednet_step_f32(mwwo_mixednet *m, const float *x /* [stride][40] */
             d[c] = acc + b->dw_b[c];
         }
         /* ring <- last (kmax-1) rows of the concat */
-        memmove(b->ring, b->ring + cin, sizeof(float) * (rows - 1) * cin);
-        memcpy(b->ring + (rows - 1) * cin, a, sizeof(float) * cin);
+        if (rows > 0) {                            /* a 1-tap kernel keeps no history */
+            memmove(b->ring, b->ring + cin, sizeof(float) * (rows - 1) * cin);
+            memcpy(b->ring + (rows - 1) * cin, a, sizeof(float) * cin);
+        }
         for (int o = 0; o < cout; ++o) {
             float acc = 0.f;
             for (int c = 0; c < cin; ++c) acc += d[c] * b->pw_w[c * cout + o];
@@ -218,8 +220,10 @@ float mwwo_mixednet_step_f32(mwwo_mixednet *m, const float *x /* [stride][40] */
     for (int k = 0; k < hr; ++k)
         for (int c = 0; c < c_last; ++c) acc += m->ring_head[k * c_last + c] * m->head_w[k * c_last + c];
     for (int c = 0; c < c_last; ++c) acc += a[c] * m->head_w[hr * c_last + c];
-    memmove(m->ring_head, m->ring_head + c_last, sizeof(float) * (hr - 1) * c_last);
-    memcpy(m->ring_head + (hr - 1) * c_last, a, sizeof(float) * c_last);
+    if (hr > 0) {
+        memmove(m->ring_head, m->ring_head + c_last, sizeof(float) * (hr - 1) * c_last);
+        memcpy(m->ring_head + (hr - 1) * c_last, a, sizeof(float) * c_last);
+    }
     const float logit = acc + m->head_b[0];
     if (logit_out) *logit_out = logit;
     return 1.0f / (1.0f + expf(-logit));
@@ -277,8 +281,10 @@ int mwwo_mixednet_step_int8(mwwo_mixednet *m, const int8_t *x /* [stride][40] */
             acc += b->qdw_bias[c];
             d[c] = requant(acc, b->qdw_mult[c], b->qdw_shift[c], zp_d, 0);
         }
-        memmove(b->qring, b->qring + cin, (size_t)(rows - 1) * cin);
-        memcpy(b->qring + (rows - 1) * cin, a, (size_t)cin);
+        if (rows > 0) {
+            memmove(b->qring, b->qring + cin, (size_t)(rows - 1) * cin);
+            memcpy(b->qring + (rows - 1) * cin, a, (size_t)cin);
+        }
         for (int o = 0; o < cout; ++o) {
             int32_t acc = 0;
             for (int c = 0; c < cin; ++c) acc += ((int32_t)d[c] - zp_d) * b->qpw_w[c * cout + o];
@@ -293,8 +299,10 @@ int mwwo_mixednet_step_int8(mwwo_mixednet *m, const int8_t *x /* [stride][40] */
     for (int k = 0; k < hr; ++k)
         for (int c = 0; c < c_last; ++c) acc += ((int32_t)m->qring_head[k * c_last + c] - zp_in) * m->qhead_w[k * c_last + c];
     for (int c = 0; c < c_last; ++c) acc += ((int32_t)a[c] - zp_in) * m->qhead_w[hr * c_last + c];
-    memmove(m->qring_head, m->qring_head + c_last, (size_t)(hr - 1) * c_last);
-    memcpy(m->qring_head + (hr - 1) * c_last, a, (size_t)c_last);
+    if (hr > 0) {
+        memmove(m->qring_head, m->qring_head + c_last, (size_t)(hr - 1) * c_last);
+        memcpy(m->qring_head + (hr - 1) * c_last, a, (size_t)c_last);
+    }
     acc += m->qhead_bias[0];
     const int8_t logit = requant(acc, m->qhead_mult[0], m->qhead_shift[0], zp_fc, 0);
     if (logit_out) *logit_out = logit;

@@ -20,7 +20,8 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        srcs = [os.path.join(HERE, "emul_frontend.cc"), os.path.join(HERE, "emul_nn.cc"), os.path.join(CSRC, "mww_tables.cc")]
+        srcs = [os.path.join(HERE, "emul_frontend.cc"), os.path.join(HERE, "emul_nn.cc"), os.path.join(HERE, "emul_generic.cc"),
+                os.path.join(CSRC, "mww_tables.cc")]
         deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
         if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
             os.makedirs(os.path.dirname(SO), exist_ok=True)
@@ -33,6 +34,10 @@ def lib():
         L.emul_nn_live_canonicalise.restype = None
         L.emul_nn_i8_live.restype = ctypes.c_int
         L.emul_nn_i8_live_canonicalise.restype = None
+        L.emul_gen_arch.restype = ctypes.c_int
+        L.emul_gen_f32.restype = ctypes.c_int
+        L.emul_gen_i8.restype = ctypes.c_int
+        L.emul_gen_fill_state_i8.restype = ctypes.c_int
         L.emul_isqrt64_round.restype = ctypes.c_uint32
         L.emul_isqrt64_round.argtypes = [ctypes.c_uint64]
         L.emul_isqrt64_round_fast.restype = ctypes.c_uint32
@@ -189,3 +194,83 @@ class NnI8Live(NnI8):
     def infer(self, rows):
         self.canonicalise()
         return super().infer(rows)
+
+
+# ---- run-time-geometry MixedNet (mww_nn_generic.cuh) --------------------------------------------------------------
+
+def gen_arch_info(arch):
+    arch = np.ascontiguousarray(arch, np.int32)
+    out = np.zeros(8, np.int64)
+    rc = lib().emul_gen_arch(_p(arch), arch.size, _p(out))
+    keys = ("rc", "state_elems", "pend_cap", "stride", "sm_elems", "macs_per_step", "ring0", "c_last")
+    return dict(zip(keys, (int(v) for v in out))) if rc == 0 else {"rc": rc}
+
+
+class GenF32:
+    """Any-architecture fp32 MixedNet stepped with the generic kernel's phase functions; `tensors` = container tensors."""
+
+    def __init__(self, tensors, n_streams):
+        self.arch = np.ascontiguousarray(tensors["arch"], np.int32)
+        info = gen_arch_info(self.arch)
+        assert info["rc"] == 0, info
+        self.info = info
+        nb = int(self.arch[4])
+        names = ["first_conv/w"]
+        for i in range(nb):
+            names += ["b%d/dw/w" % i, "b%d/dw/b" % i, "b%d/pw/w" % i, "b%d/pw/b" % i]
+        names += ["head/w", "head/b"]
+        self.arrs = [np.ascontiguousarray(tensors[n], np.float32) for n in names]
+        self.wp = (ctypes.c_void_p * len(self.arrs))(*[a.ctypes.data for a in self.arrs])
+        self.state = np.zeros((n_streams, info["state_elems"]), np.float32)
+        self.pend = np.zeros((n_streams, info["pend_cap"] * 40), np.float32)
+        self.n_pend = 0
+        self.stride = info["stride"]
+
+    def infer(self, rows):
+        rows = np.ascontiguousarray(rows)
+        S, n_rows = rows.shape[:2]
+        rt = {np.dtype(np.uint16): 0, np.dtype(np.float32): 1}[rows.dtype]
+        probs = np.zeros((S, (self.n_pend + n_rows) // self.stride + 1), np.float32)
+        n = lib().emul_gen_f32(_p(self.arch), self.arch.size, self.wp, _p(self.state), _p(self.pend), self.n_pend, _p(rows), n_rows, rt, S,
+                               _p(probs), probs.shape[1])
+        assert n >= 0, n
+        self.n_pend = (self.n_pend + n_rows) % self.stride
+        return probs[:, :n]
+
+
+class GenI8:
+    def __init__(self, q, n_streams):
+        self.arch = np.ascontiguousarray(q["arch"], np.int32)
+        info = gen_arch_info(self.arch)
+        assert info["rc"] == 0, info
+        self.info = info
+        nb = int(self.arch[4])
+        names = ["q/first_conv/w", "q/first_conv/bias", "q/first_conv/mult", "q/first_conv/shift"]
+        for i in range(nb):
+            names += ["q/b%d/dw/%s" % (i, x) for x in ("w", "bias", "mult", "shift")] + ["q/b%d/pw/%s" % (i, x) for x in ("w", "bias", "mult", "shift")]
+        names += ["q/head/w", "q/logistic_lut"]
+        self.arrs = [np.ascontiguousarray(q[n]) for n in names]
+        self.wp = (ctypes.c_void_p * len(self.arrs))(*[a.ctypes.data for a in self.arrs])
+        self.zp = np.ascontiguousarray(q["q/zps"], np.int32)
+        assert self.zp.size == 4 + 2 * nb
+        self.head3 = np.array([q["q/head/bias"][0], q["q/head/mult"][0], q["q/head/shift"][0]], np.int32)
+        self.in_scale = float(q["q/scales"][0])
+        self.state = np.zeros((n_streams, info["state_elems"]), np.int8)
+        self.pend = np.zeros((n_streams, info["pend_cap"] * 40), np.int8)
+        self.stride = info["stride"]
+        self.reset()
+
+    def reset(self):
+        assert lib().emul_gen_fill_state_i8(_p(self.arch), self.arch.size, _p(self.zp), _p(self.state), _p(self.pend), self.state.shape[0]) == 0
+        self.n_pend = 0
+
+    def infer(self, rows):
+        rows = np.ascontiguousarray(rows)
+        S, n_rows = rows.shape[:2]
+        rt = {np.dtype(np.uint16): 0, np.dtype(np.float32): 1, np.dtype(np.int8): 2}[rows.dtype]
+        probs = np.zeros((S, (self.n_pend + n_rows) // self.stride + 1), np.float32)
+        n = lib().emul_gen_i8(_p(self.arch), self.arch.size, self.wp, _p(self.zp), _p(self.head3), ctypes.c_float(self.in_scale), _p(self.state),
+                              _p(self.pend), self.n_pend, _p(rows), n_rows, rt, S, _p(probs), probs.shape[1])
+        assert n >= 0, n
+        self.n_pend = (self.n_pend + n_rows) % self.stride
+        return probs[:, :n]
