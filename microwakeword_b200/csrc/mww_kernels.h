@@ -8,6 +8,16 @@
 
 namespace mww {
 
+// Dynamic shared memory above 48 KB is opt-in per kernel AND per device (cudaFuncSetAttribute applies to the current
+// device only): a process that drives several GPUs must opt in on each of them.  `done` is the launcher's static flag set.
+inline bool first_launch_on_this_device(bool (&done)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+}
+
 cudaError_t launch_k1(const FrontendParams &P, int fb_coef_len, const int16_t *carry, int used, const int16_t *audio,
                       long long audio_stride, int n_samples, int n_streams, int n_frames, uint32_t *vout, int sm_count,
                       cudaStream_t st);

@@ -74,13 +74,12 @@ cudaError_t launch_nn_f32(const NnWeightsF32 &W, float *state, float *pend, int 
                           long long rows_stream_stride_bytes, int n_rows, int rows_are_f32, float *probs,
                           long long probs_stream_stride, float *logits, int n_streams, cudaStream_t st) {
     if (n_streams <= 0) return cudaSuccess;
-    static bool attr_set = false;
+    static bool attr_done[64] = {};
     static int pad = 0;
-    if (!attr_set) {
+    if (first_launch_on_this_device(attr_done)) {
         if (const char *e = getenv("MWW_NN_SMEM_PAD")) pad = atoi(e);       // experiment: force 1 CTA / SM
         cudaError_t e = cudaFuncSetAttribute(nn_f32_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNnSmemBytes + pad);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     nn_f32_clip_kernel<<<(unsigned)n_streams, kNnThreads, kNnSmemBytes + pad, st>>>(W, state, pend, n_pend, rows, rows_stream_stride_bytes,
                                                                              n_rows, rows_are_f32, probs, probs_stream_stride, logits);

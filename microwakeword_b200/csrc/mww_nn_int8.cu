@@ -70,11 +70,10 @@ cudaError_t launch_nn_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, int 
                          long long rows_stream_stride_bytes, int n_rows, int row_type, float *probs,
                          long long probs_stream_stride, int n_streams, cudaStream_t st) {
     if (n_streams <= 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_done[64] = {};
+    if (first_launch_on_this_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(nn_i8_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNnI8SmemBytes);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     nn_i8_clip_kernel<<<(unsigned)n_streams, kNnThreads, kNnI8SmemBytes, st>>>(W, state, pend, n_pend, rows, rows_stream_stride_bytes, n_rows,
                                                                             row_type, probs, probs_stream_stride);

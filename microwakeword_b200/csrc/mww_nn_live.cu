@@ -58,11 +58,10 @@ cudaError_t launch_nn_f32_live(const NnWeightsF32 &W, float *state, float *pend,
                                long long rows_stream_stride_bytes, int rows_are_f32, float *probs, long long probs_stride,
                                int n_streams, const LiveHeads &heads, int sm_count, cudaStream_t st) {
     if (n_streams <= 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_done[64] = {};
+    if (first_launch_on_this_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(nn_f32_live_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLiveSmemBytes);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     const int n_groups = (n_streams + kLiveStreams - 1) / kLiveStreams;
     const int grid = std::min(n_groups, 2 * sm_count);
