@@ -10,7 +10,11 @@
 
 using namespace mww;
 
-#define GEN_ALL(stmt) for (int tid = 0; tid < kGenThreads; ++tid) { stmt; }
+// Threads of a phase run one after the other; the order must not matter (a phase that reads what another thread of the
+// SAME phase writes would be a race on the GPU).  tests/test_generic_arch.py runs every comparison in both orders.
+static int g_reverse = 0;
+extern "C" void emul_gen_thread_order(int reversed) { g_reverse = reversed; }
+#define GEN_ALL(stmt) for (int t_ = 0; t_ < kGenThreads; ++t_) { const int tid = g_reverse ? kGenThreads - 1 - t_ : t_; stmt; }
 
 namespace {
 void advance(int &pos, int slots) { pos = pos + 1 == slots ? 0 : pos + 1; }

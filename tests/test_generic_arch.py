@@ -22,6 +22,15 @@ ARCHS = {
 }
 
 
+@pytest.fixture(autouse=True, params=["ascending", "descending"])
+def thread_order(request):
+    """Every test below runs twice: threads of a phase executed in ascending and in descending order.  Identical results in
+    both orders rule out a read-after-write dependency between threads inside one phase (a missing barrier)."""
+    emul.lib().emul_gen_thread_order(int(request.param == "descending"))
+    yield
+    emul.lib().emul_gen_thread_order(0)
+
+
 def _features(n_streams, n_samples, seed):
     audio = np.stack([synth_audio(n_samples, seed + i) for i in range(n_streams)])
     feats, _ = oracle.run_pipeline(None, audio, want_probs=False)
