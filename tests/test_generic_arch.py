@@ -155,3 +155,32 @@ def test_okay_nabu_generic_equals_the_compiled_in_kernels():
     n = feats.shape[1] // 3 * 3
     assert np.array_equal(emul.GenI8(q8, 2).infer(feats[:, :n]), emul.NnI8(q8, 2).infer(feats[:, :n]))
     assert np.abs(emul.GenF32(f32, 2).infer(feats[:, :n]) - emul.NnF32(f32, 2).infer(feats[:, :n])).max() <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["stride2_three_groups", "stride1_two_blocks"])      # (the test writer has no 1-tap / stateless Stream form)
+def test_tflite_file_of_another_architecture_runs_on_the_generic_phases(name):
+    """The whole drop-in chain for a model that is not okay_nabu, on the CPU: a streaming .tflite (tests/tflite_writer.py) ->
+    the product's flatbuffer recogniser -> container tensors -> the generic kernel's phase functions, against the op-by-op
+    interpreter executing the same flatbuffer bytes (oracle/tflite_interp.py): int8 identical, fp32 within 1e-5."""
+    import tflite_writer as W
+    from microwakeword_b200 import tflite_file as TF
+    from oracle.tflite_interp import Interpreter
+    spec = ARCHS[name]
+    s = spec.stride
+    feats = _features(1, 6000, 900)[0]
+    n = feats.shape[0] // s * s
+    for kind, tensors in zip(("f32", "int8"), _models(spec)):
+        blob = W.write_streaming_mixednet(tensors)
+        got = TF.tensors_from_tflite(blob)
+        assert np.array_equal(got["arch"], spec.encode())
+        it = Interpreter(blob)
+        if kind == "int8":
+            g = emul.GenI8(got, 1)
+            x = R.quantize_input(feats[:n].astype(np.float32) * R.FEATURE_SCALE, g.in_scale, int(g.zp[0]))
+            want = np.asarray([int(it.invoke(x[i:i + s]).reshape(-1)[0]) for i in range(0, n, s)], np.float32) * np.float32(1.0 / 255.0)
+            assert np.array_equal(g.infer(x[None])[0], want)
+        else:
+            g = emul.GenF32(got, 1)
+            x = (feats[:n].astype(np.float32) * R.FEATURE_SCALE).astype(np.float32)
+            want = np.asarray([float(it.invoke(x[i:i + s]).reshape(-1)[0]) for i in range(0, n, s)], np.float32)
+            assert np.abs(g.infer(x[None])[0] - want).max() <= 1e-5
