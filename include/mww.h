@@ -72,7 +72,13 @@ typedef struct mww_info {
 /* Parse an MWW model container (microwakeword_b200/model_file.py), upload the weights to `device`
  * and allocate zeroed state for `n_streams` streams.  model_blob == NULL creates a frontend-only
  * handle (mww_features works, the NN entry points return MWW_EINVAL).  On failure *out is NULL and
- * mww_last_error(NULL) describes why. */
+ * mww_last_error(NULL) describes why.
+ * Architectures: the container's `arch` tensor selects the kernels.  The okay_nabu MixedNet
+ * (notebooks/basic_training_notebook.ipynb:503-509) runs on the tensor-core kernels; any other geometry of the
+ * reference's default block structure (mixednet.py:278-386 with other --pointwise_filters / --mixconv_kernel_sizes /
+ * --first_conv_* / --stride values) runs on the run-time-geometry kernels with the same entry points, state layout
+ * rule (first-conv ring, block rings, head ring; oldest row first) and results.  mww_info.input_feature_slices is the
+ * model's stride, state_bytes_per_stream its ring state.  Topologies outside that family: MWW_EUNSUPPORTED. */
 int mww_create(const void *model_blob, size_t n_bytes, int device, int n_streams, mww_t **out);
 int mww_destroy(mww_t *h);
 const char *mww_last_error(const mww_t *h);
