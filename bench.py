@@ -430,7 +430,13 @@ def run_gpu(args):
         sh = ShardedEngine(model_blob(args.model), total, local_rank, tiles=8)
         try:
             from microwakeword_b200.sharding import PeerAudio
-            peer = PeerAudio(full, total, SAMPLES_PER_STEP, src=0, device=device)
+            if os.environ.get("MWW_PEER_OPEN") == "lib":       # opt-in: IPC handle opened in each rank's own context (sharding.py)
+                peer = PeerAudio.allocate(total, SAMPLES_PER_STEP, src=0, device=device)
+                if rank == 0:
+                    peer.buffer.copy_(full)
+                scatter["peer_open"] = "lib"
+            else:
+                peer = PeerAudio(full, total, SAMPLES_PER_STEP, src=0, device=device)
             for _ in range(2):
                 sh.reset()
                 gathered_q = sh.predict_clip_pulled(peer)
@@ -467,6 +473,10 @@ def run_gpu(args):
             scatter["pulled"] = {"value": frames_per_step_all / (pl_ms / 1e3), "unit": UNIT, "ms_per_step": pl_ms, "tiles_per_rank": sh.tiles,
                                  "note": "ranks pull their tiles from rank 0 over NVLink peer access (copy engines, CUDA IPC) while earlier tiles compute; "
                                          "NCCL only for the per-step barrier and the gather of the scores"}
+            if scatter.get("peer_open") == "lib":             # every rank is done reading before the exporter frees the buffer
+                torch.cuda.synchronize()
+                barrier()
+                peer.close()
             del peer
         except Exception as exc:                       # CUDA IPC / peer access unavailable in this container: report, do not hide
             scatter["pulled"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}

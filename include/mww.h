@@ -162,6 +162,18 @@ long long mww_launch_count(const mww_t *h);
  * Returns 0 or a negative MWW_ECUDA; no handle is involved (the message goes to mww_last_error(NULL)). */
 int mww_copy_async(void *d_dst, const void *d_src, size_t bytes, void *cu_stream);
 
+/* CUDA IPC for the multi-GPU ingest buffer, opened in the CALLER'S device context (sharding.py::PeerAudio.allocate).
+ * mww_ipc_alloc: cudaMalloc on `device` + cudaIpcGetMemHandle (64 opaque bytes to hand to the other ranks of the box).
+ * mww_ipc_open: cudaIpcOpenMemHandle(..., cudaIpcMemLazyEnablePeerAccess) with `device` (the OPENING rank's own GPU)
+ * current, so the mapping lives in that rank's context and the rank never creates a context on the exporting GPU --
+ * torch's tensor rebuild opens the handle under the exporter's device index instead, which leaves one extra context per
+ * peer on the ingest GPU (the 8-GPU ingest).  mww_ipc_close / mww_ipc_free undo them.
+ * All return 0 or a negative MWW_ECUDA / MWW_EINVAL; the message goes to mww_last_error(NULL). */
+int mww_ipc_alloc(size_t bytes, int device, void **d_ptr, unsigned char *handle64);
+int mww_ipc_open(const unsigned char *handle64, int device, void **d_ptr);
+int mww_ipc_close(void *d_ptr, int device);
+int mww_ipc_free(void *d_ptr, int device);
+
 #ifdef __cplusplus
 }
 #endif

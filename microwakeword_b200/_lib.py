@@ -21,6 +21,7 @@ EXPORTS = (
     "mww_features", "mww_infer_features", "mww_predict_clip", "mww_predict_clip_host",
     "mww_get_state", "mww_set_state", "mww_launch_count", "mww_profile_enable", "mww_profile_read",
     "mww_moving_average", "mww_false_accept_counts", "mww_positive_scores", "mww_copy_async",
+    "mww_ipc_alloc", "mww_ipc_open", "mww_ipc_close", "mww_ipc_free",
 )
 
 
@@ -92,6 +93,14 @@ def lib() -> ctypes.CDLL:
     L.mww_launch_count.argtypes = [vp]
     L.mww_copy_async.restype = i32
     L.mww_copy_async.argtypes = [vp, vp, sz, vp]
+    L.mww_ipc_alloc.restype = i32
+    L.mww_ipc_alloc.argtypes = [sz, i32, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.mww_ipc_open.restype = i32
+    L.mww_ipc_open.argtypes = [ctypes.c_char_p, i32, ctypes.POINTER(vp)]
+    L.mww_ipc_close.restype = i32
+    L.mww_ipc_close.argtypes = [vp, i32]
+    L.mww_ipc_free.restype = i32
+    L.mww_ipc_free.argtypes = [vp, i32]
     _lib = L
     return L
 

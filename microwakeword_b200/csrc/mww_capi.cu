@@ -579,6 +579,53 @@ int mww_copy_async(void *d_dst, const void *d_src, size_t bytes, void *cu_stream
     return MWW_OK;
 }
 
+namespace {
+int ipc_fail(const char *what, cudaError_t e) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return MWW_ECUDA;
+}
+}  // namespace
+
+int mww_ipc_alloc(size_t bytes, int device, void **d_ptr, unsigned char *handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!d_ptr || !handle64 || bytes == 0) { g_create_error = "mww_ipc_alloc: bad argument"; return MWW_EINVAL; }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return ipc_fail("mww_ipc_alloc: cudaSetDevice", e);
+    void *p = nullptr;
+    if ((e = cudaMalloc(&p, bytes)) != cudaSuccess) return ipc_fail("mww_ipc_alloc: cudaMalloc", e);
+    cudaIpcMemHandle_t hd;
+    if ((e = cudaIpcGetMemHandle(&hd, p)) != cudaSuccess) { cudaFree(p); return ipc_fail("mww_ipc_alloc: cudaIpcGetMemHandle", e); }
+    memcpy(handle64, &hd, 64);
+    *d_ptr = p;
+    return MWW_OK;
+}
+
+int mww_ipc_open(const unsigned char *handle64, int device, void **d_ptr) {
+    if (!d_ptr || !handle64) { g_create_error = "mww_ipc_open: bad argument"; return MWW_EINVAL; }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return ipc_fail("mww_ipc_open: cudaSetDevice", e);
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    void *p = nullptr;
+    if ((e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) return ipc_fail("mww_ipc_open: cudaIpcOpenMemHandle", e);
+    *d_ptr = p;
+    return MWW_OK;
+}
+
+int mww_ipc_close(void *d_ptr, int device) {
+    if (!d_ptr) return MWW_OK;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaIpcCloseMemHandle(d_ptr);
+    return e == cudaSuccess ? MWW_OK : ipc_fail("mww_ipc_close", e);
+}
+
+int mww_ipc_free(void *d_ptr, int device) {
+    if (!d_ptr) return MWW_OK;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaFree(d_ptr);
+    return e == cudaSuccess ? MWW_OK : ipc_fail("mww_ipc_free", e);
+}
+
 int mww_profile_enable(mww_t *h, int on) {
     if (!h) return MWW_EINVAL;
     h->profiling = on != 0;

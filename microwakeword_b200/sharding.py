@@ -158,6 +158,66 @@ class PeerAudio:
             raise RuntimeError("PeerAudio: CUDA IPC / peer access to the ingest rank's buffer is unavailable (%s)" % (err or "on another rank"))
         self.copy_stream = torch.cuda.Stream(device=self.device)
 
+    @classmethod
+    def allocate(cls, n_streams: int, n_samples: int, src: int = 0, group=None, device=None):
+        """OPT-IN variant (written after the round's GPU budget was spent; not yet run on a GPU): the ingest buffer is a
+        cudaMalloc owned by the library on the ingest rank, exported with cudaIpcGetMemHandle and opened by every other rank
+        INSIDE ITS OWN device context (mww_ipc_open, cudaIpcMemLazyEnablePeerAccess) -- no rank creates a context on the
+        ingest GPU, unlike the torch rebuild used by __init__.  On the ingest rank `self.buffer` is a torch view of the
+        allocation to write the audio into; elsewhere it is None.  Candidate fix for the 8-GPU slowdown."""
+        import torch
+        import torch.distributed as dist
+
+        self = cls.__new__(cls)
+        self.group, self.src = group, src
+        self.n_streams, self.n_samples = n_streams, n_samples
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.remote, self.buffer, self._owned, self._opened = None, None, None, None
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        L = _lib.lib()
+        handle = ctypes.create_string_buffer(64)
+        ptr = ctypes.c_void_p()
+        err = None
+        try:
+            if self.rank == src:
+                _lib.check(None, L.mww_ipc_alloc(n_streams * n_samples * 2, dev_index, ctypes.byref(ptr), handle))
+                self._owned = ptr.value
+        except Exception as exc:                                # noqa: BLE001
+            err = exc
+        box = [bytes(handle.raw) if self.rank == src else None]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=src, group=group)
+        try:
+            if err is None and self.rank != src:
+                _lib.check(None, L.mww_ipc_open(box[0], dev_index, ctypes.byref(ptr)))
+                self._opened = ptr.value
+        except Exception as exc:                                # noqa: BLE001
+            err = exc
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.close()
+            raise RuntimeError("PeerAudio.allocate: CUDA IPC is unavailable (%s)" % (err or "on another rank"))
+        self.remote_ptr = ptr.value
+        if self.rank == src:
+            iface = {"shape": (n_streams, n_samples), "typestr": "<i2", "data": (self._owned, False), "version": 3, "strides": None}
+            holder = type("MwwIpcBuffer", (), {"__cuda_array_interface__": iface})()
+            self.buffer = torch.as_tensor(holder, device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        return self
+
+    def close(self):
+        """Release what allocate() created (no-op for a PeerAudio built around a torch tensor)."""
+        dev_index = self.device.index if self.device.index is not None else 0
+        if getattr(self, "_opened", None):
+            _lib.lib().mww_ipc_close(ctypes.c_void_p(self._opened), dev_index)
+            self._opened = None
+        if getattr(self, "_owned", None):
+            self.buffer = None
+            _lib.lib().mww_ipc_free(ctypes.c_void_p(self._owned), dev_index)
+            self._owned = None
+
     def pull_tiles(self, tiles: int):
         """Start the DMA of this rank's tiles (in order, on a side stream); returns (locals, events)."""
         import torch
@@ -175,7 +235,8 @@ class PeerAudio:
             # of this process on the ingest GPU, where it is time-sliced against the ingest rank's own kernels (measured:
             # no overlap at all).  The C-ABI copy runs on this rank's stream: a pull by this GPU's copy engine.
             if c:
-                _lib.check(None, _lib.lib().mww_copy_async(local.data_ptr(), self.remote.data_ptr() + s * self.n_samples * 2,
+                base = self.remote.data_ptr() if self.remote is not None else self.remote_ptr       # torch rebuild | allocate()
+                _lib.check(None, _lib.lib().mww_copy_async(local.data_ptr(), base + s * self.n_samples * 2,
                                                           c * self.n_samples * 2, ctypes.c_void_p(self.copy_stream.cuda_stream)))
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
