@@ -192,3 +192,48 @@ def test_int8_live_step_kernel_phases_are_bit_exact():
         assert np.array_equal(nn.state, ref.state) and np.array_equal(nn.pend, ref.pend)
         rest = nn.infer(rows[:, pos:])
         assert np.array_equal(rest, want[:, got.shape[1]:got.shape[1] + rest.shape[1]])
+
+
+def test_frontend_phases_bit_exact_property_based():
+    """Hypothesis drives the amplitude structure instead of a fixed list: piecewise segments of silence, DC, full-scale
+    clipping, alternating extremes, tones and noise at random levels, cut at arbitrary sample positions (so window
+    boundaries fall anywhere), fed in two calls of arbitrary split.  Features must equal the oracle's bit for bit."""
+    from hypothesis import given, settings, strategies as st
+
+    seg = st.tuples(st.sampled_from(["zero", "dc", "clip", "alt", "tone", "noise", "impulse"]), st.integers(1, 900),
+                    st.integers(0, 32767), st.integers(0, 2 ** 31 - 1))
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(st.lists(seg, min_size=1, max_size=8), st.integers(0, 4000))
+    def run(segments, split):
+        parts = []
+        for kind, n, amp, seed in segments:
+            r = np.random.default_rng(seed)
+            t = np.arange(n)
+            if kind == "zero":
+                x = np.zeros(n)
+            elif kind == "dc":
+                x = np.full(n, amp if seed & 1 else -amp)
+            elif kind == "clip":
+                x = r.choice([-32768, 32767], n)
+            elif kind == "alt":
+                x = np.where(t % 2 == 0, amp, -amp - 1)
+            elif kind == "tone":
+                x = amp * np.sin(2 * np.pi * (50 + seed % 7900) / 16000.0 * t + seed % 7)
+            elif kind == "noise":
+                x = r.normal(0, amp / 3 + 1, n)
+            else:
+                x = np.zeros(n); x[seed % n] = amp if seed & 2 else -32768
+            parts.append(x)
+        audio = np.clip(np.round(np.concatenate(parts)), -32768, 32767).astype(np.int16)
+        if audio.size < 480:
+            audio = np.concatenate([audio, np.zeros(480 - audio.size, np.int16)])
+        audio = audio[None]
+        want, _ = oracle.run_pipeline(None, audio, want_probs=False)
+        fe = emul.Frontend(1)
+        cut = min(split, audio.shape[1])
+        got = [fe.features(audio[:, :cut]), fe.features(audio[:, cut:])] if 0 < cut < audio.shape[1] else [fe.features(audio)]
+        got = np.concatenate(got, 1)
+        assert got.shape == want.shape and np.array_equal(got, want)
+
+    run()
