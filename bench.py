@@ -86,6 +86,33 @@ def cpu_sample(n_streams: int) -> np.ndarray:
     return np.ascontiguousarray(np.tile(base, (reps, 1))[:n_streams])
 
 
+def host_cores():
+    """(threads to use, facts about the host): the affinity mask rather than os.cpu_count(), and the cgroup CPU quota when
+    the container has one -- a 128-thread box whose container may only burn 32 CPUs' worth of time is a 32-core baseline."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    facts = {"os_cpu_count": os.cpu_count(), "affinity": n}
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        facts["cgroup_cpu_max"] = "%s %s" % (quota, period)
+        if quota != "max":
+            facts["cgroup_cpus"] = float(quota) / float(period)
+    except (OSError, ValueError):
+        pass
+    return max(n, 1), facts
+
+
+def time_cpu_single_thread(kind: str) -> float:
+    """frames/s of ONE oracle thread (a few hundred ms): shows how the multi-thread figure scales on this host"""
+    import oracle
+    audio = cpu_sample(16)
+    t0 = time.perf_counter()
+    oracle.run_pipeline(model_blob(kind), audio, want_features=False, threads=1)
+    return audio.shape[0] * 298 / max(time.perf_counter() - t0, 1e-6)
+
+
 def time_cpu(kind: str, cores: int, target_s: float = 12.0):
     """Times the CPU oracle (frontend + MixedNet) over a bounded sample with `cores` threads."""
     import oracle
@@ -109,7 +136,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores, host = host_cores()
+    single = time_cpu_single_thread(args.model)
     vals, sample = [], ""
     for i in range(args.warmup + args.steps):
         v, sample = time_cpu(args.model, cores, target_s=max(2.0, min(12.0, 120.0 / max(args.warmup + args.steps, 1))))
@@ -122,6 +150,7 @@ def run_reference(args):
         "dtype": "f32" if args.model == "f32" else "int8", "data": "synthetic",
         "config": config_dict(args, max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "single_thread_value": single, "host": host,
                          "note": "the reference's own CPU path (tf.lite.Interpreter + pymicro_features) is not installable here; "
                                  "this is the C oracle restating it, one stream per thread"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -485,9 +514,10 @@ def run_gpu(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        cores, host = host_cores()
         v, sample = time_cpu(args.model, cores)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "single_thread_value": time_cpu_single_thread(args.model), "host": host}
 
     if rank == 0:
         line = {
