@@ -51,11 +51,10 @@ def parse_args():
     ap.add_argument("--model", default="f32", choices=["f32", "int8"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-scatter", action="store_true", help="skip the NCCL scatter/gather leg at N > 1")
-    ap.add_argument("--live", type=int, default=0, metavar="SAMPLES",
-                    help="also time live mode: step() calls with SAMPLES new samples per stream (e.g. 480 = one 30 ms model step)")
-    ap.add_argument("--features", action="store_true",
-                    help="also time BASELINE.json configs[3]: the feature extractor alone on 1 M 30 ms windows (streaming and stateless)")
+    ap.add_argument("--tiles", type=int, default=0, help="pipeline tiles per rank of the N > 1 ingest (0 = library default, 16)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the legs for the other BASELINE.json configurations (the other model dtype in clip mode, live 30 ms steps "
+                         "for both dtypes, feature extractor only)")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -252,20 +251,57 @@ def ncu_traffic():
     return None
 
 
+def issue_roofline(tipf, frames_per_launch, kernel_ms, clock_info):
+    sm_hz = ((clock_info or {}).get("sm_mhz") or 1965.0) * 1e6
+    peak_issue = 148 * 4 * 32 * sm_hz            # 4 schedulers/SM x 1 warp-instruction/clk x 32 threads
+    ach = tipf * frames_per_launch / (kernel_ms / 1e3)
+    return {"thread_instr_per_frame": tipf, "achieved_thread_instr_per_s": ach, "peak_thread_instr_per_s": peak_issue,
+            "frac": ach / peak_issue, "source": "instructions per frame from the committed ncu capture; duration live from CUDA events"}
+
+
+def k1_roofline(prof, S, steps, clock_info):
+    """HBM roofline of the dominant kernel (the spectral frontend kernel) from the library's own CUDA events."""
+    peak, peak_src = measured_peaks()
+    k1_ms, k1_n = prof["k1_spectral"]
+    if not k1_n:
+        return None
+    frames_per_launch = S * FRAMES_PER_STEP * steps / k1_n
+    per_launch_ms = k1_ms / k1_n
+    achieved = K1_ALG_BYTES_PER_FRAME * frames_per_launch / (per_launch_ms / 1e3) / 1e9
+    tr = ncu_traffic()
+    roof = {"bound": "hbm", "kernel": (tr or {}).get("kernel", "k1_spectral_kernel"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": peak_src, "traffic": ((tr or {}).get("dram_bytes_per_unit") or 0) * frames_per_launch or None,
+            "traffic_source": (tr or {}).get("source"),
+            "alg_bytes_per_frame": K1_ALG_BYTES_PER_FRAME, "frames_per_launch": frames_per_launch,
+            "share_of_step": k1_ms / max(sum(v[0] for v in prof.values()), 1e-9),
+            "note": "the frontend kernel is integer-ALU bound by construction (~30k thread-instructions per 320-byte frame, ncu): the HBM "
+                    "fraction is low because the kernel is instruction-issue bound; see `issue`, DESIGN.md and profiles/"}
+    tipf = (tr or {}).get("thread_instr_per_unit")
+    if tipf:
+        roof["issue"] = issue_roofline(tipf, frames_per_launch, per_launch_ms, clock_info)
+    return roof
+
+
 def run_gpu(args):
-    import torch
-    import torch.distributed as dist
-
-    from microwakeword_b200.engine import StreamEngine
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world > 1 and "CUDA_VISIBLE_DEVICES" not in os.environ:
+        # a rank only ever needs the GPUs of its own job: nothing (NCCL topology probing, IPC, a stray context) can touch the
+        # box's other GPUs (r01: blips on GPUs 4-7 during the 2-GPU run)
+        os.environ["CUDA_VISIBLE_DEVICES"] = ",".join(str(i) for i in range(int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    import torch
+    import torch.distributed as dist
+
+    from microwakeword_b200.engine import StreamEngine, bind_host_thread, host_array
+
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    affinity_before = os.sched_getaffinity(0)
+    numa_node = bind_host_thread(local_rank)           # before anything pins host memory: buffers land next to this rank's GPU
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
 
     def barrier():
         if world > 1:
@@ -279,12 +315,26 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed(fn, reps):
+        """max over ranks of the CUDA-event time of `reps` calls, in ms per call"""
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) / reps
+
     S = args.streams
+    n_probs = FRAMES_PER_STEP // 3 + 1
     eng = StreamEngine(model_blob(args.model), n_streams=S, device=local_rank)
     audio = synth_audio_device(torch, S, SAMPLES_PER_STEP, 1234 + rank, device)
-    probs = torch.empty((S, FRAMES_PER_STEP // 3 + 1), dtype=torch.float32, device=device)
+    probs = torch.empty((S, n_probs), dtype=torch.float32, device=device)
+    frames_per_step_all = S * FRAMES_PER_STEP * world
 
-    # ---- device-resident timing: `value` ----
+    # ---- the shard's own audio already resident in HBM: `value` at N = 1, `value_presharded` at N > 1 ----
     eng.reset()
     clocks = ClockSampler(local_rank) if rank == 0 else None           # samples every 100 ms from warm-up on
     for _ in range(max(args.warmup, 1)):
@@ -292,242 +342,227 @@ def run_gpu(args):
     barrier()
     l0 = eng.launch_count
     eng.profile(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        eng.predict_clip(audio, out=probs)
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = eng.launch_count - l0
+    ms_resident = timed(lambda: eng.predict_clip(audio, out=probs), args.steps)
+    launches = (eng.launch_count - l0)
     prof = eng.profile_read()
     eng.profile(False)
-    clock_info = clocks.stop() if clocks else None
-    ms_per_step = ms_total / args.steps
-    frames_per_step_all = S * FRAMES_PER_STEP * world
-    value = frames_per_step_all / (ms_per_step / 1e3)
     checksum = float(probs[:, :100].double().sum().item())
-
-    # ---- roofline of the dominant kernel (K1 spectral), from the library's own CUDA events ----
-    peak, peak_src = measured_peaks()
-    k1_ms, k1_n = prof["k1_spectral"]
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
-    roof = None
-    if k1_n:
-        frames_per_launch = S * FRAMES_PER_STEP * args.steps / k1_n
-        achieved = K1_ALG_BYTES_PER_FRAME * frames_per_launch / (k1_ms / k1_n / 1e3) / 1e9
-        tr = ncu_traffic()
-        roof = {"bound": "hbm", "kernel": "k1_spectral_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": ((tr or {}).get("dram_bytes_per_unit") or 0) * frames_per_launch or None,
-                "traffic_source": (tr or {}).get("source"),
-                "alg_bytes_per_frame": K1_ALG_BYTES_PER_FRAME, "frames_per_launch": frames_per_launch,
-                "share_of_step": k1_ms / max(sum(v[0] for v in prof.values()), 1e-9),
-                "note": "K1 is integer-ALU bound by construction (~34k thread-instructions per 320-byte frame, ncu): the HBM fraction is low "
-                        "because the kernel is instruction-issue bound; see `issue` below, DESIGN.md and profiles/"}
-        tipf = (tr or {}).get("thread_instr_per_unit")
-        if tipf:
-            sm_hz = ((clock_info or {}).get("sm_mhz") or 1965.0) * 1e6
-            peak_issue = 148 * 4 * 32 * sm_hz            # 4 schedulers/SM x 1 warp-instruction/clk x 32 threads
-            ach = tipf * frames_per_launch / (k1_ms / k1_n / 1e3)
-            roof["issue"] = {"thread_instr_per_frame": tipf, "achieved_thread_instr_per_s": ach, "peak_thread_instr_per_s": peak_issue,
-                             "frac": ach / peak_issue, "source": "instructions per frame from the committed ncu capture; duration live from CUDA events"}
 
-    # ---- e2e through the host-buffer C-ABI call ----
+    # ---- N > 1, BASELINE.json configs[4] as SURVEY.md 8(d) defines it: audio originates on rank 0, every rank pulls its
+    # block over NVLink while it computes (copy engines, CUDA IPC peer mapping), scores are gathered
+    # back on rank 0 (NCCL) -- scatter, compute and gather all inside the timed region ----
+    ingest_info, ms_per_step = None, ms_resident
+    if world > 1:
+        from microwakeword_b200.sharding import IngestBuffer, ShardedEngine, gather_probs, scatter_audio
+        total = S * world
+        ingest = IngestBuffer(total, SAMPLES_PER_STEP, src=0, device=device)
+        if rank == 0:
+            ingest.buffer[:S].copy_(audio)
+            for r in range(1, world):                  # rank 0 holds every stream's audio (each block has its own seed)
+                ingest.buffer[r * S:(r + 1) * S].copy_(synth_audio_device(torch, S, SAMPLES_PER_STEP, 1234 + r, device))
+        sh = ShardedEngine(model_blob(args.model), total, local_rank)
+        torch.cuda.synchronize()
+        gathered = None
+
+        def ingest_step():
+            nonlocal gathered
+            gathered = sh.predict_clip_ingest(ingest, tiles=args.tiles, out=probs)
+
+        sh.reset()
+        ingest_step()
+        for _ in range(max(args.warmup, 1)):
+            ingest_step()
+        l0 = sh.engine.launch_count
+        ms_per_step = timed(ingest_step, args.steps)
+        launches = sh.engine.launch_count - l0
+        ingest_checksum = float(probs[:, :100].double().sum().item())
+        # side legs, for the record: (i) where the time goes: the pull alone (copy engine, no kernels);
+        # (ii) the plain serialised NCCL scatter -> compute -> gather
+        stage = torch.empty((max(S // 16, 1), SAMPLES_PER_STEP), dtype=torch.int16, device=device)
+        from microwakeword_b200 import _lib as lib_mod
+        import ctypes
+
+        def pull_only():
+            dist.barrier()
+            rows = stage.shape[0]
+            for s0 in range(0, S if rank != 0 else 0, rows):
+                n = min(rows, S - s0)
+                lib_mod.check(None, lib_mod.lib().mww_copy_async(stage.data_ptr(), ingest.block_ptr(sh.start + s0), n * SAMPLES_PER_STEP * 2,
+                                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        pull_ms = timed(pull_only, 2)
+        # every rank's block through the ingest path == the same block computed from resident audio (both from reset state)
+        sh.reset()
+        ingest_step()
+        eng.reset()
+        same = torch.equal(eng.predict_clip(audio), probs[:, :FRAMES_PER_STEP // 3] if probs.shape[1] > FRAMES_PER_STEP // 3 else probs)
+        same_t = torch.tensor([1 if same else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(same_t, op=dist.ReduceOp.MIN)
+        eng.reset()
+
+        def nccl_serial():
+            local = scatter_audio(ingest.buffer if rank == 0 else None, total, SAMPLES_PER_STEP, src=0, device=device)
+            gather_probs(eng.predict_clip(local, out=probs), total, dst=0)
+        nccl_serial()
+        nccl_ms = timed(nccl_serial, 2)
+        ingest_info = {
+            "how": "audio for all %d streams in rank 0's HBM; every rank pulls its 65 536-stream block tile by tile with its own copy engine over "
+                   "NVLink peer access (CUDA IPC) while the previous tile computes (mww_predict_clip_remote), scores gathered to rank 0 with NCCL; "
+                   "a tiny all-reduce per step orders the pulls after the ingest rank's writes" % total,
+            "tiles_per_rank": args.tiles or 16,
+            "nvlink_bytes_out_of_rank0_per_step": S * SAMPLES_PER_STEP * 2 * (world - 1),
+            "egress_floor_ms": pull_ms, "pull_only_gbs_out_of_rank0": S * SAMPLES_PER_STEP * 2 * (world - 1) / (pull_ms / 1e3) / 1e9,
+            "value_presharded": frames_per_step_all / (ms_resident / 1e3), "ms_per_step_presharded": ms_resident,
+            "nccl_serial": {"value": frames_per_step_all / (nccl_ms / 1e3), "ms_per_step": nccl_ms,
+                            "note": "torch.distributed scatter of int16 audio from rank 0, compute, gather of float32 scores (NCCL), serialised"},
+            "probs_checksum_rank0_block": ingest_checksum,
+            "every_rank_block_equals_resident_path": bool(int(same_t.item()) == 1),
+        }
+        torch.cuda.synchronize()
+        barrier()
+        ingest.close()
+        del sh, stage
+
+    clock_info = clocks.stop() if clocks else None
+    value = frames_per_step_all / (ms_per_step / 1e3)
+    roof = k1_roofline(prof, S, args.steps, clock_info)
+
+    # ---- e2e through the host-buffer C-ABI call (pinned buffers on this GPU's NUMA node) ----
     e2e = None
     if not args.no_e2e:
-        host_audio = torch.empty((S, SAMPLES_PER_STEP), dtype=torch.int16, pin_memory=True)
-        host_audio.copy_(audio)
-        host_probs = torch.empty((S, FRAMES_PER_STEP // 3 + 1), dtype=torch.float32, pin_memory=True)
-        ha, hp = host_audio.numpy(), host_probs.numpy()
+        ha = host_array((S, SAMPLES_PER_STEP), np.int16, local_rank)
+        hp = host_array((S, n_probs), np.float32, local_rank)
+        torch.from_numpy(ha).copy_(audio)
+        torch.cuda.synchronize()
         eng.reset()
         for _ in range(2):
             eng.predict_clip_host(ha, out=hp)
-        barrier()
         e2e_steps = max(2, min(args.steps, 4))
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
         t0 = time.perf_counter()
-        a0.record()
-        for _ in range(e2e_steps):
-            eng.predict_clip_host(ha, out=hp)
-        a1.record()
-        barrier()
+        e2e_ms = timed(lambda: eng.predict_clip_host(ha, out=hp), e2e_steps)
         wall_ms = (time.perf_counter() - t0) * 1e3
-        ev_ms = a0.elapsed_time(a1)
-        e2e_ms = max_over_ranks(max(ev_ms, 0.0)) / e2e_steps
         e2e = {"value": frames_per_step_all / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": S * SAMPLES_PER_STEP * 2 * world,
-               "d2h_bytes_per_step": S * (FRAMES_PER_STEP // 3) * 4 * world, "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / e2e_steps,
-               "steps": e2e_steps, "api": "mww_predict_clip_host (pinned host int16 audio in, float32 probabilities out)",
-               "checksum_matches_device_path": bool(abs(float(host_probs[:, :100].double().sum().item()) - checksum) < 1e-3 * max(1.0, abs(checksum)))}
-        del host_audio, host_probs
+               "d2h_bytes_per_step": S * (FRAMES_PER_STEP // 3) * 4 * world, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "h2d_gbs_per_gpu": S * SAMPLES_PER_STEP * 2 / (e2e_ms / 1e3) / 1e9,
+               "api": "mww_predict_clip_host (pinned host int16 audio in, float32 probabilities out; buffers from mww_host_alloc)",
+               "host_buffers_numa_node": ha.base.base.numa_node, "rank_bound_to_numa_node": numa_node,
+               "checksum_matches_device_path": bool(abs(float(hp[:, :100].astype(np.float64).sum()) - checksum) < 1e-3 * max(1.0, abs(checksum)))}
+        del ha, hp
 
-    # ---- optional: live mode (small chunks; ring state round-trips HBM on every call) ----
-    live = None
-    if args.live:
-        n_live = args.live
+    # ---- the other single-GPU configurations of BASELINE.json, each with its own roofline (rank-local, every rank runs them) ----
+    def live_leg(kind, n_live=480):
+        """live mode: step() calls with `n_live` new samples per stream; the ring state round-trips HBM on every call"""
+        le = eng if kind == args.model else StreamEngine(model_blob(kind), n_streams=S, device=local_rank)
         calls = max(SAMPLES_PER_STEP // n_live, 1)
-        eng.reset()
+        le.reset()
         chunks = [audio[:, i * n_live:(i + 1) * n_live].contiguous() for i in range(min(calls, 8))]
         for c in chunks[:4]:
-            eng.predict_clip(c, out=probs)
-        barrier()
-        l0e, l1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        eng.profile(True)
-        l0e.record()
-        for i in range(calls):
-            eng.predict_clip(chunks[i % len(chunks)], out=probs)
-        l1e.record()
-        barrier()
-        live_ms = max_over_ranks(l0e.elapsed_time(l1e))
-        lp = eng.profile_read()
-        eng.profile(False)
-        frames = S * world * calls * (n_live // 160)
-        # live-step NN, algorithmic bytes per stream-step: every ring row read once (4 176 floats), one new
-        # row per ring + the 2-row first-conv ring written (368 floats), 3 uint16 feature rows in, one probability out
-        nn_ms = lp["mixednet"][0] / max(lp["mixednet"][1], 1)
-        eb = 4 if args.model == "f32" else 1                                        # ring element size
-        step_bytes = 4176 * eb + 368 * eb + 3 * 80 + 4
-        nn_gbs = S * step_bytes / (nn_ms / 1e3) / 1e9 if nn_ms else None
-        live = {"samples_per_call": n_live, "calls": calls, "value": frames / (live_ms / 1e3), "unit": UNIT, "ms_per_call": live_ms / calls,
-                "kernels_ms_per_call": {k: v[0] / calls for k, v in lp.items()},
-                "nn_live_hbm": {"bytes_per_stream_step": step_bytes, "achieved_gbs": nn_gbs,
-                                "frac_of_measured_hbm": nn_gbs / measured_peaks()[0] if nn_gbs else None},
-                "realtime_streams_capacity": S * world * (n_live / 16.0) / (live_ms / calls)}
+            le.predict_clip(c, out=probs)
+        state = {"i": 0}
 
-    # ---- optional: BASELINE.json configs[3], feature extractor only ----
-    feat = None
-    if args.features:
+        def one():
+            le.predict_clip(chunks[state["i"] % len(chunks)], out=probs)
+            state["i"] += 1
+        le.profile(True)
+        live_ms = timed(one, calls)
+        lp = le.profile_read()
+        le.profile(False)
+        frames = S * world * (n_live // 160)
+        # live-step NN, algorithmic bytes per stream-step (SURVEY.md 8d): every ring row read once (4 176 elements), one new
+        # row per ring + the 2-row first-conv ring written (368 elements), 3 uint16 feature rows in, one probability out
+        nn_ms = lp["mixednet"][0] / max(lp["mixednet"][1], 1)
+        eb = 4 if kind == "f32" else 1
+        step_bytes = 4176 * eb + 368 * eb + 3 * 80 + 4
+        peak, peak_src = measured_peaks()
+        nn_gbs = S * step_bytes / (nn_ms / 1e3) / 1e9 if nn_ms else None
+        out = {"workload": "configs[1]/[2] streams stepped live: %d calls of %d new samples (one model step) for %d streams, %s" % (calls, n_live, S, kind),
+               "samples_per_call": n_live, "calls": calls, "value": frames / (live_ms / 1e3), "unit": UNIT, "ms_per_call": live_ms,
+               "kernels_ms_per_call": {k: v[0] / calls for k, v in lp.items()},
+               "roofline": {"bound": "hbm", "kernel": "nn_%s_live_kernel" % ("f32" if kind == "f32" else "i8"), "achieved": nn_gbs, "peak": peak,
+                            "unit": "GB/s", "frac": nn_gbs / peak if nn_gbs else None, "peak_source": peak_src,
+                            "alg_bytes_per_stream_step": step_bytes, "kernel_ms": nn_ms, "traffic": None},
+               "realtime_streams_capacity": S * world * (n_live / 16.0) / live_ms}
+        if le is not eng:
+            le.close()
+        return out
+
+    def clip_leg(kind):
+        ce = StreamEngine(model_blob(kind), n_streams=S, device=local_rank)
+        for _ in range(3):
+            ce.predict_clip(audio, out=probs)
+        ce.profile(True)
+        steps = max(3, min(args.steps, 5))
+        ms = timed(lambda: ce.predict_clip(audio, out=probs), steps)
+        cp = ce.profile_read()
+        ce.profile(False)
+        out = {"workload": "configs[2]: %d streams x %d frames per step, okay_nabu mixednet %s, clip mode" % (S, FRAMES_PER_STEP, kind),
+               "dtype": kind, "value": S * FRAMES_PER_STEP * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+               "kernels": {k: {"ms_per_step": v[0] / steps} for k, v in cp.items()}, "roofline": k1_roofline(cp, S, steps, clock_info)}
+        ce.close()
+        return out
+
+    def features_leg():
+        """BASELINE.json configs[3]: the feature extractor alone on 1 M 30 ms windows (streaming and stateless)"""
         feat = {}
+        peak, peak_src = measured_peaks()
+        tr = ncu_traffic() or {}
         for name, fs, fn in (("streaming_4096x256", 4096, 160 * 256 + 320), ("stateless_1048576x480", 1 << 20, 480)):
             fe = StreamEngine(None, n_streams=fs, device=local_rank)
             fa = synth_audio_device(torch, fs, fn, 99 + rank, device)
             n_fr = (fn - 480) // 160 + 1
             fo = torch.empty((fs, n_fr, 40), dtype=torch.uint16, device=device)
-            for _ in range(3):
-                fe.reset()
-                fe.features(fa, out=fo)
-            barrier()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 10
-            f0.record()
-            for _ in range(reps):
+
+            def one():
                 fe.reset()                                   # every pass starts from the reset frontend state, like a new clip
                 fe.features(fa, out=fo)
-            f1.record()
-            barrier()
-            f_ms = max_over_ranks(f0.elapsed_time(f1)) / reps
+            for _ in range(3):
+                one()
+            f_ms = timed(one, 10)
             windows = fs * n_fr * world
-            feat[name] = {"windows": windows, "ms": f_ms, "windows_per_s": windows / (f_ms / 1e3),
-                          "alg_bytes_per_window": (fn * 2 + n_fr * 80) / n_fr,
-                          "achieved_gbs": fs * (fn * 2 + n_fr * 80) / (f_ms / 1e3) / 1e9}
-            del fe, fa, fo
+            alg = (fn * 2 + n_fr * 80) / n_fr
+            gbs = fs * (fn * 2 + n_fr * 80) / (f_ms / 1e3) / 1e9
+            feat[name] = {"windows": windows, "ms": f_ms, "windows_per_s": windows / (f_ms / 1e3), "alg_bytes_per_window": alg,
+                          "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src,
+                                       "traffic": None,
+                                       "issue": issue_roofline(tr["thread_instr_per_unit"], fs * n_fr, f_ms, clock_info) if tr.get("thread_instr_per_unit") else None,
+                                       "note": "integer-ALU bound like the clip frontend: the issue-slot fraction is the binding one"}}
+            fe.close()
+            del fa, fo
+        return feat
 
-    # ---- N > 1: the north_star's ingest pattern -- audio scattered from rank 0, scores gathered back (NCCL) ----
-    scatter = None
-    if world > 1 and not args.no_scatter:
-        from microwakeword_b200.sharding import gather_probs, scatter_audio
-        total = S * world
-        full = audio.repeat(world, 1) if rank == 0 else None           # rank 0 holds every stream's audio
-        eng.reset()
-        for _ in range(2):
-            local = scatter_audio(full, total, SAMPLES_PER_STEP, src=0, device=device)
-            gather_probs(eng.predict_clip(local, out=probs), total, dst=0)
-        barrier()
-        sg_steps = 3
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        s0.record()
-        for _ in range(sg_steps):
-            local = scatter_audio(full, total, SAMPLES_PER_STEP, src=0, device=device)
-            gathered = gather_probs(eng.predict_clip(local, out=probs), total, dst=0)
-        s1.record()
-        barrier()
-        sg_ms = max_over_ranks(s0.elapsed_time(s1)) / sg_steps
-        scatter = {"value": frames_per_step_all / (sg_ms / 1e3), "unit": UNIT, "ms_per_step": sg_ms, "steps": sg_steps,
-                   "nvlink_bytes_out_of_rank0_per_step": S * SAMPLES_PER_STEP * 2 * (world - 1),
-                   "note": "torch.distributed scatter of int16 audio from rank 0 + gather of float32 scores to rank 0 (NCCL), serialised with compute"}
-        # the same exchange hidden behind the compute: every rank's block is cut into 8 tiles (one engine each) and the rank
-        # PULLS tile t+1 from rank 0's buffer with copy-engine DMA over NVLink peer access (CUDA IPC) while tile t computes;
-        # no communication kernels, the scores come back through one NCCL gather.  (Pipelining the NCCL scatter itself over
-        # the same tiles was measured too: 52 - 215 ms per step at N = 2, slower than the serial exchange -- its send/recv
-        # kernels have to be co-scheduled with saturating compute grids on both GPUs)
-        from microwakeword_b200.sharding import ShardedEngine
-        eng.reset()                                     # one serial pass from the reset state as the comparison value
-        local = scatter_audio(full, total, SAMPLES_PER_STEP, src=0, device=device)
-        gathered = gather_probs(eng.predict_clip(local, out=probs), total, dst=0)
-        sh = ShardedEngine(model_blob(args.model), total, local_rank, tiles=8)
-        try:
-            from microwakeword_b200.sharding import PeerAudio
-            if os.environ.get("MWW_PEER_OPEN") == "lib":       # opt-in: IPC handle opened in each rank's own context (sharding.py)
-                peer = PeerAudio.allocate(total, SAMPLES_PER_STEP, src=0, device=device)
-                if rank == 0:
-                    peer.buffer.copy_(full)
-                scatter["peer_open"] = "lib"
-            else:
-                peer = PeerAudio(full, total, SAMPLES_PER_STEP, src=0, device=device)
-            for _ in range(2):
-                sh.reset()
-                gathered_q = sh.predict_clip_pulled(peer)
-            if rank == 0:
-                scatter["pulled_equals_serial"] = bool(torch.equal(gathered_q, gathered))
-            barrier()
-            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            q0.record()
-            for _ in range(sg_steps):
-                sh.predict_clip_pulled(peer)
-            q1.record()
-            barrier()
-            pl_ms = max_over_ranks(q0.elapsed_time(q1)) / sg_steps
-            # where the time goes: the tile engines alone on resident audio, and the pull alone
-            def timed(fn, reps=3):
-                barrier()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(reps):
-                    fn()
-                b.record()
-                barrier()
-                return max_over_ranks(a.elapsed_time(b)) / reps
-            tile_audio = [audio[s0_:s0_ + c_] for s0_, c_ in sh.tile_parts]
-            tiles_ms = timed(lambda: [e.predict_clip(a_) for e, a_ in zip(sh.engines, tile_audio)])
-            def pull_only():
-                loc, evs = peer.pull_tiles(sh.tiles)
-                for ev in evs:
-                    torch.cuda.current_stream().wait_event(ev)
-            pull_ms = timed(pull_only)
-            scatter["pulled_breakdown"] = {"tile_engines_compute_only_ms": tiles_ms, "pull_only_ms": pull_ms,
-                                           "pull_gbs_into_each_peer": S * SAMPLES_PER_STEP * 2 / (pull_ms / 1e3) / 1e9}
-            scatter["pulled"] = {"value": frames_per_step_all / (pl_ms / 1e3), "unit": UNIT, "ms_per_step": pl_ms, "tiles_per_rank": sh.tiles,
-                                 "note": "ranks pull their tiles from rank 0 over NVLink peer access (copy engines, CUDA IPC) while earlier tiles compute; "
-                                         "NCCL only for the per-step barrier and the gather of the scores"}
-            if scatter.get("peer_open") == "lib":             # every rank is done reading before the exporter frees the buffer
-                torch.cuda.synchronize()
-                barrier()
-                peer.close()
-            del peer
-        except Exception as exc:                       # CUDA IPC / peer access unavailable in this container: report, do not hide
-            scatter["pulled"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
-        del full, sh
+    extras = {}
+    if not args.no_extra:
+        other = "int8" if args.model == "f32" else "f32"
+        extras[other] = clip_leg(other)
+        extras["live"] = live_leg(args.model)
+        extras["live_" + other] = live_leg(other)
+        extras["features_only"] = features_leg()
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    # ---- CPU baseline beside it (rank 0, N = 1 only; all the host cores the container may use) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, affinity_before)
         cores, host = host_cores()
         v, sample = time_cpu(args.model, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                "single_thread_value": time_cpu_single_thread(args.model), "host": host}
 
     if rank == 0:
+        cfg = config_dict(args, world)
+        if world > 1:
+            cfg["workload"] = "configs[4]: %d synthetic 16 kHz streams x %d frames (3 s) per step on %d GPUs (65 536 per rank), audio originating on rank 0 " \
+                              "(pulled over NVLink inside the timed region), scores gathered on rank 0; okay_nabu mixednet %s, clip mode" \
+                              % (S * world, FRAMES_PER_STEP, world, args.model)
+            cfg["parallelism"] = "independent stream shards x%d; scatter (copy-engine pull over NVLink) + NCCL gather inside the timed region" % world
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.model == "f32" else "int8", "data": "synthetic",
-            "config": config_dict(args, world), "clocks": clock_info, "gpu_launches": int(launches),
-            "kernels": kernels, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "scatter_gather": scatter, "live": live, "features_only": feat, "probs_checksum": checksum,
-            "realtime_streams_capacity": value / 100.0,
+            "config": cfg, "clocks": clock_info, "gpu_launches": int(launches),
+            "kernels": kernels, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "ingest": ingest_info,
+            "probs_checksum": checksum, "realtime_streams_capacity": value / 100.0,
         }
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

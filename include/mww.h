@@ -87,8 +87,13 @@ int mww_get_info(const mww_t *h, mww_info *out);
 /* Fresh frontend + zero ring buffers.  ids == NULL (n ignored): all streams, and the lockstep
  * counters (buffered samples, pending rows) return to 0 -- the exact analogue of a new
  * MicroFrontend() / a freshly loaded interpreter.  ids != NULL: h_ids[0..n) streams get zeroed
- * state but keep the shared counters (their history reads as silence). */
+ * state but keep the shared counters (their history reads as silence) -- this is how a stream joins or
+ * leaves a handle that keeps serving the others: a constant number of launches whatever n is, and valid
+ * while the rings are rotated by live calls (fresh state is rotation-invariant).
+ * mww_reset_device_ids is the same with the id list already in DEVICE memory (e.g. produced by the
+ * detection kernels: the streams that just fired); ids outside [0, n_streams) are ignored. */
 int mww_reset(mww_t *h, const int32_t *h_ids, int n, void *cu_stream);
+int mww_reset_device_ids(mww_t *h, const int32_t *d_ids, int n, void *cu_stream);
 
 /* Fresh frontend only (what a new MicroFrontend() per clip gives the reference, audio_utils.py:52):
  * zero window buffer, zero noise estimates, buffered-sample counter 0.  NN rings are untouched --
@@ -115,9 +120,23 @@ int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long 
 
 /* Same, from/to HOST buffers: the library tiles the streams, overlaps the host->device copy of one
  * tile with the kernels of the previous one, and returns when h_probs is complete.  Pinned host
- * memory gives full-rate copies; pageable memory works too. */
+ * memory (mww_host_alloc) gives full-rate copies; pageable memory works too.  The call has no stream
+ * argument: it first waits for everything queued on the device so far (cudaDeviceSynchronize), so
+ * mww_reset / live calls issued earlier on any stream are ordered before it. */
 int mww_predict_clip_host(mww_t *h, const int16_t *h_audio, int n_samples, long long audio_stride,
                           float *h_probs, int max_probs, int *h_probs_out);
+
+/* Same pipeline with the audio somewhere this GPU can DMA from but should not compute from: device
+ * memory of a PEER GPU of the box (mapped with mww_ipc_open -- the multi-GPU ingest of BASELINE.json
+ * configs[4], "scatter stream batches") or host memory.  The streams are cut into `n_tiles` tiles
+ * (<= 0: 16); this GPU's copy engine pulls tile t+1 over NVLink / PCIe into a staging buffer while the
+ * kernels of tile t run, and the scores are written straight into d_probs on THIS device
+ * ([n_streams][max_probs]).  Asynchronous and stream-ordered on cu_stream: the call starts after the
+ * work queued on cu_stream so far and cu_stream waits for its last kernel.  A source that already lives
+ * on this GPU is computed in place (= mww_predict_clip).  If a CUDA call fails half-way the handle is
+ * left "poisoned": every stateful entry point fails until mww_reset(h, NULL, 0, stream). */
+int mww_predict_clip_remote(mww_t *h, const int16_t *src_audio, int n_samples, long long audio_stride,
+                            float *d_probs, int max_probs, int *h_probs_out, int n_tiles, void *cu_stream);
 
 /* Per-stream state snapshot for checkpoint / tests (host buffers, synchronous).
  *   h_carry    int16 [n_streams][480]   window buffer (first `frontend_buffered` samples valid)
@@ -173,6 +192,17 @@ int mww_ipc_alloc(size_t bytes, int device, void **d_ptr, unsigned char *handle6
 int mww_ipc_open(const unsigned char *handle64, int device, void **d_ptr);
 int mww_ipc_close(void *d_ptr, int device);
 int mww_ipc_free(void *d_ptr, int device);
+
+/* Pinned host memory placed on the NUMA node the GPU hangs off (/sys/bus/pci/devices/<bdf>/numa_node): the calling
+ * thread is moved to that node's CPUs (and MPOL_PREFERRED set, where the container allows it) for the duration of the
+ * cudaHostAlloc, then put back.  On a two-socket 8-GPU box the default placement puts every rank's buffer on the node
+ * the process happened to start on and the GPUs of the other socket copy across the inter-socket link (measured in
+ * r01: host->device rate per GPU fell from 54 to 40 GB/s with 8 ranks).  *numa_node_out (optional) = the node, -1 when
+ * the topology cannot be read (then this is a plain cudaHostAlloc).  mww_bind_host_thread moves the CALLING thread to
+ * the GPU's node for good (a rank calls it once, before anything else allocates). */
+int mww_host_alloc(size_t bytes, int device, void **h_ptr, int *numa_node_out);
+int mww_host_free(void *h_ptr);
+int mww_bind_host_thread(int device, int *numa_node_out);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,7 @@ EXPORTS = (
     "mww_get_state", "mww_set_state", "mww_launch_count", "mww_profile_enable", "mww_profile_read",
     "mww_moving_average", "mww_false_accept_counts", "mww_positive_scores", "mww_copy_async",
     "mww_ipc_alloc", "mww_ipc_open", "mww_ipc_close", "mww_ipc_free",
+    "mww_predict_clip_remote", "mww_reset_device_ids", "mww_host_alloc", "mww_host_free", "mww_bind_host_thread",
 )
 
 
@@ -49,9 +50,11 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _build
     if not os.path.exists(SO_PATH):
-        from . import build as _build  # raises if nvcc is unavailable
-        _build.build()
+        _build.build()                 # raises if nvcc is unavailable
+    elif os.path.exists(_build.NVCC) and _build._stale():
+        _build.build()                 # sources newer than the binary: never load a library with an older ABI
     L = ctypes.CDLL(SO_PATH)
     vp, i32, ll, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t
     pi = ctypes.POINTER(ctypes.c_int)
@@ -101,6 +104,16 @@ def lib() -> ctypes.CDLL:
     L.mww_ipc_close.argtypes = [vp, i32]
     L.mww_ipc_free.restype = i32
     L.mww_ipc_free.argtypes = [vp, i32]
+    L.mww_predict_clip_remote.restype = i32
+    L.mww_predict_clip_remote.argtypes = [vp, vp, i32, ll, vp, i32, pi, i32, vp]
+    L.mww_reset_device_ids.restype = i32
+    L.mww_reset_device_ids.argtypes = [vp, vp, i32, vp]
+    L.mww_host_alloc.restype = i32
+    L.mww_host_alloc.argtypes = [sz, i32, ctypes.POINTER(vp), pi]
+    L.mww_host_free.restype = i32
+    L.mww_host_free.argtypes = [vp]
+    L.mww_bind_host_thread.restype = i32
+    L.mww_bind_host_thread.argtypes = [i32, pi]
     _lib = L
     return L
 

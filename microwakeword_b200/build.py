@@ -16,12 +16,29 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "-cudart", "static"]
 
 
+STAMP = OUT + ".srchash"
+
+
+def source_hash() -> str:
+    """sha256 over every file of csrc/, include/mww.h and the compiler flags: what the binary was built from.  Content, not
+    mtimes -- the tree is copied to the GPU box, where timestamps mean nothing."""
+    import hashlib
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(os.path.dirname(HERE), "include", "mww.h")]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(HERE), "include", "mww.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        return open(STAMP).read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -29,13 +46,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     if not os.path.exists(NVCC):
         raise RuntimeError("nvcc not found at %s; libmww_b200.so must be prebuilt (there is no CPU fallback)" % NVCC)
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libmww_b200.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
+    import fcntl
+    with open(OUT + ".lock", "w") as lock:               # several ranks may arrive here at once: one builds, the rest wait
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale():
+            return OUT
+        tmp = OUT + ".tmp.%d" % os.getpid()
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            if os.path.exists(tmp):
+                os.unlink(tmp)
+            raise RuntimeError("nvcc failed building libmww_b200.so")
+        if verbose:
+            sys.stderr.write(res.stderr)
+        os.replace(tmp, OUT)                               # a process that has the old file mapped keeps its own copy
+        with open(STAMP, "w") as f:
+            f.write(source_hash() + "\n")
     return OUT
 
 

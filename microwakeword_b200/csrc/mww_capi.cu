@@ -4,9 +4,12 @@
 // stream tiling against a scratch budget, and the pipelined host-buffer path.  All arithmetic is
 // in the kernels (mww_frontend.cu, mww_nn.cu, mww_nn_int8.cu); there is no CPU fallback.
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <string>
@@ -85,9 +88,14 @@ struct mww_handle {
     uint32_t *d_v = nullptr; size_t v_bytes = 0;
     uint16_t *d_feat = nullptr; size_t feat_bytes = 0;
     size_t scratch_budget = (size_t)2048 << 20;
+    int min_tile_streams = 2048;       // staged path: a tile never gets fewer streams than this (MWW_MIN_TILE_STREAMS)
     // host-buffer pipeline
     cudaStream_t st_h2d = nullptr, st_compute = nullptr, st_d2h = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    cudaEvent_t ev_entry = nullptr, ev_exit = nullptr;
+    bool staged_used = false;      // ev_compute[] have been recorded by an earlier staged call
+    bool poisoned = false;
+    int32_t *d_ids = nullptr; size_t ids_cap = 0;      // device copy of a host id list (mww_reset)         // a staged call failed half-way: per-stream state is inconsistent until mww_reset(all)
     int16_t *d_audio_tile[2] = {nullptr, nullptr}; size_t audio_tile_bytes = 0;
     float *d_probs_tile[2] = {nullptr, nullptr}; size_t probs_tile_bytes = 0;
     // live-step path: rings stay rotated between live calls (mww_nn_live.cuh); all streams advance in lockstep
@@ -111,6 +119,19 @@ int cuda_fail(mww_t *h, cudaError_t e, const char *what) {
 #define CU(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(h, e_, #call); } while (0)
 
 size_t elem_size(const mww_t *h) { return h->quantized ? 1 : 4; }
+
+// every entry point runs with the handle's device current and puts the caller's device back on return (a process that
+// holds engines on several GPUs, or torch's current device, is not disturbed)
+struct DeviceGuard {
+    int prev = -1; bool switched = false; cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) { err = cudaSetDevice(device); switched = err == cudaSuccess && prev >= 0; }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define ENTER(h) DeviceGuard guard_((h)->device); if (guard_.err != cudaSuccess) return cuda_fail((h), guard_.err, "cudaSetDevice")
+#define ENTER_STATEFUL(h) ENTER(h); if ((h)->poisoned) return fail((h), MWW_ECUDA, "an earlier staged call failed half-way; per-stream state is inconsistent until mww_reset(h, NULL, 0, stream)")
 
 // RAII bracket: records an event pair around a launch when profiling is on
 struct ProfScope {
@@ -493,10 +514,10 @@ int zero_state(mww_t *h, cudaStream_t st) {
     h->n_pend = 0;
     if (!h->has_nn) return MWW_OK;
     if (h->quantized && h->generic) {
-        CU(h, launch_gen_fill_state_i8(h->G, h->GQ, static_cast<int8_t *>(h->d_nn_state), static_cast<int8_t *>(h->d_pend), h->n_streams, st));
+        CU(h, launch_gen_fill_state_i8(h->G, h->GQ, static_cast<int8_t *>(h->d_nn_state), static_cast<int8_t *>(h->d_pend), h->n_streams, nullptr, h->n_streams, st));
         h->launches += 1;
     } else if (h->quantized) {
-        CU(h, launch_fill_state_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state), static_cast<int8_t *>(h->d_pend), nullptr, h->n_streams, st));
+        CU(h, launch_fill_state_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state), static_cast<int8_t *>(h->d_pend), nullptr, h->n_streams, h->n_streams, st));
         h->launches += 1;
     } else {
         CU(h, cudaMemsetAsync(h->d_nn_state, 0, S * h->state_elems * 4, st));
@@ -510,9 +531,9 @@ int zero_state(mww_t *h, cudaStream_t st) {
 
 void destroy_impl(mww_t *h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaFree(h->d_tables); cudaFree(h->d_weights); cudaFree(h->d_carry); cudaFree(h->d_estimate);
-    cudaFree(h->d_nn_state); cudaFree(h->d_pend); cudaFree(h->d_v); cudaFree(h->d_feat);
+    cudaFree(h->d_nn_state); cudaFree(h->d_pend); cudaFree(h->d_v); cudaFree(h->d_feat); cudaFree(h->d_ids);
     for (int b = 0; b < 2; ++b) {
         cudaFree(h->d_audio_tile[b]); cudaFree(h->d_probs_tile[b]);
         if (h->ev_h2d[b]) cudaEventDestroy(h->ev_h2d[b]);
@@ -523,6 +544,8 @@ void destroy_impl(mww_t *h) {
     if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
     if (h->st_compute) cudaStreamDestroy(h->st_compute);
     if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
+    if (h->ev_entry) cudaEventDestroy(h->ev_entry);
+    if (h->ev_exit) cudaEventDestroy(h->ev_exit);
     delete h;
 }
 
@@ -538,8 +561,8 @@ int mww_create(const void *model_blob, size_t n_bytes, int device, int n_streams
     if (e != cudaSuccess || count == 0)
         return fail(nullptr, MWW_ECUDA, std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
     if (device < 0 || device >= count) return fail(nullptr, MWW_EINVAL, "mww_create: device index out of range");
-    e = cudaSetDevice(device);
-    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return cuda_fail(nullptr, guard.err, "cudaSetDevice");
     mww_t *h = new mww_handle();
     h->device = device;
     h->n_streams = n_streams;
@@ -547,6 +570,7 @@ int mww_create(const void *model_blob, size_t n_bytes, int device, int n_streams
     h->no_live = getenv("MWW_NO_LIVE") != nullptr;
     h->no_fuse = getenv("MWW_NO_FUSE") != nullptr;
     if (const char *mb = getenv("MWW_SCRATCH_MB")) { const long v = atol(mb); if (v > 0) h->scratch_budget = (size_t)v << 20; }
+    if (const char *mt = getenv("MWW_MIN_TILE_STREAMS")) { const long v = atol(mt); if (v > 0) h->min_tile_streams = (int)v; }
     h->has_nn = model_blob != nullptr;
     int rc = upload_tables(h);
     if (rc == MWW_OK && h->has_nn) rc = upload_weights(h, static_cast<const uint8_t *>(model_blob), n_bytes);
@@ -589,7 +613,8 @@ int ipc_fail(const char *what, cudaError_t e) {
 int mww_ipc_alloc(size_t bytes, int device, void **d_ptr, unsigned char *handle64) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     if (!d_ptr || !handle64 || bytes == 0) { g_create_error = "mww_ipc_alloc: bad argument"; return MWW_EINVAL; }
-    cudaError_t e = cudaSetDevice(device);
+    DeviceGuard guard(device);
+    cudaError_t e = guard.err;
     if (e != cudaSuccess) return ipc_fail("mww_ipc_alloc: cudaSetDevice", e);
     void *p = nullptr;
     if ((e = cudaMalloc(&p, bytes)) != cudaSuccess) return ipc_fail("mww_ipc_alloc: cudaMalloc", e);
@@ -602,7 +627,8 @@ int mww_ipc_alloc(size_t bytes, int device, void **d_ptr, unsigned char *handle6
 
 int mww_ipc_open(const unsigned char *handle64, int device, void **d_ptr) {
     if (!d_ptr || !handle64) { g_create_error = "mww_ipc_open: bad argument"; return MWW_EINVAL; }
-    cudaError_t e = cudaSetDevice(device);
+    DeviceGuard guard(device);
+    cudaError_t e = guard.err;
     if (e != cudaSuccess) return ipc_fail("mww_ipc_open: cudaSetDevice", e);
     cudaIpcMemHandle_t hd;
     memcpy(&hd, handle64, 64);
@@ -614,14 +640,16 @@ int mww_ipc_open(const unsigned char *handle64, int device, void **d_ptr) {
 
 int mww_ipc_close(void *d_ptr, int device) {
     if (!d_ptr) return MWW_OK;
-    cudaError_t e = cudaSetDevice(device);
+    DeviceGuard guard(device);
+    cudaError_t e = guard.err;
     if (e == cudaSuccess) e = cudaIpcCloseMemHandle(d_ptr);
     return e == cudaSuccess ? MWW_OK : ipc_fail("mww_ipc_close", e);
 }
 
 int mww_ipc_free(void *d_ptr, int device) {
     if (!d_ptr) return MWW_OK;
-    cudaError_t e = cudaSetDevice(device);
+    DeviceGuard guard(device);
+    cudaError_t e = guard.err;
     if (e == cudaSuccess) e = cudaFree(d_ptr);
     return e == cudaSuccess ? MWW_OK : ipc_fail("mww_ipc_free", e);
 }
@@ -634,7 +662,7 @@ int mww_profile_enable(mww_t *h, int on) {
 
 int mww_profile_read(mww_t *h, double *ms4, long long *counts4) {
     if (!h || !ms4 || !counts4) return MWW_EINVAL;
-    CU(h, cudaSetDevice(h->device));
+    ENTER(h);
     CU(h, cudaDeviceSynchronize());
     for (int c = 0; c < 4; ++c) {
         std::vector<cudaEvent_t> &v = h->prof_ev[c];
@@ -661,36 +689,87 @@ int mww_get_info(const mww_t *h, mww_info *o) {
     return MWW_OK;
 }
 
+namespace {
+
+// 4-byte fill of one per-stream record for a list of stream ids (device memory); ids outside [0, n_streams) are skipped
+__global__ void fill_by_id_kernel(uint32_t *__restrict__ base, long long words_per_stream, uint32_t value, const int32_t *__restrict__ ids,
+                                  int n_ids, int n_streams) {
+    const long long total = (long long)n_ids * words_per_stream;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long k = i / words_per_stream;
+        const int id = ids[k];
+        if (id < 0 || id >= n_streams) continue;
+        base[(long long)id * words_per_stream + (i - k * words_per_stream)] = value;
+    }
+}
+
+int fill_by_id(mww_t *h, void *base, size_t bytes_per_stream, const int32_t *d_ids, int n, cudaStream_t st) {
+    const long long words = (long long)(bytes_per_stream / 4);
+    const long long total = words * n;
+    if (total <= 0) return MWW_OK;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
+    fill_by_id_kernel<<<blocks, 256, 0, st>>>(static_cast<uint32_t *>(base), words, 0u, d_ids, n, h->n_streams);
+    CU(h, cudaGetLastError());
+    h->launches += 1;
+    return MWW_OK;
+}
+
+// fresh state for the listed streams: a handful of launches whatever the length of the list
+int reset_by_id(mww_t *h, const int32_t *d_ids, int n, cudaStream_t st) {
+    if (n <= 0) return MWW_OK;
+    int rc = fill_by_id(h, h->d_carry, kWindow * sizeof(int16_t), d_ids, n, st);
+    if (rc == MWW_OK) rc = fill_by_id(h, h->d_estimate, kNumChannels * sizeof(uint32_t), d_ids, n, st);
+    if (rc != MWW_OK || !h->has_nn) return rc;
+    if (h->quantized && h->generic) {
+        CU(h, launch_gen_fill_state_i8(h->G, h->GQ, static_cast<int8_t *>(h->d_nn_state), static_cast<int8_t *>(h->d_pend), n, d_ids, h->n_streams, st));
+        h->launches += 1;
+    } else if (h->quantized) {
+        CU(h, launch_fill_state_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state), static_cast<int8_t *>(h->d_pend), d_ids, n, h->n_streams, st));
+        h->launches += 1;
+    } else {
+        // zero rings are rotation-invariant, so streams of a handle whose rings are rotated (live mode) can be reset in place
+        rc = fill_by_id(h, h->d_nn_state, (size_t)h->state_elems * 4, d_ids, n, st);
+        if (rc == MWW_OK) rc = fill_by_id(h, h->d_pend, (size_t)h->pend_cap * kNumChannels * 4, d_ids, n, st);
+    }
+    return rc;
+}
+
+}  // namespace
+
 int mww_reset(mww_t *h, const int32_t *h_ids, int n, void *cu_stream) {
     if (!h) return MWW_EINVAL;
-    CU(h, cudaSetDevice(h->device));
+    ENTER(h);
     cudaStream_t st = static_cast<cudaStream_t>(cu_stream);
-    if (!h_ids) return zero_state(h, st);
-    for (int i = 0; i < n; ++i) {
-        const int id = h_ids[i];
-        if (id < 0 || id >= h->n_streams) return fail(h, MWW_EINVAL, "mww_reset: stream id out of range");
-        CU(h, cudaMemsetAsync(h->d_carry + (size_t)id * kWindow, 0, kWindow * sizeof(int16_t), st));
-        CU(h, cudaMemsetAsync(h->d_estimate + (size_t)id * kNumChannels, 0, kNumChannels * sizeof(uint32_t), st));
-        if (!h->has_nn) continue;
-        if (h->quantized && h->generic) {
-            CU(h, launch_gen_fill_state_i8(h->G, h->GQ, static_cast<int8_t *>(h->d_nn_state) + (size_t)id * h->state_elems,
-                                           static_cast<int8_t *>(h->d_pend) + (size_t)id * h->pend_cap * kNumChannels, 1, st));
-            h->launches += 1;
-        } else if (h->quantized) {
-            CU(h, launch_fill_state_i8(h->Wq, static_cast<int8_t *>(h->d_nn_state) + (size_t)id * h->state_elems,
-                                       static_cast<int8_t *>(h->d_pend) + (size_t)id * h->pend_cap * kNumChannels, nullptr, 1, st));
-            h->launches += 1;
-        } else {
-            CU(h, cudaMemsetAsync(static_cast<float *>(h->d_nn_state) + (size_t)id * h->state_elems, 0, (size_t)h->state_elems * 4, st));
-            CU(h, cudaMemsetAsync(static_cast<float *>(h->d_pend) + (size_t)id * h->pend_cap * kNumChannels, 0, (size_t)h->pend_cap * kNumChannels * 4, st));
+    if (!h_ids) {
+        if (h->poisoned) {          // whatever the failed staged call left in flight is gone before the state is rebuilt
+            cudaDeviceSynchronize();
+            h->poisoned = false;
         }
+        return zero_state(h, st);
     }
-    return MWW_OK;
+    if (h->poisoned) return fail(h, MWW_ECUDA, "handle needs mww_reset(h, NULL, 0, stream) after a failed staged call");
+    if (n <= 0) return MWW_OK;
+    for (int i = 0; i < n; ++i)
+        if (h_ids[i] < 0 || h_ids[i] >= h->n_streams) return fail(h, MWW_EINVAL, "mww_reset: stream id out of range");
+    if ((size_t)n > h->ids_cap) {
+        if (h->d_ids) { CU(h, cudaStreamSynchronize(st)); cudaFree(h->d_ids); h->d_ids = nullptr; h->ids_cap = 0; }
+        const size_t cap = std::max<size_t>((size_t)n, 1024);
+        CU(h, cudaMalloc(&h->d_ids, cap * sizeof(int32_t)));
+        h->ids_cap = cap;
+    }
+    CU(h, cudaMemcpyAsync(h->d_ids, h_ids, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    return reset_by_id(h, h->d_ids, n, st);
+}
+
+int mww_reset_device_ids(mww_t *h, const int32_t *d_ids, int n, void *cu_stream) {
+    if (!h || (n > 0 && !d_ids) || n < 0) return MWW_EINVAL;
+    ENTER_STATEFUL(h);
+    return reset_by_id(h, d_ids, n, static_cast<cudaStream_t>(cu_stream));
 }
 
 int mww_reset_frontend(mww_t *h, void *cu_stream) {
     if (!h) return MWW_EINVAL;
-    CU(h, cudaSetDevice(h->device));
+    ENTER_STATEFUL(h);
     cudaStream_t st = static_cast<cudaStream_t>(cu_stream);
     const size_t S = (size_t)h->n_streams;
     CU(h, cudaMemsetAsync(h->d_carry, 0, S * kWindow * sizeof(int16_t), st));
@@ -703,7 +782,7 @@ int mww_features(mww_t *h, const int16_t *d_audio, int n_samples, long long audi
                  int *h_rows_out, void *cu_stream) {
     if (!h) return MWW_EINVAL;
     if (n_samples < 0 || (n_samples > 0 && !d_audio) || audio_stride < n_samples) return fail(h, MWW_EINVAL, "mww_features: bad audio arguments");
-    CU(h, cudaSetDevice(h->device));
+    ENTER_STATEFUL(h);
     cudaStream_t st = static_cast<cudaStream_t>(cu_stream);
     const int n_frames = frames_for(h->used, n_samples);
     if (n_frames > max_rows || (n_frames > 0 && !d_feat)) return fail(h, MWW_EINVAL, "mww_features: feature buffer too small for the rows this call emits");
@@ -731,7 +810,7 @@ int mww_infer_features(mww_t *h, const void *d_rows, int row_type, int n_rows, l
     if (n_rows < 0 || (n_rows > 0 && !d_rows) || rows_stride < n_rows) return fail(h, MWW_EINVAL, "mww_infer_features: bad row arguments");
     if (row_type < 0 || row_type > 2) return fail(h, MWW_EINVAL, "mww_infer_features: unknown row_type");
     if (!h->has_nn) return fail(h, MWW_EINVAL, "mww_infer_features: frontend-only handle (created without a model)");
-    CU(h, cudaSetDevice(h->device));
+    ENTER_STATEFUL(h);
     const int n_steps = (h->n_pend + n_rows) / h->stride;
     if (n_steps > max_probs || (n_steps > 0 && !d_probs)) return fail(h, MWW_EINVAL, "mww_infer_features: probability buffer too small");
     int rc = begin_nn_call(h, n_rows, static_cast<cudaStream_t>(cu_stream));
@@ -749,7 +828,7 @@ int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long 
     if (!h) return MWW_EINVAL;
     if (n_samples < 0 || (n_samples > 0 && !d_audio) || audio_stride < n_samples) return fail(h, MWW_EINVAL, "mww_predict_clip: bad audio arguments");
     if (!h->has_nn) return fail(h, MWW_EINVAL, "mww_predict_clip: frontend-only handle (created without a model)");
-    CU(h, cudaSetDevice(h->device));
+    ENTER_STATEFUL(h);
     cudaStream_t st = static_cast<cudaStream_t>(cu_stream);
     const int n_frames = frames_for(h->used, n_samples);
     const int n_steps = (h->n_pend + n_frames) / h->stride;
@@ -778,78 +857,131 @@ int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long 
     return MWW_OK;
 }
 
-int mww_predict_clip_host(mww_t *h, const int16_t *h_audio, int n_samples, long long audio_stride, float *h_probs, int max_probs,
-                          int *h_probs_out) {
-    if (!h) return MWW_EINVAL;
-    if (n_samples < 0 || (n_samples > 0 && !h_audio) || audio_stride < n_samples) return fail(h, MWW_EINVAL, "mww_predict_clip_host: bad audio arguments");
-    if (!h->has_nn) return fail(h, MWW_EINVAL, "mww_predict_clip_host: frontend-only handle (created without a model)");
-    CU(h, cudaSetDevice(h->device));
-    const int n_frames = frames_for(h->used, n_samples);
-    const int n_steps = (h->n_pend + n_frames) / h->stride;
-    if (n_steps > max_probs || (n_steps > 0 && !h_probs)) return fail(h, MWW_EINVAL, "mww_predict_clip_host: probability buffer too small");
-    if (!h->st_compute) {
-        CU(h, cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
-        CU(h, cudaStreamCreateWithFlags(&h->st_compute, cudaStreamNonBlocking));
-        CU(h, cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; ++b) {
-            CU(h, cudaEventCreateWithFlags(&h->ev_h2d[b], cudaEventDisableTiming));
-            CU(h, cudaEventCreateWithFlags(&h->ev_compute[b], cudaEventDisableTiming));
-            CU(h, cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming));
-        }
+// ---- staged path: the audio does not live on this GPU ------------------------------------------------------------
+// Shared by mww_predict_clip_host (source = host memory, destination = host memory) and mww_predict_clip_remote (source =
+// host memory or device memory of a PEER GPU mapped into this process, destination = this GPU).  The streams are cut into
+// tiles; a copy stream brings tile t+1 into one of two staging buffers (cudaMemcpyAsync, cudaMemcpyDefault: the copy
+// engine of THIS GPU pulls over PCIe or NVLink, no SM is involved on either side) while the kernels of tile t run on the
+// compute stream, and for a host destination a third stream drains the scores.
+namespace {
+
+int ensure_pipeline(mww_t *h) {
+    if (h->st_compute) return MWW_OK;
+    CU(h, cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
+    CU(h, cudaStreamCreateWithFlags(&h->st_compute, cudaStreamNonBlocking));
+    CU(h, cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        CU(h, cudaEventCreateWithFlags(&h->ev_h2d[b], cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&h->ev_compute[b], cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming));
     }
-    // tile so that copies and kernels of neighbouring tiles overlap: at least 16 tiles when there are enough streams (the
-    // last tile's kernels are the only part of the compute the host->device stream cannot hide), but never fewer than
-    // 2 048 streams per tile so that every launch still fills the GPU
-    int tile = tile_streams(h, n_frames, true);
-    tile = std::max(1, std::min(tile, std::max((h->n_streams + 15) / 16, std::min(h->n_streams, 2048))));
-    int rc = ensure_scratch(h, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 2);
-    if (rc) return rc;
-    const size_t a_bytes = (size_t)tile * std::max(n_samples, 1) * sizeof(int16_t);
-    const size_t p_bytes = (size_t)tile * std::max(n_steps, 1) * sizeof(float);
-    if (a_bytes > h->audio_tile_bytes || p_bytes > h->probs_tile_bytes) {
-        CU(h, cudaDeviceSynchronize());
-        for (int b = 0; b < 2; ++b) {
-            cudaFree(h->d_audio_tile[b]); cudaFree(h->d_probs_tile[b]);
-            h->d_audio_tile[b] = nullptr; h->d_probs_tile[b] = nullptr;
-        }
-        h->audio_tile_bytes = h->probs_tile_bytes = 0;
-        for (int b = 0; b < 2; ++b) {
-            CU(h, cudaMalloc(&h->d_audio_tile[b], a_bytes));
-            CU(h, cudaMalloc(&h->d_probs_tile[b], p_bytes));
-        }
-        h->audio_tile_bytes = a_bytes; h->probs_tile_bytes = p_bytes;
-    }
-    rc = begin_nn_call(h, n_frames, h->st_compute);
-    if (rc) return rc;
+    CU(h, cudaEventCreateWithFlags(&h->ev_entry, cudaEventDisableTiming));
+    CU(h, cudaEventCreateWithFlags(&h->ev_exit, cudaEventDisableTiming));
+    return MWW_OK;
+}
+
+// the tile loop proper; any error leaves work in flight -- the caller drains the streams and poisons the handle
+int staged_tiles(mww_t *h, const int16_t *src, int n_samples, long long audio_stride, float *dst, int max_probs, bool dst_is_host,
+                 int tile, int n_frames, int n_steps) {
     int it = 0;
     for (int first = 0; first < h->n_streams; first += tile, ++it) {
         const int n = std::min(tile, h->n_streams - first);
         const int b = it & 1;
-        // the audio buffer is free once the kernels of the tile that used it two iterations ago are done
+        // the staging buffer is free once the kernels of the tile that used it two iterations ago are done
         if (it >= 2) CU(h, cudaStreamWaitEvent(h->st_h2d, h->ev_compute[b], 0));
-        if (n_samples > 0)
-            CU(h, cudaMemcpy2DAsync(h->d_audio_tile[b], (size_t)n_samples * 2, h_audio + (size_t)first * audio_stride, (size_t)audio_stride * 2,
-                                    (size_t)n_samples * 2, n, cudaMemcpyHostToDevice, h->st_h2d));
+        if (n_samples > 0) {
+            const int16_t *from = src + (size_t)first * audio_stride;
+            if (audio_stride == n_samples)       // contiguous block: one linear DMA
+                CU(h, cudaMemcpyAsync(h->d_audio_tile[b], from, (size_t)n * n_samples * 2, cudaMemcpyDefault, h->st_h2d));
+            else
+                CU(h, cudaMemcpy2DAsync(h->d_audio_tile[b], (size_t)n_samples * 2, from, (size_t)audio_stride * 2, (size_t)n_samples * 2, n,
+                                        cudaMemcpyDefault, h->st_h2d));
+        }
         CU(h, cudaEventRecord(h->ev_h2d[b], h->st_h2d));
         CU(h, cudaStreamWaitEvent(h->st_compute, h->ev_h2d[b], 0));
-        if (it >= 2) CU(h, cudaStreamWaitEvent(h->st_compute, h->ev_d2h[b], 0));   // probs buffer drained
-        rc = run_frontend_tile(h, first, n, h->d_audio_tile[b], n_samples, n_samples, n_frames, h->d_feat, (long long)n_frames * kNumChannels, h->st_compute);
+        if (dst_is_host && it >= 2) CU(h, cudaStreamWaitEvent(h->st_compute, h->ev_d2h[b], 0));   // score staging buffer drained
+        int rc = run_frontend_tile(h, first, n, h->d_audio_tile[b], n_samples, n_samples, n_frames, h->d_feat, (long long)n_frames * kNumChannels, h->st_compute);
         if (rc) return rc;
-        rc = run_nn_tile(h, first, n, h->d_feat, MWW_ROWS_U16, n_frames, n_frames, h->d_probs_tile[b], std::max(n_steps, 1), h->st_compute);
+        float *tile_probs = dst_is_host ? h->d_probs_tile[b] : dst + (size_t)first * max_probs;
+        const long long tile_probs_stride = dst_is_host ? std::max(n_steps, 1) : max_probs;
+        rc = run_nn_tile(h, first, n, h->d_feat, MWW_ROWS_U16, n_frames, n_frames, tile_probs, tile_probs_stride, h->st_compute);
         if (rc) return rc;
         if (n_samples > 0) {
             rc = run_carry_tile(h, first, n, h->d_audio_tile[b], n_samples, n_samples, n_frames, h->st_compute);
             if (rc) return rc;
         }
         CU(h, cudaEventRecord(h->ev_compute[b], h->st_compute));
-        CU(h, cudaStreamWaitEvent(h->st_d2h, h->ev_compute[b], 0));
-        if (n_steps > 0)
-            CU(h, cudaMemcpy2DAsync(h_probs + (size_t)first * max_probs, (size_t)max_probs * 4, h->d_probs_tile[b], (size_t)std::max(n_steps, 1) * 4,
-                                    (size_t)n_steps * 4, n, cudaMemcpyDeviceToHost, h->st_d2h));
-        CU(h, cudaEventRecord(h->ev_d2h[b], h->st_d2h));
+        if (dst_is_host) {
+            CU(h, cudaStreamWaitEvent(h->st_d2h, h->ev_compute[b], 0));
+            if (n_steps > 0)
+                CU(h, cudaMemcpy2DAsync(dst + (size_t)first * max_probs, (size_t)max_probs * 4, h->d_probs_tile[b], (size_t)std::max(n_steps, 1) * 4,
+                                        (size_t)n_steps * 4, n, cudaMemcpyDeviceToHost, h->st_d2h));
+            CU(h, cudaEventRecord(h->ev_d2h[b], h->st_d2h));
+        }
     }
-    CU(h, cudaStreamSynchronize(h->st_d2h));
-    CU(h, cudaStreamSynchronize(h->st_compute));
+    return MWW_OK;
+}
+
+// `caller` != nullptr-or-legacy semantics: the call is ordered after everything queued on `caller` so far, and `caller`
+// is made to wait for the call's last kernel (asynchronous variant).  host_sync: return only when dst is complete.
+int predict_clip_staged(mww_t *h, const char *who, const int16_t *src, int n_samples, long long audio_stride, float *dst, int max_probs,
+                        int *h_probs_out, bool dst_is_host, int want_tiles, cudaStream_t caller, bool host_sync) {
+    const int n_frames = frames_for(h->used, n_samples);
+    const int n_steps = (h->n_pend + n_frames) / h->stride;
+    if (n_steps > max_probs || (n_steps > 0 && !dst)) return fail(h, MWW_EINVAL, std::string(who) + ": probability buffer too small");
+    int rc = ensure_pipeline(h);
+    if (rc) return rc;
+    // tile so that copies and kernels of neighbouring tiles overlap: 16 tiles by default when there are enough streams (the
+    // first tile's copy and the last tile's kernels are the only parts that cannot hide behind each other), but never
+    // fewer than 2 048 streams per tile so that every launch still fills the GPU
+    if (want_tiles <= 0) want_tiles = 16;
+    int tile = tile_streams(h, n_frames, true);
+    tile = std::max(1, std::min(tile, std::max((h->n_streams + want_tiles - 1) / want_tiles, std::min(h->n_streams, h->min_tile_streams))));
+    rc = ensure_scratch(h, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 2);
+    if (rc) return rc;
+    const size_t a_bytes = (size_t)tile * std::max(n_samples, 1) * sizeof(int16_t);
+    const size_t p_bytes = dst_is_host ? (size_t)tile * std::max(n_steps, 1) * sizeof(float) : 0;
+    if (a_bytes > h->audio_tile_bytes || p_bytes > h->probs_tile_bytes) {
+        CU(h, cudaDeviceSynchronize());
+        for (int b = 0; b < 2; ++b) {
+            cudaFree(h->d_audio_tile[b]); cudaFree(h->d_probs_tile[b]);
+            h->d_audio_tile[b] = nullptr; h->d_probs_tile[b] = nullptr;
+        }
+        const size_t a_new = std::max(a_bytes, h->audio_tile_bytes), p_new = std::max(p_bytes, h->probs_tile_bytes);
+        h->audio_tile_bytes = h->probs_tile_bytes = 0;
+        for (int b = 0; b < 2; ++b) {
+            CU(h, cudaMalloc(&h->d_audio_tile[b], a_new));
+            if (p_new) CU(h, cudaMalloc(&h->d_probs_tile[b], p_new));
+        }
+        h->audio_tile_bytes = a_new; h->probs_tile_bytes = p_new;
+    }
+    // order the private streams after the caller's outstanding work (mww_reset, earlier live calls, the producer of a
+    // device-resident source) and after whatever an earlier staged call still has in flight on the staging buffers
+    CU(h, cudaEventRecord(h->ev_entry, caller));
+    CU(h, cudaStreamWaitEvent(h->st_h2d, h->ev_entry, 0));
+    CU(h, cudaStreamWaitEvent(h->st_compute, h->ev_entry, 0));
+    if (h->staged_used)
+        for (int b = 0; b < 2; ++b) CU(h, cudaStreamWaitEvent(h->st_h2d, h->ev_compute[b], 0));
+    rc = begin_nn_call(h, n_frames, h->st_compute);
+    if (rc == MWW_OK) {
+        h->staged_used = true;
+        rc = staged_tiles(h, src, n_samples, audio_stride, dst, max_probs, dst_is_host, tile, n_frames, n_steps);
+    }
+    if (rc != MWW_OK) {
+        // some tiles' carry / ring state may already be updated, others not: drain and refuse further stateful calls
+        const std::string msg = h->err;
+        cudaStreamSynchronize(h->st_h2d); cudaStreamSynchronize(h->st_compute); cudaStreamSynchronize(h->st_d2h);
+        h->poisoned = true;
+        h->err = msg + " (staged call aborted; mww_reset(h, NULL, 0, stream) required)";
+        return rc;
+    }
+    if (host_sync) {
+        CU(h, cudaStreamSynchronize(h->st_d2h));
+        CU(h, cudaStreamSynchronize(h->st_compute));
+    } else {
+        CU(h, cudaEventRecord(h->ev_exit, h->st_compute));
+        CU(h, cudaStreamWaitEvent(caller, h->ev_exit, 0));
+    }
     end_nn_call(h, n_frames);
     h->used = h->used + n_samples - n_frames * kHop;
     h->n_pend = (h->n_pend + n_frames) % h->stride;
@@ -857,9 +989,139 @@ int mww_predict_clip_host(mww_t *h, const int16_t *h_audio, int n_samples, long 
     return MWW_OK;
 }
 
+}  // namespace
+
+int mww_predict_clip_host(mww_t *h, const int16_t *h_audio, int n_samples, long long audio_stride, float *h_probs, int max_probs,
+                          int *h_probs_out) {
+    if (!h) return MWW_EINVAL;
+    if (n_samples < 0 || (n_samples > 0 && !h_audio) || audio_stride < n_samples) return fail(h, MWW_EINVAL, "mww_predict_clip_host: bad audio arguments");
+    if (!h->has_nn) return fail(h, MWW_EINVAL, "mww_predict_clip_host: frontend-only handle (created without a model)");
+    ENTER_STATEFUL(h);
+    // The call has no stream argument, so it cannot be ordered after one particular stream: it waits for everything the
+    // device has been given so far (mww_reset / live calls queued on any stream touch the same per-stream state).
+    CU(h, cudaDeviceSynchronize());
+    return predict_clip_staged(h, "mww_predict_clip_host", h_audio, n_samples, audio_stride, h_probs, max_probs, h_probs_out, true, 0, nullptr, true);
+}
+
+int mww_predict_clip_remote(mww_t *h, const int16_t *src_audio, int n_samples, long long audio_stride, float *d_probs, int max_probs,
+                            int *h_probs_out, int n_tiles, void *cu_stream) {
+    if (!h) return MWW_EINVAL;
+    if (n_samples < 0 || (n_samples > 0 && !src_audio) || audio_stride < n_samples) return fail(h, MWW_EINVAL, "mww_predict_clip_remote: bad audio arguments");
+    if (!h->has_nn) return fail(h, MWW_EINVAL, "mww_predict_clip_remote: frontend-only handle (created without a model)");
+    bool local = n_samples == 0;
+    if (!local) {
+        DeviceGuard guard(h->device);
+        cudaPointerAttributes at;
+        memset(&at, 0, sizeof at);
+        if (cudaPointerGetAttributes(&at, src_audio) != cudaSuccess) { cudaGetLastError(); memset(&at, 0, sizeof at); }
+        local = (at.type == cudaMemoryTypeDevice && at.device == h->device) || at.type == cudaMemoryTypeManaged;
+    }
+    if (local) return mww_predict_clip(h, src_audio, n_samples, audio_stride, d_probs, max_probs, h_probs_out, cu_stream);   // nothing to stage
+    ENTER_STATEFUL(h);
+    return predict_clip_staged(h, "mww_predict_clip_remote", src_audio, n_samples, audio_stride, d_probs, max_probs, h_probs_out, false, n_tiles,
+                               static_cast<cudaStream_t>(cu_stream), false);
+}
+
+// ---- host memory next to the GPU ---------------------------------------------------------------------------------
+namespace {
+
+int device_numa_node(int device) {
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char *c = bdf; *c; ++c) if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+// CPUs of a NUMA node that the calling thread is allowed to run on (empty set: unknown node / nothing allowed)
+bool node_cpus(int node, cpu_set_t *out) {
+    CPU_ZERO(out);
+    if (node < 0) return false;
+    char path[96];
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    char buf[4096];
+    const bool got = fgets(buf, sizeof buf, f) != nullptr;
+    fclose(f);
+    if (!got) return false;
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return false;
+    int n = 0;
+    for (char *p = buf; *p;) {
+        char *end;
+        const long a = strtol(p, &end, 10);
+        if (end == p) break;
+        long b = a;
+        if (*end == '-') { p = end + 1; b = strtol(p, &end, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &allowed)) { CPU_SET(c, out); ++n; }
+        p = *end == ',' ? end + 1 : end;
+        if (*end != ',') break;
+    }
+    return n > 0;
+}
+
+// MPOL_PREFERRED on one node for the calling thread (best effort: containers may forbid the syscall)
+void prefer_node(int node) {
+#ifdef SYS_set_mempolicy
+    if (node < 0 || node >= 1024) { syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0); return; }
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof mask * 8);
+#else
+    (void)node;
+#endif
+}
+
+}  // namespace
+
+int mww_bind_host_thread(int device, int *numa_node_out) {
+    const int node = device_numa_node(device);
+    if (numa_node_out) *numa_node_out = node;
+    cpu_set_t cpus;
+    if (!node_cpus(node, &cpus)) return MWW_OK;          // unknown topology: leave the thread where it is
+    if (sched_setaffinity(0, sizeof cpus, &cpus) != 0) { g_create_error = "mww_bind_host_thread: sched_setaffinity failed"; return MWW_EINVAL; }
+    return MWW_OK;
+}
+
+int mww_host_alloc(size_t bytes, int device, void **h_ptr, int *numa_node_out) {
+    if (!h_ptr || bytes == 0) { g_create_error = "mww_host_alloc: bad argument"; return MWW_EINVAL; }
+    *h_ptr = nullptr;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return ipc_fail("mww_host_alloc: cudaSetDevice", guard.err);
+    const int node = device_numa_node(device);
+    if (numa_node_out) *numa_node_out = node;
+    // pages are placed where the pinning thread runs: move this thread next to the GPU for the duration of the allocation
+    cpu_set_t before, cpus;
+    CPU_ZERO(&before);
+    const bool have_before = sched_getaffinity(0, sizeof before, &before) == 0;
+    const bool moved = have_before && node_cpus(node, &cpus) && sched_setaffinity(0, sizeof cpus, &cpus) == 0;
+    if (moved) prefer_node(node);
+    void *p = nullptr;
+    const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (moved) { prefer_node(-1); sched_setaffinity(0, sizeof before, &before); }
+    if (e != cudaSuccess) return ipc_fail("mww_host_alloc: cudaHostAlloc", e);
+    *h_ptr = p;
+    return MWW_OK;
+}
+
+int mww_host_free(void *h_ptr) {
+    if (!h_ptr) return MWW_OK;
+    const cudaError_t e = cudaFreeHost(h_ptr);
+    return e == cudaSuccess ? MWW_OK : ipc_fail("mww_host_free", e);
+}
+
 int mww_get_state(mww_t *h, int16_t *h_carry, uint32_t *h_estimate, void *h_nn, void *h_pending) {
     if (!h) return MWW_EINVAL;
-    CU(h, cudaSetDevice(h->device));
+    ENTER_STATEFUL(h);
     CU(h, cudaDeviceSynchronize());
     if (h_nn) {                                    // the exported layout is always the canonical oldest-first one
         const int rc = canonicalise_rings(h, nullptr);
@@ -880,7 +1142,7 @@ int mww_set_state(mww_t *h, const int16_t *h_carry, int frontend_buffered, const
     if (!h) return MWW_EINVAL;
     if (frontend_buffered < 0 || frontend_buffered >= kWindow || pending_rows < 0 || pending_rows > h->stride - 1)
         return fail(h, MWW_EINVAL, "mww_set_state: counters out of range");
-    CU(h, cudaSetDevice(h->device));
+    ENTER(h);
     CU(h, cudaDeviceSynchronize());
     const size_t S = (size_t)h->n_streams;
     if (h_carry) CU(h, cudaMemcpy(h->d_carry, h_carry, S * kWindow * 2, cudaMemcpyHostToDevice));

@@ -45,7 +45,8 @@ namespace mww {
 cudaError_t launch_nn_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, int n_pend, const void *rows,
                          long long rows_stream_stride_bytes, int n_rows, int row_type, float *probs,
                          long long probs_stream_stride, int n_streams, cudaStream_t st);
-cudaError_t launch_fill_state_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, void *unused, int n_streams, cudaStream_t st);
+// zero-point fill of streams 0 .. n (ids == nullptr) or of the n listed streams
+cudaError_t launch_fill_state_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, const int32_t *ids, int n, int n_streams, cudaStream_t st);
 }  // namespace mww
 
 #include "mww_nn_live.cuh"
@@ -73,5 +74,6 @@ cudaError_t launch_nn_generic_f32(const GenArch &A, const GenWeightsF32 &W, floa
 cudaError_t launch_nn_generic_i8(const GenArch &A, const GenWeightsI8 &W, int8_t *state, int8_t *pend, int n_pend, const void *rows,
                                  long long rows_stream_stride_bytes, int n_rows, int row_type, float *probs, long long probs_stream_stride,
                                  int n_streams, cudaStream_t st);
-cudaError_t launch_gen_fill_state_i8(const GenArch &A, const GenWeightsI8 &W, int8_t *state, int8_t *pend, int n_streams, cudaStream_t st);
+cudaError_t launch_gen_fill_state_i8(const GenArch &A, const GenWeightsI8 &W, int8_t *state, int8_t *pend, int n, const int32_t *ids, int n_streams,
+                                     cudaStream_t st);
 }  // namespace mww

@@ -97,12 +97,15 @@ nn_generic_i8_kernel(GenArch A, GenWeightsI8 W, int8_t *__restrict__ state, int8
     gen_i8_tail_store(tid, gsmi, A, my_state, my_pend, A.ring0 + n_pend + n_rows - A.stride * n_steps, pos);
 }
 
-__global__ void gen_fill_state_i8_kernel(GenArch A, GenWeightsI8 W, int8_t *__restrict__ state, int8_t *__restrict__ pend, int n_streams) {
+__global__ void gen_fill_state_i8_kernel(GenArch A, GenWeightsI8 W, int8_t *__restrict__ state, int8_t *__restrict__ pend,
+                                         const int32_t *__restrict__ ids, int n, int n_streams) {
     const long long per = (long long)A.state_elems + (long long)A.pend_cap * kNumChannels;
-    const long long total = (long long)n_streams * per;
+    const long long total = (long long)n * per;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long s = i / per;
-        const int e = (int)(i - s * per);
+        const long long k = i / per;
+        const int e = (int)(i - k * per);
+        const long long s = ids ? ids[k] : k;
+        if (s < 0 || s >= n_streams) continue;
         if (e < A.state_elems) state[s * A.state_elems + e] = gen_i8_reset_value(A, W, e);
         else pend[s * (long long)A.pend_cap * kNumChannels + (e - A.state_elems)] = (int8_t)W.zp[0];
     }
@@ -141,11 +144,12 @@ cudaError_t launch_nn_generic_i8(const GenArch &A, const GenWeightsI8 &W, int8_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_gen_fill_state_i8(const GenArch &A, const GenWeightsI8 &W, int8_t *state, int8_t *pend, int n_streams, cudaStream_t st) {
-    if (n_streams <= 0) return cudaSuccess;
-    const long long total = (long long)n_streams * ((long long)A.state_elems + (long long)A.pend_cap * kNumChannels);
+cudaError_t launch_gen_fill_state_i8(const GenArch &A, const GenWeightsI8 &W, int8_t *state, int8_t *pend, int n, const int32_t *ids, int n_streams,
+                                     cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const long long total = (long long)n * ((long long)A.state_elems + (long long)A.pend_cap * kNumChannels);
     const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    gen_fill_state_i8_kernel<<<blocks, 256, 0, st>>>(A, W, state, pend, n_streams);
+    gen_fill_state_i8_kernel<<<blocks, 256, 0, st>>>(A, W, state, pend, ids, n, n_streams);
     return cudaGetLastError();
 }
 

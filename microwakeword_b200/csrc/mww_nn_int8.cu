@@ -56,11 +56,15 @@ nn_i8_clip_kernel(NnWeightsI8 W, int8_t *__restrict__ state, int8_t *__restrict_
     nnq_tail_write(tid, smi, my_state, my_pend, W, tail);
 }
 
-__global__ void fill_state_i8_kernel(NnWeightsI8 W, int8_t *__restrict__ state, int8_t *__restrict__ pend, int n_streams) {
-    const long long total = (long long)n_streams * (kStateFloats + 2 * kNumChannels);
+// ids == nullptr: streams 0 .. n; otherwise the n listed streams (ids outside [0, n_streams) are skipped)
+__global__ void fill_state_i8_kernel(NnWeightsI8 W, int8_t *__restrict__ state, int8_t *__restrict__ pend, const int32_t *__restrict__ ids, int n,
+                                     int n_streams) {
+    const long long total = (long long)n * (kStateFloats + 2 * kNumChannels);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long s = i / (kStateFloats + 2 * kNumChannels);
-        const int e = (int)(i - s * (kStateFloats + 2 * kNumChannels));
+        const long long k = i / (kStateFloats + 2 * kNumChannels);
+        const int e = (int)(i - k * (kStateFloats + 2 * kNumChannels));
+        const long long s = ids ? ids[k] : k;
+        if (s < 0 || s >= n_streams) continue;
         if (e < kStateFloats) state[s * kStateFloats + e] = nnq_reset_value(W, e);
         else pend[s * 2 * kNumChannels + (e - kStateFloats)] = (int8_t)W.zp[0];
     }
@@ -80,11 +84,11 @@ cudaError_t launch_nn_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, int 
     return cudaGetLastError();
 }
 
-cudaError_t launch_fill_state_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, void *, int n_streams, cudaStream_t st) {
-    if (n_streams <= 0) return cudaSuccess;
-    const long long total = (long long)n_streams * (kStateFloats + 2 * kNumChannels);
+cudaError_t launch_fill_state_i8(const NnWeightsI8 &W, int8_t *state, int8_t *pend, const int32_t *ids, int n, int n_streams, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const long long total = (long long)n * (kStateFloats + 2 * kNumChannels);
     const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
-    fill_state_i8_kernel<<<blocks, 256, 0, st>>>(W, state, pend, n_streams);
+    fill_state_i8_kernel<<<blocks, 256, 0, st>>>(W, state, pend, ids, n, n_streams);
     return cudaGetLastError();
 }
 

@@ -27,6 +27,40 @@ def _torch():
     return torch
 
 
+class _PinnedBlock:
+    """Owner of one mww_host_alloc allocation; numpy arrays built on it keep it alive through their .base chain."""
+
+    def __init__(self, nbytes: int, device: int):
+        L = _lib.lib()
+        ptr, node = ctypes.c_void_p(), ctypes.c_int(-1)
+        _lib.check(None, L.mww_host_alloc(max(int(nbytes), 1), int(device), ctypes.byref(ptr), ctypes.byref(node)))
+        self.ptr, self.nbytes, self.numa_node = ptr.value, int(nbytes), node.value
+        self.__array_interface__ = {"shape": (max(int(nbytes), 1),), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().mww_host_free(ctypes.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def host_array(shape, dtype=np.int16, device: int = 0) -> np.ndarray:
+    """Pinned, GPU-local (NUMA) host array; `.base.base.numa_node` tells where it landed (-1: topology unknown)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    block = _PinnedBlock(n, device)
+    return np.asarray(block)[:n].view(dtype).reshape(shape)
+
+
+def bind_host_thread(device: int) -> int:
+    """Move the calling thread (and the threads it starts later) to the CPUs of the GPU's NUMA node; returns the node or -1."""
+    node = ctypes.c_int(-1)
+    _lib.check(None, _lib.lib().mww_bind_host_thread(int(device), ctypes.byref(node)))
+    return node.value
+
+
 class StreamEngine:
     """`model`: path to (or bytes of) an MWW container or a streaming ``.tflite`` flatbuffer (recognised and converted by
     ``tflite_file``, inference.py:36-45), or None for a frontend-only engine."""
@@ -104,12 +138,20 @@ class StreamEngine:
 
     # ------------------------------------------------------------------ operations
     def reset(self, stream_ids=None):
-        """Fresh frontend + zero rings for all streams (None) or for the given stream ids."""
+        """Fresh frontend + zero rings for all streams (None) or for the given stream ids (a host sequence, or a CUDA int32
+        tensor -- e.g. the streams a detection kernel just flagged; no host round trip).  A constant number of launches
+        whatever the length of the list: streams join / leave a live handle without disturbing the others."""
         if stream_ids is None:
             _lib.check(self._h, self._L.mww_reset(self._h, None, 0, self._cu_stream()))
-        else:
-            ids = np.ascontiguousarray(stream_ids, np.int32)
-            _lib.check(self._h, self._L.mww_reset(self._h, ids.ctypes.data, ids.size, self._cu_stream()))
+            return
+        torch = _torch()
+        if isinstance(stream_ids, torch.Tensor) and stream_ids.is_cuda:
+            if stream_ids.dtype != torch.int32 or stream_ids.dim() != 1 or not stream_ids.is_contiguous():
+                raise ValueError("device stream ids must be a contiguous 1-D CUDA int32 tensor")
+            _lib.check(self._h, self._L.mww_reset_device_ids(self._h, stream_ids.data_ptr(), stream_ids.numel(), self._cu_stream()))
+            return
+        ids = np.ascontiguousarray(stream_ids, np.int32).reshape(-1)
+        _lib.check(self._h, self._L.mww_reset(self._h, ids.ctypes.data, ids.size, self._cu_stream()))
 
     def reset_frontend(self):
         _lib.check(self._h, self._L.mww_reset_frontend(self._h, self._cu_stream()))
@@ -176,6 +218,30 @@ class StreamEngine:
         _lib.check(self._h, self._L.mww_predict_clip_host(self._h, audio.ctypes.data, n, audio.strides[0] // 2 if n else 0, out.ctypes.data,
                                                           out.shape[1], ctypes.byref(got)))
         return out[:, :got.value]
+
+    def predict_clip_remote(self, src_ptr: int, n_samples: int, stride: int | None = None, tiles: int = 0, out=None):
+        """Audio int16 [S, n_samples] at address `src_ptr` -- device memory of a PEER GPU mapped into this process
+        (sharding.IngestBuffer.block_ptr) or host memory -- pulled tile by tile by this GPU's copy engine while the previous
+        tile computes (mww_predict_clip_remote).  Returns float32 CUDA probabilities [S, steps]; stream-ordered like predict_clip."""
+        torch = _torch()
+        n = int(n_samples)
+        buffered = self.frontend_buffered
+        rows = (buffered + n - WINDOW) // HOP + 1 if buffered + n >= WINDOW else 0
+        steps = (self.pending_rows + rows) // self.stride
+        if out is None:
+            out = torch.empty((self.n_streams, max(steps, 1)), dtype=torch.float32, device=self._dev())
+        elif out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous() or out.dim() != 2 or out.shape[0] != self.n_streams:
+            raise ValueError("out must be a contiguous CUDA float32 tensor [n_streams, >= steps]")
+        got = ctypes.c_int(0)
+        _lib.check(self._h, self._L.mww_predict_clip_remote(self._h, ctypes.c_void_p(int(src_ptr)), n, int(stride) if stride else n, out.data_ptr(),
+                                                           out.shape[1], ctypes.byref(got), int(tiles), self._cu_stream()))
+        return out[:, :got.value]
+
+    # ------------------------------------------------------------------ pinned host buffers next to the GPU
+    def host_buffer(self, shape, dtype=np.int16) -> np.ndarray:
+        """Pinned host array on the NUMA node this engine's GPU hangs off (mww_host_alloc): full-rate predict_clip_host copies
+        on a two-socket box whatever CPU the caller runs on.  Freed when the array (and every view of it) is gone."""
+        return host_array(shape, dtype, self.device)
 
     # ------------------------------------------------------------------ per-kernel device timing
     KERNEL_CLASSES = ("k1_spectral", "k2_temporal", "mixednet", "carry_update")

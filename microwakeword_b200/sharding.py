@@ -39,6 +39,8 @@ def scatter_audio(audio, n_streams: int, n_samples: int, src: int = 0, group=Non
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     parts = partition(n_streams, world)
     if device is None:
+        if audio is None and dist.get_backend(group) == "nccl":
+            raise ValueError("scatter_audio: ranks that pass no audio must name their CUDA device (NCCL moves device tensors only)")
         device = audio.device if audio is not None else torch.device("cpu")
     local = torch.empty((parts[rank][1], n_samples), dtype=torch.int16, device=device)
     if rank == src and (tuple(audio.shape) != (n_streams, n_samples) or audio.dtype != torch.int16):
@@ -109,152 +111,95 @@ def scatter_audio_tiles(audio, n_streams: int, n_samples: int, tiles: int, src: 
     return locals_, works
 
 
-class PeerAudio:
-    """The ingest rank's audio buffer mapped into every rank's address space (CUDA IPC over NVLink peer access), so that
-    a rank PULLS its tiles with copy-engine DMA (cudaMemcpyPeerAsync): no communication kernel occupies SMs on either
-    side and no send/recv rendezvous has to be co-scheduled with the compute kernels -- which is what made the NCCL
-    tile pipeline slower than the serial exchange.  One box only (the north_star's 8 x B200).
+class IngestBuffer:
+    """The ingest rank's audio buffer, readable by every GPU of the box (BASELINE.json configs[4]: "audio originates on rank
+    0").  The buffer is a cudaMalloc owned by the library on the ingest rank, exported with cudaIpcGetMemHandle; every
+    other rank opens the handle INSIDE ITS OWN device context (mww_ipc_open, cudaIpcMemLazyEnablePeerAccess), so no rank
+    ever creates a context on the ingest GPU.  A rank then hands `block_ptr()` -- the address of its own block inside the
+    remote buffer -- to StreamEngine.predict_clip_remote, whose copy engine pulls tile t+1 over NVLink while tile t
+    computes: no communication kernel occupies an SM on either side and nothing has to be co-scheduled with the compute
+    grids.  One box only.
 
-        peer = PeerAudio(full_audio_or_None, n_streams, n_samples, src=0)     # once per buffer (collective)
-        probs = peer.pull_compute_gather(compute, tiles=8)                     # every step (collective)
+        with IngestBuffer(n_streams, n_samples, src=0, device=dev) as ingest:   # collective
+            if rank == 0: ingest.buffer.copy_(audio)                             # the ingest rank fills it (its current stream)
+            probs = sharded.predict_clip_ingest(ingest)                          # collective, every step
 
-    Ordering per step: a barrier makes the ingest rank's writes to the buffer (stream-ordered before its barrier) visible
-    before any peer's copies start; the final gather of the scores is what tells the ingest rank that every peer has
-    finished reading, so it may refill the buffer after pull_compute_gather() returns on its stream."""
+    Ordering per step (predict_clip_ingest): a one-element all-reduce after the ingest rank's writes (stream-ordered before its
+    contribution) and before any peer's copies; the final gather of the scores tells the ingest rank that every peer has
+    finished reading, so it may refill the buffer once predict_clip_ingest has returned on its stream."""
 
-    def __init__(self, audio_on_src, n_streams: int, n_samples: int, src: int = 0, group=None, device=None):
-        import torch
-        import torch.distributed as dist
-        from torch.multiprocessing.reductions import reduce_tensor
-
-        self.group, self.src = group, src
-        self.n_streams, self.n_samples = n_streams, n_samples
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        if self.rank == src:
-            if tuple(audio_on_src.shape) != (n_streams, n_samples) or audio_on_src.dtype != torch.int16 or not audio_on_src.is_cuda \
-                    or not audio_on_src.is_contiguous():
-                raise ValueError("PeerAudio: the ingest rank must pass a contiguous CUDA int16 [%d, %d]" % (n_streams, n_samples))
-            torch.cuda.current_stream().synchronize()          # the IPC handle carries no stream ordering of earlier writes
-        box = [reduce_tensor(audio_on_src) if self.rank == src and self.world > 1 else None]
-        if self.world > 1:
-            dist.broadcast_object_list(box, src=src, group=group)
-        err = None
-        try:
-            if self.rank == src:
-                self.remote = audio_on_src
-            else:
-                rebuild, args = box[0]
-                self.remote = rebuild(*args)                    # a tensor on the ingest rank's device, readable from here
-                probe = torch.empty(16, dtype=torch.int16, device=self.device)
-                probe.copy_(self.remote.view(-1)[:16])          # peer access really works from this process
-                torch.cuda.synchronize(self.device)
-        except Exception as exc:                                # noqa: BLE001 -- reported on every rank below
-            err = exc
-        # agree on the outcome (also: nobody drops the handle before everybody has opened it)
-        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) == 0:
-            raise RuntimeError("PeerAudio: CUDA IPC / peer access to the ingest rank's buffer is unavailable (%s)" % (err or "on another rank"))
-        self.copy_stream = torch.cuda.Stream(device=self.device)
-
-    @classmethod
-    def allocate(cls, n_streams: int, n_samples: int, src: int = 0, group=None, device=None):
-        """OPT-IN variant (written after the round's GPU budget was spent; not yet run on a GPU): the ingest buffer is a
-        cudaMalloc owned by the library on the ingest rank, exported with cudaIpcGetMemHandle and opened by every other rank
-        INSIDE ITS OWN device context (mww_ipc_open, cudaIpcMemLazyEnablePeerAccess) -- no rank creates a context on the
-        ingest GPU, unlike the torch rebuild used by __init__.  On the ingest rank `self.buffer` is a torch view of the
-        allocation to write the audio into; elsewhere it is None.  Candidate fix for the 8-GPU slowdown."""
+    def __init__(self, n_streams: int, n_samples: int, src: int = 0, group=None, device=None):
         import torch
         import torch.distributed as dist
 
-        self = cls.__new__(cls)
         self.group, self.src = group, src
-        self.n_streams, self.n_samples = n_streams, n_samples
+        self.n_streams, self.n_samples = int(n_streams), int(n_samples)
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.remote, self.buffer, self._owned, self._opened = None, None, None, None
-        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        device = torch.device(device)
+        self.dev_index = device.index if device.index is not None else torch.cuda.current_device()   # resolved once, used everywhere
+        self.device = torch.device("cuda", self.dev_index)
+        self.buffer, self._owned, self._opened, self.base_ptr = None, None, None, None
         L = _lib.lib()
         handle = ctypes.create_string_buffer(64)
         ptr = ctypes.c_void_p()
         err = None
         try:
             if self.rank == src:
-                _lib.check(None, L.mww_ipc_alloc(n_streams * n_samples * 2, dev_index, ctypes.byref(ptr), handle))
+                _lib.check(None, L.mww_ipc_alloc(self.n_streams * self.n_samples * 2, self.dev_index, ctypes.byref(ptr), handle))
                 self._owned = ptr.value
-        except Exception as exc:                                # noqa: BLE001
+        except Exception as exc:                                # noqa: BLE001 -- agreed on below
             err = exc
         box = [bytes(handle.raw) if self.rank == src else None]
         if self.world > 1:
             dist.broadcast_object_list(box, src=src, group=group)
         try:
             if err is None and self.rank != src:
-                _lib.check(None, L.mww_ipc_open(box[0], dev_index, ctypes.byref(ptr)))
+                _lib.check(None, L.mww_ipc_open(box[0], self.dev_index, ctypes.byref(ptr)))
                 self._opened = ptr.value
         except Exception as exc:                                # noqa: BLE001
             err = exc
         ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # also: nobody proceeds before everybody has opened the handle
         if int(ok.item()) == 0:
             self.close()
-            raise RuntimeError("PeerAudio.allocate: CUDA IPC is unavailable (%s)" % (err or "on another rank"))
-        self.remote_ptr = ptr.value
+            raise RuntimeError("IngestBuffer: CUDA IPC / peer access to the ingest rank's buffer is unavailable (%s)" % (err or "on another rank"))
+        self.base_ptr = ptr.value
+        self.token = torch.zeros(1, dtype=torch.int32, device=self.device)      # per-step ordering token (predict_clip_ingest)
         if self.rank == src:
-            iface = {"shape": (n_streams, n_samples), "typestr": "<i2", "data": (self._owned, False), "version": 3, "strides": None}
+            iface = {"shape": (self.n_streams, self.n_samples), "typestr": "<i2", "data": (self._owned, False), "version": 3, "strides": None}
             holder = type("MwwIpcBuffer", (), {"__cuda_array_interface__": iface})()
             self.buffer = torch.as_tensor(holder, device=self.device)
-        self.copy_stream = torch.cuda.Stream(device=self.device)
-        return self
+
+    def block_ptr(self, first_stream: int) -> int:
+        """Address (valid in THIS process) of stream `first_stream` inside the ingest buffer."""
+        return self.base_ptr + int(first_stream) * self.n_samples * 2
 
     def close(self):
-        """Release what allocate() created (no-op for a PeerAudio built around a torch tensor)."""
-        dev_index = self.device.index if self.device.index is not None else 0
+        """Unmap (peers) / free (ingest rank).  The ingest rank must only free after every peer is done reading: callers
+        synchronise and barrier first (predict_clip_ingest's gather already orders the last read before its return)."""
         if getattr(self, "_opened", None):
-            _lib.lib().mww_ipc_close(ctypes.c_void_p(self._opened), dev_index)
+            _lib.lib().mww_ipc_close(ctypes.c_void_p(self._opened), self.dev_index)
             self._opened = None
         if getattr(self, "_owned", None):
             self.buffer = None
-            _lib.lib().mww_ipc_free(ctypes.c_void_p(self._owned), dev_index)
+            _lib.lib().mww_ipc_free(ctypes.c_void_p(self._owned), self.dev_index)
             self._owned = None
+        self.base_ptr = None
 
-    def pull_tiles(self, tiles: int):
-        """Start the DMA of this rank's tiles (in order, on a side stream); returns (locals, events)."""
-        import torch
-        import torch.distributed as dist
+    def __enter__(self):
+        return self
 
-        dist.barrier(group=self.group)                          # the buffer is complete on the ingest rank (see class docstring)
-        blocks = tile_blocks(self.n_streams, self.world, tiles)
-        cur = torch.cuda.current_stream(self.device)
-        self.copy_stream.wait_stream(cur)
-        locals_, events = [], []
-        for blk in blocks:
-            s, c = blk[self.rank]
-            local = torch.empty((c, self.n_samples), dtype=torch.int16, device=self.device)
-            # torch's Tensor.copy_ would issue a cross-device copy on the SOURCE device's stream, i.e. in a second context
-            # of this process on the ingest GPU, where it is time-sliced against the ingest rank's own kernels (measured:
-            # no overlap at all).  The C-ABI copy runs on this rank's stream: a pull by this GPU's copy engine.
-            if c:
-                base = self.remote.data_ptr() if self.remote is not None else self.remote_ptr       # torch rebuild | allocate()
-                _lib.check(None, _lib.lib().mww_copy_async(local.data_ptr(), base + s * self.n_samples * 2,
-                                                          c * self.n_samples * 2, ctypes.c_void_p(self.copy_stream.cuda_stream)))
-            ev = torch.cuda.Event()
-            ev.record(self.copy_stream)
-            local.record_stream(self.copy_stream)
-            locals_.append(local)
-            events.append(ev)
-        return locals_, events
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
-    def pull_compute_gather(self, compute, tiles: int = 8):
-        import torch
-
-        locals_, events = self.pull_tiles(tiles)
-        cur = torch.cuda.current_stream(self.device)
-        outs = []
-        for t, (local, ev) in enumerate(zip(locals_, events)):
-            cur.wait_event(ev)
-            outs.append(compute(t, local))
-        return gather_probs(torch.cat(outs, 0), self.n_streams, dst=self.src, group=self.group)
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:                                       # noqa: BLE001 -- interpreter shutdown
+            pass
 
 
 def scatter_compute_gather(audio_on_src, n_streams: int, n_samples: int, compute, tiles: int = 8, src: int = 0, group=None, device=None):
@@ -303,10 +248,13 @@ class ShardedEngine:
     """This rank's block of streams as `tiles` StreamEngines over contiguous sub-blocks (tiles = 1: one engine).
     More than one tile lets predict_clip_scattered() overlap the NVLink scatter of tile t+1 with the kernels of tile t."""
 
-    def __init__(self, model, n_streams_total: int, device_index: int, group=None, tiles: int = 1):
+    def __init__(self, model, n_streams_total: int, device_index: int, group=None, tiles: int = 1, engine_factory=None):
         import torch.distributed as dist
 
-        from .engine import StreamEngine
+        if engine_factory is None:
+            from .engine import StreamEngine
+        else:
+            StreamEngine = engine_factory          # tests: a CPU stand-in with the StreamEngine surface (gloo, no GPU)
         self.group = group
         self.n_total = n_streams_total
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -330,6 +278,23 @@ class ShardedEngine:
         return scatter_compute_gather(audio_on_src, self.n_total, n_samples, lambda t, local: self.engines[t].predict_clip(local),
                                       tiles=self.tiles, src=src, group=self.group, device=torch.device("cuda", self.engine.device))
 
-    def predict_clip_pulled(self, peer: "PeerAudio"):
-        """Same result with the audio pulled over NVLink by copy engines (PeerAudio) instead of NCCL send/recv kernels."""
-        return peer.pull_compute_gather(lambda t, local: self.engines[t].predict_clip(local), tiles=self.tiles)
+    def predict_clip_ingest(self, ingest: "IngestBuffer", tiles: int = 0, out=None):
+        """Audio sits in `ingest` on its src rank; every rank pulls and computes its own block (one engine, the library's
+        staged pipeline: copy engine over NVLink || kernels), scores are gathered on the src rank.  Returns [n_total, steps]
+        there, None elsewhere.  `tiles` = pipeline depth per rank (<= 0: the library default of 16)."""
+        import torch.distributed as dist
+
+        if ingest.n_streams != self.n_total:
+            raise ValueError("IngestBuffer holds %d streams, the engine shards %d" % (ingest.n_streams, self.n_total))
+        if len(self.engines) != 1:
+            raise ValueError("predict_clip_ingest uses one engine per rank (ShardedEngine(..., tiles=1)); the tiling happens inside the library")
+        # the buffer is complete on the ingest rank before any peer starts copying (IngestBuffer docstring).  A one-element
+        # all-reduce is stream-ordered on every rank (the pull is queued behind it) and, unlike dist.barrier() on NCCL, does not
+        # stall the host, so the next step's launches are already queued while this one runs.
+        token = getattr(ingest, "token", None)
+        if token is not None:
+            dist.all_reduce(token, group=self.group)
+        else:
+            dist.barrier(group=self.group)
+        local = self.engine.predict_clip_remote(ingest.block_ptr(self.start), ingest.n_samples, tiles=tiles, out=out)
+        return gather_probs(local, self.n_total, dst=ingest.src, group=self.group)

@@ -404,33 +404,132 @@ def test_nonstreaming_batch_equals_keras_nonstreaming_graph(torch_cuda):
         m.predict_nonstreaming(windows[:, :100])
 
 
-def test_tiled_ingest_pull_equals_one_engine(torch_cuda):
-    """The multi-GPU ingest path on one GPU (world size 1, NCCL): a rank's block cut into tiles, each tile pulled through
-    mww_copy_async on a side stream while the previous tile computes, scores gathered -- identical to one engine over the
-    whole block, across two consecutive calls (every tile engine carries its own streaming state)."""
+def _single_rank_group(torch):
     import socket
 
     import torch.distributed as dist
-
-    from microwakeword_b200.engine import StreamEngine
-    from microwakeword_b200.sharding import PeerAudio, ShardedEngine
-    torch = torch_cuda
-    blob = _blob("okay_nabu_synth_int8.mww")
-    audio = np.stack([synth_audio(9600, 900 + i) for i in range(13)])          # 13 streams -> ragged tiles 4,3,3,3
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    return dist
+
+
+@pytest.mark.parametrize("kind", ["f32", "int8"])
+def test_staged_remote_path_equals_resident_path_and_oracle(torch_cuda, kind, monkeypatch):
+    """mww_predict_clip_remote with a source this GPU has to DMA from (pinned host memory stands in for a peer GPU's buffer
+    on a one-GPU box): ragged tiles 4,4,4,1, two staging buffers, scores written straight into the device output --
+    identical to the resident path, across two consecutive calls (state carried), and to the oracle."""
+    from microwakeword_b200.engine import StreamEngine, host_array
+    torch = torch_cuda
+    monkeypatch.setenv("MWW_MIN_TILE_STREAMS", "1")
+    blob = _blob("okay_nabu_synth_%s.mww" % kind)
+    audio = np.stack([synth_audio(9600, 900 + i) for i in range(13)])
+    pinned = host_array(audio.shape, np.int16, 0)
+    pinned[:] = audio
+    dev = torch.from_numpy(audio).cuda()
+    one = StreamEngine(blob, n_streams=13)
+    staged = StreamEngine(blob, n_streams=13)
+    for call in range(2):
+        want = one.predict_clip(dev)
+        got = staged.predict_clip_remote(pinned.ctypes.data, 9600, tiles=4)
+        assert got.shape == want.shape and torch.equal(got, want), call
+    _, ref = oracle.run_pipeline(blob, np.concatenate([audio, audio], 1), want_features=False)
+    err = np.abs(want.cpu().numpy() - ref[:, -want.shape[1]:]).max()           # the second call's steps are the last ones
+    assert (err == 0.0) if kind == "int8" else (err <= F32_TOL)
+    # a device-resident source is computed in place (no staging)
+    a, b = StreamEngine(blob, n_streams=13), StreamEngine(blob, n_streams=13)
+    assert torch.equal(a.predict_clip_remote(dev.data_ptr(), 9600), b.predict_clip(dev))
+
+
+def test_host_path_is_ordered_after_reset(torch_cuda):
+    """reset() runs asynchronously on the caller's stream, predict_clip_host on the library's private
+    non-blocking streams -- the host call must still see the reset state (65 536 streams make the memset long enough to race)."""
+    from microwakeword_b200.engine import StreamEngine
+    torch = torch_cuda
+    blob = _blob("okay_nabu_synth_int8.mww")
+    S = 65536
+    base = np.stack([synth_audio(1600, 40 + i) for i in range(16)])
+    audio = np.ascontiguousarray(np.tile(base, (S // 16, 1)))
+    eng = StreamEngine(blob, n_streams=S)
+    first = eng.predict_clip_host(audio).copy()
+    side = torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(side):                 # the reset is queued on a non-default stream
+            eng.reset()
+        again = eng.predict_clip_host(audio)
+        assert np.array_equal(again, first)
+
+
+def test_reset_by_id_list_host_and_device(torch_cuda):
+    """mww_reset(ids) / mww_reset_device_ids: the listed streams restart from fresh state (history = silence) while the rest
+    of the handle carries on, in live mode (rotated rings) as well; one batch of launches whatever the list length."""
+    from microwakeword_b200.engine import StreamEngine
+    torch = torch_cuda
+    for kind in ("f32", "int8"):
+        blob = _blob("okay_nabu_synth_%s.mww" % kind)
+        S = 64
+        audio = np.stack([synth_audio(480 * 40, 300 + i) for i in range(S)])
+        dev = torch.from_numpy(audio).cuda()
+        eng, fresh = StreamEngine(blob, n_streams=S), StreamEngine(blob, n_streams=S)
+        for i in range(20):                                   # 20 live steps: rings are rotated now
+            eng.step(dev[:, 480 * i:480 * (i + 1)].contiguous())
+        ids = [3, 17, 40, 63]
+        l0 = eng.launch_count
+        eng.reset(ids[:2])
+        eng.reset(torch.tensor(ids[2:], dtype=torch.int32, device="cuda"))
+        assert eng.launch_count - l0 <= 12
+        # expected: a freshly created engine (new MicroFrontend + freshly loaded interpreter, audio_utils.py:52 /
+        # inference.py:36-39) put on the handle's shared phase (buffered samples all zero, pending-row count)
+        d = fresh.state_dict()
+        d["frontend_buffered"], d["pending_rows"] = eng.frontend_buffered, eng.pending_rows
+        fresh.load_state_dict(d)
+        for i in range(20, 40):
+            chunk = dev[:, 480 * i:480 * (i + 1)].contiguous()
+            got, want = eng.step(chunk), fresh.step(chunk)
+            assert torch.equal(got[ids], want[ids]), (kind, i)
+        st, sf = eng.state_dict(), fresh.state_dict()
+        for k in ("carry", "estimate", "nn", "pending"):
+            assert np.array_equal(st[k][ids], sf[k][ids]), (kind, k)
+        others = [i for i in range(S) if i not in ids]
+        assert not np.array_equal(st["nn"][others], sf["nn"][others])
+
+
+def test_ingest_buffer_single_rank(torch_cuda, monkeypatch):
+    """The multi-GPU ingest path with world size 1 (NCCL): IngestBuffer allocation / IPC export, predict_clip_ingest =
+    barrier + (in-place on the ingest rank) compute + gather -- identical to one engine, two consecutive calls."""
+    from microwakeword_b200.engine import StreamEngine
+    from microwakeword_b200.sharding import IngestBuffer, ShardedEngine
+    torch = torch_cuda
+    blob = _blob("okay_nabu_synth_int8.mww")
+    audio = np.stack([synth_audio(9600, 900 + i) for i in range(13)])
+    dist = _single_rank_group(torch)
     try:
         dev = torch.from_numpy(audio).cuda()
         one = StreamEngine(blob, n_streams=13)
-        sh = ShardedEngine(blob, 13, 0, tiles=4)
-        assert [c for _, c in sh.tile_parts] == [4, 3, 3, 3]
-        peer = PeerAudio(dev, 13, 9600, src=0)
-        for _ in range(2):
-            want = one.predict_clip(dev)
-            got = sh.predict_clip_pulled(peer)
-            assert got.shape == want.shape and torch.equal(got, want)
+        sh = ShardedEngine(blob, 13, 0)
+        with IngestBuffer(13, 9600, src=0, device=torch.device("cuda", 0)) as ingest:
+            ingest.buffer.copy_(dev)
+            for _ in range(2):
+                want = one.predict_clip(dev)
+                got = sh.predict_clip_ingest(ingest)
+                assert got.shape == want.shape and torch.equal(got, want)
+            torch.cuda.synchronize()
     finally:
         dist.destroy_process_group()
+
+
+def test_pinned_host_array_and_numa_binding(torch_cuda):
+    from microwakeword_b200.engine import bind_host_thread, host_array
+    a = host_array((1024, 480), np.int16, 0)
+    a[:] = 7
+    assert a.shape == (1024, 480) and a.dtype == np.int16 and int(a.sum()) == 7 * 1024 * 480
+    node = a.base.base.numa_node if hasattr(a.base, "base") else None
+    t = torch_cuda.from_numpy(a)
+    assert t.cuda().sum().item() == 7 * 1024 * 480
+    before = os.sched_getaffinity(0)
+    got = bind_host_thread(0)
+    after = os.sched_getaffinity(0)
+    assert after <= before and len(after) >= 1 and (got == -1 or node in (None, got))
+    os.sched_setaffinity(0, before)

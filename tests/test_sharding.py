@@ -105,3 +105,97 @@ def test_two_rank_scatter_compute_gather_equals_single_process(n_streams, tiles)
         assert p.exitcode == 0
     want = np.load(os.path.join(GOLDEN, "batch_probs_int8.npy"))[:n_streams]
     assert np.array_equal(got, want)
+
+
+# ---- the pulled ingest (IngestBuffer + predict_clip_ingest): host logic under gloo ------------------------------------
+
+class _OracleEngine:
+    """CPU stand-in with the StreamEngine surface predict_clip_ingest uses: reads int16 [n_streams, n] at a raw address
+    (here: a shared-memory segment standing in for the peer-mapped ingest buffer) and runs the oracle from carried state."""
+
+    def __init__(self, model, n_streams=1, device=0):
+        self.blob, self.n_streams, self.history = model, n_streams, None
+
+    def predict_clip_remote(self, src_ptr, n_samples, stride=None, tiles=0, out=None):
+        import ctypes
+
+        import torch
+
+        import oracle
+        raw = (ctypes.c_int16 * (self.n_streams * n_samples)).from_address(src_ptr)
+        new = np.frombuffer(raw, np.int16).reshape(self.n_streams, n_samples).copy()
+        self.history = new if self.history is None else np.concatenate([self.history, new], 1)
+        _, p = oracle.run_pipeline(self.blob, self.history, want_features=False)
+        done = getattr(self, "steps_done", 0)
+        self.steps_done = p.shape[1]
+        return torch.from_numpy(np.ascontiguousarray(p[:, done:]))
+
+
+class _ShmIngest:
+    """IngestBuffer's surface over a POSIX shared-memory segment (one box, no GPU)."""
+
+    def __init__(self, name, n_streams, n_samples, src=0):
+        from multiprocessing import shared_memory
+        self.shm = shared_memory.SharedMemory(name=name)
+        self.n_streams, self.n_samples, self.src = n_streams, n_samples, src
+        self.view = np.ndarray((n_streams, n_samples), np.int16, buffer=self.shm.buf)
+
+    def block_ptr(self, first_stream):
+        return self.view[first_stream:].ctypes.data if first_stream < self.n_streams else self.view.ctypes.data
+
+
+def _ingest_worker(rank, world, port, n_streams, shm_name, q):
+    import torch.distributed as dist
+
+    from microwakeword_b200.sharding import ShardedEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        audio = np.load(os.path.join(GOLDEN, "batch_audio.npy"))[:n_streams]
+        half = audio.shape[1] // 2 // 160 * 160
+        blob = open(os.path.join(GOLDEN, "okay_nabu_synth_int8.mww"), "rb").read()
+        ingest = _ShmIngest(shm_name, n_streams, half)
+        sh = ShardedEngine(blob, n_streams, 0, engine_factory=_OracleEngine)
+        outs = []
+        for call in range(2):                        # two steps: the ingest rank refills the buffer between them
+            if rank == 0:
+                ingest.view[:] = audio[:, call * half:(call + 1) * half]
+            outs.append(sh.predict_clip_ingest(ingest))
+            dist.barrier()
+        if rank == 0:
+            q.put(np.concatenate([o.numpy() for o in outs], 1))
+        else:
+            assert outs == [None, None]
+        del ingest.view
+        ingest.shm.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_streams", [12, 11])
+def test_two_rank_pulled_ingest_equals_single_process(n_streams):
+    import torch.multiprocessing as mp
+    from multiprocessing import shared_memory
+
+    import oracle
+    audio = np.load(os.path.join(GOLDEN, "batch_audio.npy"))[:n_streams]
+    half = audio.shape[1] // 2 // 160 * 160
+    shm = shared_memory.SharedMemory(create=True, size=n_streams * half * 2)
+    try:
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_ingest_worker, args=(r, 2, port, n_streams, shm.name, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        got = q.get(timeout=120)
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    finally:
+        shm.close()
+        shm.unlink()
+    blob = open(os.path.join(GOLDEN, "okay_nabu_synth_int8.mww"), "rb").read()
+    _, want = oracle.run_pipeline(blob, audio[:, :2 * half], want_features=False)
+    assert got.shape == want.shape and np.array_equal(got, want)
