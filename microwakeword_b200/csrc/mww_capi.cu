@@ -62,7 +62,6 @@ struct mww_handle {
     // constant tables
     uint8_t *d_tables = nullptr;
     FrontendParams P;
-    int fb_coef_len = 0;
     // weights
     uint8_t *d_weights = nullptr;
     NnWeightsF32 W;
@@ -168,9 +167,16 @@ int frames_for(int used, int n_samples) {
     return total >= kWindow ? (int)((total - kWindow) / kHop + 1) : 0;
 }
 
-// streams per tile so that the K1->K2 scratch (and optional feature scratch) fits the budget
+// Long calls over enough streams run K1 + the temporal chain in one kernel (one CTA per stream) and need no K1->K2 scratch.
+bool clip_fuses(const mww_t *h, int n_frames) { return !h->no_fuse && frontend_clip_fuses(h->n_streams, n_frames, h->sm_count); }
+size_t v_scratch_bytes(const mww_t *h, int tile, int n_frames) {
+    return clip_fuses(h, n_frames) ? 0 : (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4;
+}
+
+// streams per tile so that the K1->K2 scratch (when the call needs one) and the optional feature scratch fit the budget
 int tile_streams(const mww_t *h, int n_frames, bool need_feat) {
-    const size_t per_stream = (size_t)std::max(n_frames, 1) * kNumChannels * (4 + (need_feat ? 2 : 0));
+    const size_t per_stream = (size_t)std::max(n_frames, 1) * kNumChannels * ((clip_fuses(h, n_frames) ? 0 : 4) + (need_feat ? 2 : 0));
+    if (per_stream == 0) return h->n_streams;
     size_t t = h->scratch_budget / per_stream;
     if (t < 1) t = 1;
     if (t > (size_t)h->n_streams) t = (size_t)h->n_streams;
@@ -184,14 +190,23 @@ int run_frontend_tile(mww_t *h, int first, int n, const int16_t *d_audio, long l
     if (!h->no_fuse && frontend_fusable(h->used, n_samples, n_frames)) {
         // short call: K1 + K2 + carry update in one launch (run_carry_tile sees the same predicate and does nothing)
         ProfScope p(h, 0, st);
-        CU(h, launch_frontend_fused(h->P, h->fb_coef_len, h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n,
+        CU(h, launch_frontend_fused(h->P, h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n,
                                     n_frames, h->d_estimate + (size_t)first * kNumChannels, d_feat, feat_stream_stride, st));
+        h->launches += 1;
+        return MWW_OK;
+    }
+    if (clip_fuses(h, n_frames)) {
+        // long call, one CTA per stream: K1 and the temporal chain in one launch, features written directly (whatever the
+        // size of this particular tile -- the scratch was sized for the fused form)
+        ProfScope p(h, 0, st);
+        CU(h, launch_frontend_clip_fused(h->P, h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n, n_frames,
+                                         h->d_estimate + (size_t)first * kNumChannels, d_feat, feat_stream_stride, st));
         h->launches += 1;
         return MWW_OK;
     }
     {
         ProfScope p(h, 0, st);
-        CU(h, launch_k1(h->P, h->fb_coef_len, h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n,
+        CU(h, launch_k1(h->P, h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n,
                         n_frames, h->d_v, h->sm_count, st));
     }
     {
@@ -306,10 +321,9 @@ bool upload(uint8_t *base, size_t &cursor, const void *src, size_t bytes, const 
 int upload_tables(mww_t *h) {
     HostTables t;
     build_host_tables(&t);
-    if (!t.ok || t.fb_coef.size() > (size_t)kFbCoefMax) return fail(h, MWW_EINVAL, "frontend table construction failed");
+    if (!t.ok || t.fb_coef.size() != (size_t)kFbCoefWords) return fail(h, MWW_EINVAL, "frontend table construction failed");
     for (int s = 0; s < kFbSlots; ++s)
         if (t.fb_slot_len[s] != kFbLen[s]) return fail(h, MWW_EINVAL, "filterbank schedule differs from the trip counts the kernel was compiled for");
-    h->fb_coef_len = (int)t.fb_coef.size();
     const size_t total = 64 * 1024;
     CU(h, cudaMalloc(&h->d_tables, total));
     size_t cur = 0;
@@ -317,7 +331,7 @@ int upload_tables(mww_t *h) {
     bool ok = upload(h->d_tables, cur, t.win_pairs, sizeof t.win_pairs, &h->P.win_pairs, &e) &&
               upload(h->d_tables, cur, t.tw, sizeof t.tw, &h->P.tw, &e) &&
               upload(h->d_tables, cur, t.super_tw, sizeof t.super_tw, &h->P.super_tw, &e) &&
-              upload(h->d_tables, cur, t.fb_coef.data(), t.fb_coef.size() * sizeof(int16_t), &h->P.fb_coef, &e) &&
+              upload(h->d_tables, cur, t.fb_coef.data(), t.fb_coef.size() * sizeof(int32_t), &h->P.fb_coef, &e) &&
               upload(h->d_tables, cur, &t.fb_slots[0][0], sizeof t.fb_slots, &h->P.fb_slots, &e) &&
               upload(h->d_tables, cur, t.gain_lut, sizeof t.gain_lut, &h->P.gain_lut, &e) &&
               upload(h->d_tables, cur, t.log_lut, sizeof t.log_lut, &h->P.log_lut, &e);
@@ -787,7 +801,7 @@ int mww_features(mww_t *h, const int16_t *d_audio, int n_samples, long long audi
     const int n_frames = frames_for(h->used, n_samples);
     if (n_frames > max_rows || (n_frames > 0 && !d_feat)) return fail(h, MWW_EINVAL, "mww_features: feature buffer too small for the rows this call emits");
     const int tile = tile_streams(h, n_frames, false);
-    int rc = ensure_scratch(h, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4, 0);
+    int rc = ensure_scratch(h, v_scratch_bytes(h, tile, n_frames), 0);
     if (rc) return rc;
     for (int first = 0; first < h->n_streams; first += tile) {
         const int n = std::min(tile, h->n_streams - first);
@@ -834,7 +848,7 @@ int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long 
     const int n_steps = (h->n_pend + n_frames) / h->stride;
     if (n_steps > max_probs || (n_steps > 0 && !d_probs)) return fail(h, MWW_EINVAL, "mww_predict_clip: probability buffer too small");
     const int tile = tile_streams(h, n_frames, true);
-    int rc = ensure_scratch(h, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 2);
+    int rc = ensure_scratch(h, v_scratch_bytes(h, tile, n_frames), (size_t)tile * std::max(n_frames, 1) * kNumChannels * 2);
     if (rc) return rc;
     rc = begin_nn_call(h, n_frames, st);
     if (rc) return rc;
@@ -937,7 +951,7 @@ int predict_clip_staged(mww_t *h, const char *who, const int16_t *src, int n_sam
     if (want_tiles <= 0) want_tiles = 16;
     int tile = tile_streams(h, n_frames, true);
     tile = std::max(1, std::min(tile, std::max((h->n_streams + want_tiles - 1) / want_tiles, std::min(h->n_streams, h->min_tile_streams))));
-    rc = ensure_scratch(h, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4, (size_t)tile * std::max(n_frames, 1) * kNumChannels * 2);
+    rc = ensure_scratch(h, v_scratch_bytes(h, tile, n_frames), (size_t)tile * std::max(n_frames, 1) * kNumChannels * 2);
     if (rc) return rc;
     const size_t a_bytes = (size_t)tile * std::max(n_samples, 1) * sizeof(int16_t);
     const size_t p_bytes = dst_is_host ? (size_t)tile * std::max(n_steps, 1) * sizeof(float) : 0;

@@ -1,6 +1,7 @@
 // mww_frontend.cu -- sm_100a kernels of the batched micro-frontend (see mww_frontend_dev.cuh for the
 // phase decomposition and the reference citations).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "mww_frontend_dev.cuh"
 #include "mww_kernels.h"
@@ -47,22 +48,34 @@ __device__ __forceinline__ void k1_packed_load_audio_async(int tid, K1Smem &sm, 
 }
 
 // K1: grid = (streams, group_chunks); 256 threads; 16 frames of one stream per iteration.
-__global__ void __launch_bounds__(kK1Threads, 3)
-k1_spectral_kernel(FrontendParams P, int fb_coef_len, const int16_t *__restrict__ carry, int used,
+// kFuseK2 (grid.y == 1: the CTA walks all of its stream's groups in order): the temporal chain -- noise estimate, PCAN, log --
+// runs from shared memory right behind the filterbank and the kernel writes the uint16 feature rows itself; no V round trip
+// through HBM (148 + 169 B per frame in r01), no K2 launch, no scratch buffer.
+// kOcc = CTAs per SM the kernel is compiled for: 3 keeps the per-lane FFT twiddles in registers (80 registers), 4 reads them
+// from shared memory (64 registers).
+template <bool kFuseK2, int kOcc>
+__global__ void __launch_bounds__(kK1Threads, kOcc)
+k1_spectral_kernel(FrontendParams P, const int16_t *__restrict__ carry, int used,
                    const int16_t *__restrict__ audio, long long audio_stride, int n_samples, int n_frames,
-                   int groups_per_block, int vec_ok, uint32_t *__restrict__ vout) {
-    __shared__ __align__(16) K1Smem sm;
+                   int groups_per_block, int vec_ok, uint32_t *__restrict__ vout, uint32_t *__restrict__ estimate,
+                   uint16_t *__restrict__ feat, long long feat_stream_stride) {
+    extern __shared__ __align__(16) unsigned char k1_smem_raw[];
+    K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_smem_raw);
     const int tid = threadIdx.x;
     const long long s = blockIdx.x;
     K1Lane lane;
-    k1_lane_init(tid, P, lane);
-    for (int i = tid; i < fb_coef_len; i += kK1Threads) sm.fb_coef[i] = P.fb_coef[i];
+    if (kOcc <= 3) k1_lane_init(tid, P, lane);
+    else k1_stage_lane_twiddles(tid, sm, P);
+    const K1LaneShared lane_sh{&sm.lane_tw[tid & 15][0]};
+    k1_stage_tables(tid, sm, P);
 
     const int n_groups = (n_frames + kFramesPerGroup - 1) / kFramesPerGroup;
     const int g_begin = blockIdx.y * groups_per_block;
     const int g_end = min(g_begin + groups_per_block, n_groups);
     const int16_t *my_carry = carry + s * kWindow;
     const int16_t *my_audio = audio + s * audio_stride;
+    uint32_t est = 0;                          // fused: thread ch < 40 carries channel ch's noise estimate across the groups
+    if (kFuseK2 && tid < kNumChannels) est = estimate[s * kNumChannels + tid];
     if (g_begin < g_end) {
         if (vec_ok) k1_load_audio_async(tid, sm, 0, my_carry, used, my_audio, n_samples, g_begin * kFramesPerGroup);
         else k1_load_audio(tid, sm, 0, my_carry, used, my_audio, n_samples, g_begin * kFramesPerGroup);
@@ -79,29 +92,42 @@ k1_spectral_kernel(FrontendParams P, int fb_coef_len, const int16_t *__restrict_
         K1Pass1Ctx ctx;
         k1_window_fft1<2>(tid, sm, buf, (kHop / 2) * (tid >> 4), P, ctx);
         __syncthreads();
-        k1_fft_pass2(tid, sm, lane);
+        if (kOcc <= 3) k1_fft_pass2(tid, sm, lane); else k1_fft_pass2(tid, sm, lane_sh);
         __syncthreads();
         k1_real_energy(tid, sm, P);
         __syncthreads();
         const int f = f0 + (tid >> 4);
-        k1_filterbank(tid, sm, P, f < n_frames ? vout + (s * n_frames + f) * kNumChannels : nullptr);
-        // hazards: the next iteration's top barrier orders filterbank's reads of B/shift before the next
-        // window_fft1 rewrites them; A is rewritten only after two more barriers
+        if (!kFuseK2) {
+            k1_filterbank(tid, sm, P, f < n_frames ? vout + (s * n_frames + f) * kNumChannels : nullptr);
+            // hazards: the next iteration's top barrier orders filterbank's reads of B/shift before the next
+            // window_fft1 rewrites them; A is rewritten only after two more barriers
+        } else {
+            // sm.A is free from here on (real_energy consumed it): row fl receives the frame's 40 channel values
+            k1_filterbank(tid, sm, P, &sm.A[tid >> 4][0]);
+            __syncthreads();
+            const int n_valid = min(kFramesPerGroup, n_frames - f0);
+            if (tid < kNumChannels) k2_group_chain(tid, sm, n_valid, est);       // estimates -> sm.B (the energies are dead)
+            __syncthreads();
+            k2_group_outputs(tid, sm, n_valid, feat + s * feat_stream_stride + (long long)f0 * kNumChannels);
+            // hazards: the next iteration's top barrier orders these reads of A / B before window_fft1 rewrites B
+        }
     }
+    if (kFuseK2 && tid < kNumChannels) estimate[s * kNumChannels + tid] = est;
 }
 
 // K1 for short calls (n_frames <= 8, e.g. the three frames of a 30 ms live step): one CTA = `spc` streams x `fps`
 // frames, so the 16 frame slots stay (almost) full instead of serving 3 of 16.
 __global__ void __launch_bounds__(kK1Threads, 3)
-k1_spectral_packed_kernel(FrontendParams P, int fb_coef_len, const int16_t *__restrict__ carry, int used,
+k1_spectral_packed_kernel(FrontendParams P, const int16_t *__restrict__ carry, int used,
                           const int16_t *__restrict__ audio, long long audio_stride, int n_samples, int n_streams, int fps, int spc,
                           int vec_ok, uint32_t *__restrict__ vout) {
-    __shared__ __align__(16) K1Smem sm;
+    extern __shared__ __align__(16) unsigned char k1_smem_raw[];
+    K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_smem_raw);
     const int tid = threadIdx.x;
     const long long s0 = (long long)blockIdx.x * spc;
     K1Lane lane;
     k1_lane_init(tid, P, lane);
-    for (int i = tid; i < fb_coef_len; i += kK1Threads) sm.fb_coef[i] = P.fb_coef[i];
+    k1_stage_tables(tid, sm, P);
     if (vec_ok) {
         k1_packed_load_audio_async(tid, sm, carry, used, audio, audio_stride, n_samples, s0, n_streams, spc, fps);
         cp_async_commit_and_wait_all();
@@ -127,15 +153,16 @@ k1_spectral_packed_kernel(FrontendParams P, int fb_coef_len, const int16_t *__re
 // audio.  Saves the V round trip through HBM and two launches per live step.  Requires new_used <= 2 hops (the staged
 // span ends 2 hops after the last frame's start) -- the launcher checks.
 __global__ void __launch_bounds__(kK1Threads, 3)
-k1k2_packed_kernel(FrontendParams P, int fb_coef_len, int16_t *__restrict__ carry, int used, const int16_t *__restrict__ audio,
+k1k2_packed_kernel(FrontendParams P, int16_t *__restrict__ carry, int used, const int16_t *__restrict__ audio,
                    long long audio_stride, int n_samples, int n_streams, int fps, int spc, int vec_ok, uint32_t *__restrict__ estimate,
                    uint16_t *__restrict__ feat, long long feat_stream_stride, int new_used) {
-    __shared__ __align__(16) K1Smem sm;
+    extern __shared__ __align__(16) unsigned char k1_smem_raw[];
+    K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_smem_raw);
     const int tid = threadIdx.x;
     const long long s0 = (long long)blockIdx.x * spc;
     K1Lane lane;
     k1_lane_init(tid, P, lane);
-    for (int i = tid; i < fb_coef_len; i += kK1Threads) sm.fb_coef[i] = P.fb_coef[i];
+    k1_stage_tables(tid, sm, P);
     if (vec_ok) {
         k1_packed_load_audio_async(tid, sm, carry, used, audio, audio_stride, n_samples, s0, n_streams, spc, fps);
         cp_async_commit_and_wait_all();
@@ -161,7 +188,7 @@ k1k2_packed_kernel(FrontendParams P, int fb_coef_len, int16_t *__restrict__ carr
             const uint32_t smoothing = (ch & 1) ? kOddSmoothing : kEvenSmoothing;
             uint32_t est = estimate[s * kNumChannels + ch];
             uint16_t *out = feat + s * feat_stream_stride + ch;
-            for (int f = 0; f < fps; ++f) out[(long long)f * kNumChannels] = k2_channel_step(sm.A[sl * fps + f][ch], est, smoothing, P.gain_lut, P.log_lut);
+            for (int f = 0; f < fps; ++f) out[(long long)f * kNumChannels] = k2_channel_step(sm.A[sl * fps + f][ch], est, smoothing, sm.gain_lut, sm.log_lut);
             estimate[s * kNumChannels + ch] = est;
         }
     }
@@ -243,18 +270,39 @@ carry_update_kernel(int16_t *__restrict__ carry, int used, const int16_t *__rest
 // ---------------------------------------------------------------------------------------------
 // launchers
 
-cudaError_t launch_k1(const FrontendParams &P, int fb_coef_len, const int16_t *carry, int used, const int16_t *audio,
+namespace {
+// K1Smem is above the 48 KB static limit: dynamic shared memory, opted in per kernel and per device
+template <typename K>
+cudaError_t k1_opt_in(K kernel, bool (&done)[64]) {
+    if (!first_launch_on_this_device(done)) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1SmemBytes);
+}
+}  // namespace
+
+bool frontend_clip_fuses(int n_streams, int n_frames, int sm_count) {
+    // one CTA per stream walks the stream's groups in order; below ~12 CTAs per SM's worth of streams the frames of a stream
+    // are spread over several CTAs instead (grid.y > 1) and the temporal chain stays a separate kernel
+    return n_frames > 8 && (long long)n_streams >= (long long)sm_count * 3 * 4;
+}
+
+cudaError_t launch_k1(const FrontendParams &P, const int16_t *carry, int used, const int16_t *audio,
                       long long audio_stride, int n_samples, int n_streams, int n_frames, uint32_t *vout, int sm_count,
                       cudaStream_t st) {
     if (n_frames <= 0 || n_streams <= 0) return cudaSuccess;
     const int vec_ok = (used % 8 == 0) && (n_samples % 8 == 0) && (audio_stride % 8 == 0) &&
                        (reinterpret_cast<uintptr_t>(audio) % 16 == 0) && (reinterpret_cast<uintptr_t>(carry) % 16 == 0);
     if (n_frames <= 8 && n_streams >= 2) {
+        static bool done[64] = {};
+        cudaError_t e = k1_opt_in(k1_spectral_packed_kernel, done);
+        if (e != cudaSuccess) return e;
         const int spc = k1_packed_streams(n_frames);
         const unsigned grid = (unsigned)((n_streams + spc - 1) / spc);
-        k1_spectral_packed_kernel<<<grid, kK1Threads, 0, st>>>(P, fb_coef_len, carry, used, audio, audio_stride, n_samples, n_streams, n_frames, spc, vec_ok, vout);
+        k1_spectral_packed_kernel<<<grid, kK1Threads, kK1SmemBytes, st>>>(P, carry, used, audio, audio_stride, n_samples, n_streams, n_frames, spc, vec_ok, vout);
         return cudaGetLastError();
     }
+    static bool done[64] = {};
+    cudaError_t e = k1_opt_in(k1_spectral_kernel<false, 3>, done);
+    if (e != cudaSuccess) return e;
     const int n_groups = (n_frames + kFramesPerGroup - 1) / kFramesPerGroup;
     // enough CTAs to fill the chip a few times over, but keep per-CTA setup amortised when streams abound
     int chunks = 1;
@@ -263,7 +311,29 @@ cudaError_t launch_k1(const FrontendParams &P, int fb_coef_len, const int16_t *c
     const int gpb = (n_groups + chunks - 1) / chunks;
     chunks = (n_groups + gpb - 1) / gpb;
     dim3 grid((unsigned)n_streams, (unsigned)chunks);
-    k1_spectral_kernel<<<grid, kK1Threads, 0, st>>>(P, fb_coef_len, carry, used, audio, audio_stride, n_samples, n_frames, gpb, vec_ok, vout);
+    k1_spectral_kernel<false, 3><<<grid, kK1Threads, kK1SmemBytes, st>>>(P, carry, used, audio, audio_stride, n_samples, n_frames, gpb, vec_ok, vout,
+                                                                      nullptr, nullptr, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frontend_clip_fused(const FrontendParams &P, const int16_t *carry, int used, const int16_t *audio, long long audio_stride,
+                                       int n_samples, int n_streams, int n_frames, uint32_t *estimate, uint16_t *feat, long long feat_stream_stride,
+                                       cudaStream_t st) {
+    if (n_frames <= 0 || n_streams <= 0) return cudaSuccess;
+    static bool done3[64] = {}, done4[64] = {};
+    static const int occ = getenv("MWW_K1_OCC") ? atoi(getenv("MWW_K1_OCC")) : 4;
+    cudaError_t e = occ == 3 ? k1_opt_in(k1_spectral_kernel<true, 3>, done3) : k1_opt_in(k1_spectral_kernel<true, 4>, done4);
+    if (e != cudaSuccess) return e;
+    const int vec_ok = (used % 8 == 0) && (n_samples % 8 == 0) && (audio_stride % 8 == 0) &&
+                       (reinterpret_cast<uintptr_t>(audio) % 16 == 0) && (reinterpret_cast<uintptr_t>(carry) % 16 == 0);
+    const int n_groups = (n_frames + kFramesPerGroup - 1) / kFramesPerGroup;
+    dim3 grid((unsigned)n_streams, 1u);
+    if (occ == 3)
+        k1_spectral_kernel<true, 3><<<grid, kK1Threads, kK1SmemBytes, st>>>(P, carry, used, audio, audio_stride, n_samples, n_frames, n_groups, vec_ok,
+                                                                            nullptr, estimate, feat, feat_stream_stride);
+    else
+        k1_spectral_kernel<true, 4><<<grid, kK1Threads, kK1SmemBytes, st>>>(P, carry, used, audio, audio_stride, n_samples, n_frames, n_groups, vec_ok,
+                                                                            nullptr, estimate, feat, feat_stream_stride);
     return cudaGetLastError();
 }
 
@@ -272,15 +342,18 @@ bool frontend_fusable(int used, int n_samples, int n_frames) {
     return n_frames >= 1 && n_frames <= 8 && new_used >= 0 && new_used <= 2 * kHop;
 }
 
-cudaError_t launch_frontend_fused(const FrontendParams &P, int fb_coef_len, int16_t *carry, int used, const int16_t *audio,
+cudaError_t launch_frontend_fused(const FrontendParams &P, int16_t *carry, int used, const int16_t *audio,
                                   long long audio_stride, int n_samples, int n_streams, int n_frames, uint32_t *estimate, uint16_t *feat,
                                   long long feat_stream_stride, cudaStream_t st) {
     if (n_streams <= 0) return cudaSuccess;
+    static bool done[64] = {};
+    cudaError_t e = k1_opt_in(k1k2_packed_kernel, done);
+    if (e != cudaSuccess) return e;
     const int vec_ok = (used % 8 == 0) && (n_samples % 8 == 0) && (audio_stride % 8 == 0) &&
                        (reinterpret_cast<uintptr_t>(audio) % 16 == 0) && (reinterpret_cast<uintptr_t>(carry) % 16 == 0);
     const int spc = k1_packed_streams(n_frames);
     const unsigned grid = (unsigned)((n_streams + spc - 1) / spc);
-    k1k2_packed_kernel<<<grid, kK1Threads, 0, st>>>(P, fb_coef_len, carry, used, audio, audio_stride, n_samples, n_streams, n_frames, spc, vec_ok,
+    k1k2_packed_kernel<<<grid, kK1Threads, kK1SmemBytes, st>>>(P, carry, used, audio, audio_stride, n_samples, n_streams, n_frames, spc, vec_ok,
                                                     estimate, feat, feat_stream_stride, used + n_samples - n_frames * kHop);
     return cudaGetLastError();
 }

@@ -40,14 +40,30 @@ struct K1Smem {
     int16_t audio[2][kGroupSamples];   // double buffered: group g+1 is prefetched (cp.async) while g is processed
     uint16_t lane_max[kFramesPerGroup][16];
     int32_t shift[kFramesPerGroup];
-    int16_t fb_coef[kFbCoefMax];
+    int32_t fb_coef[kFbCoefWords];     // span coefficients, [slot][lane][stride] (mww_tables.h)
+    int16_t gain_lut[128];             // PCAN / log tables for the temporal chain fused behind the filterbank
+    uint16_t log_lut[132];
+    uint32_t lane_tw[16][15];          // stage-3 / stage-4 twiddles of lane b (packed re | im << 16), see K1LaneShared
 };
+// 50.6 KB: above the 48 KB static limit, so the kernels take it as dynamic shared memory (opt-in per kernel and device)
+constexpr int kK1SmemBytes = (int)sizeof(K1Smem);
+
+// tables every K1-family kernel keeps in shared memory for its whole lifetime
+MWW_HD void k1_stage_tables(int tid, K1Smem &sm, const FrontendParams &P) {
+    for (int i = tid; i < kFbCoefWords; i += kK1Threads) sm.fb_coef[i] = P.fb_coef[i];
+    for (int i = tid; i < 128; i += kK1Threads) sm.gain_lut[i] = P.gain_lut[i];
+    for (int i = tid; i < 132; i += kK1Threads) sm.log_lut[i] = P.log_lut[i];
+}
 
 // per-thread constants that do not depend on the frame (kept in registers across groups)
 struct K1Lane {
     int32_t t3r[3], t3i[3];     // stage-3 twiddles tw[4b], tw[8b], tw[12b]
     int32_t t4r[12], t4i[12];   // stage-4 twiddles tw[k'], tw[2k'], tw[3k'] for k' = 16j + b
 };
+
+// The same constants read from shared memory where they are used (15 conflict-free LDS per group) instead of living in 30
+// registers: the clip kernel then fits 64 registers = 4 CTAs per SM (r02: 24 -> 32 resident warps on an issue-bound kernel).
+struct K1LaneShared { const uint32_t *row; };   // &sm.lane_tw[b][0]: [0..3) stage 3, [3 + 3j + q] stage 4
 
 // ---------------------------------------------------------------------------------------------
 // Q15 primitives of KissFFT FIXED_POINT=16
@@ -154,6 +170,20 @@ MWW_HD void k1_lane_init(int tid, const FrontendParams &P, K1Lane &L) {
         }
     }
 }
+
+MWW_HD void k1_stage_lane_twiddles(int tid, K1Smem &sm, const FrontendParams &P) {
+    for (int i = tid; i < 16 * 15; i += kK1Threads) {
+        const int b = i / 15, e = i - 15 * b;
+        int idx;
+        if (e < 3) idx = 4 * b * (e + 1);
+        else { const int j = (e - 3) / 3, q = (e - 3) - 3 * j; idx = (16 * j + b) * (q + 1); }
+        sm.lane_tw[b][e] = P.tw[idx];
+    }
+}
+MWW_HD void lane_tw3(const K1Lane &L, int q, int32_t &wr, int32_t &wi) { wr = L.t3r[q]; wi = L.t3i[q]; }
+MWW_HD void lane_tw4(const K1Lane &L, int i, int32_t &wr, int32_t &wi) { wr = L.t4r[i]; wi = L.t4i[i]; }
+MWW_HD void lane_tw3(const K1LaneShared &L, int q, int32_t &wr, int32_t &wi) { const uint32_t w = L.row[q]; wr = unpack_lo(w); wi = unpack_hi(w); }
+MWW_HD void lane_tw4(const K1LaneShared &L, int i, int32_t &wr, int32_t &wi) { const uint32_t w = L.row[3 + i]; wr = unpack_lo(w); wi = unpack_hi(w); }
 
 // P0: bring the group's audio span into shared memory.  The stream's sample sequence is
 // carry[0 .. used) followed by audio[0 .. n_samples); group g needs samples [160*f0, 160*f0 + 2880).
@@ -279,7 +309,8 @@ MWW_HD void k1_packed_load_audio(int tid, K1Smem &sm, const int16_t *carry, int 
 MWW_HD int k1_packed_pair_base(int fl, int fps) { return (fl / fps) * ((fps + 2) * (kHop / 2)) + (kHop / 2) * (fl % fps); }
 
 // P3: transpose (lane b gathers position b of every 16-point block), FFT stages 3 and 4
-MWW_HD void k1_fft_pass2(int tid, K1Smem &sm, const K1Lane &L) {
+template <typename LaneT>
+MWW_HD void k1_fft_pass2(int tid, K1Smem &sm, const LaneT &L) {
     const int fl = tid >> 4, b = tid & 15;
     int32_t yr[16], yi[16];
 #pragma unroll
@@ -294,8 +325,9 @@ MWW_HD void k1_fft_pass2(int tid, K1Smem &sm, const K1Lane &L) {
         for (int q = 0; q < 4; ++q) { yr[4 * c + q] = fixdiv4(yr[4 * c + q]); yi[4 * c + q] = fixdiv4(yi[4 * c + q]); }
 #pragma unroll
         for (int q = 1; q < 4; ++q) {
-            int32_t mr, mi;
-            cmul_q15(yr[4 * c + q], yi[4 * c + q], L.t3r[q - 1], L.t3i[q - 1], mr, mi);
+            int32_t mr, mi, wr, wi;
+            lane_tw3(L, q - 1, wr, wi);
+            cmul_q15(yr[4 * c + q], yi[4 * c + q], wr, wi, mr, mi);
             yr[4 * c + q] = mr; yi[4 * c + q] = mi;
         }
         bfly4_core(yr[4 * c], yi[4 * c], yr[4 * c + 1], yi[4 * c + 1], yr[4 * c + 2], yi[4 * c + 2], yr[4 * c + 3], yi[4 * c + 3]);
@@ -308,8 +340,9 @@ MWW_HD void k1_fft_pass2(int tid, K1Smem &sm, const K1Lane &L) {
         for (int q = 0; q < 4; ++q) { yr[4 * q + j] = fixdiv4(sext16(yr[4 * q + j])); yi[4 * q + j] = fixdiv4(sext16(yi[4 * q + j])); }
 #pragma unroll
         for (int q = 1; q < 4; ++q) {
-            int32_t mr, mi;
-            cmul_q15(yr[4 * q + j], yi[4 * q + j], L.t4r[3 * j + q - 1], L.t4i[3 * j + q - 1], mr, mi);
+            int32_t mr, mi, wr, wi;
+            lane_tw4(L, 3 * j + q - 1, wr, wi);
+            cmul_q15(yr[4 * q + j], yi[4 * q + j], wr, wi, mr, mi);
             yr[4 * q + j] = mr; yi[4 * q + j] = mi;
         }
         bfly4_core(yr[j], yi[j], yr[4 + j], yi[4 + j], yr[8 + j], yi[8 + j], yr[12 + j], yi[12 + j]);
@@ -322,7 +355,7 @@ MWW_HD void k1_fft_pass2(int tid, K1Smem &sm, const K1Lane &L) {
 // P4: split the packed complex FFT into the real spectrum and take |X|^2
 MWW_HD void k1_real_energy(int tid, K1Smem &sm, const FrontendParams &P) {
     const int fl = tid >> 4, l = tid & 15;
-    if (l == 0) sm.B[fl][0] = 0;   // DC is never read with a non-zero weight; keep it defined
+    if (l == 0) { sm.B[fl][0] = 0; sm.B[fl][kEnergyOffset] = 0; }   // words below the first bin only ever meet zero coefficients; keep them defined
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
         const int k = 1 + 16 * t + l;
@@ -338,12 +371,22 @@ MWW_HD void k1_real_energy(int tid, K1Smem &sm, const FrontendParams &P) {
         tr = sext16(tr); ti = sext16(ti);                    // C_MUL stores into int16
         const int32_t ar = sext16((f1r + tr) >> 1), ai = sext16((f1i + ti) >> 1);
         const int32_t br = sext16((f1r - tr) >> 1), bi = sext16((ti - f1i) >> 1);
-        sm.B[fl][k] = (uint32_t)(ar * ar) + (uint32_t)(ai * ai);
-        sm.B[fl][kNcfft - k] = (uint32_t)(br * br) + (uint32_t)(bi * bi);   // for k = 128 this (later) store wins, as in the library
+        sm.B[fl][k + kEnergyOffset] = (uint32_t)(ar * ar) + (uint32_t)(ai * ai);
+        sm.B[fl][kNcfft - k + kEnergyOffset] = (uint32_t)(br * br) + (uint32_t)(bi * bi);   // for k = 128 this (later) store wins, as in the library
     }
 }
 
-// P5: mel filterbank (64-bit accumulate), rounded sqrt, undo the input scaling
+// P5: mel filterbank (64-bit accumulate), rounded sqrt, undo the input scaling.  Energies and int32 coefficients come in
+// two per 64-bit shared-memory load from even, conflict-free start words (mww_tables.h).
+struct Pair32 { uint32_t x, y; };
+MWW_HD Pair32 load_pair(const uint32_t *p) {
+#if defined(__CUDA_ARCH__)
+    const uint2 v = *reinterpret_cast<const uint2 *>(p);
+    return Pair32{v.x, v.y};
+#else
+    return Pair32{p[0], p[1]};
+#endif
+}
 MWW_HD void k1_filterbank(int tid, K1Smem &sm, const FrontendParams &P, uint32_t *vout_frame /* [40] or nullptr */) {
     const int fl = tid >> 4, l = tid & 15;
     const int sh = sm.shift[fl];
@@ -352,14 +395,14 @@ MWW_HD void k1_filterbank(int tid, K1Smem &sm, const FrontendParams &P, uint32_t
         if (fb_len(s) == 0) continue;
         const FbSlot slot = P.fb_slots[l * kFbSlots + s];
         int64_t acc = 0;
-        const uint32_t *e = &sm.B[fl][slot.bin0];
-        const uint32_t *cf = reinterpret_cast<const uint32_t *>(&sm.fb_coef[slot.coef_off]);   // coef_off is even
+        const uint32_t *e = &sm.B[fl][slot.word0];
+        const uint32_t *cf = reinterpret_cast<const uint32_t *>(&sm.fb_coef[slot.coef_off]);
 #pragma unroll
         for (int j = 0; j < fb_len(s) / 2; ++j) {
-            const uint32_t cw = cf[j];
+            const Pair32 ev = load_pair(e + 2 * j), cv = load_pair(cf + 2 * j);
             // energy widened as int32, like the library
-            acc = mad_wide_s32((int32_t)e[2 * j], unpack_lo(cw), acc);
-            acc = mad_wide_s32((int32_t)e[2 * j + 1], unpack_hi(cw), acc);
+            acc = mad_wide_s32((int32_t)ev.x, (int32_t)cv.x, acc);
+            acc = mad_wide_s32((int32_t)ev.y, (int32_t)cv.y, acc);
         }
         if (slot.ch >= 0 && vout_frame) vout_frame[slot.ch] = isqrt64_round_fast((uint64_t)acc) >> sh;
     }
@@ -399,12 +442,17 @@ MWW_HD uint32_t log_scale(uint32_t x, const uint16_t *lut) {
     return ((loge << kLogScaleShift) + 32768u) >> 16;
 }
 
-// one frame of noise reduction + PCAN + log for one channel; `est` is the persistent noise estimate
-MWW_HD uint16_t k2_channel_step(uint32_t v, uint32_t &est, uint32_t smoothing, const int16_t *gain_lut, const uint16_t *log_lut) {
+// The only frame-to-frame recurrence of the frontend: the noise estimate.  Returns the new
+// estimate; everything else of a frame's temporal chain (k2_output) depends on it but not on other frames.
+MWW_HD uint32_t k2_estimate_update(uint32_t v, uint32_t est, uint32_t smoothing) {
     const uint32_t scaled = v << kSmoothingBits;
-    uint32_t e = (uint32_t)((((uint64_t)scaled * smoothing) + ((uint64_t)est * ((1u << kNoiseBits) - smoothing))) >> kNoiseBits);
-    est = e;
-    if (e > scaled) e = scaled;
+    return (uint32_t)((((uint64_t)scaled * smoothing) + ((uint64_t)est * ((1u << kNoiseBits) - smoothing))) >> kNoiseBits);
+}
+
+// noise subtraction, PCAN and log for one channel of one frame, given the estimate AFTER this frame's update
+MWW_HD uint16_t k2_output(uint32_t v, uint32_t est, const int16_t *gain_lut, const uint16_t *log_lut) {
+    const uint32_t scaled = v << kSmoothingBits;
+    const uint32_t e = est > scaled ? scaled : est;
     const uint32_t fl = (uint32_t)(((uint64_t)v * kMinSignalRemaining) >> kNoiseBits);
     const uint32_t sub = (scaled - e) >> kSmoothingBits;
     uint32_t sig = sub > fl ? sub : fl;
@@ -414,6 +462,32 @@ MWW_HD uint16_t k2_channel_step(uint32_t v, uint32_t &est, uint32_t smoothing, c
     sig <<= kLogCorrectionBits;
     sig = sig > 1 ? log_scale(sig, log_lut) : 0;
     return (uint16_t)(sig < 0xFFFFu ? sig : 0xFFFFu);
+}
+
+// one frame of noise reduction + PCAN + log for one channel; `est` is the persistent noise estimate
+MWW_HD uint16_t k2_channel_step(uint32_t v, uint32_t &est, uint32_t smoothing, const int16_t *gain_lut, const uint16_t *log_lut) {
+    est = k2_estimate_update(v, est, smoothing);
+    return k2_output(v, est, gain_lut, log_lut);
+}
+
+// ---- temporal chain fused behind the filterbank (clip kernel with one CTA per stream) -------------------------------
+// After k1_filterbank has left the group's sqrt values in sm.A[frame][channel]:
+//   phase 1 (threads 0..39, one per channel): the estimate recurrence over the group's frames, in order; the estimate
+//            after each frame goes to sm.B[frame][channel] (the energies are dead by now), the running value stays in
+//            the thread's register across groups;
+//   phase 2 (all 256 threads): the 16 x 40 (frame, channel) outputs are independent given the estimates.
+MWW_HD void k2_group_chain(int ch, K1Smem &sm, int n_valid, uint32_t &est) {
+    const uint32_t smoothing = (ch & 1) ? kOddSmoothing : kEvenSmoothing;
+    for (int f = 0; f < n_valid; ++f) {
+        est = k2_estimate_update(sm.A[f][ch], est, smoothing);
+        sm.B[f][ch] = est;
+    }
+}
+MWW_HD void k2_group_outputs(int tid, K1Smem &sm, int n_valid, uint16_t *feat_group /* [n_valid][40] */) {
+    for (int i = tid; i < n_valid * kNumChannels; i += kK1Threads) {
+        const int f = i / kNumChannels, ch = i - f * kNumChannels;
+        feat_group[i] = k2_output(sm.A[f][ch], sm.B[f][ch], sm.gain_lut, sm.log_lut);
+    }
 }
 
 }  // namespace mww

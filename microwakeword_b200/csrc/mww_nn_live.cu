@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "mww_kernels.h"
 #include "mww_nn_live.cuh"
@@ -54,19 +55,86 @@ nn_f32_live_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
     }
 }
 
+// v2 (mww_nn_live.cuh "warp-specialised live step"): threads 0..255 = layer chain, 256..767 = ring streamers
+constexpr int kBarChain = 1, kBarFull0 = 2, kBarEmpty0 = 4;         // named barriers: full / empty come in pairs (buffer 0, 1)
+__global__ void __launch_bounds__(kLive2Threads, 1)
+nn_f32_live2_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict__ pend, int n_pend, const void *__restrict__ rows,
+                    long long rows_stream_stride_bytes, int rows_are_f32, float *__restrict__ probs, long long probs_stride,
+                    int n_streams, LiveHeads heads) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    for (int L = 1; L < 4; ++L) {                                   // 1x1 weights of blocks 1..3, resident for the whole launch
+        float *dst = sm + (L == 1 ? kLiveOffPw1 : (L == 2 ? kLiveOffPw2 : kLiveOffPw3));
+        for (int e = tid; e < 64 * 64; e += kLive2Threads) dst[(e >> 6) * kWLd + (e & 63)] = W.pw_w[L][e];
+    }
+    live2_stage_taps(tid, kLive2Threads, sm, W, heads);
+    __syncthreads();
+    const int n_groups = (n_streams + kLiveStreams - 1) / kLiveStreams;
+    if (tid >= kLive2ChainThreads) {
+        // ---- streamers: P of group k into buffer k & 1, at most two groups ahead of the chain ----
+        const int st = tid - kLive2ChainThreads;
+        int k = 0;
+        for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++k) {
+            const int buf = k & 1;
+            if (k >= 2) bar_sync(kBarEmpty0 + buf, kLive2Threads);                  // the chain is done with this buffer
+            const long long s0 = (long long)g * kLiveStreams;
+            live2_stream_group(st, sm, W, state, s0, min(kLiveStreams, n_streams - (int)s0), sm + kLive2OffP + buf * kLive2PFloats);
+            bar_arrive(kBarFull0 + buf, kLive2Threads);
+        }
+        return;
+    }
+    // ---- chain ----
+    LiveInput in;
+    in.state = state; in.pend = pend; in.n_pend = n_pend; in.rows = rows;
+    in.rows_stream_stride_bytes = rows_stream_stride_bytes; in.rows_are_f32 = rows_are_f32;
+    int k = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++k) {
+        const int buf = k & 1;
+        const float *p_buf = sm + kLive2OffP + buf * kLive2PFloats;
+        const long long s0 = (long long)g * kLiveStreams;
+        const int n_valid = min(kLiveStreams, n_streams - (int)s0);
+        live2_build_a(tid, sm, in, s0, n_valid);
+        bar_sync(kBarChain, kLive2ChainThreads);
+        live_first_conv_mma(tid, sm, W);
+        bar_sync(kBarFull0 + buf, kLive2Threads);                                   // P of this group is complete (and H is written)
+        live2_write_tail(tid, sm, in, state, pend, s0, n_valid);                    // A is dead: new first-conv ring + pending rows
+        live2_dw_from_p<0>(tid, sm, W, state, s0, n_valid, heads.h[0], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
+        live_pointwise_mma<0>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
+        live2_dw_from_p<1>(tid, sm, W, state, s0, n_valid, heads.h[1], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
+        live_pointwise_mma<1>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
+        live2_dw_from_p<2>(tid, sm, W, state, s0, n_valid, heads.h[2], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
+        live_pointwise_mma<2>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
+        live2_dw_from_p<3>(tid, sm, W, state, s0, n_valid, heads.h[3], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
+        live_pointwise_mma<3>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
+        live2_dw_from_p<4>(tid, sm, W, state, s0, n_valid, heads.h[4], p_buf);
+        bar_arrive(kBarEmpty0 + buf, kLive2Threads);                                // last read of this P buffer
+        bar_sync(kBarChain, kLive2ChainThreads);
+        live_head_finish(tid, sm, W, s0, n_valid, probs, probs_stride);
+        bar_sync(kBarChain, kLive2ChainThreads);                                    // D / A are rewritten by the next group
+    }
+}
+
 cudaError_t launch_nn_f32_live(const NnWeightsF32 &W, float *state, float *pend, int n_pend, const void *rows,
                                long long rows_stream_stride_bytes, int rows_are_f32, float *probs, long long probs_stride,
                                int n_streams, const LiveHeads &heads, int sm_count, cudaStream_t st) {
     if (n_streams <= 0) return cudaSuccess;
     static bool attr_done[64] = {};
+    static const bool v1 = getenv("MWW_LIVE_V1") != nullptr;        // A/B switch kept for the r02 measurement
     if (first_launch_on_this_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(nn_f32_live_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLiveSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_f32_live2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLive2SmemBytes);
         if (e != cudaSuccess) return e;
     }
     const int n_groups = (n_streams + kLiveStreams - 1) / kLiveStreams;
-    const int grid = std::min(n_groups, 2 * sm_count);
-    nn_f32_live_kernel<<<grid, kLiveThreads, kLiveSmemBytes, st>>>(W, state, pend, n_pend, rows, rows_stream_stride_bytes, rows_are_f32, probs,
-                                                                   probs_stride, n_streams, heads);
+    if (v1) {
+        const int grid = std::min(n_groups, 2 * sm_count);
+        nn_f32_live_kernel<<<grid, kLiveThreads, kLiveSmemBytes, st>>>(W, state, pend, n_pend, rows, rows_stream_stride_bytes, rows_are_f32, probs,
+                                                                       probs_stride, n_streams, heads);
+    } else {
+        const int grid = std::min(n_groups, sm_count);
+        nn_f32_live2_kernel<<<grid, kLive2Threads, kLive2SmemBytes, st>>>(W, state, pend, n_pend, rows, rows_stream_stride_bytes, rows_are_f32, probs,
+                                                                          probs_stride, n_streams, heads);
+    }
     return cudaGetLastError();
 }
 

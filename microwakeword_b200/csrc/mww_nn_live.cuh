@@ -277,6 +277,160 @@ MWW_HD void live_canonicalise_column(float *state, long long s, int col, const L
     for (int j = 0; j < R; ++j) ring[j * C] = tmp[j];
 }
 
+// =====================================================================================================================
+// v2: warp-specialised live step (r02).  ncu on the kernel above: issue-active 20 %, 16 resident warps per SM, stall samples
+// spread evenly over every phase -- the whole kernel runs latency-bound because a CTA's ring loads and its layer chain take
+// turns.  The old ring rows do not depend on this step's activations, so
+//     P[column] = bias + sum over the R old rows of tap(row) * x(row)           ("streamers", 16 warps)
+// can be computed for stream group g+1 while the layer chain of group g runs   ("chain", 8 warps)
+//     first conv -> { D = fma(tap_new, x_new, P) ; store x_new over the oldest ring row ; 1x1 + ReLU } x 4 -> head.
+// The arithmetic and its order are exactly those of live_ring_pass, so the two kernels are bit-identical.  One CTA of 768
+// threads per SM, P double-buffered in shared memory and handed over with named barriers; the streamers keep R (or 2 R)
+// independent 128-byte row segments in flight per thread all the time, which is what an HBM-bound kernel wants.
+constexpr int kLive2ChainThreads = 256;
+constexpr int kLive2StreamThreads = 512;
+constexpr int kLive2Threads = kLive2ChainThreads + kLive2StreamThreads;
+constexpr int kLive2PPitch = 33;                              // P[column][stream]: odd pitch -> conflict-free on both sides
+constexpr int kLive2Cols = 32 + 64 * 4;                       // 288 ring columns per stream (blocks 0..3, head)
+constexpr int kLive2PFloats = kLive2Cols * kLive2PPitch;      // one P buffer
+constexpr int kLive2WrotFloats = 4 * 32 + (10 + 14 + 22 + 16) * 64;   // taps of the OLD rows, per physical row (rotation applied)
+constexpr int kLive2OffP = kLiveSmemFloats;                   // the chain's regions keep their v1 offsets
+constexpr int kLive2OffWrot = kLive2OffP + 2 * kLive2PFloats;
+constexpr int kLive2SmemFloats = kLive2OffWrot + kLive2WrotFloats;
+constexpr int kLive2SmemBytes = kLive2SmemFloats * 4;         // 200.2 KB: one CTA per SM
+MWW_HD constexpr int live2_col_base(int i) { return i == 0 ? 0 : 32 + 64 * (i - 1); }
+MWW_HD constexpr int live2_wrot_base(int i) { return i == 0 ? 0 : (i == 1 ? 128 : (i == 2 ? 128 + 640 : (i == 3 ? 128 + 640 + 896 : 128 + 640 + 896 + 1408))); }
+
+// once per CTA: tap of every PHYSICAL old row p of ring i (logical row (p - head) mod R), [p][channel]
+MWW_HD void live2_stage_taps(int tid, int n_threads, float *sm, const NnWeightsF32 &W, const LiveHeads &heads) {
+    float *wr = sm + kLive2OffWrot;
+    for (int i = 0; i < 5; ++i) {
+        const int R = live_ring_rows(i), C = live_ring_cols(i), head = heads.h[i];
+        const float *src = i < 4 ? W.dw_w[i] : W.head_w;          // [R + 1][C]; row R is the newest tap (stays with the chain)
+        for (int e = tid; e < R * C; e += n_threads) {
+            const int p = e / C, c = e - p * C;
+            const int j = p - head < 0 ? p - head + R : p - head;
+            wr[live2_wrot_base(i) + e] = src[j * C + c];
+        }
+    }
+}
+
+// streamer thread st (0..511): P of ring I for the 32 streams of one group.  Consecutive threads = consecutive channels of
+// one stream (128-byte coalesced row segments); 512 is a multiple of the ring's channel count, so a thread's channel -- and
+// with it its R taps -- is the same for all of its items.
+template <int I>
+MWW_HD void live2_stream_ring(int st, float *sm, const NnWeightsF32 &W, const float *state, long long s0, int n_valid, float *p_buf) {
+    constexpr int R = live_ring_rows(I), C = live_ring_cols(I);
+    constexpr int items = kLiveStreams * C / kLive2StreamThreads;     // 2 (block 0) or 4
+    constexpr int U = R <= 14 ? 2 : 1;                                // items in flight per thread
+    constexpr int ring_off = kStateOff[I + 1];
+    const int c = st % C, s_first = st / C;
+    const float *wr = sm + kLive2OffWrot + live2_wrot_base(I) + c;
+    float w[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) w[r] = wr[r * C];
+    const float bias = I < 4 ? W.dw_b[I < 4 ? I : 0][c] : 0.f;
+    float *p_col = p_buf + (live2_col_base(I) + c) * kLive2PPitch;
+#pragma unroll 1
+    for (int it = 0; it < items; it += U) {
+        float x[U][R];
+        int sl[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            sl[u] = s_first + (it + u) * (kLive2StreamThreads / C);
+            const bool ok = sl[u] < n_valid;
+            const float *ring = state + (size_t)(s0 + (ok ? sl[u] : 0)) * kStateFloats + ring_off + c;
+#pragma unroll
+            for (int r = 0; r < R; ++r) x[u][r] = ok ? ring[r * C] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float acc = bias;
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc = fmaf(w[r], x[u][r], acc);
+            p_col[sl[u]] = acc;
+        }
+    }
+}
+MWW_HD void live2_stream_group(int st, float *sm, const NnWeightsF32 &W, const float *state, long long s0, int n_valid, float *p_buf) {
+    live2_stream_ring<3>(st, sm, W, state, s0, n_valid, p_buf);        // longest rings first: their loads overlap the rest
+    live2_stream_ring<4>(st, sm, W, state, s0, n_valid, p_buf);
+    live2_stream_ring<2>(st, sm, W, state, s0, n_valid, p_buf);
+    live2_stream_ring<1>(st, sm, W, state, s0, n_valid, p_buf);
+    live2_stream_ring<0>(st, sm, W, state, s0, n_valid, p_buf);
+}
+
+// chain: first-conv window without per-thread copies kept across the barrier (the new first-conv ring is read back from
+// the A operand, the new pending rows from the caller's rows)
+template <bool F32ROWS>
+MWW_HD void live2_build_a_t(int tid, float *sm, const LiveInput &in, long long s0, int n_valid) {
+    const int warp = tid >> 5;
+    const unsigned lane = (unsigned)(tid & 31), np40 = (unsigned)in.n_pend * (unsigned)kNumChannels;
+    float *a = sm + kLiveOffA;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int sl = warp * 4 + q;
+        const bool ok = sl < n_valid;
+        const size_t su = (size_t)(s0 + (ok ? sl : 0));
+        const float *st = in.state + su * (size_t)kStateFloats;
+        const float *pd = in.pend + su * (size_t)(2 * kNumChannels);
+        const char *rb = static_cast<const char *>(in.rows) + su * (size_t)in.rows_stream_stride_bytes;
+        const float *rf = reinterpret_cast<const float *>(rb);
+        const uint16_t *r16 = reinterpret_cast<const uint16_t *>(rb);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const unsigned k = lane + 32u * (unsigned)i, kk = k < 199u ? k : 199u;
+            const bool in_ring = kk < 80u, in_pend = !in_ring && kk < 80u + np40, is_row = !in_ring && !in_pend;
+            const unsigned e = is_row ? kk - 80u - np40 : 0u;
+            const float *fp = in_ring ? st + kk : (in_pend ? pd + (kk - 80u) : (F32ROWS ? rf + e : st));
+            float v = *fp;
+            if (!F32ROWS) {
+                const float u = (float)r16[e] * kFeatureScale;
+                v = is_row ? u : v;
+            }
+            v = (ok && k < 200u) ? v : 0.f;
+            if (k < 200u) a[k * (unsigned)kLivePitch + (unsigned)sl] = v;
+        }
+    }
+}
+MWW_HD void live2_build_a(int tid, float *sm, const LiveInput &in, long long s0, int n_valid) {
+    if (in.rows_are_f32) live2_build_a_t<true>(tid, sm, in, s0, n_valid);
+    else live2_build_a_t<false>(tid, sm, in, s0, n_valid);
+}
+// after the first conv has consumed A (and a barrier): new first-conv ring = window[120:200], new pending rows = the
+// call's last n_pend rows.  Thread -> (stream = tid / 8, 8 threads per stream)
+MWW_HD void live2_write_tail(int tid, const float *sm, const LiveInput &in, float *state, float *pend, long long s0, int n_valid) {
+    const int sl = tid >> 3, part = tid & 7;
+    if (sl >= n_valid) return;
+    const size_t su = (size_t)(s0 + sl);
+    const float *a = sm + kLiveOffA;
+    for (int k = part; k < 80; k += 8) state[su * (size_t)kStateFloats + k] = a[(120 + k) * kLivePitch + sl];
+    const int np40 = in.n_pend * kNumChannels;
+    for (int e = part; e < np40; e += 8) pend[su * (size_t)(2 * kNumChannels) + e] = live_row_value(in, su, (unsigned)(3 * kNumChannels - np40 + e));
+}
+
+// chain: depthwise of block L (I = L) or head partial (I = 4) from the streamers' P: D = fma(newest tap, x_new, P); the new
+// row replaces the oldest physical row of the ring
+template <int I>
+MWW_HD void live2_dw_from_p(int tid, float *sm, const NnWeightsF32 &W, float *state, long long s0, int n_valid, int head, const float *p_buf) {
+    constexpr int R = live_ring_rows(I), C = live_ring_cols(I);
+    constexpr int per = kLiveStreams * C / kLive2ChainThreads;       // 4 or 8 streams per thread
+    constexpr int ring_off = kStateOff[I + 1];
+    const int c = tid % C, sub = tid / C;
+    const float wn = (I < 4 ? W.dw_w[I < 4 ? I : 0] : W.head_w)[R * C + c];
+    const float *h = sm + kLiveOffH + c * kLivePitch;
+    float *d = sm + kLiveOffD + c * kLivePitch;
+    const float *p_col = p_buf + (live2_col_base(I) + c) * kLive2PPitch;
+#pragma unroll
+    for (int i = 0; i < per; ++i) {
+        const int sl = sub * per + i;
+        const bool ok = sl < n_valid;
+        const float xn = h[sl];
+        d[sl] = ok ? fmaf(wn, xn, p_col[sl]) : 0.f;
+        if (ok) state[(size_t)(s0 + sl) * kStateFloats + ring_off + head * C + c] = xn;
+    }
+}
+
 #if defined(__CUDACC__)
 // ---- L2 prefetch of ring data one stage ahead (cp.async.bulk.prefetch.L2: no registers, no shared memory, no barrier) ----
 // The layer chain is serial (ring read -> depthwise -> barrier -> MMA -> barrier -> next ring read), so a CTA's ring loads
@@ -315,6 +469,10 @@ MWW_D void live_prefetch_next_window(int tid, const T *state, const T *pend, con
     const char *rb = static_cast<const char *>(rows) + su * (size_t)rows_stream_stride_bytes;
     if ((reinterpret_cast<uintptr_t>(rb) & 15) == 0) l2_prefetch(rb, row_bytes & ~15u);
 }
+
+// named barriers of the warp-specialised kernel (barrier 0 is __syncthreads)
+MWW_D void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+MWW_D void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // first conv on tensor cores: 8 warps = 2 stream tiles x 4 channel tiles, K = 200 (25 k-steps), B fragments from L2
 MWW_D void live_first_conv_mma(int tid, float *sm, const NnWeightsF32 &W) {

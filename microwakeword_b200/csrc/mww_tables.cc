@@ -87,43 +87,82 @@ bool make_filterbank(HostTables *t) {
     std::vector<Span> spans;
     for (int c = 0; c < kNumChannels; ++c) spans.push_back({c, t->chan_start[c], t->chan_start[c + 2] - t->chan_start[c]});
     std::sort(spans.begin(), spans.end(), [](const Span &a, const Span &b) { return a.n != b.n ? a.n > b.n : a.ch < b.ch; });
-    // longest-processing-time assignment of the 40 spans to 16 lanes, at most kFbSlots each
+    // Every lane runs the same trip count per slot (the loops are unrolled to the slot's longest span), so only the
+    // grouping matters: the 16 longest spans share slot 0, the next 16 slot 1, the remaining 8 slot 2.
     std::vector<Span> lane[kFbLanes];
-    int load[kFbLanes] = {0};
-    for (const Span &s : spans) {
-        int best = -1;
-        for (int l = 0; l < kFbLanes; ++l)
-            if ((int)lane[l].size() < kFbSlots && (best < 0 || load[l] < load[best])) best = l;
-        lane[best].push_back(s);
-        load[best] += s.n;
-    }
+    for (size_t i = 0; i < spans.size(); ++i) lane[i % kFbLanes].push_back(spans[i]);
     for (int s = 0; s < kFbSlots; ++s) {
         t->fb_slot_len[s] = 0;
         for (int l = 0; l < kFbLanes; ++l)
             if ((int)lane[l].size() > s) t->fb_slot_len[s] = std::max(t->fb_slot_len[s], lane[l][s].n);
-        t->fb_slot_len[s] = (t->fb_slot_len[s] + 1) & ~1;   // even: coefficients are fetched two per word
+        t->fb_slot_len[s] = (t->fb_slot_len[s] + 1) & ~1;   // even: energies and coefficients are fetched two per load
     }
-    t->fb_coef.clear();
-    for (int l = 0; l < kFbLanes; ++l)
-        for (int s = 0; s < kFbSlots; ++s) {
-            FbSlot &slot = t->fb_slots[l][s];
-            slot.coef_off = (int16_t)t->fb_coef.size();
+    // Start word of every span: bin0 + kEnergyOffset - d with d >= 0 leading zero coefficients, even, n + d within the slot's
+    // trip count, and (start / 2) mod 16 distinct over the 16 lanes of a slot (Kuhn's augmenting-path matching of lanes to
+    // the 16 bank pairs).  Lanes without a span in a slot take one of the left-over keys (their loads still execute).
+    int start_word[kFbLanes][kFbSlots];
+    for (int s = 0; s < kFbSlots; ++s) {
+        const int L = t->fb_slot_len[s];
+        if (L == 0) { for (int l = 0; l < kFbLanes; ++l) start_word[l][s] = 0; continue; }
+        int cand[kFbLanes][16];                       // cand[l][key] = start word realising `key` for lane l, or -1
+        for (int l = 0; l < kFbLanes; ++l) {
+            for (int k = 0; k < 16; ++k) cand[l][k] = -1;
             if ((int)lane[l].size() > s) {
                 const Span &sp = lane[l][s];
-                slot.ch = (int16_t)sp.ch; slot.bin0 = (int16_t)sp.bin0; slot.n = (int16_t)sp.n;
-                // keep padded reads inside the 272-word energy row
-                if (slot.bin0 + t->fb_slot_len[s] > 272) return false;
-                for (int j = 0; j < t->fb_slot_len[s]; ++j) {
-                    const int b = sp.bin0 + j;
-                    int16_t c = 0;
-                    if (j < sp.n) c = (b < t->chan_start[sp.ch + 1]) ? t->bin_unweight[b] : t->bin_weight[b];
-                    t->fb_coef.push_back(c);
+                for (int d = 0; d + sp.n <= L; ++d) {
+                    const int st = sp.bin0 + kEnergyOffset - d;
+                    if (st < 0 || (st & 1) || st + L > 272) continue;
+                    if (cand[l][(st / 2) % 16] < 0) cand[l][(st / 2) % 16] = st;     // smallest shift wins
                 }
             } else {
-                slot.ch = -1; slot.bin0 = 0; slot.n = 0;
-                for (int j = 0; j < t->fb_slot_len[s]; ++j) t->fb_coef.push_back(0);
+                for (int k = 0; k < 16; ++k) cand[l][k] = 2 * k;
             }
         }
+        int owner[16];
+        for (int k = 0; k < 16; ++k) owner[k] = -1;
+        struct Aug {
+            static bool run(int l, int (*cand)[16], int *owner, bool *seen) {
+                for (int k = 0; k < 16; ++k) {
+                    if (cand[l][k] < 0 || seen[k]) continue;
+                    seen[k] = true;
+                    if (owner[k] < 0 || run(owner[k], cand, owner, seen)) { owner[k] = l; return true; }
+                }
+                return false;
+            }
+        };
+        for (int l = 0; l < kFbLanes; ++l) {
+            bool seen[16] = {false};
+            if (!Aug::run(l, cand, owner, seen)) return false;      // no conflict-free schedule: the kernel constants need revisiting
+        }
+        for (int k = 0; k < 16; ++k) start_word[owner[k]][s] = cand[owner[k]][k];
+    }
+    t->fb_coef.assign(kFbCoefWords, 0);
+    int slot_base = 0;
+    for (int s = 0; s < kFbSlots; ++s) {
+        if (t->fb_slot_len[s] == 0) continue;
+        if (s >= 3 || t->fb_slot_len[s] > kFbCoefStride[s]) return false;
+        for (int l = 0; l < kFbLanes; ++l) {
+            FbSlot &slot = t->fb_slots[l][s];
+            slot.coef_off = (int16_t)(slot_base + l * kFbCoefStride[s]);
+            slot.word0 = (int16_t)start_word[l][s];
+            if ((int)lane[l].size() > s) {
+                const Span &sp = lane[l][s];
+                slot.ch = (int16_t)sp.ch; slot.n = (int16_t)sp.n;
+                for (int j = 0; j < sp.n; ++j) {
+                    const int b = sp.bin0 + j;
+                    const int w = b + kEnergyOffset - slot.word0;            // position inside the padded span
+                    if (w < 0 || w >= t->fb_slot_len[s]) return false;
+                    t->fb_coef[slot.coef_off + w] = (b < t->chan_start[sp.ch + 1]) ? t->bin_unweight[b] : t->bin_weight[b];
+                }
+            } else {
+                slot.ch = -1; slot.n = 0;
+            }
+        }
+        slot_base += kFbLanes * kFbCoefStride[s];
+    }
+    for (int l = 0; l < kFbLanes; ++l)
+        for (int s = 0; s < kFbSlots; ++s)
+            if (t->fb_slot_len[s] == 0) { FbSlot &slot = t->fb_slots[l][s]; slot.ch = -1; slot.word0 = 0; slot.n = 0; slot.coef_off = 0; }
     return true;
 }
 

@@ -28,9 +28,12 @@ def lib():
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + srcs, check=True)
         L = ctypes.CDLL(SO)
         L.emul_features.restype = ctypes.c_int
+        L.emul_features_fused.restype = ctypes.c_int
+        L.emul_fb_schedule.restype = None
         L.emul_nn_f32.restype = ctypes.c_int
         L.emul_nn_i8.restype = ctypes.c_int
         L.emul_nn_f32_live.restype = ctypes.c_int
+        L.emul_nn_f32_live2.restype = ctypes.c_int
         L.emul_nn_live_canonicalise.restype = None
         L.emul_nn_i8_live.restype = ctypes.c_int
         L.emul_nn_i8_live_canonicalise.restype = None
@@ -69,15 +72,28 @@ class Frontend:
         self.estimate = np.zeros((n_streams, 40), np.uint32)
         self.used = 0
 
-    def features(self, audio):
+    def features(self, audio, fused=False, order=0):
+        """fused=True: the phases of the one-launch clip kernel (filterbank -> estimate chain -> outputs from shared memory)"""
         audio = np.ascontiguousarray(audio, np.int16)
         S, N = audio.shape
         rows = (self.used + N) // 160 + 1
         feat = np.zeros((S, rows, 40), np.uint16)
         nu = ctypes.c_int(0)
-        n = lib().emul_features(_p(audio), S, N, _p(self.carry), self.used, _p(self.estimate), _p(feat), rows, ctypes.byref(nu))
+        if fused:
+            n = lib().emul_features_fused(_p(audio), S, N, _p(self.carry), self.used, _p(self.estimate), _p(feat), rows, ctypes.byref(nu), int(order))
+        else:
+            n = lib().emul_features(_p(audio), S, N, _p(self.carry), self.used, _p(self.estimate), _p(feat), rows, ctypes.byref(nu))
+        assert n >= 0
         self.used = nu.value
         return feat[:, :n]
+
+
+def fb_schedule():
+    """(slots [16 lanes][4 slots][ch, word0, n, coef_off], coef int32 [800]) of the mel accumulation"""
+    slots = np.zeros((16, 4, 4), np.int16)
+    coef = np.zeros(800, np.int32)
+    lib().emul_fb_schedule(_p(slots), _p(coef))
+    return slots, coef
 
 
 F32_NAMES = ["first_conv/w"] + ["b%d/dw/w" % i for i in range(4)] + ["b%d/dw/b" % i for i in range(4)] + \
@@ -109,17 +125,23 @@ class NnF32Live(NnF32):
 
     RING_ROWS = (4, 10, 14, 22, 16)
 
-    def __init__(self, *a, **kw):
+    def __init__(self, *a, version=2, order=0, **kw):
+        """version 1: the r01 kernel (every CTA alternates ring loads and layer chain); 2: the warp-specialised one"""
         super().__init__(*a, **kw)
         self.heads = np.zeros(5, np.int32)
+        self.version, self.order = version, order
 
     def step(self, rows3):
         rows3 = np.ascontiguousarray(rows3)
         S = rows3.shape[0]
         assert rows3.shape[1:] == (3, 40)
         probs = np.zeros((S, 1), np.float32)
-        lib().emul_nn_f32_live(self.wp, _p(self.state), _p(self.pend), self.n_pend, _p(rows3), int(rows3.dtype == np.float32), S, _p(probs), 1,
-                               _p(self.heads))
+        if self.version == 2:
+            lib().emul_nn_f32_live2(self.wp, _p(self.state), _p(self.pend), self.n_pend, _p(rows3), int(rows3.dtype == np.float32), S, _p(probs), 1,
+                                    _p(self.heads), int(self.order))
+        else:
+            lib().emul_nn_f32_live(self.wp, _p(self.state), _p(self.pend), self.n_pend, _p(rows3), int(rows3.dtype == np.float32), S, _p(probs), 1,
+                                   _p(self.heads))
         self.heads = ((self.heads + 1) % np.asarray(self.RING_ROWS, np.int32)).astype(np.int32)
         return probs[:, 0]
 

@@ -81,7 +81,7 @@ int emul_features(const int16_t *audio, int n_streams, int n_samples, int16_t *c
         for (long long s0 = 0; s0 < n_streams; s0 += spc) {
             memset(sm, 0xA5, sizeof *sm);
             for (int tid = 0; tid < kK1Threads; ++tid) k1_lane_init(tid, g_params, lanes[tid]);
-            for (size_t i = 0; i < g_tables.fb_coef.size(); ++i) sm->fb_coef[i] = g_tables.fb_coef[i];
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_stage_tables(tid, *sm, g_params);
             for (int tid = 0; tid < kK1Threads; ++tid) k1_packed_load_audio(tid, *sm, carry, used, audio, n_samples, n_samples, s0, n_streams, spc, fps);
             std::vector<K1Pass1Ctx> ctx(kK1Threads);
             for (int part = 0; part < 2; ++part)
@@ -102,7 +102,7 @@ int emul_features(const int16_t *audio, int n_streams, int n_samples, int16_t *c
     for (int s = 0; s < n_streams; ++s) {
         memset(sm, 0xA5, sizeof *sm);   // poison: phases must not depend on stale shared memory
         for (int tid = 0; tid < kK1Threads; ++tid) k1_lane_init(tid, g_params, lanes[tid]);
-        for (size_t i = 0; i < g_tables.fb_coef.size(); ++i) sm->fb_coef[i] = g_tables.fb_coef[i];
+        for (int tid = 0; tid < kK1Threads; ++tid) k1_stage_tables(tid, *sm, g_params);
         const int16_t *my_carry = carry + (size_t)s * kWindow;
         const int16_t *my_audio = audio + (size_t)s * n_samples;
         for (int g = 0; g < n_groups; ++g) {
@@ -142,6 +142,71 @@ int emul_features(const int16_t *audio, int n_streams, int n_samples, int16_t *c
     }
     if (new_used_out) *new_used_out = new_used;
     return n_frames;
+}
+
+// Mirrors the fused clip kernel (k1_spectral_kernel<true>): one "CTA" per stream walks the groups in order; after the
+// filterbank the temporal chain runs from shared memory (k2_group_chain on threads 0..39, then k2_group_outputs on all 256).
+// `order` 0 = ascending thread order inside every phase, 1 = descending (an intra-phase race would show as a difference).
+int emul_features_fused(const int16_t *audio, int n_streams, int n_samples, int16_t *carry, int used, uint32_t *estimate,
+                        uint16_t *feat, int max_rows, int *new_used_out, int order) {
+    ensure_tables();
+    const int total = used + n_samples;
+    const int n_frames = total >= kWindow ? (total - kWindow) / kHop + 1 : 0;
+    const int consumed = n_frames * kHop;
+    const int new_used = total - consumed;
+    if (n_frames > max_rows) return -1;
+    K1Smem *sm = new K1Smem;
+    std::vector<K1Lane> lanes(kK1Threads);
+    const int n_groups = (n_frames + kFramesPerGroup - 1) / kFramesPerGroup;
+    auto T = [&](int i) { return order ? kK1Threads - 1 - i : i; };
+    for (int s = 0; s < n_streams; ++s) {
+        memset(sm, 0xA5, sizeof *sm);
+        for (int i = 0; i < kK1Threads; ++i) k1_stage_lane_twiddles(T(i), *sm, g_params);     // the 4-CTA/SM variant: twiddles from shared memory
+        for (int i = 0; i < kK1Threads; ++i) k1_stage_tables(T(i), *sm, g_params);
+        const int16_t *my_carry = carry + (size_t)s * kWindow;
+        const int16_t *my_audio = audio + (size_t)s * n_samples;
+        uint32_t est[kNumChannels];
+        for (int ch = 0; ch < kNumChannels; ++ch) est[ch] = estimate[(size_t)s * kNumChannels + ch];
+        for (int g = 0; g < n_groups; ++g) {
+            const int f0 = g * kFramesPerGroup;
+            const int buf = g & 1;
+            for (int i = 0; i < kK1Threads; ++i) k1_load_audio(T(i), *sm, buf, my_carry, used, my_audio, n_samples, f0);
+            std::vector<K1Pass1Ctx> ctx(kK1Threads);
+            for (int i = 0; i < kK1Threads; ++i) k1_window_fft1<0>(T(i), *sm, buf, (kHop / 2) * (T(i) >> 4), g_params, ctx[T(i)]);
+            for (int i = 0; i < kK1Threads; ++i) k1_window_fft1<1>(T(i), *sm, buf, (kHop / 2) * (T(i) >> 4), g_params, ctx[T(i)]);
+            for (int i = 0; i < kK1Threads; ++i) k1_fft_pass2(T(i), *sm, K1LaneShared{&sm->lane_tw[T(i) & 15][0]});
+            for (int i = 0; i < kK1Threads; ++i) k1_real_energy(T(i), *sm, g_params);
+            for (int i = 0; i < kK1Threads; ++i) k1_filterbank(T(i), *sm, g_params, &sm->A[T(i) >> 4][0]);
+            const int n_valid = n_frames - f0 < kFramesPerGroup ? n_frames - f0 : kFramesPerGroup;
+            for (int i = 0; i < kK1Threads; ++i) if (T(i) < kNumChannels) k2_group_chain(T(i), *sm, n_valid, est[T(i)]);
+            for (int i = 0; i < kK1Threads; ++i) k2_group_outputs(T(i), *sm, n_valid, feat + ((size_t)s * max_rows + f0) * kNumChannels);
+        }
+        for (int ch = 0; ch < kNumChannels; ++ch) estimate[(size_t)s * kNumChannels + ch] = est[ch];
+    }
+    delete sm;
+    for (int s = 0; s < n_streams; ++s) {
+        int16_t tmp[kWindow] = {0};
+        int16_t *c = carry + (size_t)s * kWindow;
+        for (int i = 0; i < new_used; ++i) {
+            const int vi = consumed + i;
+            tmp[i] = vi < used ? c[vi] : audio[(size_t)s * n_samples + (vi - used)];
+        }
+        memcpy(c, tmp, sizeof tmp);
+    }
+    if (new_used_out) *new_used_out = new_used;
+    return n_frames;
+}
+
+// filterbank schedule for the conflict-freedom test: slots16x4x4 = (ch, word0, n, coef_off) per lane and slot
+void emul_fb_schedule(int16_t *slots16x4x4, int32_t *coef800) {
+    ensure_tables();
+    for (int l = 0; l < kFbLanes; ++l)
+        for (int s = 0; s < kFbSlots; ++s) {
+            const FbSlot &q = g_tables.fb_slots[l][s];
+            int16_t *o = slots16x4x4 + (l * kFbSlots + s) * 4;
+            o[0] = q.ch; o[1] = q.word0; o[2] = q.n; o[3] = q.coef_off;
+        }
+    for (int i = 0; i < kFbCoefWords; ++i) coef800[i] = g_tables.fb_coef[i];
 }
 
 }  // extern "C"

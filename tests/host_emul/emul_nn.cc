@@ -356,6 +356,51 @@ extern "C" int emul_nn_f32_live(const float *const *wp, float *state, float *pen
     return 1;
 }
 
+// v2: the warp-specialised live kernel (nn_f32_live2_kernel).  Streamers (512 threads) fill P for a group, then the chain
+// (256 threads) consumes it; on the GPU the streamers run up to two groups ahead -- the emulation runs them one group at a
+// time, which is the order the named barriers enforce per buffer.  `order` 1 walks every phase's threads in descending order.
+extern "C" int emul_nn_f32_live2(const float *const *wp, float *state, float *pend, int n_pend, const void *rows, int rows_are_f32,
+                                 int n_streams, float *probs, int probs_stride, const int *heads5, int order) {
+    NnWeightsF32 W;
+    W.w0 = wp[0];
+    for (int i = 0; i < 4; ++i) { W.dw_w[i] = wp[1 + i]; W.dw_b[i] = wp[5 + i]; W.pw_w[i] = wp[9 + i]; W.pw_b[i] = wp[13 + i]; }
+    W.head_w = wp[17]; W.head_b = wp[18];
+    LiveHeads heads;
+    for (int i = 0; i < 5; ++i) heads.h[i] = heads5[i];
+    LiveInput in;
+    in.state = state; in.pend = pend; in.n_pend = n_pend; in.rows = rows;
+    in.rows_stream_stride_bytes = 3 * kNumChannels * (rows_are_f32 ? 4 : 2); in.rows_are_f32 = rows_are_f32;
+    std::vector<float> smv(kLive2SmemFloats, -777.f);
+    float *sm = smv.data();
+#define CHAIN(stmt) for (int i_ = 0; i_ < kLive2ChainThreads; ++i_) { const int tid = order ? kLive2ChainThreads - 1 - i_ : i_; stmt; }
+#define STREAM(stmt) for (int i_ = 0; i_ < kLive2StreamThreads; ++i_) { const int st = order ? kLive2StreamThreads - 1 - i_ : i_; stmt; }
+    for (int tid = 0; tid < kLive2Threads; ++tid)
+        for (int L = 1; L < 4; ++L) {
+            float *dst = sm + (L == 1 ? kLiveOffPw1 : (L == 2 ? kLiveOffPw2 : kLiveOffPw3));
+            for (int e = tid; e < 64 * 64; e += kLive2Threads) dst[(e >> 6) * kWLd + (e & 63)] = W.pw_w[L][e];
+        }
+    for (int tid = 0; tid < kLive2Threads; ++tid) live2_stage_taps(tid, kLive2Threads, sm, W, heads);
+    const int n_groups = (n_streams + kLiveStreams - 1) / kLiveStreams;
+    for (int g = 0; g < n_groups; ++g) {
+        const long long s0 = (long long)g * kLiveStreams;
+        const int n_valid = n_streams - (int)s0 < kLiveStreams ? n_streams - (int)s0 : kLiveStreams;
+        float *p_buf = sm + kLive2OffP + (g & 1) * kLive2PFloats;
+        STREAM(live2_stream_group(st, sm, W, state, s0, n_valid, p_buf));
+        CHAIN(live2_build_a(tid, sm, in, s0, n_valid));
+        emul_live_first_conv(sm, W);
+        CHAIN(live2_write_tail(tid, sm, in, state, pend, s0, n_valid));
+        CHAIN(live2_dw_from_p<0>(tid, sm, W, state, s0, n_valid, heads.h[0], p_buf)); emul_live_pointwise<0>(sm, W);
+        CHAIN(live2_dw_from_p<1>(tid, sm, W, state, s0, n_valid, heads.h[1], p_buf)); emul_live_pointwise<1>(sm, W);
+        CHAIN(live2_dw_from_p<2>(tid, sm, W, state, s0, n_valid, heads.h[2], p_buf)); emul_live_pointwise<2>(sm, W);
+        CHAIN(live2_dw_from_p<3>(tid, sm, W, state, s0, n_valid, heads.h[3], p_buf)); emul_live_pointwise<3>(sm, W);
+        CHAIN(live2_dw_from_p<4>(tid, sm, W, state, s0, n_valid, heads.h[4], p_buf));
+        CHAIN(live_head_finish(tid, sm, W, s0, n_valid, probs, probs_stride));
+    }
+#undef CHAIN
+#undef STREAM
+    return 1;
+}
+
 extern "C" void emul_nn_live_canonicalise(float *state, int n_streams, const int *heads5) {
     LiveHeads heads;
     for (int i = 0; i < 5; ++i) heads.h[i] = heads5[i];

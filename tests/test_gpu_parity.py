@@ -488,10 +488,18 @@ def test_reset_by_id_list_host_and_device(torch_cuda):
         for i in range(20, 40):
             chunk = dev[:, 480 * i:480 * (i + 1)].contiguous()
             got, want = eng.step(chunk), fresh.step(chunk)
-            assert torch.equal(got[ids], want[ids]), (kind, i)
+            # fp32: the live kernel sums the depthwise taps in physical ring order, and the two handles' rings are rotated
+            # differently (20 steps apart), so the summation order -- not the values summed -- differs
+            if kind == "int8":
+                assert torch.equal(got[ids], want[ids]), (kind, i)
+            else:
+                assert (got[ids] - want[ids]).abs().max().item() <= F32_TOL, (kind, i)
         st, sf = eng.state_dict(), fresh.state_dict()
         for k in ("carry", "estimate", "nn", "pending"):
-            assert np.array_equal(st[k][ids], sf[k][ids]), (kind, k)
+            if kind == "int8" or k in ("carry", "estimate"):
+                assert np.array_equal(st[k][ids], sf[k][ids]), (kind, k)
+            else:
+                assert np.abs(st[k][ids] - sf[k][ids]).max() <= 1e-4, (kind, k)
         others = [i for i in range(S) if i not in ids]
         assert not np.array_equal(st["nn"][others], sf["nn"][others])
 

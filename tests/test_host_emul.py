@@ -19,7 +19,7 @@ def test_product_tables_equal_oracle_tables():
     for k in ("window", "bin_weight", "bin_unweight", "chan_start", "gain_lut", "log_lut", "twiddles", "super_twiddles"):
         assert np.array_equal(t[k], o[k]), k
     assert t["info"][0] == 5 and t["info"][1] == 241 and t["info"][2] == 1
-    assert t["info"][3] <= 1024           # span coefficients fit the shared-memory copy
+    assert t["info"][3] == 800            # span coefficients: int32 [slot][lane][stride] copy in shared memory
     assert sum(t["info"][4:8]) <= 48      # per-lane trip count of the balanced filterbank schedule
 
 
@@ -74,6 +74,66 @@ def test_frontend_phases_bit_exact_random_edge_and_adversarial():
     got = emul.Frontend(audio.shape[0]).features(audio)
     want, _ = oracle.run_pipeline(None, audio, want_probs=False)
     assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_filterbank_schedule_is_bank_conflict_free_and_complete():
+    """r01's ncu capture put every one of K1's shared-memory bank conflicts (34 % of its wavefronts) on the per-lane
+    energy loads of the mel accumulation.  The table builder now picks even start words whose (word / 2) mod 16 is a
+    permutation over the 16 lanes of a slot, so each 64-bit load of a half-warp (= one frame) covers the 32 banks exactly
+    once -- for the energies and for the int32 coefficient rows; and the shifted / padded spans still reproduce the
+    triangular weights of every channel."""
+    slots, coef = emul.fb_schedule()
+    t = emul.tables()
+    lens = [int(v) for v in t["info"][4:8]]
+    assert lens == [28, 12, 6, 0]
+    seen_channels = set()
+    for s, L in enumerate(lens):
+        if L == 0:
+            continue
+        for j in range(0, L, 2):                                  # the j-th 64-bit load of the slot
+            e_words = slots[:, s, 1].astype(int) + j
+            c_words = slots[:, s, 3].astype(int) + j
+            for words in (e_words, c_words):
+                assert np.all(words % 2 == 0)
+                assert sorted((words // 2) % 16) == list(range(16)), (s, j)
+        for lane in range(16):
+            ch, word0, n, off = (int(v) for v in slots[lane, s])
+            assert 0 <= word0 and word0 + L <= 272 and 0 <= off and off + L <= 800
+            row = coef[off:off + L]
+            if ch < 0:
+                assert not row.any()
+                continue
+            seen_channels.add(ch)
+            # row position w holds the coefficient of FFT bin word0 + w - 1 (energy of bin k lives at word k + 1)
+            b0, b1, b2 = (int(t["chan_start"][ch + i]) for i in range(3))
+            want = np.zeros(L, np.int64)
+            for b in range(b0, b2):
+                want[b + 1 - word0] = t["bin_unweight"][b] if b < b1 else t["bin_weight"][b]
+            assert np.array_equal(row, want), (lane, s, ch)
+    assert seen_channels == set(range(40))
+
+
+def test_fused_clip_frontend_phases_bit_exact_and_order_independent():
+    """The one-launch clip frontend (filterbank -> estimate recurrence on 40 threads -> 640 independent outputs per group,
+    all from shared memory) against the oracle: multi-group calls, a ragged last group, chunked feeding with carried state,
+    and ascending vs descending thread order inside every phase (an intra-phase race would make them differ)."""
+    rng = np.random.default_rng(3)
+    rows = [synth_audio(16000, 170 + i) for i in range(4)] + [e[:16000] for e in edge_case_audio(16000)[:6]]
+    rows.append(rng.choice([-32768, 32767], 16000).astype(np.int16))
+    audio = np.stack(rows)
+    want, _ = oracle.run_pipeline(None, audio, want_probs=False)
+    for order in (0, 1):
+        got = emul.Frontend(audio.shape[0]).features(audio, fused=True, order=order)       # 98 frames: 6 groups + 2 frames
+        assert got.shape == want.shape and np.array_equal(got, want), order
+    fe, sep = emul.Frontend(audio.shape[0]), emul.Frontend(audio.shape[0])
+    pos, parts = 0, []
+    for n in (4000, 1760, 6400, 3840):                                # fused and separate phases interleave on one state
+        fused = len(parts) % 2 == 0
+        parts.append(fe.features(audio[:, pos:pos + n], fused=fused))
+        sep.features(audio[:, pos:pos + n])
+        assert np.array_equal(fe.estimate, sep.estimate) and np.array_equal(fe.carry, sep.carry)
+        pos += n
+    assert np.array_equal(np.concatenate(parts, 1), want)
 
 
 def test_frontend_phases_chunked_stream_and_multi_group():
@@ -144,8 +204,8 @@ def test_live_step_kernel_phases_match_oracle_and_interleave_with_clip():
     S = 70
     audio = np.stack([synth_audio(9600, 900 + i) for i in range(S)])
     feats, want = oracle.run_pipeline(MF.write_container(t), audio)            # 58 rows -> 19 probabilities
-    for n_first in (3, 4, 5):                                                   # first call leaves 0 / 1 / 2 rows pending
-        nn = emul.NnF32Live(t, S)
+    for n_first, version, order in ((3, 2, 0), (4, 2, 1), (5, 2, 0), (4, 1, 0)):   # first call leaves 0 / 1 / 2 rows pending
+        nn = emul.NnF32Live(t, S, version=version, order=order)
         got = [nn.infer(feats[:, :n_first])]                                   # clip-kernel phases: 1 step (+ pending)
         pos = n_first
         while pos + 3 <= feats.shape[1]:
@@ -163,6 +223,11 @@ def test_live_step_kernel_phases_match_oracle_and_interleave_with_clip():
         rest = nn.infer(feats[:, pos:])
         tail = want[:, got.shape[1]:got.shape[1] + rest.shape[1]]
         assert rest.shape == tail.shape and (rest.size == 0 or np.abs(rest - tail).max() <= 1e-5)
+    # the warp-specialised kernel performs the r01 kernel's arithmetic in the same order: bit-identical, state included
+    a, b = emul.NnF32Live(t, S, version=1), emul.NnF32Live(t, S, version=2)
+    for pos in range(0, 30, 3):
+        assert np.array_equal(a.step(feats[:, pos:pos + 3]), b.step(feats[:, pos:pos + 3]))
+    assert np.array_equal(a.state, b.state) and np.array_equal(a.pend, b.pend)
 
 
 def test_int8_live_step_kernel_phases_are_bit_exact():

@@ -1,0 +1,16 @@
+set -x
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for v in v1 v2; do
+if [ $v = v1 ]; then export MWW_LIVE_V1=1; else unset MWW_LIVE_V1; fi
+python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_live_$v.json 2> gpurun_out/bench_live_$v.err; tail -c 500 gpurun_out/bench_live_$v.err
+python - <<PY
+import json
+d = json.load(open("gpurun_out/bench_live_$v.json"))
+for k in ("live", "live_int8"):
+    print("$v", k, "ms/call %.4f" % d[k]["ms_per_call"], {a: round(b, 4) for a, b in d[k]["kernels_ms_per_call"].items()}, "hbm frac %.3f" % d[k]["roofline"]["frac"])
+PY
+done
+unset MWW_LIVE_V1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:nn_f32_live2_kernel -s 6 -c 1 -o gpurun_out/nn_live2 -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_live2.log 2>&1; tail -2 gpurun_out/ncu_live2.log
+bash tools/sanitize.sh 2>&1 | tail -12
