@@ -78,7 +78,12 @@ typedef struct mww_info {
  * reference's default block structure (mixednet.py:278-386 with other --pointwise_filters / --mixconv_kernel_sizes /
  * --first_conv_* / --stride values) runs on the run-time-geometry kernels with the same entry points, state layout
  * rule (first-conv ring, block rings, head ring; oldest row first) and results.  mww_info.input_feature_slices is the
- * model's stride, state_bytes_per_stream its ring state.  Topologies outside that family: MWW_EUNSUPPORTED. */
+ * model's stride, state_bytes_per_stream its ring state.  A block whose largest MixConv kernel is 1 has no MixConv
+ * layer in the reference graph (mixednet.py:346-348); the container carries it as the exact identity depthwise stage
+ * (tap 1, bias 0; int8: weight 1, multiplier 1.0, the previous tensor's quantisation) so the block structure stays
+ * uniform and results are those of the reference graph.  Topologies outside that family -- repeat_in_block > 1,
+ * residual branches (mixednet.py:336-358), pooled / attention heads (:362-381), first_conv_kernel_size < stride --
+ * are answered with MWW_EUNSUPPORTED; okay_nabu and the models of esphome/micro-wake-word-models' v2 family use none. */
 int mww_create(const void *model_blob, size_t n_bytes, int device, int n_streams, mww_t **out);
 int mww_destroy(mww_t *h);
 const char *mww_last_error(const mww_t *h);

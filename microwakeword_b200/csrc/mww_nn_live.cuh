@@ -318,38 +318,40 @@ MWW_HD void live2_stage_taps(int tid, int n_threads, float *sm, const NnWeightsF
 // streamer thread st (0..511): P of ring I for the 32 streams of one group.  Consecutive threads = consecutive channels of
 // one stream (128-byte coalesced row segments); 512 is a multiple of the ring's channel count, so a thread's channel -- and
 // with it its R taps -- is the same for all of its items.
+// Software-pipelined: the R row loads of item i + 1 are issued BEFORE the R multiply-adds of item i, so a warp always has
+// between R and 2 R independent 128-byte requests in flight (r02, first version: loads and FMAs alternated, the average
+// fell to ~R / 2 per warp and the streamers -- 60 % of the kernel's stall samples -- pulled only 3.0 TB/s).  The taps are read
+// from shared memory at use (one conflict-free LDS per FMA) so the two row sets fit the 80-register budget of a 768-thread CTA.
 template <int I>
 MWW_HD void live2_stream_ring(int st, float *sm, const NnWeightsF32 &W, const float *state, long long s0, int n_valid, float *p_buf) {
     constexpr int R = live_ring_rows(I), C = live_ring_cols(I);
     constexpr int items = kLiveStreams * C / kLive2StreamThreads;     // 2 (block 0) or 4
-    constexpr int U = R <= 14 ? 2 : 1;                                // items in flight per thread
+    constexpr int step = kLive2StreamThreads / C;                      // stream distance between a thread's items
     constexpr int ring_off = kStateOff[I + 1];
     const int c = st % C, s_first = st / C;
     const float *wr = sm + kLive2OffWrot + live2_wrot_base(I) + c;
-    float w[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) w[r] = wr[r * C];
     const float bias = I < 4 ? W.dw_b[I < 4 ? I : 0][c] : 0.f;
     float *p_col = p_buf + (live2_col_base(I) + c) * kLive2PPitch;
-#pragma unroll 1
-    for (int it = 0; it < items; it += U) {
-        float x[U][R];
-        int sl[U];
+    float x[2][R];
+    {
+        const bool ok = s_first < n_valid;
+        const float *ring = state + (size_t)(s0 + (ok ? s_first : 0)) * kStateFloats + ring_off + c;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            sl[u] = s_first + (it + u) * (kLive2StreamThreads / C);
-            const bool ok = sl[u] < n_valid;
-            const float *ring = state + (size_t)(s0 + (ok ? sl[u] : 0)) * kStateFloats + ring_off + c;
+        for (int r = 0; r < R; ++r) x[0][r] = ok ? ring[r * C] : 0.f;
+    }
 #pragma unroll
-            for (int r = 0; r < R; ++r) x[u][r] = ok ? ring[r * C] : 0.f;
+    for (int it = 0; it < items; ++it) {
+        const int sl = s_first + it * step;
+        if (it + 1 < items) {
+            const bool ok = sl + step < n_valid;
+            const float *ring = state + (size_t)(s0 + (ok ? sl + step : 0)) * kStateFloats + ring_off + c;
+#pragma unroll
+            for (int r = 0; r < R; ++r) x[(it + 1) & 1][r] = ok ? ring[r * C] : 0.f;
         }
+        float acc = bias;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            float acc = bias;
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc = fmaf(w[r], x[u][r], acc);
-            p_col[sl[u]] = acc;
-        }
+        for (int r = 0; r < R; ++r) acc = fmaf(wr[r * C], x[it & 1][r], acc);
+        p_col[sl] = acc;
     }
 }
 MWW_HD void live2_stream_group(int st, float *sm, const NnWeightsF32 &W, const float *state, long long s0, int n_valid, float *p_buf) {

@@ -394,9 +394,48 @@ class _Recogniser:
                 i += 1
             pw = compute[i]
             i += 1
-            if pw.code != OP_CONV_2D or not dws:
-                self.fail(pw, "expected DEPTHWISE_CONV_2D group(s) followed by a 1x1 CONV_2D (blocks without MixConv are not supported)")
+            if pw.code != OP_CONV_2D:
+                self.fail(pw, "expected DEPTHWISE_CONV_2D group(s) followed by a 1x1 CONV_2D")
             b = len(pw_filters)
+            if not dws:
+                # A block whose largest MixConv kernel is 1 has NO MixConv layer in the reference graph (mixednet.py:346-348): the
+                # 1x1 conv reads the previous activation directly.  The container keeps one uniform block structure, so the block
+                # gets the exact identity as its depthwise stage (tap 1, bias 0; int8: weight 1 at scale 1, multiplier 1.0, the
+                # previous tensor's quantisation on both sides).
+                pf = self.t(pw.inputs[1])
+                if len(pf.shape) != 4 or pf.shape[1:] != (1, 1, cin):
+                    self.fail(pw, "filter shape %s is not [filters, 1, 1, %d]" % (pf.shape, cin))
+                if pw.inputs[0] != cur:
+                    self.fail(pw, "1x1 conv of a block without MixConv does not read the previous layer's output")
+                if pw.opt(1, "i", 1) != 1 or pw.opt(2, "i", 1) != 1:
+                    self.fail(pw, "1x1 conv with a stride")
+                relu, nxt = self.conv_act(pw, 3)
+                if not relu:
+                    self.fail(pw, "1x1 conv without ReLU (mixednet.py:359)")
+                cout = pf.shape[0]
+                pw_w = pf.data()[:, 0, 0, :].T
+                pb = bias_of(pw, cout)
+                if quantized:                                                       # "depthwise output" = the previous tensor itself
+                    scales.append(scales[-1])
+                    zps.append(zps[-1])
+                act_q(self.t(nxt))
+                if quantized:
+                    m1, s1 = quantize_multiplier(1.0)
+                    out["q/b%d/dw/w" % b] = np.ones((1, cin), np.int8)
+                    out["q/b%d/dw/bias" % b] = np.zeros(cin, np.int32)
+                    out["q/b%d/dw/mult" % b] = np.full(cin, m1, np.int32)
+                    out["q/b%d/dw/shift" % b] = np.full(cin, s1, np.int32)
+                    weights_q("b%d/pw" % b, pf, pw_w, pb, cout, scales[-2], scales[-1])
+                else:
+                    out["b%d/dw/w" % b] = np.ones((1, cin), np.float32)
+                    out["b%d/dw/b" % b] = np.zeros(cin, np.float32)
+                    out["b%d/dw/ksize" % b] = np.ones(cin, np.int32)
+                    out["b%d/pw/w" % b] = np.ascontiguousarray(pw_w.astype(np.float32))
+                    out["b%d/pw/b" % b] = (np.zeros(cout, np.float32) if pb is None else pb.data().reshape(-1).astype(np.float32))
+                pw_filters.append(cout)
+                ksizes.append((1,))
+                cur, cin = nxt, cout
+                continue
             # depthwise groups: each reads the LAST k rows of its channel slice of the block's ring memory
             groups = []
             for dw in dws:

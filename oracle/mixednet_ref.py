@@ -100,9 +100,10 @@ def init_synthetic(spec: Spec = OKAY_NABU, seed: int = 0) -> dict:
     for i in range(spec.n_blocks):
         cin, cout = spec.cin(i), spec.pointwise_filters[i]
         dws, dbs = [], []
-        for n, k in zip(spec.splits(i), spec.mixconv_kernel_sizes[i]):
-            dws.append((rng.normal(0, 1, (k, n)) * np.sqrt(2.0 / k)).astype(np.float32))
-            dbs.append(rng.normal(0, 0.05, n).astype(np.float32))
+        if max(spec.mixconv_kernel_sizes[i]) > 1:          # mixednet.py:346-348: a block whose largest kernel is 1 has NO MixConv layer
+            for n, k in zip(spec.splits(i), spec.mixconv_kernel_sizes[i]):
+                dws.append((rng.normal(0, 1, (k, n)) * np.sqrt(2.0 / k)).astype(np.float32))
+                dbs.append(rng.normal(0, 0.05, n).astype(np.float32))
         p["b%d/dw/kernels" % i] = dws
         p["b%d/dw/biases" % i] = dbs
         p["b%d/pw/kernel" % i] = (rng.normal(0, 1, (cin, cout)) * np.sqrt(2.0 / cin)).astype(np.float32)
@@ -127,7 +128,12 @@ def fold_bn(spec: Spec, p: dict) -> dict:
         b = np.zeros(cin, np.float32)
         kk = np.zeros(cin, np.int32)
         c0 = 0
-        for kern, bias, k in zip(p["b%d/dw/kernels" % i], p["b%d/dw/biases" % i], ks):
+        if kmax == 1:
+            # no MixConv in the graph (mixednet.py:346-348): the container's depthwise stage is the exact identity
+            # (tap 1, bias 0), so every kernel keeps one uniform block structure
+            w[:] = 1.0
+            kk[:] = 1
+        for kern, bias, k in zip(p["b%d/dw/kernels" % i], p["b%d/dw/biases" % i], ks if kmax > 1 else ()):
             n = kern.shape[1]
             w[kmax - k:, c0:c0 + n] = kern  # the LAST k rows of the ring window are used
             b[c0:c0 + n] = bias
@@ -174,18 +180,20 @@ class KerasStreamingF32:
         net = np.einsum("kf,kfo->o", mem, p["first_conv/kernel"], dtype=np.float32)[None, :]
         net = np.maximum(net, np.float32(0))
         for i in range(s.n_blocks):
-            # MixConv: Stream(Identity, ring=max(k)-1)  mixednet.py:202-206
-            mem = np.concatenate([self.st_block[i], net], 0)
-            self.st_block[i] = mem[-self.st_block[i].shape[0]:]
             ks = s.mixconv_kernel_sizes[i]
-            outs, c0 = [], 0
-            for kern, bias, k, n in zip(p["b%d/dw/kernels" % i], p["b%d/dw/biases" % i], ks, s.splits(i)):
-                part = mem[:, c0:c0 + n]
-                if len(ks) > 1:
-                    part = part[-k:]          # StridedKeep, strided_drop.py:80-84
-                outs.append((part * kern).sum(0, dtype=np.float32) + bias)  # DepthwiseConv2D valid
-                c0 += n
-            net = np.concatenate(outs)[None, :].astype(np.float32)
+            if max(ks) > 1:                   # mixednet.py:346-348: no MixConv at all when the largest kernel is 1
+                # MixConv: Stream(Identity, ring=max(k)-1)  mixednet.py:202-206
+                mem = np.concatenate([self.st_block[i], net], 0)
+                if self.st_block[i].shape[0]:
+                    self.st_block[i] = mem[-self.st_block[i].shape[0]:]
+                outs, c0 = [], 0
+                for kern, bias, k, n in zip(p["b%d/dw/kernels" % i], p["b%d/dw/biases" % i], ks, s.splits(i)):
+                    part = mem[:, c0:c0 + n]
+                    if len(ks) > 1:
+                        part = part[-k:]          # StridedKeep, strided_drop.py:80-84
+                    outs.append((part * kern).sum(0, dtype=np.float32) + bias)  # DepthwiseConv2D valid
+                    c0 += n
+                net = np.concatenate(outs)[None, :].astype(np.float32)
             # Conv2D 1x1 no bias -> BatchNormalization (inference form) -> ReLU   mixednet.py:349-360
             net = (net @ p["b%d/pw/kernel" % i]).astype(np.float32)
             inv = (p["b%d/bn/gamma" % i] / np.sqrt(p["b%d/bn/var" % i] + np.float32(BN_EPS))).astype(np.float32)
@@ -222,7 +230,8 @@ class FoldedStreamingF32:
         net = np.maximum(np.einsum("kf,kfo->o", mem, t["first_conv/w"], dtype=np.float32), np.float32(0))
         for i in range(s.n_blocks):
             mem = np.concatenate([self.st_block[i], net[None, :]], 0)
-            self.st_block[i] = mem[-self.st_block[i].shape[0]:]
+            if self.st_block[i].shape[0]:            # a 0-row ring (1-tap block) stays empty: mem[-0:] would be the whole window
+                self.st_block[i] = mem[-self.st_block[i].shape[0]:]
             d = (mem * t["b%d/dw/w" % i]).sum(0, dtype=np.float32) + t["b%d/dw/b" % i]
             net = np.maximum((d @ t["b%d/pw/w" % i]).astype(np.float32) + t["b%d/pw/b" % i], np.float32(0))
         mem = np.concatenate([self.st_head, net[None, :]], 0)
@@ -243,7 +252,8 @@ class FoldedStreamingF32:
         acts["c0"] = net
         for i in range(s.n_blocks):
             mem = np.concatenate([self.st_block[i], net[None, :]], 0)
-            self.st_block[i] = mem[-self.st_block[i].shape[0]:]
+            if self.st_block[i].shape[0]:            # a 0-row ring (1-tap block) stays empty: mem[-0:] would be the whole window
+                self.st_block[i] = mem[-self.st_block[i].shape[0]:]
             d = (mem * t["b%d/dw/w" % i]).sum(0, dtype=np.float32) + t["b%d/dw/b" % i]
             acts["d%d" % (i + 1)] = d
             net = np.maximum((d @ t["b%d/pw/w" % i]).astype(np.float32) + t["b%d/pw/b" % i], np.float32(0))
@@ -385,6 +395,11 @@ def quantize_model(tensors: dict, calib_features: np.ndarray) -> dict:
     scales, zps = {}, {}
     for n in names[:-1]:
         scales[n], zps[n] = _act_qparams(lo[n], hi[n])
+    identity = [max(ks) == 1 for ks in spec.mixconv_kernel_sizes]
+    for i, ident in enumerate(identity):
+        if ident:   # no MixConv, hence no tensor between the previous activation and the 1x1 conv (mixednet.py:346-348)
+            prev = "c0" if i == 0 else "p%d" % i
+            scales["d%d" % (i + 1)], zps["d%d" % (i + 1)] = scales[prev], zps[prev]
     scales["prob"], zps["prob"] = np.float32(1.0 / 256.0), -128  # TFLite LOGISTIC int8 output params
 
     q = {"arch": tensors["arch"].copy()}
@@ -411,7 +426,16 @@ def quantize_model(tensors: dict, calib_features: np.ndarray) -> dict:
     prev = "c0"
     for i in range(spec.n_blocks):
         d, pn = "d%d" % (i + 1), "p%d" % (i + 1)
-        conv_layer("q/b%d/dw" % i, tensors["b%d/dw/w" % i], tensors["b%d/dw/b" % i], scales[prev], scales[d], 1)
+        if identity[i]:
+            # exact integer identity: weight 1 at weight scale 1, multiplier 1.0 = (2^30, shift 1), bias 0, same qparams in and out
+            cin_i = tensors["b%d/dw/w" % i].shape[1]
+            m1, s1 = quantize_multiplier(1.0)
+            q["q/b%d/dw/w" % i] = np.ones((1, cin_i), np.int8)
+            q["q/b%d/dw/bias" % i] = np.zeros(cin_i, np.int32)
+            q["q/b%d/dw/mult" % i] = np.full(cin_i, m1, np.int32)
+            q["q/b%d/dw/shift" % i] = np.full(cin_i, s1, np.int32)
+        else:
+            conv_layer("q/b%d/dw" % i, tensors["b%d/dw/w" % i], tensors["b%d/dw/b" % i], scales[prev], scales[d], 1)
         conv_layer("q/b%d/pw" % i, tensors["b%d/pw/w" % i], tensors["b%d/pw/b" % i], scales[d], scales[pn], 1)
         prev = pn
     # FULLY_CONNECTED: per-tensor symmetric weights
@@ -481,7 +505,8 @@ class StreamingInt8:
         for i in range(s.n_blocks):
             d, pn = "d%d" % (i + 1), "p%d" % (i + 1)
             mem = np.concatenate([self.st_block[i], net[None, :]], 0)
-            self.st_block[i] = mem[-self.st_block[i].shape[0]:]
+            if self.st_block[i].shape[0]:            # a 0-row ring (1-tap block) stays empty: mem[-0:] would be the whole window
+                self.st_block[i] = mem[-self.st_block[i].shape[0]:]
             acc = ((mem.astype(np.int64) - zp[prev]) * q["q/b%d/dw/w" % i].astype(np.int64)).sum(0) + q["q/b%d/dw/bias" % i]
             dq = self._requant(acc, "q/b%d/dw" % i, zp[d], False)
             acc = (dq.astype(np.int64) - zp[d]) @ q["q/b%d/pw/w" % i].astype(np.int64) + q["q/b%d/pw/bias" % i]

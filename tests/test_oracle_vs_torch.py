@@ -20,6 +20,7 @@ SPECS = {
     "okay_nabu": R.Spec(),
     "stride2_three_groups": R.Spec(16, 6, 2, (40,), ((7, 11, 13),), head_rows=9),
     "uneven_split": R.Spec(20, 4, 1, (50, 30), ((3, 5, 7), (5, 9)), head_rows=4),       # 50 channels / 3 groups -> 18, 16, 16
+    "block_without_mixconv": R.Spec(24, 6, 2, (32, 16, 24), ((3, 5), (1,), (7,)), head_rows=4),   # mixednet.py:346-348
 }
 
 
@@ -30,15 +31,16 @@ def keras_graph_logits(spec, p, x):
     net = torch.relu(F.conv1d(t, w0, stride=spec.stride))                                 # Conv2D((k0, 1), strides=(stride, 1), 'valid', no bias) + ReLU
     for i in range(spec.n_blocks):
         ks = spec.mixconv_kernel_sizes[i]
-        splits = [net.shape[1] // len(ks)] * len(ks)
-        splits[0] += net.shape[1] - sum(splits)                                            # _split_channels
-        outs = []
-        for xs, k, kern, bias in zip(torch.split(net, splits, dim=1), ks, p["b%d/dw/kernels" % i], p["b%d/dw/biases" % i]):
-            w = torch.from_numpy(kern.astype(np.float64)).T[:, None, :]                    # Keras (k, channels) -> (channels, 1, k)
-            outs.append(F.conv1d(xs, w, torch.from_numpy(bias.astype(np.float64)), groups=xs.shape[1]))   # DepthwiseConv2D((k, 1), 'valid')
-        keep = outs[-1].shape[2]
-        outs = [o[:, :, o.shape[2] - keep:] for o in outs]                                  # StridedDrop: drop the EARLIEST rows
-        net = torch.cat(outs, 1)
+        if max(ks) > 1:                                                                     # mixednet.py:346-348: otherwise no MixConv layer at all
+            splits = [net.shape[1] // len(ks)] * len(ks)
+            splits[0] += net.shape[1] - sum(splits)                                        # _split_channels
+            outs = []
+            for xs, k, kern, bias in zip(torch.split(net, splits, dim=1), ks, p["b%d/dw/kernels" % i], p["b%d/dw/biases" % i]):
+                w = torch.from_numpy(kern.astype(np.float64)).T[:, None, :]                # Keras (k, channels) -> (channels, 1, k)
+                outs.append(F.conv1d(xs, w, torch.from_numpy(bias.astype(np.float64)), groups=xs.shape[1]))   # DepthwiseConv2D((k, 1), 'valid')
+            keep = outs[-1].shape[2]
+            outs = [o[:, :, o.shape[2] - keep:] for o in outs]                              # StridedDrop: drop the EARLIEST rows
+            net = torch.cat(outs, 1)
         pw = torch.from_numpy(p["b%d/pw/kernel" % i].astype(np.float64)).T[:, :, None]     # (in, out) -> (out, in, 1)
         net = F.conv1d(net, pw)                                                             # Conv2D(filters, 1, no bias)
         g, b = (torch.from_numpy(p["b%d/bn/%s" % (i, n)].astype(np.float64))[None, :, None] for n in ("gamma", "beta"))

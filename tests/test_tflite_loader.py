@@ -66,6 +66,41 @@ def test_interpreter_equals_oracle_on_recognised_tensors(kind):
     assert first == it2.invoke(x[0:3]).reshape(-1)[0]
 
 
+@pytest.mark.parametrize("kind", ["f32", "int8"])
+def test_block_without_mixconv_round_trips(kind):
+    """mixednet.py:346-348: a block whose largest kernel is 1 has no MixConv layer -- no ring, no depthwise op, the 1x1
+    conv reads the previous activation.  Writer (Keras-shaped graph) -> recogniser (identity depthwise in the container) ->
+    interpreter of the written bytes == oracle on the recognised tensors; and the Keras-form model (which really has no
+    layer there) == the folded container form."""
+    spec = R.Spec(24, 5, 2, (32, 16, 24), ((3, 5), (1,), (7,)), head_rows=4)
+    p = R.init_synthetic(spec, 11)
+    assert p["b1/dw/kernels"] == [] and len(p["b0/dw/kernels"]) == 2
+    t = R.fold_bn(spec, p)
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0, 26, (60, 2, 40)).astype(np.float32)
+    keras, folded = R.KerasStreamingF32(spec, p), R.FoldedStreamingF32(t)
+    assert max(abs(float(keras.step(c)) - float(folded.step(c))) for c in x) <= 2e-6
+    if kind == "int8":
+        t = R.quantize_model(t, x[:40])
+        assert np.array_equal(t["q/b1/dw/w"], np.ones((1, 32), np.int8)) and t["q/scales"][4] == t["q/scales"][3] and t["q/zps"][4] == t["q/zps"][3]
+    blob = W.write_streaming_mixednet(t)
+    got = TF.tensors_from_tflite(blob)
+    assert sorted(got) == sorted(t)
+    for k in t:
+        assert got[k].dtype == t[k].dtype and got[k].shape == t[k].shape and np.array_equal(got[k], t[k]), k
+    it = Interpreter(blob)
+    assert not any("dw_1" in name or "stream_2" in name for name in it.tensor_names()) if hasattr(it, "tensor_names") else True
+    if kind == "int8":
+        model = R.StreamingInt8(got)
+        for c in x:
+            qc = R.quantize_input(c, model.input_scale, model.input_zero_point)
+            assert int(it.invoke(qc).reshape(-1)[0]) == model.step(qc)
+    else:
+        model = R.FoldedStreamingF32(got)
+        for c in x:
+            assert abs(float(it.invoke(c).reshape(-1)[0]) - float(model.step(c))) <= 2e-6
+
+
 def test_unsupported_graphs_fail_loudly():
     t = _tensors("f32")
     # 1. not a flatbuffer / wrong identifier

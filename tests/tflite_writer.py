@@ -304,6 +304,24 @@ def write_streaming_mixednet(tensors: dict) -> bytes:
         ks = arch.mixconv_kernel_sizes[b]
         kmax = max(ks)
         dq, pq = "d%d" % (b + 1), "p%d" % (b + 1)
+        if kmax == 1:
+            # mixednet.py:346-348: no MixConv layer at all -- the 1x1 conv reads the previous activation tensor
+            cout = arch.pointwise_filters[b]
+            d = cur
+            if quant:
+                wq = np.transpose(tensors["q/b%d/pw/w" % b])[:, None, None, :]
+                sw = wscales("b%d/pw" % b, aq[prev_q][0], aq[pq][0], cout)
+                wt = gw.tensor("pw_%d/kernel" % b, wq.shape, np.int8, data=wq, scale=sw, zero_point=np.zeros(cout, np.int64), qdim=0)
+                bt = gw.tensor("pw_%d/bias" % b, (cout,), np.int32, data=tensors["q/b%d/pw/bias" % b], scale=sw * np.float32(aq[prev_q][0]),
+                               zero_point=np.zeros(cout, np.int64))
+            else:
+                wf = np.transpose(tensors["b%d/pw/w" % b])[:, None, None, :]
+                wt = gw.tensor("pw_%d/kernel" % b, wf.shape, np.float32, data=wf)
+                bt = gw.tensor("pw_%d/bias" % b, (cout,), np.float32, data=tensors["b%d/pw/b" % b])
+            cur = act("pw_%d/Relu" % b, (1, 1, 1, cout), pq)
+            gw.op("CONV_2D", [d, wt, bt], [cur], act=1)
+            cin, prev_q = cout, pq
+            continue
         mem = ring("stream_%d" % (b + 1), cur, kmax - 1, cin, prev_q)
         split = [cin // len(ks)] * len(ks)
         split[0] += cin - sum(split)
