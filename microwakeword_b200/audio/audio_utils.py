@@ -9,6 +9,7 @@ import numpy as np
 from ..model_file import FEATURE_SCALE
 
 _engine = None
+_batch_engines = {}        # (device, capacity) -> frontend-only StreamEngine kept across calls (no cudaMalloc / table upload per batch)
 
 
 def to_int16(audio_samples: np.ndarray) -> np.ndarray:
@@ -36,6 +37,20 @@ def _frontend_engine(device: int = 0):
         from ..engine import StreamEngine
         _engine = StreamEngine(None, n_streams=1, device=device)
     return _engine
+
+
+def _batch_engine(device: int, n: int):
+    """Frontend-only engine with at least `n` streams, reused across calls (capacities are powers of two >= 16)."""
+    from ..engine import StreamEngine
+    cap = 16
+    while cap < n:
+        cap *= 2
+    key = (device, cap)
+    if key not in _batch_engines:
+        if len(_batch_engines) >= 4:                          # a handful of capacities is plenty; drop the smallest
+            _batch_engines.pop(min(_batch_engines, key=lambda k: k[1])).close()
+        _batch_engines[key] = StreamEngine(None, n_streams=cap, device=device)
+    return _batch_engines[key]
 
 
 def generate_features_for_clip(audio_samples: np.ndarray, step_ms: int = 20, use_c: bool = True, device: int = 0):
@@ -78,20 +93,18 @@ def generate_features_for_clips(clips, use_c: bool = True, device: int = 0):
     """
     import torch
 
-    from ..engine import StreamEngine
-
     clips = [to_int16(np.asarray(c)).reshape(-1) for c in clips]
     if not clips:
         return []
     fed = [clip_samples_fed(c.size) if use_c else c.size for c in clips]
     rows = [max((n - 480) // 160 + 1, 0) if n >= 480 else 0 for n in fed]
     n_max = max(max(fed), 1)
-    batch = np.zeros((len(clips), n_max), np.int16)
+    eng = _batch_engine(device, len(clips))                  # persistent; capacity >= len(clips), spare streams see silence
+    batch = np.zeros((eng.n_streams, n_max), np.int16)
     for i, (c, n) in enumerate(zip(clips, fed)):
         batch[i, :n] = c[:n]
-    eng = StreamEngine(None, n_streams=len(clips), device=device)
+    eng.reset_frontend()
     feat = eng.features(torch.from_numpy(batch).to(eng._dev())).view(torch.int16).cpu().numpy().view(np.uint16)
-    eng.close()
     out = []
     for i, r in enumerate(rows):
         f = feat[i, :r]

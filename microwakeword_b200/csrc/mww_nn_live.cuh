@@ -298,6 +298,7 @@ constexpr int kLive2OffP = kLiveSmemFloats;                   // the chain's reg
 constexpr int kLive2OffWrot = kLive2OffP + 2 * kLive2PFloats;
 constexpr int kLive2SmemFloats = kLive2OffWrot + kLive2WrotFloats;
 constexpr int kLive2SmemBytes = kLive2SmemFloats * 4;         // 200.2 KB: one CTA per SM
+static_assert(kLive2OffWrot % 4 == 0, "16-byte loads of the tap table");
 MWW_HD constexpr int live2_col_base(int i) { return i == 0 ? 0 : 32 + 64 * (i - 1); }
 MWW_HD constexpr int live2_wrot_base(int i) { return i == 0 ? 0 : (i == 1 ? 128 : (i == 2 ? 128 + 640 : (i == 3 ? 128 + 640 + 896 : 128 + 640 + 896 + 1408))); }
 
@@ -318,41 +319,49 @@ MWW_HD void live2_stage_taps(int tid, int n_threads, float *sm, const NnWeightsF
 // streamer thread st (0..511): P of ring I for the 32 streams of one group.  Consecutive threads = consecutive channels of
 // one stream (128-byte coalesced row segments); 512 is a multiple of the ring's channel count, so a thread's channel -- and
 // with it its R taps -- is the same for all of its items.
-// Software-pipelined: the R row loads of item i + 1 are issued BEFORE the R multiply-adds of item i, so a warp always has
-// between R and 2 R independent 128-byte requests in flight (r02, first version: loads and FMAs alternated, the average
-// fell to ~R / 2 per warp and the streamers -- 60 % of the kernel's stall samples -- pulled only 3.0 TB/s).  The taps are read
-// from shared memory at use (one conflict-free LDS per FMA) so the two row sets fit the 80-register budget of a 768-thread CTA.
+// Streamer thread <-> (stream, FOUR consecutive channels): a ring row is C consecutive floats and a ring R consecutive rows,
+// so C / 4 neighbouring lanes read one whole row with 16-byte loads and a thread's successive loads walk its stream's ring
+// front to back -- every stream's 1 - 5.6 KB ring is read as one sequential burst.  (r02 measurements: with one channel per
+// thread -- 128-byte pieces scattered over 32 streams' states -- three different ways of keeping loads in flight all
+// stopped at 3.0 TB/s; it was the DRAM access pattern, not the amount in flight.)  Rows are taken CH at a time to bound
+// registers; the multiply-adds run in physical row order, so the sums are bit-identical to live_ring_pass.
+struct Quad { float x, y, z, w; };
+MWW_HD Quad load_quad(const float *p) {
+#if defined(__CUDA_ARCH__)
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    return Quad{v.x, v.y, v.z, v.w};
+#else
+    return Quad{p[0], p[1], p[2], p[3]};
+#endif
+}
 template <int I>
 MWW_HD void live2_stream_ring(int st, float *sm, const NnWeightsF32 &W, const float *state, long long s0, int n_valid, float *p_buf) {
     constexpr int R = live_ring_rows(I), C = live_ring_cols(I);
-    constexpr int items = kLiveStreams * C / kLive2StreamThreads;     // 2 (block 0) or 4
-    constexpr int step = kLive2StreamThreads / C;                      // stream distance between a thread's items
+    constexpr int lanes = C / 4;                                       // threads per stream: 8 (block 0) or 16
+    constexpr int CH = R < 8 ? R : (R % 8 == 0 ? 8 : (R % 7 == 0 ? 7 : (R == 22 ? 11 : 5)));   // rows in flight: 4, 5, 7, 11, 8
+    static_assert(R % CH == 0, "row chunking");
     constexpr int ring_off = kStateOff[I + 1];
-    const int c = st % C, s_first = st / C;
+    const int sl = st / lanes, c = 4 * (st % lanes);
+    if (sl >= kLiveStreams) return;                                    // block 0 needs only half of the streamer threads
+    const bool ok = sl < n_valid;
+    const float *ring = state + (size_t)(s0 + (ok ? sl : 0)) * kStateFloats + ring_off + c;
     const float *wr = sm + kLive2OffWrot + live2_wrot_base(I) + c;
-    const float bias = I < 4 ? W.dw_b[I < 4 ? I : 0][c] : 0.f;
-    float *p_col = p_buf + (live2_col_base(I) + c) * kLive2PPitch;
-    float x[2][R];
-    {
-        const bool ok = s_first < n_valid;
-        const float *ring = state + (size_t)(s0 + (ok ? s_first : 0)) * kStateFloats + ring_off + c;
+    Quad acc;
+    if (I < 4) acc = load_quad(W.dw_b[I < 4 ? I : 0] + c); else acc = Quad{0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int r0 = 0; r0 < R; r0 += CH) {
+        Quad x[CH];
 #pragma unroll
-        for (int r = 0; r < R; ++r) x[0][r] = ok ? ring[r * C] : 0.f;
-    }
+        for (int r = 0; r < CH; ++r) x[r] = ok ? load_quad(ring + (r0 + r) * C) : Quad{0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int it = 0; it < items; ++it) {
-        const int sl = s_first + it * step;
-        if (it + 1 < items) {
-            const bool ok = sl + step < n_valid;
-            const float *ring = state + (size_t)(s0 + (ok ? sl + step : 0)) * kStateFloats + ring_off + c;
-#pragma unroll
-            for (int r = 0; r < R; ++r) x[(it + 1) & 1][r] = ok ? ring[r * C] : 0.f;
+        for (int r = 0; r < CH; ++r) {
+            const Quad w = load_quad(wr + (r0 + r) * C);
+            acc.x = fmaf(w.x, x[r].x, acc.x); acc.y = fmaf(w.y, x[r].y, acc.y);
+            acc.z = fmaf(w.z, x[r].z, acc.z); acc.w = fmaf(w.w, x[r].w, acc.w);
         }
-        float acc = bias;
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc = fmaf(wr[r * C], x[it & 1][r], acc);
-        p_col[sl] = acc;
     }
+    float *p_col = p_buf + (live2_col_base(I) + c) * kLive2PPitch + sl;
+    p_col[0] = acc.x; p_col[kLive2PPitch] = acc.y; p_col[2 * kLive2PPitch] = acc.z; p_col[3 * kLive2PPitch] = acc.w;
 }
 MWW_HD void live2_stream_group(int st, float *sm, const NnWeightsF32 &W, const float *state, long long s0, int n_valid, float *p_buf) {
     live2_stream_ring<3>(st, sm, W, state, s0, n_valid, p_buf);        // longest rings first: their loads overlap the rest

@@ -139,34 +139,60 @@ class Model:
     def reset(self, stream_ids=None):
         self.engine.reset(stream_ids)
 
-    def predict_nonstreaming(self, spectrograms: np.ndarray) -> np.ndarray:
-        """Batched NON-streaming evaluation (SURVEY.md 8 f-4; what the reference's Keras model computes on
-        `[batch, spectrogram_length, 40]` windows in train.py:41-163 / data.py:301-311): one probability per window.
+    def _arch(self):
+        """MixedNet hyper-parameters of the loaded model (the container's `arch` tensor)."""
+        if getattr(self, "_arch_cache", None) is None:
+            from . import model_file as MF
+            self._arch_cache = MF.Arch.decode(MF.read_container(self.engine._blob)["arch"])
+        return self._arch_cache
 
-        Every conv of the graph is 'valid', so the non-streaming output equals the streaming model's LAST step when the
-        rings hold real data (README.md:27-28).  The first conv's streaming windows start one row before a multiple of
-        the stride (stream.py:253-255), so one leading row is prepended; the window must be at least one receptive
-        field long (204 rows for okay_nabu, model_train_eval.py:64-88) for every ring to be filled with real data.
-        """
+    def nonstreaming_length(self) -> int:
+        """Rows of the shortest window the non-streaming graph accepts = its receptive field (model_train_eval.py:64-88 run
+        backwards): every ring and the head window filled with real data.  204 for okay_nabu."""
+        a = self._arch()
+        span = sum(a.block_ring_rows(i) for i in range(a.n_blocks)) + a.head_rows - 1
+        return a.first_conv_kernel_size + a.stride * span
+
+    def predict_nonstreaming(self, spectrograms: np.ndarray, batch_size: int = 1024) -> np.ndarray:
+        """Batched NON-streaming evaluation (SURVEY.md 8 f-4; what the reference's Keras model computes on
+        `[batch, spectrogram_length, 40]` windows in train.py:41-163 with batch_size=1024): one probability per window.
+
+        Every conv of the graph is 'valid', so the non-streaming output equals the streaming model's LAST step once every
+        ring holds real data (README.md:27-28).  The streaming first conv keeps k0 - stride rows of history
+        (stream.py:253-255), so step j reads rows [j s - (k0 - s), (j + 1) s): d = (-(k0 - s)) mod s leading rows are
+        prepended to put the steps on the non-streaming positions (d = 1 for okay_nabu), and trailing rows the strided
+        'valid' conv would not reach are dropped.  Works for every geometry the engine loads, float or int8 (for a quantised
+        model this is the int8 streaming graph's last step: float rows are quantised on load, inference.py:127-147).
+        Windows go through a persistent engine of `batch_size` streams (the reference's evaluate batch)."""
         import torch
         x = np.asarray(spectrograms)
         if x.ndim != 3 or x.shape[2] != NUM_FEATURES:
             raise ValueError("spectrograms must have shape [batch, T, 40]")
-        if self.is_quantized_model:
-            raise NotImplementedError("non-streaming evaluation is defined for the float model (the reference evaluates the Keras model)")
+        a = self._arch()
+        k0, s = a.first_conv_kernel_size, a.stride
         b, t = x.shape[0], x.shape[1]
-        if self.engine.state_elements != 4176 or self.engine.stride != 3:
-            raise NotImplementedError("non-streaming evaluation is implemented for the okay_nabu geometry (its receptive field is hard-wired below)")
-        if (t - 5) // 3 + 1 < 67:
-            raise ValueError("window shorter than the model's receptive field (204 rows)")
+        if t < self.nonstreaming_length():
+            raise ValueError("window shorter than the model's receptive field (%d rows)" % self.nonstreaming_length())
         if x.dtype == np.uint16:
             x = x.astype(np.float32) * np.float32(FEATURE_SCALE)
         x = np.ascontiguousarray(x, np.float32)
-        rows = np.concatenate([np.zeros((b, 1, NUM_FEATURES), np.float32), x], 1)
-        eng = StreamEngine(self.engine._blob, n_streams=b, device=self.engine.device)
-        probs = eng.infer(torch.from_numpy(rows).to(eng._dev()))
-        out = probs[:, (t - 5) // 3 + 1].cpu().numpy()       # streaming step s covers non-streaming window s - 1
-        eng.close()
+        d = (-(k0 - s)) % s
+        t_used = k0 + s * ((t - k0) // s)                        # rows the strided 'valid' first conv reaches
+        steps = (t_used + d) // s
+        cap = max(1, min(int(batch_size), b))
+        eng = getattr(self, "_ns_engine", None)
+        if eng is None or eng.n_streams != cap:
+            if eng is not None:
+                eng.close()
+            eng = self._ns_engine = StreamEngine(self.engine._blob, n_streams=cap, device=self.engine.device)
+        out = np.empty(b, np.float32)
+        rows = np.zeros((cap, t_used + d, NUM_FEATURES), np.float32)
+        for first in range(0, b, cap):
+            n = min(cap, b - first)
+            rows[:n, d:] = x[first:first + n, :t_used]
+            eng.reset()                                           # every window starts from zero rings, like a fresh Keras call
+            probs = eng.infer(torch.from_numpy(rows).to(eng._dev()))
+            out[first:first + n] = probs[:n, steps - 1].cpu().numpy()
         return out
 
     # ------------------------------------------------------------------ helpers

@@ -55,3 +55,44 @@ def compute_false_accepts_per_hour(streaming_probabilities_list, cutoffs, ignore
 def positive_score(probs, window: int = 5, ignore_slices_after_accept: int = 25) -> np.float32:
     m = moving_average(np.asarray(probs, np.float32)[ignore_slices_after_accept:], window)
     return np.float32(np.nan) if m.size == 0 else np.float32(m.max())
+
+
+def false_rejection_rates(positive_scores, cutoffs) -> np.ndarray:
+    """test.py:376-381: share of positive samples whose score does NOT exceed each cutoff (strict >)."""
+    s = np.asarray(positive_scores, np.float64)
+    return np.asarray([1 - int((s > c).sum()) / len(s) for c in np.asarray(cutoffs, np.float64)], np.float64)
+
+
+def generate_roc_curve(false_accepts_per_hour, false_rejections, cutoffs, max_faph: float = 2.0):
+    """test.py:140-204 restated: ROC coordinates (faph ascending) from per-cutoff faph / false-rejection rates.
+
+    Quirks of the reference that a drop-in keeps: the interpolated first point takes BOTH ordinates from the last
+    cutoff above max_faph (test.py:168-171 reads index - 1 twice, so it is that cutoff's rejection rate, no interpolation
+    in y), the interpolation constant is the literal 2.0 rather than max_faph (:173), its cutoff is the midpoint of the
+    two neighbouring cutoffs (:174-176), a repeated faph keeps only its first (= lowest-cutoff) point (:190-196), and a
+    curve that never reaches 0 faph gets the closing point (0, 1) with cutoff 0 (:198-202)."""
+    faph = np.asarray(false_accepts_per_hour, np.float64)
+    frr = np.asarray(false_rejections, np.float64)
+    cut = np.asarray(cutoffs, np.float64)
+    if faph[0] > max_faph:
+        k = 1
+        while faph[k] > max_faph:
+            k += 1
+        x0, x1, y = faph[k - 1], faph[k], frr[k - 1]
+        first = ((y * (x1 - 2.0) + y * (2.0 - x0)) / (x1 - x0), (cut[k] + cut[k - 1]) / 2.0)
+    else:
+        k = 0
+        first = (frr[0], cut[0])
+    xs, ys, cs = [max_faph], [first[0]], [first[1]]
+    for i in range(k, len(frr)):
+        if faph[i] != xs[-1]:
+            xs.append(faph[i]); ys.append(frr[i]); cs.append(cut[i])
+    if xs[-1] > 0:
+        xs.append(0.0); ys.append(1.0); cs.append(0.0)
+    return np.asarray(xs[::-1]), np.asarray(ys[::-1]), np.asarray(cs[::-1])
+
+
+def roc_auc(x, y) -> float:
+    """test.py:391 np.trapz(y, x)"""
+    x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+    return float(np.sum((x[1:] - x[:-1]) * (y[1:] + y[:-1]) / 2.0))

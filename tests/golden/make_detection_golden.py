@@ -44,10 +44,23 @@ def main():
     pos_max = np.asarray([np.max(sliding_window_view(t[ignore:], window).mean(axis=-1)) if len(t) - ignore >= window else np.nan
                           for t in tracks], np.float32)                                # test.py:364-373
     flat = np.concatenate([np.asarray(t, np.float32) for t in tracks])
+    # false-rejection side + ROC curve (test.py:375-388), again by executing the reference's own generate_roc_curve
+    roc_ref = reference_function("generate_roc_curve")
+    pos = [float(v) for v in pos_max if not np.isnan(v)] + [float(v) for v in rng.beta(2.0, 1.2, 40)]      # positive-sample scores
+    frr = []
+    for cutoff in cutoffs:                                                                 # test.py:376-381, verbatim arithmetic
+        true_accepts = sum(i > cutoff for i in pos)
+        frr.append(1 - true_accepts / len(pos))
+    roc = {}
+    for name, f in (("a", faph), ("b", faph * 0.01), ("c", np.maximum(faph - faph[60], 0.0))):   # above / below max_faph, reaching 0
+        x, y, c = roc_ref(false_accepts_per_hour=f, false_rejections=frr, cutoffs=cutoffs)
+        roc["roc_%s_faph" % name], roc["roc_%s_x" % name], roc["roc_%s_y" % name], roc["roc_%s_c" % name] = f, x, y, c
+        roc["roc_%s_auc" % name] = np.trapz(y, x) if hasattr(np, "trapz") else np.trapezoid(y, x)     # test.py:391
     np.savez(os.path.join(HERE, "detection_golden.npz"), probs=flat, lengths=np.asarray(lengths, np.int32),
              moving=np.concatenate(moving).astype(np.float32), cutoffs=cutoffs, faph=faph, pos_max=pos_max,
-             window=window, ignore=ignore, stride=stride, step_s=step_s)
+             window=window, ignore=ignore, stride=stride, step_s=step_s, pos_scores=np.asarray(pos, np.float64), frr=np.asarray(frr, np.float64), **roc)
     print("tracks", lengths, "faph[0,50,90,100] =", faph[[0, 50, 90, 100]], "pos_max", pos_max)
+    print("roc points", {k: v.shape for k, v in roc.items() if k.endswith("_x")}, "auc", [float(roc["roc_%s_auc" % n]) for n in "abc"])
 
 
 if __name__ == "__main__":
