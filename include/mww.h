@@ -67,6 +67,7 @@ typedef struct mww_info {
     int32_t pending_rows;          /* feature rows waiting for a full stride */
     int32_t sm_count;
     int32_t macs_per_step;
+    int32_t hop_samples;           /* samples between feature windows (mww_set_window_step; default 160 = 10 ms) */
 } mww_info;
 
 /* Parse an MWW model container (microwakeword_b200/model_file.py), upload the weights to `device`
@@ -104,6 +105,12 @@ int mww_reset_device_ids(mww_t *h, const int32_t *d_ids, int n, void *cu_stream)
  * zero window buffer, zero noise estimates, buffered-sample counter 0.  NN rings are untouched --
  * the reference never resets the interpreter between clips (inference.py:52-64, test.py:335-341). */
 int mww_reset_frontend(mww_t *h, void *cu_stream);
+
+/* window_step of the frontend in samples (audio_utils.py:69-81 forwards step_ms to the TF op, whose default on this path is
+ * 20 ms = 320 samples; pymicro_features hard-wires 10 ms = 160, the default here).  Any even value in [16, 480]; only while
+ * the frontend holds no buffered samples (after create / mww_reset / mww_reset_frontend).  With a hop other than 160 every
+ * call runs the run-time-hop kernel (one CTA per stream); the row counts below use this hop in place of 160. */
+int mww_set_window_step(mww_t *h, int hop_samples);
 
 /* Frontend only.  d_audio: int16 [n_streams][n_samples] with row pitch `audio_stride` samples.
  * Appends the samples to every stream's window buffer and emits one uint16[40] row per completed

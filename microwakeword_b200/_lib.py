@@ -23,6 +23,7 @@ EXPORTS = (
     "mww_moving_average", "mww_false_accept_counts", "mww_positive_scores", "mww_copy_async",
     "mww_ipc_alloc", "mww_ipc_open", "mww_ipc_close", "mww_ipc_free",
     "mww_predict_clip_remote", "mww_reset_device_ids", "mww_host_alloc", "mww_host_free", "mww_bind_host_thread",
+    "mww_set_window_step",
 )
 
 
@@ -34,6 +35,7 @@ class MwwInfo(ctypes.Structure):
         ("output_scale", ctypes.c_float), ("output_zero_point", ctypes.c_int32),
         ("state_bytes_per_stream", ctypes.c_int32), ("frontend_buffered", ctypes.c_int32),
         ("pending_rows", ctypes.c_int32), ("sm_count", ctypes.c_int32), ("macs_per_step", ctypes.c_int32),
+        ("hop_samples", ctypes.c_int32),
     ]
 
 
@@ -112,6 +114,8 @@ def lib() -> ctypes.CDLL:
     L.mww_host_alloc.argtypes = [sz, i32, ctypes.POINTER(vp), pi]
     L.mww_host_free.restype = i32
     L.mww_host_free.argtypes = [vp]
+    L.mww_set_window_step.restype = i32
+    L.mww_set_window_step.argtypes = [vp, i32]
     L.mww_bind_host_thread.restype = i32
     L.mww_bind_host_thread.argtypes = [i32, pi]
     _lib = L

@@ -59,8 +59,8 @@ def generate_features_for_clip(audio_samples: np.ndarray, step_ms: int = 20, use
     use_c=True  (default): pymicro_features semantics -- fresh frontend, 10 ms hop regardless of
                 ``step_ms`` (the reference ignores it on this path), strict-'<' chunk loop; returns
                 float32 [T, 40] = uint16 features * 0.0390625.
-    use_c=False: TensorFlow audio_microfrontend op semantics (audio_utils.py:69-81) -- every full window
-                of the clip, returns uint16 [T, 40]; only window_step = 10 ms is available here.
+    use_c=False: TensorFlow audio_microfrontend op semantics (audio_utils.py:69-81) -- every full window of the clip
+                at window_step = step_ms (default 20 ms, like the reference), returns uint16 [T, 40].
     """
     import torch
 
@@ -69,10 +69,12 @@ def generate_features_for_clip(audio_samples: np.ndarray, step_ms: int = 20, use
     eng.reset_frontend()
     if use_c:
         fed = clip_samples_fed(audio.size)
+        eng.set_window_step(160)                                 # pymicro_features hard-wires 10 ms; step_ms is ignored like the reference
     else:
-        if step_ms != 10:
-            raise ValueError("the B200 frontend implements the 10 ms hop all shipped models use (SURVEY.md Appendix D.2)")
+        if int(step_ms) != step_ms or not 1 <= step_ms <= 30:
+            raise ValueError("window_step must be a whole number of milliseconds in [1, 30]")
         fed = audio.size
+        eng.set_window_step(16 * int(step_ms))
     if fed == 0:
         return np.zeros((0, 40), np.float32 if use_c else np.uint16)
     dev = torch.from_numpy(np.ascontiguousarray(audio[:fed])).to(eng._dev()).unsqueeze(0)
@@ -100,6 +102,8 @@ def generate_features_for_clips(clips, use_c: bool = True, device: int = 0):
     rows = [max((n - 480) // 160 + 1, 0) if n >= 480 else 0 for n in fed]
     n_max = max(max(fed), 1)
     eng = _batch_engine(device, len(clips))                  # persistent; capacity >= len(clips), spare streams see silence
+    eng.reset_frontend()
+    eng.set_window_step(160)
     batch = np.zeros((eng.n_streams, n_max), np.int16)
     for i, (c, n) in enumerate(zip(clips, fed)):
         batch[i, :n] = c[:n]

@@ -74,6 +74,7 @@ struct mww_handle {
     void *d_nn_state = nullptr;     // float or int8 [S][state_elems]   (4176 for okay_nabu)
     void *d_pend = nullptr;         // float or int8 [S][pend_cap][40]  (2 rows for stride 3)
     int used = 0, n_pend = 0;
+    int hop = kHop;                 // samples between feature windows (mww_set_window_step; 160 = the 10 ms of every shipped model)
     // geometry: the compiled-in okay_nabu kernels, or the run-time-geometry path (mww_nn_generic.cuh) for any other arch
     bool generic = false;
     GenArch G{};
@@ -162,13 +163,15 @@ int ensure_scratch(mww_t *h, size_t v_bytes, size_t feat_bytes) {
     return MWW_OK;
 }
 
-int frames_for(int used, int n_samples) {
-    const long long total = (long long)used + n_samples;
-    return total >= kWindow ? (int)((total - kWindow) / kHop + 1) : 0;
+int frames_for(const mww_t *h, int n_samples) {
+    const long long total = (long long)h->used + n_samples;
+    return total >= kWindow ? (int)((total - kWindow) / h->hop + 1) : 0;
 }
 
 // Long calls over enough streams run K1 + the temporal chain in one kernel (one CTA per stream) and need no K1->K2 scratch.
-bool clip_fuses(const mww_t *h, int n_frames) { return !h->no_fuse && frontend_clip_fuses(h->n_streams, n_frames, h->sm_count); }
+bool clip_fuses(const mww_t *h, int n_frames) {
+    return h->hop != kHop || (!h->no_fuse && frontend_clip_fuses(h->n_streams, n_frames, h->sm_count));     // the run-time-hop kernel is always fused
+}
 size_t v_scratch_bytes(const mww_t *h, int tile, int n_frames) {
     return clip_fuses(h, n_frames) ? 0 : (size_t)tile * std::max(n_frames, 1) * kNumChannels * 4;
 }
@@ -187,6 +190,13 @@ int tile_streams(const mww_t *h, int n_frames, bool need_feat) {
 int run_frontend_tile(mww_t *h, int first, int n, const int16_t *d_audio, long long audio_stride, int n_samples,
                       int n_frames, uint16_t *d_feat, long long feat_stream_stride, cudaStream_t st) {
     if (n_frames <= 0) return MWW_OK;
+    if (h->hop != kHop) {
+        ProfScope p(h, 0, st);
+        CU(h, launch_frontend_hop(h->P, h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n, n_frames, h->hop,
+                                  h->d_estimate + (size_t)first * kNumChannels, d_feat, feat_stream_stride, st));
+        h->launches += 1;
+        return MWW_OK;
+    }
     if (!h->no_fuse && frontend_fusable(h->used, n_samples, n_frames)) {
         // short call: K1 + K2 + carry update in one launch (run_carry_tile sees the same predicate and does nothing)
         ProfScope p(h, 0, st);
@@ -219,9 +229,9 @@ int run_frontend_tile(mww_t *h, int first, int n, const int16_t *d_audio, long l
 
 int run_carry_tile(mww_t *h, int first, int n, const int16_t *d_audio, long long audio_stride, int n_samples, int n_frames,
                    cudaStream_t st) {
-    const int consumed = n_frames * kHop;
+    const int consumed = n_frames * h->hop;
     const int new_used = h->used + n_samples - consumed;
-    if (!h->no_fuse && n_frames > 0 && frontend_fusable(h->used, n_samples, n_frames)) return MWW_OK;     // done by the fused frontend kernel
+    if (h->hop == kHop && !h->no_fuse && n_frames > 0 && frontend_fusable(h->used, n_samples, n_frames)) return MWW_OK;     // done by the fused frontend kernel
     ProfScope p(h, 3, st);
     CU(h, launch_carry_update(h->d_carry + (size_t)first * kWindow, h->used, d_audio, audio_stride, n_samples, n, consumed, new_used, st));
     h->launches += 1;
@@ -700,6 +710,7 @@ int mww_get_info(const mww_t *h, mww_info *o) {
     o->state_bytes_per_stream = (int)(h->state_elems * elem_size(h));
     o->frontend_buffered = h->used; o->pending_rows = h->n_pend;
     o->sm_count = h->sm_count; o->macs_per_step = (int)h->macs_per_step;
+    o->hop_samples = h->hop;
     return MWW_OK;
 }
 
@@ -781,6 +792,15 @@ int mww_reset_device_ids(mww_t *h, const int32_t *d_ids, int n, void *cu_stream)
     return reset_by_id(h, d_ids, n, static_cast<cudaStream_t>(cu_stream));
 }
 
+int mww_set_window_step(mww_t *h, int hop_samples) {
+    if (!h) return MWW_EINVAL;
+    if (hop_samples < 16 || hop_samples > kWindow || (hop_samples & 1))
+        return fail(h, MWW_EUNSUPPORTED, "mww_set_window_step: the hop must be an even number of samples in [16, 480] (window_step 1 .. 30 ms)");
+    if (h->used != 0) return fail(h, MWW_EINVAL, "mww_set_window_step: the frontend holds buffered samples; reset it first");
+    h->hop = hop_samples;
+    return MWW_OK;
+}
+
 int mww_reset_frontend(mww_t *h, void *cu_stream) {
     if (!h) return MWW_EINVAL;
     ENTER_STATEFUL(h);
@@ -798,7 +818,7 @@ int mww_features(mww_t *h, const int16_t *d_audio, int n_samples, long long audi
     if (n_samples < 0 || (n_samples > 0 && !d_audio) || audio_stride < n_samples) return fail(h, MWW_EINVAL, "mww_features: bad audio arguments");
     ENTER_STATEFUL(h);
     cudaStream_t st = static_cast<cudaStream_t>(cu_stream);
-    const int n_frames = frames_for(h->used, n_samples);
+    const int n_frames = frames_for(h, n_samples);
     if (n_frames > max_rows || (n_frames > 0 && !d_feat)) return fail(h, MWW_EINVAL, "mww_features: feature buffer too small for the rows this call emits");
     const int tile = tile_streams(h, n_frames, false);
     int rc = ensure_scratch(h, v_scratch_bytes(h, tile, n_frames), 0);
@@ -813,7 +833,7 @@ int mww_features(mww_t *h, const int16_t *d_audio, int n_samples, long long audi
         rc = run_carry_tile(h, 0, h->n_streams, d_audio, audio_stride, n_samples, n_frames, st);
         if (rc) return rc;
     }
-    h->used = h->used + n_samples - n_frames * kHop;
+    h->used = h->used + n_samples - n_frames * h->hop;
     if (h_rows_out) *h_rows_out = n_frames;
     return MWW_OK;
 }
@@ -844,7 +864,7 @@ int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long 
     if (!h->has_nn) return fail(h, MWW_EINVAL, "mww_predict_clip: frontend-only handle (created without a model)");
     ENTER_STATEFUL(h);
     cudaStream_t st = static_cast<cudaStream_t>(cu_stream);
-    const int n_frames = frames_for(h->used, n_samples);
+    const int n_frames = frames_for(h, n_samples);
     const int n_steps = (h->n_pend + n_frames) / h->stride;
     if (n_steps > max_probs || (n_steps > 0 && !d_probs)) return fail(h, MWW_EINVAL, "mww_predict_clip: probability buffer too small");
     const int tile = tile_streams(h, n_frames, true);
@@ -865,7 +885,7 @@ int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long 
         rc = run_carry_tile(h, 0, h->n_streams, d_audio, audio_stride, n_samples, n_frames, st);
         if (rc) return rc;
     }
-    h->used = h->used + n_samples - n_frames * kHop;
+    h->used = h->used + n_samples - n_frames * h->hop;
     h->n_pend = (h->n_pend + n_frames) % h->stride;
     if (h_probs_out) *h_probs_out = n_steps;
     return MWW_OK;
@@ -940,7 +960,7 @@ int staged_tiles(mww_t *h, const int16_t *src, int n_samples, long long audio_st
 // is made to wait for the call's last kernel (asynchronous variant).  host_sync: return only when dst is complete.
 int predict_clip_staged(mww_t *h, const char *who, const int16_t *src, int n_samples, long long audio_stride, float *dst, int max_probs,
                         int *h_probs_out, bool dst_is_host, int want_tiles, cudaStream_t caller, bool host_sync) {
-    const int n_frames = frames_for(h->used, n_samples);
+    const int n_frames = frames_for(h, n_samples);
     const int n_steps = (h->n_pend + n_frames) / h->stride;
     if (n_steps > max_probs || (n_steps > 0 && !dst)) return fail(h, MWW_EINVAL, std::string(who) + ": probability buffer too small");
     int rc = ensure_pipeline(h);
@@ -997,7 +1017,7 @@ int predict_clip_staged(mww_t *h, const char *who, const int16_t *src, int n_sam
         CU(h, cudaStreamWaitEvent(caller, h->ev_exit, 0));
     }
     end_nn_call(h, n_frames);
-    h->used = h->used + n_samples - n_frames * kHop;
+    h->used = h->used + n_samples - n_frames * h->hop;
     h->n_pend = (h->n_pend + n_frames) % h->stride;
     if (h_probs_out) *h_probs_out = n_steps;
     return MWW_OK;

@@ -115,6 +115,48 @@ k1_spectral_kernel(FrontendParams P, const int16_t *__restrict__ carry, int used
     if (kFuseK2 && tid < kNumChannels) estimate[s * kNumChannels + tid] = est;
 }
 
+// Run-time hop variant of the fused clip kernel (any even hop <= 480 samples, i.e. window_step up to 30 ms): one CTA per
+// stream, groups of k1_hop_frames_per_group(hop) frames, single-buffered audio staging.  Used only when the handle's hop is
+// not the 10 ms every shipped model uses; the 10 ms kernels above stay specialised.
+__global__ void __launch_bounds__(kK1Threads, 3)
+k1_spectral_hop_kernel(FrontendParams P, const int16_t *__restrict__ carry, int used, const int16_t *__restrict__ audio,
+                       long long audio_stride, int n_samples, int n_frames, int hop, uint32_t *__restrict__ estimate,
+                       uint16_t *__restrict__ feat, long long feat_stream_stride) {
+    extern __shared__ __align__(16) unsigned char k1_smem_raw[];
+    K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_smem_raw);
+    const int tid = threadIdx.x;
+    const long long s = blockIdx.x;
+    K1Lane lane;
+    k1_lane_init(tid, P, lane);
+    k1_stage_tables(tid, sm, P);
+    const int fpg = k1_hop_frames_per_group(hop);
+    const int n_groups = (n_frames + fpg - 1) / fpg;
+    const int16_t *my_carry = carry + s * kWindow;
+    const int16_t *my_audio = audio + s * audio_stride;
+    uint32_t est = 0;
+    if (tid < kNumChannels) est = estimate[s * kNumChannels + tid];
+    for (int g = 0; g < n_groups; ++g) {
+        const int f0 = g * fpg;
+        __syncthreads();                       // everyone is done with the previous group's staging area, A and B
+        k1_hop_load_audio(tid, sm, my_carry, used, my_audio, n_samples, hop * f0, (fpg - 1) * hop + kWindow);
+        __syncthreads();
+        K1Pass1Ctx ctx;
+        k1_window_fft1<2>(tid, sm, 0, k1_hop_pair_base(tid >> 4, hop, fpg), P, ctx);
+        __syncthreads();
+        k1_fft_pass2(tid, sm, lane);
+        __syncthreads();
+        k1_real_energy(tid, sm, P);
+        __syncthreads();
+        k1_filterbank(tid, sm, P, &sm.A[tid >> 4][0]);
+        __syncthreads();
+        const int n_valid = min(fpg, n_frames - f0);
+        if (tid < kNumChannels) k2_group_chain(tid, sm, n_valid, est);
+        __syncthreads();
+        k2_group_outputs(tid, sm, n_valid, feat + s * feat_stream_stride + (long long)f0 * kNumChannels);
+    }
+    if (tid < kNumChannels) estimate[s * kNumChannels + tid] = est;
+}
+
 // K1 for short calls (n_frames <= 8, e.g. the three frames of a 30 ms live step): one CTA = `spc` streams x `fps`
 // frames, so the 16 frame slots stay (almost) full instead of serving 3 of 16.
 __global__ void __launch_bounds__(kK1Threads, 3)
@@ -334,6 +376,18 @@ cudaError_t launch_frontend_clip_fused(const FrontendParams &P, const int16_t *c
     else
         k1_spectral_kernel<true, 4><<<grid, kK1Threads, kK1SmemBytes, st>>>(P, carry, used, audio, audio_stride, n_samples, n_frames, n_groups, vec_ok,
                                                                             nullptr, estimate, feat, feat_stream_stride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frontend_hop(const FrontendParams &P, const int16_t *carry, int used, const int16_t *audio, long long audio_stride,
+                                int n_samples, int n_streams, int n_frames, int hop, uint32_t *estimate, uint16_t *feat,
+                                long long feat_stream_stride, cudaStream_t st) {
+    if (n_frames <= 0 || n_streams <= 0) return cudaSuccess;
+    static bool done[64] = {};
+    cudaError_t e = k1_opt_in(k1_spectral_hop_kernel, done);
+    if (e != cudaSuccess) return e;
+    k1_spectral_hop_kernel<<<(unsigned)n_streams, kK1Threads, kK1SmemBytes, st>>>(P, carry, used, audio, audio_stride, n_samples, n_frames, hop,
+                                                                                 estimate, feat, feat_stream_stride);
     return cudaGetLastError();
 }
 

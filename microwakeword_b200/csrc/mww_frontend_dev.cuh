@@ -198,6 +198,25 @@ MWW_HD void k1_load_audio(int tid, K1Smem &sm, int buf, const int16_t *carry, in
     }
 }
 
+// ---- run-time hop (window_step != 10 ms; audio_utils.py:69-81 forwards step_ms to the TF op, default 20) ----
+// A group holds `fpg` frames whose windows start `hop` samples apart; the whole staging area (both halves of the double
+// buffer, 5 760 samples) is one span of (fpg - 1) * hop + 480 samples, loaded without prefetch.
+MWW_HD int k1_hop_frames_per_group(int hop) {
+    const int by_span = (2 * kGroupSamples - kWindow) / hop + 1;
+    return by_span < kFramesPerGroup ? by_span : kFramesPerGroup;
+}
+MWW_HD void k1_hop_load_audio(int tid, K1Smem &sm, const int16_t *carry, int used, const int16_t *audio, int n_samples, int base, int span) {
+    int16_t *dst = &sm.audio[0][0];
+    for (int i = tid; i < span; i += kK1Threads) {
+        const int vi = base + i;
+        int16_t s = 0;
+        if (vi < used) s = carry[vi];
+        else if (vi - used < n_samples) s = audio[vi - used];
+        dst[i] = s;
+    }
+}
+MWW_HD int k1_hop_pair_base(int fl, int hop, int fpg) { return (hop / 2) * (fl < fpg ? fl : fpg - 1); }
+
 // P1+P2 fused: Hann window (Q12) on the 15 sample pairs this lane owns in FFT pass 1, |max| across the
 // frame's 16 lanes (half a warp), scaling to 15 significant bits, radix-4 stages 1 and 2 on the 16
 // register-resident points.  PART 0 / 1 are the two halves for the host emulation (the half-warp exchange

@@ -27,6 +27,10 @@ bool frontend_clip_fuses(int n_streams, int n_frames, int sm_count);
 cudaError_t launch_frontend_clip_fused(const FrontendParams &P, const int16_t *carry, int used, const int16_t *audio, long long audio_stride,
                                        int n_samples, int n_streams, int n_frames, uint32_t *estimate, uint16_t *feat, long long feat_stream_stride,
                                        cudaStream_t st);
+// any even hop <= 480 samples (window_step != 10 ms): K1 + temporal chain, one CTA per stream, features written directly
+cudaError_t launch_frontend_hop(const FrontendParams &P, const int16_t *carry, int used, const int16_t *audio, long long audio_stride,
+                                int n_samples, int n_streams, int n_frames, int hop, uint32_t *estimate, uint16_t *feat,
+                                long long feat_stream_stride, cudaStream_t st);
 // short calls (<= 8 frames per stream, <= 2 hops left over): K1 + K2 + carry update in one launch
 bool frontend_fusable(int used, int n_samples, int n_frames);
 cudaError_t launch_frontend_fused(const FrontendParams &P, int16_t *carry, int used, const int16_t *audio,

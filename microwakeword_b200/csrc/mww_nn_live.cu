@@ -34,7 +34,7 @@ nn_f32_live_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
         __syncthreads();
         live_prefetch_rings<3, 3>(tid, state, s0, n_valid);
         live_write_tail(tid, state, pend, s0, n_valid, keep);
-        live_first_conv_mma(tid, sm, W);
+        live_first_conv_mma(tid, sm, W.w0, 32);
         __syncthreads();
         live_depthwise<0>(tid, sm, W, state, s0, n_valid, heads.h[0]); __syncthreads();
         live_pointwise_mma<0>(tid, sm, W); __syncthreads();
@@ -60,14 +60,16 @@ constexpr int kBarChain = 1, kBarFull0 = 2, kBarEmpty0 = 4;         // named bar
 __global__ void __launch_bounds__(kLive2Threads, 1)
 nn_f32_live2_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict__ pend, int n_pend, const void *__restrict__ rows,
                     long long rows_stream_stride_bytes, int rows_are_f32, float *__restrict__ probs, long long probs_stride,
-                    int n_streams, LiveHeads heads) {
+                    int n_streams, LiveHeads heads, int debug_mode) {
+    // debug_mode (MWW_LIVE_MODE, timing experiments only -- results are garbage): 1 = streamers skip their loads, 2 = the chain
+    // skips its work; both keep the barrier protocol, so the other side runs at its own pace
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x;
     for (int L = 1; L < 4; ++L) {                                   // 1x1 weights of blocks 1..3, resident for the whole launch
         float *dst = sm + (L == 1 ? kLiveOffPw1 : (L == 2 ? kLiveOffPw2 : kLiveOffPw3));
         for (int e = tid; e < 64 * 64; e += kLive2Threads) dst[(e >> 6) * kWLd + (e & 63)] = W.pw_w[L][e];
     }
-    live2_stage_taps(tid, kLive2Threads, sm, W, heads);
+    live2_stage_chain_tables(tid, kLive2Threads, sm, W);
     __syncthreads();
     const int n_groups = (n_streams + kLiveStreams - 1) / kLiveStreams;
     if (tid >= kLive2ChainThreads) {
@@ -78,7 +80,10 @@ nn_f32_live2_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict
             const int buf = k & 1;
             if (k >= 2) bar_sync(kBarEmpty0 + buf, kLive2Threads);                  // the chain is done with this buffer
             const long long s0 = (long long)g * kLiveStreams;
-            live2_stream_group(st, sm, W, state, s0, min(kLiveStreams, n_streams - (int)s0), sm + kLive2OffP + buf * kLive2PFloats);
+            // the chain reads this group's first-conv window one group from now: ask the L2 for it (no registers, no wait)
+            if (st < kLiveThreads && debug_mode != 1)
+                live_prefetch_next_window(st, state, pend, rows, rows_stream_stride_bytes, rows_are_f32 ? 480u : 240u, s0, n_streams);
+            if (debug_mode != 1) live2_stream_group(st, W, state, s0, min(kLiveStreams, n_streams - (int)s0), heads, sm + kLive2OffP + buf * kLive2PFloats);
             bar_arrive(kBarFull0 + buf, kLive2Threads);
         }
         return;
@@ -93,23 +98,28 @@ nn_f32_live2_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict
         const float *p_buf = sm + kLive2OffP + buf * kLive2PFloats;
         const long long s0 = (long long)g * kLiveStreams;
         const int n_valid = min(kLiveStreams, n_streams - (int)s0);
+        if (debug_mode == 2) {
+            bar_sync(kBarFull0 + buf, kLive2Threads);
+            bar_arrive(kBarEmpty0 + buf, kLive2Threads);
+            continue;
+        }
         live2_build_a(tid, sm, in, s0, n_valid);
         bar_sync(kBarChain, kLive2ChainThreads);
-        live_first_conv_mma(tid, sm, W);
+        live_first_conv_mma(tid, sm, sm + kLive2OffW0, kLive2W0Pitch);
         bar_sync(kBarFull0 + buf, kLive2Threads);                                   // P of this group is complete (and H is written)
         live2_write_tail(tid, sm, in, state, pend, s0, n_valid);                    // A is dead: new first-conv ring + pending rows
-        live2_dw_from_p<0>(tid, sm, W, state, s0, n_valid, heads.h[0], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
-        live_pointwise_mma<0>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
-        live2_dw_from_p<1>(tid, sm, W, state, s0, n_valid, heads.h[1], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
-        live_pointwise_mma<1>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
-        live2_dw_from_p<2>(tid, sm, W, state, s0, n_valid, heads.h[2], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
-        live_pointwise_mma<2>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
-        live2_dw_from_p<3>(tid, sm, W, state, s0, n_valid, heads.h[3], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
-        live_pointwise_mma<3>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
-        live2_dw_from_p<4>(tid, sm, W, state, s0, n_valid, heads.h[4], p_buf);
+        live2_dw_from_p<0>(tid, sm, state, s0, n_valid, heads.h[0], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
+        live_pointwise_mma<0, true>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
+        live2_dw_from_p<1>(tid, sm, state, s0, n_valid, heads.h[1], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
+        live_pointwise_mma<1, true>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
+        live2_dw_from_p<2>(tid, sm, state, s0, n_valid, heads.h[2], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
+        live_pointwise_mma<2, true>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
+        live2_dw_from_p<3>(tid, sm, state, s0, n_valid, heads.h[3], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
+        live_pointwise_mma<3, true>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
+        live2_dw_from_p<4>(tid, sm, state, s0, n_valid, heads.h[4], p_buf);
         bar_arrive(kBarEmpty0 + buf, kLive2Threads);                                // last read of this P buffer
         bar_sync(kBarChain, kLive2ChainThreads);
-        live_head_finish(tid, sm, W, s0, n_valid, probs, probs_stride);
+        live_head_finish_b(tid, sm, sm[kLive2OffSmall + kLive2SmallHeadBias], s0, n_valid, probs, probs_stride);
         bar_sync(kBarChain, kLive2ChainThreads);                                    // D / A are rewritten by the next group
     }
 }
@@ -120,6 +130,7 @@ cudaError_t launch_nn_f32_live(const NnWeightsF32 &W, float *state, float *pend,
     if (n_streams <= 0) return cudaSuccess;
     static bool attr_done[64] = {};
     static const bool v1 = getenv("MWW_LIVE_V1") != nullptr;        // A/B switch kept for the r02 measurement
+    static const int debug_mode = getenv("MWW_LIVE_MODE") ? atoi(getenv("MWW_LIVE_MODE")) : 0;
     if (first_launch_on_this_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(nn_f32_live_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLiveSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_f32_live2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLive2SmemBytes);
@@ -133,7 +144,7 @@ cudaError_t launch_nn_f32_live(const NnWeightsF32 &W, float *state, float *pend,
     } else {
         const int grid = std::min(n_groups, sm_count);
         nn_f32_live2_kernel<<<grid, kLive2Threads, kLive2SmemBytes, st>>>(W, state, pend, n_pend, rows, rows_stream_stride_bytes, rows_are_f32, probs,
-                                                                          probs_stride, n_streams, heads);
+                                                                          probs_stride, n_streams, heads, debug_mode);
     }
     return cudaGetLastError();
 }

@@ -157,16 +157,20 @@ MWW_HD void live_fc_store_tile(float *sm, int r0, int n0, int lane, const float 
         h[o * kLivePitch + row] = c[i] > 0.f ? c[i] : 0.f;
     }
 }
-template <int L>
-MWW_HD void live_pw_store_tile(float *sm, const NnWeightsF32 &W, int r0, int n0, int lane, const float (&c)[4]) {
+// `bias` = the block's 64 folded-BatchNorm biases (global memory in v1, shared memory in v2)
+MWW_HD void live_pw_store_tile_b(float *sm, const float *bias, int r0, int n0, int lane, const float (&c)[4]) {
     const int g = lane >> 2, tig = lane & 3;
     float *h = sm + kLiveOffH;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int row = r0 + g + ((i & 2) ? 8 : 0), o = n0 + 2 * tig + (i & 1);
-        const float v = c[i] + W.pw_b[L][o];
+        const float v = c[i] + bias[o];
         h[o * kLivePitch + row] = v > 0.f ? v : 0.f;
     }
+}
+template <int L>
+MWW_HD void live_pw_store_tile(float *sm, const NnWeightsF32 &W, int r0, int n0, int lane, const float (&c)[4]) {
+    live_pw_store_tile_b(sm, W.pw_b[L], r0, n0, lane, c);
 }
 
 // ---- depthwise of block L for (stream, channel) columns: ring rows stream through registers ----
@@ -254,12 +258,15 @@ MWW_HD void live_head_partial(int tid, float *sm, const NnWeightsF32 &W, float *
         for (int u = 0; u < U; ++u) d[sub * per + i + u] = ok[u] ? out[u] : 0.f;
     }
 }
-MWW_HD void live_head_finish(int tid, const float *sm, const NnWeightsF32 &W, long long s0, int n_valid, float *probs, long long probs_stride) {
+MWW_HD void live_head_finish_b(int tid, const float *sm, float head_bias, long long s0, int n_valid, float *probs, long long probs_stride) {
     if (tid >= kLiveStreams || tid >= n_valid) return;
     const float *d = sm + kLiveOffD + tid;
     float acc = 0.f;
     for (int c = 0; c < 64; ++c) acc += d[c * kLivePitch];
-    probs[(s0 + tid) * probs_stride] = nn_sigmoid(acc + W.head_b[0]);
+    probs[(s0 + tid) * probs_stride] = nn_sigmoid(acc + head_bias);
+}
+MWW_HD void live_head_finish(int tid, const float *sm, const NnWeightsF32 &W, long long s0, int n_valid, float *probs, long long probs_stride) {
+    live_head_finish_b(tid, sm, W.head_b[0], s0, n_valid, probs, probs_stride);
 }
 
 // ---- back to the canonical layout: one (stream, ring, channel) column per call ----
@@ -293,38 +300,41 @@ constexpr int kLive2Threads = kLive2ChainThreads + kLive2StreamThreads;
 constexpr int kLive2PPitch = 33;                              // P[column][stream]: odd pitch -> conflict-free on both sides
 constexpr int kLive2Cols = 32 + 64 * 4;                       // 288 ring columns per stream (blocks 0..3, head)
 constexpr int kLive2PFloats = kLive2Cols * kLive2PPitch;      // one P buffer
-constexpr int kLive2WrotFloats = 4 * 32 + (10 + 14 + 22 + 16) * 64;   // taps of the OLD rows, per physical row (rotation applied)
 constexpr int kLive2OffP = kLiveSmemFloats;                   // the chain's regions keep their v1 offsets
-constexpr int kLive2OffWrot = kLive2OffP + 2 * kLive2PFloats;
-constexpr int kLive2SmemFloats = kLive2OffWrot + kLive2WrotFloats;
-constexpr int kLive2SmemBytes = kLive2SmemFloats * 4;         // 200.2 KB: one CTA per SM
-static_assert(kLive2OffWrot % 4 == 0, "16-byte loads of the tap table");
+// Everything the CHAIN reads besides its own activations lives in shared memory: measured alone the chain takes 0.23 ms and the
+// streamers 0.23 ms, together 0.41 ms -- with the first conv's and block 0's weights, the newest taps and the biases coming from
+// L2 / L1, every dependent global access of the latency-bound chain slowed down 2-3x while the streamers saturated the memory
+// system.  (The streamers' old-row taps moved the other way, to L1-cached global reads, to make room.)
+constexpr int kLive2W0Pitch = 40;                             // first-conv weights [200][40]: pitch = 8 (mod 32) like kWLd
+constexpr int kLive2OffW0 = kLive2OffP + 2 * kLive2PFloats;
+constexpr int kLive2OffPw0 = kLive2OffW0 + 200 * kLive2W0Pitch;
+constexpr int kLive2OffSmall = kLive2OffPw0 + 32 * kWLd;      // newest taps [288], depthwise... 1x1 biases [4][64], head bias
+constexpr int kLive2SmallTaps = 0, kLive2SmallPwBias = kLive2Cols, kLive2SmallHeadBias = kLive2Cols + 256;
+constexpr int kLive2SmemFloats = kLive2OffSmall + kLive2Cols + 256 + 8;
+constexpr int kLive2SmemBytes = kLive2SmemFloats * 4;         // 227.2 KB of the 227 KB (232 448 B) a CTA may have
+static_assert(kLive2SmemBytes <= 232448, "shared memory per CTA");
 MWW_HD constexpr int live2_col_base(int i) { return i == 0 ? 0 : 32 + 64 * (i - 1); }
 MWW_HD constexpr int live2_wrot_base(int i) { return i == 0 ? 0 : (i == 1 ? 128 : (i == 2 ? 128 + 640 : (i == 3 ? 128 + 640 + 896 : 128 + 640 + 896 + 1408))); }
 
-// once per CTA: tap of every PHYSICAL old row p of ring i (logical row (p - head) mod R), [p][channel]
-MWW_HD void live2_stage_taps(int tid, int n_threads, float *sm, const NnWeightsF32 &W, const LiveHeads &heads) {
-    float *wr = sm + kLive2OffWrot;
-    for (int i = 0; i < 5; ++i) {
-        const int R = live_ring_rows(i), C = live_ring_cols(i), head = heads.h[i];
-        const float *src = i < 4 ? W.dw_w[i] : W.head_w;          // [R + 1][C]; row R is the newest tap (stays with the chain)
-        for (int e = tid; e < R * C; e += n_threads) {
-            const int p = e / C, c = e - p * C;
-            const int j = p - head < 0 ? p - head + R : p - head;
-            wr[live2_wrot_base(i) + e] = src[j * C + c];
-        }
+// once per CTA: the chain's constants
+MWW_HD void live2_stage_chain_tables(int tid, int n_threads, float *sm, const NnWeightsF32 &W) {
+    for (int e = tid; e < 200 * 32; e += n_threads) sm[kLive2OffW0 + (e >> 5) * kLive2W0Pitch + (e & 31)] = W.w0[e];
+    for (int e = tid; e < 32 * 64; e += n_threads) sm[kLive2OffPw0 + (e >> 6) * kWLd + (e & 63)] = W.pw_w[0][e];
+    float *small = sm + kLive2OffSmall;
+    for (int e = tid; e < kLive2Cols; e += n_threads) {        // newest tap (row R of the [R + 1][C] table) of every ring column
+        int i = 0, c = e;
+        while (c >= live_ring_cols(i)) { c -= live_ring_cols(i); ++i; }
+        small[kLive2SmallTaps + e] = (i < 4 ? W.dw_w[i] : W.head_w)[live_ring_rows(i) * live_ring_cols(i) + c];
     }
+    for (int e = tid; e < 256; e += n_threads) small[kLive2SmallPwBias + e] = W.pw_b[e >> 6][e & 63];
+    if (tid == 0) small[kLive2SmallHeadBias] = W.head_b[0];
 }
 
-// streamer thread st (0..511): P of ring I for the 32 streams of one group.  Consecutive threads = consecutive channels of
-// one stream (128-byte coalesced row segments); 512 is a multiple of the ring's channel count, so a thread's channel -- and
-// with it its R taps -- is the same for all of its items.
-// Streamer thread <-> (stream, FOUR consecutive channels): a ring row is C consecutive floats and a ring R consecutive rows,
-// so C / 4 neighbouring lanes read one whole row with 16-byte loads and a thread's successive loads walk its stream's ring
-// front to back -- every stream's 1 - 5.6 KB ring is read as one sequential burst.  (r02 measurements: with one channel per
-// thread -- 128-byte pieces scattered over 32 streams' states -- three different ways of keeping loads in flight all
-// stopped at 3.0 TB/s; it was the DRAM access pattern, not the amount in flight.)  Rows are taken CH at a time to bound
-// registers; the multiply-adds run in physical row order, so the sums are bit-identical to live_ring_pass.
+// Streamer thread <-> (stream, FOUR consecutive channels): C / 4 neighbouring lanes read one whole ring row with 16-byte
+// loads, so a ring costs a quarter of the load instructions / L1 requests of the one-channel-per-thread mapping (the chain's
+// shared-memory traffic goes through the same LSU pipe).  Rows are taken CH at a time and double-buffered: the loads of chunk
+// k + 1 are issued before the multiply-adds of chunk k.  Multiply-adds run in physical row order (bit-identical sums); the
+// tap of physical row r is row (r - head) mod R of the [R + 1][C] table, read through L1 as one 16-byte load per row.
 struct Quad { float x, y, z, w; };
 MWW_HD Quad load_quad(const float *p) {
 #if defined(__CUDA_ARCH__)
@@ -334,41 +344,58 @@ MWW_HD Quad load_quad(const float *p) {
     return Quad{p[0], p[1], p[2], p[3]};
 #endif
 }
+MWW_HD Quad load_quad_ro(const float *p) {
+#if defined(__CUDA_ARCH__)
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    return Quad{v.x, v.y, v.z, v.w};
+#else
+    return Quad{p[0], p[1], p[2], p[3]};
+#endif
+}
 template <int I>
-MWW_HD void live2_stream_ring(int st, float *sm, const NnWeightsF32 &W, const float *state, long long s0, int n_valid, float *p_buf) {
+MWW_HD void live2_stream_ring(int st, const NnWeightsF32 &W, const float *state, long long s0, int n_valid, int head, float *p_buf) {
     constexpr int R = live_ring_rows(I), C = live_ring_cols(I);
     constexpr int lanes = C / 4;                                       // threads per stream: 8 (block 0) or 16
-    constexpr int CH = R < 8 ? R : (R % 8 == 0 ? 8 : (R % 7 == 0 ? 7 : (R == 22 ? 11 : 5)));   // rows in flight: 4, 5, 7, 11, 8
+    constexpr int CH = R == 4 ? 4 : (R == 10 ? 5 : (R == 14 ? 7 : (R == 22 ? 11 : 8)));   // rows per chunk
+    constexpr int NCH = R / CH;
     static_assert(R % CH == 0, "row chunking");
     constexpr int ring_off = kStateOff[I + 1];
     const int sl = st / lanes, c = 4 * (st % lanes);
     if (sl >= kLiveStreams) return;                                    // block 0 needs only half of the streamer threads
     const bool ok = sl < n_valid;
     const float *ring = state + (size_t)(s0 + (ok ? sl : 0)) * kStateFloats + ring_off + c;
-    const float *wr = sm + kLive2OffWrot + live2_wrot_base(I) + c;
+    const float *taps = (I < 4 ? W.dw_w[I < 4 ? I : 0] : W.head_w) + c;
+    const int j0 = head == 0 ? 0 : R - head;
     Quad acc;
-    if (I < 4) acc = load_quad(W.dw_b[I < 4 ? I : 0] + c); else acc = Quad{0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int r0 = 0; r0 < R; r0 += CH) {
-        Quad x[CH];
+    if (I < 4) acc = load_quad_ro(W.dw_b[I < 4 ? I : 0] + c); else acc = Quad{0.f, 0.f, 0.f, 0.f};
+    Quad x[2][CH];
 #pragma unroll
-        for (int r = 0; r < CH; ++r) x[r] = ok ? load_quad(ring + (r0 + r) * C) : Quad{0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < CH; ++r) x[0][r] = ok ? load_quad(ring + r * C) : Quad{0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        if (k + 1 < NCH) {
+#pragma unroll
+            for (int r = 0; r < CH; ++r) x[(k + 1) & 1][r] = ok ? load_quad(ring + ((k + 1) * CH + r) * C) : Quad{0.f, 0.f, 0.f, 0.f};
+        }
 #pragma unroll
         for (int r = 0; r < CH; ++r) {
-            const Quad w = load_quad(wr + (r0 + r) * C);
-            acc.x = fmaf(w.x, x[r].x, acc.x); acc.y = fmaf(w.y, x[r].y, acc.y);
-            acc.z = fmaf(w.z, x[r].z, acc.z); acc.w = fmaf(w.w, x[r].w, acc.w);
+            const int pr = k * CH + r;
+            const int j = pr < head ? j0 + pr : pr - head;                 // (pr - head) mod R
+            const Quad w = load_quad_ro(taps + j * C);
+            const Quad v = x[k & 1][r];
+            acc.x = fmaf(w.x, v.x, acc.x); acc.y = fmaf(w.y, v.y, acc.y);
+            acc.z = fmaf(w.z, v.z, acc.z); acc.w = fmaf(w.w, v.w, acc.w);
         }
     }
     float *p_col = p_buf + (live2_col_base(I) + c) * kLive2PPitch + sl;
     p_col[0] = acc.x; p_col[kLive2PPitch] = acc.y; p_col[2 * kLive2PPitch] = acc.z; p_col[3 * kLive2PPitch] = acc.w;
 }
-MWW_HD void live2_stream_group(int st, float *sm, const NnWeightsF32 &W, const float *state, long long s0, int n_valid, float *p_buf) {
-    live2_stream_ring<3>(st, sm, W, state, s0, n_valid, p_buf);        // longest rings first: their loads overlap the rest
-    live2_stream_ring<4>(st, sm, W, state, s0, n_valid, p_buf);
-    live2_stream_ring<2>(st, sm, W, state, s0, n_valid, p_buf);
-    live2_stream_ring<1>(st, sm, W, state, s0, n_valid, p_buf);
-    live2_stream_ring<0>(st, sm, W, state, s0, n_valid, p_buf);
+MWW_HD void live2_stream_group(int st, const NnWeightsF32 &W, const float *state, long long s0, int n_valid, const LiveHeads &heads, float *p_buf) {
+    live2_stream_ring<3>(st, W, state, s0, n_valid, heads.h[3], p_buf);        // longest rings first: their loads overlap the rest
+    live2_stream_ring<4>(st, W, state, s0, n_valid, heads.h[4], p_buf);
+    live2_stream_ring<2>(st, W, state, s0, n_valid, heads.h[2], p_buf);
+    live2_stream_ring<1>(st, W, state, s0, n_valid, heads.h[1], p_buf);
+    live2_stream_ring<0>(st, W, state, s0, n_valid, heads.h[0], p_buf);
 }
 
 // chain: first-conv window without per-thread copies kept across the barrier (the new first-conv ring is read back from
@@ -423,12 +450,13 @@ MWW_HD void live2_write_tail(int tid, const float *sm, const LiveInput &in, floa
 // chain: depthwise of block L (I = L) or head partial (I = 4) from the streamers' P: D = fma(newest tap, x_new, P); the new
 // row replaces the oldest physical row of the ring
 template <int I>
-MWW_HD void live2_dw_from_p(int tid, float *sm, const NnWeightsF32 &W, float *state, long long s0, int n_valid, int head, const float *p_buf) {
+MWW_HD void live2_dw_from_p(int tid, float *sm, float *state, long long s0, int n_valid, int head, const float *p_buf) {
     constexpr int R = live_ring_rows(I), C = live_ring_cols(I);
     constexpr int per = kLiveStreams * C / kLive2ChainThreads;       // 4 or 8 streams per thread
     constexpr int ring_off = kStateOff[I + 1];
+    (void)R;
     const int c = tid % C, sub = tid / C;
-    const float wn = (I < 4 ? W.dw_w[I < 4 ? I : 0] : W.head_w)[R * C + c];
+    const float wn = sm[kLive2OffSmall + kLive2SmallTaps + live2_col_base(I) + c];
     const float *h = sm + kLiveOffH + c * kLivePitch;
     float *d = sm + kLiveOffD + c * kLivePitch;
     const float *p_col = p_buf + (live2_col_base(I) + c) * kLive2PPitch;
@@ -486,7 +514,7 @@ MWW_D void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(i
 MWW_D void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // first conv on tensor cores: 8 warps = 2 stream tiles x 4 channel tiles, K = 200 (25 k-steps), B fragments from L2
-MWW_D void live_first_conv_mma(int tid, float *sm, const NnWeightsF32 &W) {
+MWW_D void live_first_conv_mma(int tid, float *sm, const float *w0, int w0_pitch) {
     const int warp = tid >> 5, lane = tid & 31;
     const int r0 = 16 * (warp >> 2), n0 = 8 * (warp & 3);
     const float *a_base = sm + kLiveOffA;
@@ -495,7 +523,7 @@ MWW_D void live_first_conv_mma(int tid, float *sm, const NnWeightsF32 &W) {
     for (int ks = 0; ks < 25; ++ks) {
         FragA a;
         FragB b;
-        load_frag_b(W.w0, 32, 8 * ks, n0, lane, b);
+        load_frag_b(w0, w0_pitch, 8 * ks, n0, lane, b);
         load_frag_a(a_base, kLivePitch, 8 * ks, r0, lane, a);
         mma_tf32(c, a.lo, b.hi);
         mma_tf32(c, a.hi, b.lo);
@@ -504,14 +532,16 @@ MWW_D void live_first_conv_mma(int tid, float *sm, const NnWeightsF32 &W) {
     live_fc_store_tile(sm, r0, n0, lane, c);
 }
 // 1x1 of block L: 8 warps = 2 stream tiles x 4 pairs of channel tiles
-template <int L>
+// SMEM_ALL (v2): block 0's weights and every bias come from shared memory too
+template <int L, bool SMEM_ALL = false>
 MWW_D void live_pointwise_mma(int tid, float *sm, const NnWeightsF32 &W) {
     constexpr int cin = kGeom[L].cin;
     const int warp = tid >> 5, lane = tid & 31;
     const int r0 = 16 * (warp >> 2), n0 = 16 * (warp & 3);
     const float *d = sm + kLiveOffD;
-    const float *wsm = L == 0 ? W.pw_w[0] : sm + live_pw_offset<L>();       // block 0: B fragments straight from L2
-    constexpr int wld = L == 0 ? 64 : kWLd;
+    const float *wsm = L == 0 ? (SMEM_ALL ? sm + kLive2OffPw0 : W.pw_w[0]) : sm + live_pw_offset<L>();   // v1 block 0: B fragments straight from L2
+    constexpr int wld = (L == 0 && !SMEM_ALL) ? 64 : kWLd;
+    const float *bias = SMEM_ALL ? sm + kLive2OffSmall + kLive2SmallPwBias + 64 * L : W.pw_b[L];
     float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll 2
     for (int ks = 0; ks < cin / 8; ++ks) {
@@ -524,8 +554,8 @@ MWW_D void live_pointwise_mma(int tid, float *sm, const NnWeightsF32 &W) {
         mma_tf32(c[0], a.hi, b0.lo); mma_tf32(c[1], a.hi, b1.lo);
         mma_tf32(c[0], a.hi, b0.hi); mma_tf32(c[1], a.hi, b1.hi);
     }
-    live_pw_store_tile<L>(sm, W, r0, n0, lane, c[0]);
-    live_pw_store_tile<L>(sm, W, r0, n0 + 8, lane, c[1]);
+    live_pw_store_tile_b(sm, bias, r0, n0, lane, c[0]);
+    live_pw_store_tile_b(sm, bias, r0, n0 + 8, lane, c[1]);
 }
 #endif
 

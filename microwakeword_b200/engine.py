@@ -91,6 +91,7 @@ class StreamEngine:
         # geometry of the loaded model (mww_get_info): feature rows per model step, ring-state elements per stream
         self.stride = max(int(self.info.input_feature_slices), 1)
         self.state_elements = int(self.info.state_bytes_per_stream) // (1 if self.is_quantized else 4) if blob is not None else 0
+        self.hop = HOP          # samples between feature windows (set_window_step)
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -153,6 +154,12 @@ class StreamEngine:
         ids = np.ascontiguousarray(stream_ids, np.int32).reshape(-1)
         _lib.check(self._h, self._L.mww_reset(self._h, ids.ctypes.data, ids.size, self._cu_stream()))
 
+    def set_window_step(self, hop_samples: int):
+        """window_step of the frontend in samples (mww_set_window_step): 160 = the 10 ms pymicro_features hard-wires (default),
+        320 = the 20 ms default of the TF-op path (audio_utils.py:29,73).  Only while no samples are buffered."""
+        _lib.check(self._h, self._L.mww_set_window_step(self._h, int(hop_samples)))
+        self.hop = int(hop_samples)
+
     def reset_frontend(self):
         _lib.check(self._h, self._L.mww_reset_frontend(self._h, self._cu_stream()))
 
@@ -160,7 +167,7 @@ class StreamEngine:
         """int16 CUDA tensor [S, N] -> uint16 CUDA tensor [S, rows, 40] (rows may be 0); `out` reuses a caller buffer."""
         torch = _torch()
         n, stride = self._check_audio(audio)
-        rows = max((self.frontend_buffered + n - WINDOW) // HOP + 1, 0) if self.frontend_buffered + n >= WINDOW else 0
+        rows = max((self.frontend_buffered + n - WINDOW) // self.hop + 1, 0) if self.frontend_buffered + n >= WINDOW else 0
         if out is None:
             out = torch.empty((self.n_streams, max(rows, 1), NUM_FEATURES), dtype=torch.uint16, device=self._dev())
         elif (out.dtype != torch.uint16 or not out.is_cuda or not out.is_contiguous() or out.dim() != 3 or out.shape[0] != self.n_streams
@@ -191,7 +198,7 @@ class StreamEngine:
         torch = _torch()
         n, stride = self._check_audio(audio)
         buffered = self.frontend_buffered
-        rows = (buffered + n - WINDOW) // HOP + 1 if buffered + n >= WINDOW else 0
+        rows = (buffered + n - WINDOW) // self.hop + 1 if buffered + n >= WINDOW else 0
         steps = (self.pending_rows + rows) // self.stride
         if out is None:
             out = torch.empty((self.n_streams, max(steps, 1)), dtype=torch.float32, device=self._dev())
@@ -210,7 +217,7 @@ class StreamEngine:
             audio = np.ascontiguousarray(audio)
         n = audio.shape[1]
         buffered = self.frontend_buffered
-        rows = (buffered + n - WINDOW) // HOP + 1 if buffered + n >= WINDOW else 0
+        rows = (buffered + n - WINDOW) // self.hop + 1 if buffered + n >= WINDOW else 0
         steps = (self.pending_rows + rows) // self.stride
         if out is None:
             out = np.empty((self.n_streams, max(steps, 1)), np.float32)
@@ -226,7 +233,7 @@ class StreamEngine:
         torch = _torch()
         n = int(n_samples)
         buffered = self.frontend_buffered
-        rows = (buffered + n - WINDOW) // HOP + 1 if buffered + n >= WINDOW else 0
+        rows = (buffered + n - WINDOW) // self.hop + 1 if buffered + n >= WINDOW else 0
         steps = (self.pending_rows + rows) // self.stride
         if out is None:
             out = torch.empty((self.n_streams, max(steps, 1)), dtype=torch.float32, device=self._dev())

@@ -148,7 +148,7 @@ class Model:
 
     def nonstreaming_length(self) -> int:
         """Rows of the shortest window the non-streaming graph accepts = its receptive field (model_train_eval.py:64-88 run
-        backwards): every ring and the head window filled with real data.  204 for okay_nabu."""
+        backwards): every ring and the head window filled with real data.  203 for okay_nabu (the reference trains on 204-row windows)."""
         a = self._arch()
         span = sum(a.block_ring_rows(i) for i in range(a.n_blocks)) + a.head_rows - 1
         return a.first_conv_kernel_size + a.stride * span

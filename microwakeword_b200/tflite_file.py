@@ -73,6 +73,8 @@ class Table:
         if not p:
             return ""
         n = struct.unpack_from("<I", self.buf, p)[0]
+        if p + 4 + n > len(self.buf):
+            raise TfliteError("flatbuffer string runs past the end of the file")
         return bytes(self.buf[p + 4:p + 4 + n]).decode("utf-8", "replace")
 
     def vector(self, idx: int, dtype) -> np.ndarray:
@@ -90,6 +92,8 @@ class Table:
         if not p:
             return []
         n = struct.unpack_from("<I", self.buf, p)[0]
+        if p + 4 + 4 * n > len(self.buf):
+            raise TfliteError("flatbuffer vector of tables runs past the end of the file")
         out = []
         for i in range(n):
             e = p + 4 + 4 * i
@@ -630,8 +634,18 @@ class _Recogniser:
 
 
 def tensors_from_tflite(blob: bytes) -> dict:
-    """TFL3 flatbuffer bytes -> the tensor dictionary ``model_file.write_container`` serialises."""
-    return _Recogniser(Graph(blob)).run()
+    """TFL3 flatbuffer bytes -> the tensor dictionary ``model_file.write_container`` serialises.
+    Whatever is wrong with the bytes -- truncated file, offsets pointing outside it, indices outside a vector, shapes that do
+    not multiply out -- surfaces as TfliteError: a file this reader cannot vouch for is rejected, never half-read."""
+    blob = bytes(blob)
+    if len(blob) < 8 or blob[4:8] != FILE_IDENTIFIER:
+        raise TfliteError("not a TFL3 flatbuffer (file identifier missing)")
+    try:
+        return _Recogniser(Graph(blob)).run()
+    except TfliteError:
+        raise
+    except (struct.error, IndexError, KeyError, ValueError, OverflowError, TypeError, AttributeError, RecursionError, MemoryError, ZeroDivisionError) as exc:
+        raise TfliteError("malformed flatbuffer (%s: %s)" % (type(exc).__name__, exc)) from exc
 
 
 def is_tflite(blob: bytes) -> bool:

@@ -31,5 +31,5 @@ def spectrogram_generator(clips, step_ms=20, split_spectrogram_duration_s=None, 
     """The reference's generator on a list of clips: one clip at a time through the (oracle) frontend."""
     import oracle
     for clip in clips:
-        spec = oracle.generate_features_for_clip(clip)
+        spec = oracle.generate_features_for_clip(clip).astype(np.float32) * np.float32(0.0390625)     # audio_utils.py:60-62 (float output)
         yield from clip_spectrograms(spec, step_ms, split_spectrogram_duration_s, slide_frames)

@@ -29,6 +29,7 @@ def lib():
         L = ctypes.CDLL(SO)
         L.emul_features.restype = ctypes.c_int
         L.emul_features_fused.restype = ctypes.c_int
+        L.emul_features_hop.restype = ctypes.c_int
         L.emul_fb_schedule.restype = None
         L.emul_nn_f32.restype = ctypes.c_int
         L.emul_nn_i8.restype = ctypes.c_int
@@ -72,11 +73,19 @@ class Frontend:
         self.estimate = np.zeros((n_streams, 40), np.uint32)
         self.used = 0
 
-    def features(self, audio, fused=False, order=0):
-        """fused=True: the phases of the one-launch clip kernel (filterbank -> estimate chain -> outputs from shared memory)"""
+    def features(self, audio, fused=False, order=0, hop=160):
+        """fused=True: the phases of the one-launch clip kernel (filterbank -> estimate chain -> outputs from shared memory);
+        hop != 160: the run-time window-step kernel"""
         audio = np.ascontiguousarray(audio, np.int16)
         S, N = audio.shape
-        rows = (self.used + N) // 160 + 1
+        rows = (self.used + N) // min(hop, 160) + 1
+        if hop != 160:
+            feat = np.zeros((S, rows, 40), np.uint16)
+            nu = ctypes.c_int(0)
+            n = lib().emul_features_hop(_p(audio), S, N, _p(self.carry), self.used, _p(self.estimate), _p(feat), rows, ctypes.byref(nu), int(hop))
+            assert n >= 0
+            self.used = nu.value
+            return feat[:, :n]
         feat = np.zeros((S, rows, 40), np.uint16)
         nu = ctypes.c_int(0)
         if fused:

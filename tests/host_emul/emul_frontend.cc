@@ -197,6 +197,56 @@ int emul_features_fused(const int16_t *audio, int n_streams, int n_samples, int1
     return n_frames;
 }
 
+// Mirrors k1_spectral_hop_kernel (run-time window step): groups of k1_hop_frames_per_group(hop) frames, single staging area.
+int emul_features_hop(const int16_t *audio, int n_streams, int n_samples, int16_t *carry, int used, uint32_t *estimate,
+                      uint16_t *feat, int max_rows, int *new_used_out, int hop) {
+    ensure_tables();
+    const int total = used + n_samples;
+    const int n_frames = total >= kWindow ? (total - kWindow) / hop + 1 : 0;
+    const int consumed = n_frames * hop;
+    const int new_used = total - consumed;
+    if (n_frames > max_rows || new_used < 0 || new_used >= kWindow) return -1;
+    K1Smem *sm = new K1Smem;
+    std::vector<K1Lane> lanes(kK1Threads);
+    const int fpg = k1_hop_frames_per_group(hop);
+    const int n_groups = (n_frames + fpg - 1) / fpg;
+    for (int s = 0; s < n_streams; ++s) {
+        memset(sm, 0xA5, sizeof *sm);
+        for (int tid = 0; tid < kK1Threads; ++tid) k1_lane_init(tid, g_params, lanes[tid]);
+        for (int tid = 0; tid < kK1Threads; ++tid) k1_stage_tables(tid, *sm, g_params);
+        const int16_t *my_carry = carry + (size_t)s * kWindow;
+        const int16_t *my_audio = audio + (size_t)s * n_samples;
+        uint32_t est[kNumChannels];
+        for (int ch = 0; ch < kNumChannels; ++ch) est[ch] = estimate[(size_t)s * kNumChannels + ch];
+        for (int g = 0; g < n_groups; ++g) {
+            const int f0 = g * fpg;
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_hop_load_audio(tid, *sm, my_carry, used, my_audio, n_samples, hop * f0, (fpg - 1) * hop + kWindow);
+            std::vector<K1Pass1Ctx> ctx(kK1Threads);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_window_fft1<0>(tid, *sm, 0, k1_hop_pair_base(tid >> 4, hop, fpg), g_params, ctx[tid]);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_window_fft1<1>(tid, *sm, 0, k1_hop_pair_base(tid >> 4, hop, fpg), g_params, ctx[tid]);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_fft_pass2(tid, *sm, lanes[tid]);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_real_energy(tid, *sm, g_params);
+            for (int tid = 0; tid < kK1Threads; ++tid) k1_filterbank(tid, *sm, g_params, &sm->A[tid >> 4][0]);
+            const int n_valid = n_frames - f0 < fpg ? n_frames - f0 : fpg;
+            for (int tid = 0; tid < kNumChannels; ++tid) k2_group_chain(tid, *sm, n_valid, est[tid]);
+            for (int tid = 0; tid < kK1Threads; ++tid) k2_group_outputs(tid, *sm, n_valid, feat + ((size_t)s * max_rows + f0) * kNumChannels);
+        }
+        for (int ch = 0; ch < kNumChannels; ++ch) estimate[(size_t)s * kNumChannels + ch] = est[ch];
+    }
+    delete sm;
+    for (int s = 0; s < n_streams; ++s) {
+        int16_t tmp[kWindow] = {0};
+        int16_t *c = carry + (size_t)s * kWindow;
+        for (int i = 0; i < new_used; ++i) {
+            const int vi = consumed + i;
+            tmp[i] = vi < used ? c[vi] : audio[(size_t)s * n_samples + (vi - used)];
+        }
+        memcpy(c, tmp, sizeof tmp);
+    }
+    if (new_used_out) *new_used_out = new_used;
+    return n_frames;
+}
+
 // filterbank schedule for the conflict-freedom test: slots16x4x4 = (ch, word0, n, coef_off) per lane and slot
 void emul_fb_schedule(int16_t *slots16x4x4, int32_t *coef800) {
     ensure_tables();

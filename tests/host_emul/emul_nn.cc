@@ -285,19 +285,19 @@ extern "C" int32_t emul_mbqm(int32_t x, int32_t mult, int32_t shift) { return mb
 
 // ---- live-step fp32 kernel (mww_nn_live.cuh) ---------------------------------------------------------------
 namespace {
-void emul_live_first_conv(float *sm, const NnWeightsF32 &W) {
+void emul_live_first_conv(float *sm, const float *w0, int w0_pitch) {
     for (int warp = 0; warp < kLiveThreads / 32; ++warp) {
         const int r0 = 16 * (warp >> 2), n0 = 8 * (warp & 3);
         float c[32][4] = {};
         for (int ks = 0; ks < 25; ++ks) {
             FragA a[32]; FragB b[32];
-            for (int lane = 0; lane < 32; ++lane) { load_frag_b(W.w0, 32, 8 * ks, n0, lane, b[lane]); load_frag_a(sm + kLiveOffA, kLivePitch, 8 * ks, r0, lane, a[lane]); }
+            for (int lane = 0; lane < 32; ++lane) { load_frag_b(w0, w0_pitch, 8 * ks, n0, lane, b[lane]); load_frag_a(sm + kLiveOffA, kLivePitch, 8 * ks, r0, lane, a[lane]); }
             warp_mma_3xtf32(c, a, b);
         }
         for (int lane = 0; lane < 32; ++lane) live_fc_store_tile(sm, r0, n0, lane, c[lane]);
     }
 }
-template <int L>
+template <int L, bool SMEM_ALL = false>
 void emul_live_pointwise(float *sm, const NnWeightsF32 &W) {
     constexpr int cin = kGeom[L].cin;
     for (int warp = 0; warp < kLiveThreads / 32; ++warp) {
@@ -307,15 +307,16 @@ void emul_live_pointwise(float *sm, const NnWeightsF32 &W) {
             FragA a[32]; FragB b0[32], b1[32];
             for (int lane = 0; lane < 32; ++lane) {
                 load_frag_a(sm + kLiveOffD, kLivePitch, 8 * ks, r0, lane, a[lane]);
-                const float *wsm = L == 0 ? W.pw_w[0] : sm + live_pw_offset<L>();
-                const int wld = L == 0 ? 64 : kWLd;
+                const float *wsm = L == 0 ? (SMEM_ALL ? sm + kLive2OffPw0 : W.pw_w[0]) : sm + live_pw_offset<L>();
+                const int wld = (L == 0 && !SMEM_ALL) ? 64 : kWLd;
                 load_frag_b(wsm, wld, 8 * ks, n0, lane, b0[lane]);
                 load_frag_b(wsm, wld, 8 * ks, n0 + 8, lane, b1[lane]);
             }
             warp_mma_3xtf32(c[0], a, b0);
             warp_mma_3xtf32(c[1], a, b1);
         }
-        for (int lane = 0; lane < 32; ++lane) { live_pw_store_tile<L>(sm, W, r0, n0, lane, c[0][lane]); live_pw_store_tile<L>(sm, W, r0, n0 + 8, lane, c[1][lane]); }
+        const float *bias = SMEM_ALL ? sm + kLive2OffSmall + kLive2SmallPwBias + 64 * L : W.pw_b[L];
+        for (int lane = 0; lane < 32; ++lane) { live_pw_store_tile_b(sm, bias, r0, n0, lane, c[0][lane]); live_pw_store_tile_b(sm, bias, r0, n0 + 8, lane, c[1][lane]); }
     }
 }
 }  // namespace
@@ -344,7 +345,7 @@ extern "C" int emul_nn_f32_live(const float *const *wp, float *state, float *pen
         ALLL(live_build_a(tid, sm, in, s0, n_valid, KP(tid)));
         ALLL(live_write_tail(tid, state, pend, s0, n_valid, KP(tid)));
 #undef KP
-        emul_live_first_conv(sm, W);
+        emul_live_first_conv(sm, W.w0, 32);
         ALLL(live_depthwise<0>(tid, sm, W, state, s0, n_valid, heads.h[0])); emul_live_pointwise<0>(sm, W);
         ALLL(live_depthwise<1>(tid, sm, W, state, s0, n_valid, heads.h[1])); emul_live_pointwise<1>(sm, W);
         ALLL(live_depthwise<2>(tid, sm, W, state, s0, n_valid, heads.h[2])); emul_live_pointwise<2>(sm, W);
@@ -379,22 +380,22 @@ extern "C" int emul_nn_f32_live2(const float *const *wp, float *state, float *pe
             float *dst = sm + (L == 1 ? kLiveOffPw1 : (L == 2 ? kLiveOffPw2 : kLiveOffPw3));
             for (int e = tid; e < 64 * 64; e += kLive2Threads) dst[(e >> 6) * kWLd + (e & 63)] = W.pw_w[L][e];
         }
-    for (int tid = 0; tid < kLive2Threads; ++tid) live2_stage_taps(tid, kLive2Threads, sm, W, heads);
+    for (int tid = 0; tid < kLive2Threads; ++tid) live2_stage_chain_tables(tid, kLive2Threads, sm, W);
     const int n_groups = (n_streams + kLiveStreams - 1) / kLiveStreams;
     for (int g = 0; g < n_groups; ++g) {
         const long long s0 = (long long)g * kLiveStreams;
         const int n_valid = n_streams - (int)s0 < kLiveStreams ? n_streams - (int)s0 : kLiveStreams;
         float *p_buf = sm + kLive2OffP + (g & 1) * kLive2PFloats;
-        STREAM(live2_stream_group(st, sm, W, state, s0, n_valid, p_buf));
+        STREAM(live2_stream_group(st, W, state, s0, n_valid, heads, p_buf));
         CHAIN(live2_build_a(tid, sm, in, s0, n_valid));
-        emul_live_first_conv(sm, W);
+        emul_live_first_conv(sm, sm + kLive2OffW0, kLive2W0Pitch);
         CHAIN(live2_write_tail(tid, sm, in, state, pend, s0, n_valid));
-        CHAIN(live2_dw_from_p<0>(tid, sm, W, state, s0, n_valid, heads.h[0], p_buf)); emul_live_pointwise<0>(sm, W);
-        CHAIN(live2_dw_from_p<1>(tid, sm, W, state, s0, n_valid, heads.h[1], p_buf)); emul_live_pointwise<1>(sm, W);
-        CHAIN(live2_dw_from_p<2>(tid, sm, W, state, s0, n_valid, heads.h[2], p_buf)); emul_live_pointwise<2>(sm, W);
-        CHAIN(live2_dw_from_p<3>(tid, sm, W, state, s0, n_valid, heads.h[3], p_buf)); emul_live_pointwise<3>(sm, W);
-        CHAIN(live2_dw_from_p<4>(tid, sm, W, state, s0, n_valid, heads.h[4], p_buf));
-        CHAIN(live_head_finish(tid, sm, W, s0, n_valid, probs, probs_stride));
+        CHAIN(live2_dw_from_p<0>(tid, sm, state, s0, n_valid, heads.h[0], p_buf)); emul_live_pointwise<0, true>(sm, W);
+        CHAIN(live2_dw_from_p<1>(tid, sm, state, s0, n_valid, heads.h[1], p_buf)); emul_live_pointwise<1, true>(sm, W);
+        CHAIN(live2_dw_from_p<2>(tid, sm, state, s0, n_valid, heads.h[2], p_buf)); emul_live_pointwise<2, true>(sm, W);
+        CHAIN(live2_dw_from_p<3>(tid, sm, state, s0, n_valid, heads.h[3], p_buf)); emul_live_pointwise<3, true>(sm, W);
+        CHAIN(live2_dw_from_p<4>(tid, sm, state, s0, n_valid, heads.h[4], p_buf));
+        CHAIN(live_head_finish_b(tid, sm, sm[kLive2OffSmall + kLive2SmallHeadBias], s0, n_valid, probs, probs_stride));
     }
 #undef CHAIN
 #undef STREAM

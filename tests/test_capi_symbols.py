@@ -28,7 +28,12 @@ def test_every_declared_symbol_is_exported():
 
 def test_info_struct_layout_matches_header():
     from microwakeword_b200 import _lib
-    assert ctypes.sizeof(_lib.MwwInfo) == 14 * 4
+    # every field of `struct mww_info` in include/mww.h is a 4-byte scalar: count them in the header itself
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "mww.h")).read()
+    body = hdr[hdr.index("typedef struct mww_info {"):hdr.index("} mww_info;")]
+    fields = re.findall(r"^\s*(?:int32_t|float)\s+(\w+);", body, re.M)
+    assert [n for n, _ in _lib.MwwInfo._fields_] == fields and ctypes.sizeof(_lib.MwwInfo) == 4 * len(fields)
 
 
 def test_no_cpu_fallback_without_a_gpu():

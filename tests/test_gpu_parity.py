@@ -541,3 +541,48 @@ def test_pinned_host_array_and_numa_binding(torch_cuda):
     after = os.sched_getaffinity(0)
     assert after <= before and len(after) >= 1 and (got == -1 or node in (None, got))
     os.sched_setaffinity(0, before)
+
+
+@pytest.mark.parametrize("step_ms", [20, 10, 30, 7, 25])
+def test_tf_op_path_honours_window_step(torch_cuda, step_ms):
+    """a3 (audio_utils.py:69-81): use_c=False forwards step_ms to the frontend op; default 20 ms.  Bit-exact against the oracle
+    frontend constructed with that step, whole clips and chunked streaming (carry with a hop that is not 10 ms)."""
+    from microwakeword.audio.audio_utils import generate_features_for_clip
+    from microwakeword_b200.engine import StreamEngine
+    torch = torch_cuda
+    clips = [synth_audio(16000, 60 + step_ms), edge_case_audio(9000)[2], synth_audio(700, 3)]
+    for clip in clips:
+        fe = oracle.Frontend((16000, 30, step_ms, 40, 125.0, 7500.0))
+        fe.reset()
+        want = fe.stream(clip)
+        got = generate_features_for_clip(clip, step_ms=step_ms, use_c=False)
+        assert got.dtype == np.uint16 and got.shape == want.shape and np.array_equal(got, want), (step_ms, clip.size)
+    if step_ms == 20:
+        assert np.array_equal(generate_features_for_clip(clips[0], use_c=False), want_default(clips[0]))
+    # streaming with carried state, many streams (one CTA per stream), odd chunk sizes
+    audio = np.stack([synth_audio(12000, 90 + i) for i in range(9)])
+    eng = StreamEngine(None, n_streams=9)
+    eng.set_window_step(16 * step_ms)
+    parts, pos = [], 0
+    for n in (5000, 1234, 16, 3000, 2750):
+        parts.append(_u16(eng.features(torch.from_numpy(np.ascontiguousarray(audio[:, pos:pos + n])).cuda())))
+        pos += n
+    got = np.concatenate(parts, 1)
+    for i in range(9):
+        fe = oracle.Frontend((16000, 30, step_ms, 40, 125.0, 7500.0))
+        fe.reset()
+        want = fe.stream(audio[i])
+        assert got[i].shape == want.shape and np.array_equal(got[i], want), (step_ms, i)
+    if eng.frontend_buffered:                # a 30 ms step consumes the 12 000 samples exactly
+        with pytest.raises(Exception):
+            eng.set_window_step(320)         # samples are buffered
+    eng.reset_frontend()
+    eng.set_window_step(160)
+    with pytest.raises(Exception):
+        eng.set_window_step(481)
+
+
+def want_default(clip):
+    fe = oracle.Frontend((16000, 30, 20, 40, 125.0, 7500.0))
+    fe.reset()
+    return fe.stream(clip)

@@ -136,6 +136,28 @@ def test_fused_clip_frontend_phases_bit_exact_and_order_independent():
     assert np.array_equal(np.concatenate(parts, 1), want)
 
 
+@pytest.mark.parametrize("step_ms", [20, 30, 7, 25, 1])
+def test_run_time_window_step_phases_bit_exact(step_ms):
+    """window_step != 10 ms (audio_utils.py:69-81, default 20): groups of fewer than 16 frames when the hop is long, frames
+    overlapping heavily when it is short, leftover samples carried between odd-sized chunks -- against the oracle frontend
+    built with that step."""
+    hop = 16 * step_ms
+    audio = np.stack([synth_audio(9000, 310 + i) for i in range(2)] + [edge_case_audio(9000)[1]])
+    want = []
+    for row in audio:
+        fe = oracle.Frontend((16000, 30, step_ms, 40, 125.0, 7500.0))
+        fe.reset()
+        want.append(fe.stream(row))
+    want = np.stack(want)
+    got = emul.Frontend(3).features(audio, hop=hop)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    fe, pos, parts = emul.Frontend(3), 0, []
+    for n in (2000, 16, 1234, 3750, 2000):
+        parts.append(fe.features(audio[:, pos:pos + n], hop=hop))
+        pos += n
+    assert np.array_equal(np.concatenate(parts, 1), want)
+
+
 def test_frontend_phases_chunked_stream_and_multi_group():
     audio = np.stack([synth_audio(16000, 70 + i) for i in range(3)])     # 98 frames -> 7 groups of 16
     want, _ = oracle.run_pipeline(None, audio, want_probs=False)

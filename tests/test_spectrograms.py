@@ -73,7 +73,8 @@ def test_ragged_store_round_trip(tmp_path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["plain", "slide", "split", "augmented_random"])
 def test_gpu_generator_equals_reference_loop(torch_cuda, mode):
-    lengths = [16000, 4000, 23999, 800, 40000, 480, 31000]
+    # clips shorter than slide_frames rows make the reference's sliding_window_view raise: only the plain / split modes get them
+    lengths = [16000, 4000, 23999, 800, 40000, 480, 31000] if mode in ("plain", "split") else [16000, 4000, 23999, 2600, 40000, 31000]
     clips = [synth_audio(n, 700 + i) for i, n in enumerate(lengths)]
     kw = dict(plain={}, slide=dict(slide_frames=10, step_ms=10), split=dict(split_spectrogram_duration_s=0.5, step_ms=10),
               augmented_random=dict(slide_frames=3, step_ms=10))[mode]
@@ -91,6 +92,6 @@ def test_gpu_generator_equals_reference_loop(torch_cuda, mode):
         assert a.dtype == np.float32 and a.shape == b.shape and np.array_equal(a, b)
     one = gen.get_random_spectrogram()
     import oracle
-    assert np.array_equal(one, oracle.generate_features_for_clip(aug.augment_clip(clips[1]) if aug else clips[1]))
+    assert np.array_equal(one, oracle.generate_features_for_clip(aug.augment_clip(clips[1]) if aug else clips[1]).astype(np.float32) * np.float32(0.0390625))
     from microwakeword.audio.spectrograms import SpectrogramGeneration
     assert SpectrogramGeneration is S.SpectrogramGeneration

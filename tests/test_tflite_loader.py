@@ -195,3 +195,49 @@ def test_model_loads_tflite_and_matches_container(kind, tmp_path, torch_cuda):
         x = feats.astype(np.float32) * R.FEATURE_SCALE
         want = [float(it.invoke(x[3 * s:3 * s + 3]).reshape(-1)[0]) for s in range(40)]
         assert np.abs(np.asarray(a[:40]) - np.asarray(want)).max() <= 1e-5
+
+
+@pytest.mark.parametrize("kind", ["f32", "int8"])
+def test_reader_survives_truncation_and_corruption(kind):
+    """a real converter-written file is the first thing that will break the reader, so it must fail
+    LOUDLY and only with TfliteError -- never an IndexError / struct.error from deep inside, never a hang, never a silently
+    different model.  Every prefix of the file (sampled), and single-byte corruptions all over the metadata region (vtables,
+    offsets, operator codes, tensor shapes) and the data region."""
+    import time
+    t = _tensors(kind)
+    blob = W.write_streaming_mixednet(t)
+    good = TF.tensors_from_tflite(blob)
+    rng = np.random.default_rng(123)
+    t0 = time.time()
+    cuts = sorted(set([0, 1, 4, 7, 8, 12, len(blob) - 1] + [int(v) for v in rng.integers(0, len(blob), 250)]))
+    for n in cuts:
+        with pytest.raises(TF.TfliteError):
+            TF.tensors_from_tflite(blob[:n])
+    outcomes = {"raised": 0, "same": 0, "different_weights": 0}
+    positions = [int(v) for v in rng.integers(0, len(blob), 1200)]
+    for pos in positions:
+        b = bytearray(blob)
+        b[pos] ^= int(rng.integers(1, 256))
+        try:
+            got = TF.tensors_from_tflite(bytes(b))
+        except TF.TfliteError:
+            outcomes["raised"] += 1
+            continue
+        # a flip that survives must have landed in tensor DATA (weights / biases / quantisation numbers): the structure --
+        # architecture, tensor names, shapes, dtypes -- is what it was
+        assert sorted(got) == sorted(good)
+        assert np.array_equal(got["arch"], good["arch"])
+        assert all(got[k].shape == good[k].shape and got[k].dtype == good[k].dtype for k in good)
+        outcomes["same" if all(np.array_equal(got[k], good[k]) for k in good) else "different_weights"] += 1
+    assert outcomes["raised"] > 50 and time.time() - t0 < 120, outcomes
+
+
+def test_reader_accepts_operator_and_tensor_permutations():
+    """The converter is free to order tensors, buffers and (topologically) operators differently from this repo's writer: the
+    recogniser must depend on the dataflow only.  Tensors are renumbered at random, and independent operators are swapped."""
+    t = _tensors("int8")
+    base = TF.tensors_from_tflite(W.write_streaming_mixednet(t))
+    for seed in range(4):
+        blob = W.write_streaming_mixednet(t, shuffle_seed=seed)
+        got = TF.tensors_from_tflite(blob)
+        assert sorted(got) == sorted(base) and all(np.array_equal(got[k], base[k]) for k in base), seed

@@ -227,8 +227,10 @@ def _sweights(w):
     return dict(scale=None, zero_point=None)
 
 
-def write_streaming_mixednet(tensors: dict) -> bytes:
-    """``model_file`` tensor dictionary (fp32 or int8) -> TFL3 bytes of the equivalent streaming graph."""
+def write_streaming_mixednet(tensors: dict, shuffle_seed=None) -> bytes:
+    """``model_file`` tensor dictionary (fp32 or int8) -> TFL3 bytes of the equivalent streaming graph.
+    shuffle_seed: renumber the main subgraph's tensors and the model's buffers at random (the converter's numbering is not
+    this writer's; a reader must follow the dataflow, not the indices)."""
     from microwakeword_b200 import model_file as MF
     arch = MF.Arch.decode(tensors["arch"])
     quant = MF.is_quantized(tensors)
@@ -393,4 +395,24 @@ def write_streaming_mixednet(tensors: dict) -> bytes:
     if quant:
         out = gw.tensor("StatefulPartitionedCall:0", (1, 1), np.uint8, scale=[1.0 / 256.0], zero_point=[0])
         gw.op("QUANTIZE", [prob], [out])
+    if shuffle_seed is not None:
+        rng = np.random.default_rng(shuffle_seed)
+        n = len(gw.tensors)
+        perm = rng.permutation(n)                         # old index i -> new index perm[i]
+        new_tensors = [None] * n
+        for i, t in enumerate(gw.tensors):
+            new_tensors[perm[i]] = t
+        gw.tensors = new_tensors
+        gw.ops = [(name, [int(perm[i]) for i in ins], [int(perm[i]) for i in outs], o) for name, ins, outs, o in gw.ops]
+        t_in, out = int(perm[t_in]), int(perm[out])
+        nb = len(gw.buffers)
+        bperm = np.concatenate([[0], 1 + rng.permutation(nb - 1)]) if nb > 1 else np.arange(nb)      # buffer 0 stays the empty one
+        new_buffers = [None] * nb
+        for i, raw in enumerate(gw.buffers):
+            new_buffers[bperm[i]] = raw
+        gw.buffers = new_buffers
+        for t in gw.tensors:
+            t["buffer"] = int(bperm[t["buffer"]])
+        for t in init_tensors:
+            t["buffer"] = int(bperm[t["buffer"]])
     return gw.serialise([t_in], [out], init=(init_tensors, init_ops))
