@@ -100,6 +100,11 @@ def host_cores():
             facts["cgroup_cpus"] = float(quota) / float(period)
     except (OSError, ValueError):
         pass
+    # threads to use = what the container may actually burn: oversubscribing a 16-CPU quota with 128 threads cost the r01
+    # baseline a third of its throughput
+    if facts.get("cgroup_cpus"):
+        n = min(n, max(int(facts["cgroup_cpus"] + 0.999), 1))
+    facts["threads_used"] = max(n, 1)
     return max(n, 1), facts
 
 
@@ -395,9 +400,20 @@ def run_gpu(args):
         sh.reset()
         ingest_step()
         eng.reset()
-        same = torch.equal(eng.predict_clip(audio), probs[:, :FRAMES_PER_STEP // 3] if probs.shape[1] > FRAMES_PER_STEP // 3 else probs)
-        same_t = torch.tensor([1 if same else 0], dtype=torch.int32, device=device)
-        dist.all_reduce(same_t, op=dist.ReduceOp.MIN)
+        resident = eng.predict_clip(audio)
+        pulled = probs[:, :resident.shape[1]]
+        same = torch.equal(resident, pulled)
+        # the block this rank pulled is the audio it synthesised itself (same seed, generated on another GPU of the same kind)
+        mine = torch.empty_like(audio)
+        lib_mod.check(None, lib_mod.lib().mww_copy_async(mine.data_ptr(), ingest.block_ptr(sh.start), S * SAMPLES_PER_STEP * 2,
+                                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        audio_same = torch.equal(mine, audio)
+        diag = torch.tensor([1 if same else 0, 1 if audio_same else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(diag, op=dist.ReduceOp.MIN)
+        max_diff = torch.tensor([float((resident - pulled).abs().max().item())], dtype=torch.float64, device=device)
+        dist.all_reduce(max_diff, op=dist.ReduceOp.MAX)
+        same_t = diag[:1]
+        del mine
         eng.reset()
 
         def nccl_serial():
@@ -417,6 +433,8 @@ def run_gpu(args):
                             "note": "torch.distributed scatter of int16 audio from rank 0, compute, gather of float32 scores (NCCL), serialised"},
             "probs_checksum_rank0_block": ingest_checksum,
             "every_rank_block_equals_resident_path": bool(int(same_t.item()) == 1),
+            "every_rank_pulled_audio_equals_own_synthesis": bool(int(diag[1].item()) == 1),
+            "max_abs_prob_difference_to_resident_path": float(max_diff.item()),
         }
         torch.cuda.synchronize()
         barrier()
@@ -569,6 +587,11 @@ def run_gpu(args):
 
 
 def main():
+    # libraries print to stdout on their own (NCCL's version banner, for one): keep the real stdout for the ONE JSON line and
+    # send everything else to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -56,7 +56,7 @@ nn_f32_live_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict_
 }
 
 // v2 (mww_nn_live.cuh "warp-specialised live step"): threads 0..255 = layer chain, 256..767 = ring streamers
-constexpr int kBarChain = 1, kBarFull0 = 2, kBarEmpty0 = 4;         // named barriers: full / empty come in pairs (buffer 0, 1)
+constexpr int kBarChain = 1, kBarFull0 = 2, kBarEmpty0 = 4, kBarAEmpty = 6;   // named barriers: full / empty come in pairs (buffer 0, 1)
 __global__ void __launch_bounds__(kLive2Threads, 1)
 nn_f32_live2_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict__ pend, int n_pend, const void *__restrict__ rows,
                     long long rows_stream_stride_bytes, int rows_are_f32, float *__restrict__ probs, long long probs_stride,
@@ -72,42 +72,43 @@ nn_f32_live2_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict
     live2_stage_chain_tables(tid, kLive2Threads, sm, W);
     __syncthreads();
     const int n_groups = (n_streams + kLiveStreams - 1) / kLiveStreams;
+    LiveInput in;
+    in.state = state; in.pend = pend; in.n_pend = n_pend; in.rows = rows;
+    in.rows_stream_stride_bytes = rows_stream_stride_bytes; in.rows_are_f32 = rows_are_f32;
     if (tid >= kLive2ChainThreads) {
-        // ---- streamers: P of group k into buffer k & 1, at most two groups ahead of the chain ----
+        // ---- streamers: P of group k into buffer k & 1 (at most two groups ahead of the chain), then the group's first-conv
+        // window into A as soon as the chain's first conv of the previous group has let go of it ----
         const int st = tid - kLive2ChainThreads;
         int k = 0;
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++k) {
             const int buf = k & 1;
-            if (k >= 2) bar_sync(kBarEmpty0 + buf, kLive2Threads);                  // the chain is done with this buffer
+            if (k >= 2) bar_sync(kBarEmpty0 + buf, kLive2Threads);                  // the chain is done with this P buffer
             const long long s0 = (long long)g * kLiveStreams;
-            // the chain reads this group's first-conv window one group from now: ask the L2 for it (no registers, no wait)
-            if (st < kLiveThreads && debug_mode != 1)
-                live_prefetch_next_window(st, state, pend, rows, rows_stream_stride_bytes, rows_are_f32 ? 480u : 240u, s0, n_streams);
-            if (debug_mode != 1) live2_stream_group(st, W, state, s0, min(kLiveStreams, n_streams - (int)s0), heads, sm + kLive2OffP + buf * kLive2PFloats);
+            const int n_valid = min(kLiveStreams, n_streams - (int)s0);
+            if (debug_mode != 1) live2_stream_group(st, W, state, s0, n_valid, heads, sm + kLive2OffP + buf * kLive2PFloats);
+            if (k >= 1) bar_sync(kBarAEmpty, kLive2Threads);                        // first conv + tail of group k - 1 have read A
+            if (debug_mode != 1) live2_build_a<kLive2StreamThreads>(st, sm, in, s0, n_valid);
             bar_arrive(kBarFull0 + buf, kLive2Threads);
         }
         return;
     }
-    // ---- chain ----
-    LiveInput in;
-    in.state = state; in.pend = pend; in.n_pend = n_pend; in.rows = rows;
-    in.rows_stream_stride_bytes = rows_stream_stride_bytes; in.rows_are_f32 = rows_are_f32;
+    // ---- chain: shared memory in, ring rows / scores out; no global load on its critical path ----
     int k = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++k) {
         const int buf = k & 1;
         const float *p_buf = sm + kLive2OffP + buf * kLive2PFloats;
         const long long s0 = (long long)g * kLiveStreams;
         const int n_valid = min(kLiveStreams, n_streams - (int)s0);
+        bar_sync(kBarFull0 + buf, kLive2Threads);                                   // P and A of this group are complete
         if (debug_mode == 2) {
-            bar_sync(kBarFull0 + buf, kLive2Threads);
+            bar_arrive(kBarAEmpty, kLive2Threads);
             bar_arrive(kBarEmpty0 + buf, kLive2Threads);
             continue;
         }
-        live2_build_a(tid, sm, in, s0, n_valid);
-        bar_sync(kBarChain, kLive2ChainThreads);
         live_first_conv_mma(tid, sm, sm + kLive2OffW0, kLive2W0Pitch);
-        bar_sync(kBarFull0 + buf, kLive2Threads);                                   // P of this group is complete (and H is written)
-        live2_write_tail(tid, sm, in, state, pend, s0, n_valid);                    // A is dead: new first-conv ring + pending rows
+        bar_sync(kBarChain, kLive2ChainThreads);                                    // H complete, every warp is done reading A as an operand
+        live2_write_tail(tid, sm, in, state, pend, s0, n_valid);                    // new first-conv ring + pending rows, from A
+        bar_arrive(kBarAEmpty, kLive2Threads);
         live2_dw_from_p<0>(tid, sm, state, s0, n_valid, heads.h[0], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
         live_pointwise_mma<0, true>(tid, sm, W); bar_sync(kBarChain, kLive2ChainThreads);
         live2_dw_from_p<1>(tid, sm, state, s0, n_valid, heads.h[1], p_buf); bar_sync(kBarChain, kLive2ChainThreads);
@@ -120,7 +121,7 @@ nn_f32_live2_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict
         bar_arrive(kBarEmpty0 + buf, kLive2Threads);                                // last read of this P buffer
         bar_sync(kBarChain, kLive2ChainThreads);
         live_head_finish_b(tid, sm, sm[kLive2OffSmall + kLive2SmallHeadBias], s0, n_valid, probs, probs_stride);
-        bar_sync(kBarChain, kLive2ChainThreads);                                    // D / A are rewritten by the next group
+        bar_sync(kBarChain, kLive2ChainThreads);                                    // D is rewritten by the next group
     }
 }
 

@@ -400,14 +400,17 @@ MWW_HD void live2_stream_group(int st, const NnWeightsF32 &W, const float *state
 
 // chain: first-conv window without per-thread copies kept across the barrier (the new first-conv ring is read back from
 // the A operand, the new pending rows from the caller's rows)
-template <bool F32ROWS>
+// NT = threads that share the work (512: the streamers build the window one group ahead of the chain, r02: with the chain
+// loading it itself, 64 % of the chain's stall samples sat in this phase -- its loads queue behind the streamers' in the LSU)
+template <bool F32ROWS, int NT>
 MWW_HD void live2_build_a_t(int tid, float *sm, const LiveInput &in, long long s0, int n_valid) {
+    constexpr int QPW = kLiveStreams / (NT / 32);                  // streams per warp
     const int warp = tid >> 5;
     const unsigned lane = (unsigned)(tid & 31), np40 = (unsigned)in.n_pend * (unsigned)kNumChannels;
     float *a = sm + kLiveOffA;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int sl = warp * 4 + q;
+    for (int q = 0; q < QPW; ++q) {
+        const int sl = warp * QPW + q;
         const bool ok = sl < n_valid;
         const size_t su = (size_t)(s0 + (ok ? sl : 0));
         const float *st = in.state + su * (size_t)kStateFloats;
@@ -431,12 +434,15 @@ MWW_HD void live2_build_a_t(int tid, float *sm, const LiveInput &in, long long s
         }
     }
 }
+template <int NT>
 MWW_HD void live2_build_a(int tid, float *sm, const LiveInput &in, long long s0, int n_valid) {
-    if (in.rows_are_f32) live2_build_a_t<true>(tid, sm, in, s0, n_valid);
-    else live2_build_a_t<false>(tid, sm, in, s0, n_valid);
+    if (in.rows_are_f32) live2_build_a_t<true, NT>(tid, sm, in, s0, n_valid);
+    else live2_build_a_t<false, NT>(tid, sm, in, s0, n_valid);
 }
-// after the first conv has consumed A (and a barrier): new first-conv ring = window[120:200], new pending rows = the
-// call's last n_pend rows.  Thread -> (stream = tid / 8, 8 threads per stream)
+// after the first conv has consumed A (and a barrier): new first-conv ring = window[120:200], read back from the A operand;
+// new pending rows = the call's last n_pend rows, which are NOT part of the window -- read from the caller's rows (only when
+// rows are pending at all; the steady state of hop-aligned 30 ms steps has none, so the chain then issues no global load).
+// Thread -> (stream = tid / 8, 8 threads per stream)
 MWW_HD void live2_write_tail(int tid, const float *sm, const LiveInput &in, float *state, float *pend, long long s0, int n_valid) {
     const int sl = tid >> 3, part = tid & 7;
     if (sl >= n_valid) return;

@@ -387,7 +387,7 @@ extern "C" int emul_nn_f32_live2(const float *const *wp, float *state, float *pe
         const int n_valid = n_streams - (int)s0 < kLiveStreams ? n_streams - (int)s0 : kLiveStreams;
         float *p_buf = sm + kLive2OffP + (g & 1) * kLive2PFloats;
         STREAM(live2_stream_group(st, W, state, s0, n_valid, heads, p_buf));
-        CHAIN(live2_build_a(tid, sm, in, s0, n_valid));
+        STREAM(live2_build_a<kLive2StreamThreads>(st, sm, in, s0, n_valid));
         emul_live_first_conv(sm, sm + kLive2OffW0, kLive2W0Pitch);
         CHAIN(live2_write_tail(tid, sm, in, state, pend, s0, n_valid));
         CHAIN(live2_dw_from_p<0>(tid, sm, state, s0, n_valid, heads.h[0], p_buf)); emul_live_pointwise<0, true>(sm, W);
