@@ -18,6 +18,7 @@
 #include "../../include/mww.h"
 #include "mww_kernels.h"
 #include "mww_nn_i8_prep.h"
+#include "mww_nn_tc.h"
 
 using namespace mww;
 
@@ -65,6 +66,8 @@ struct mww_handle {
     // weights
     uint8_t *d_weights = nullptr;
     NnWeightsF32 W;
+    TcWeights TW{};                 // fp32 okay_nabu: pre-split weights for the tcgen05 clip kernel (mww_nn_tc.cu)
+    bool no_tc = false;             // MWW_NO_TC: keep the mma.sync clip kernel (A/B measurements)
     NnWeightsI8 Wq;
     float in_scale = 0.f, out_scale = 0.f;
     int in_zp = 0, out_zp = 0;
@@ -311,6 +314,16 @@ int run_nn_tile(mww_t *h, int first, int n, const void *d_rows, int row_type, lo
         h->launches += 1;
         return MWW_OK;
     }
+    if (!h->no_tc && row_type == MWW_ROWS_U16 && (h->n_pend + n_rows) / 3 >= kTcMinSteps && reinterpret_cast<uintptr_t>(d_rows) % 16 == 0 &&
+        (rows_stream_stride_rows * kNumChannels * 2) % 16 == 0) {
+        // long calls on raw frontend rows: time is the M = 128 dimension of tcgen05.mma (mww_nn_tc.cu)
+        CU(h, launch_nn_f32_tc(h->W, h->TW, static_cast<float *>(h->d_nn_state) + (size_t)first * h->state_elems,
+                               static_cast<float *>(h->d_pend) + (size_t)first * h->pend_cap * kNumChannels, h->n_pend,
+                               static_cast<const uint16_t *>(d_rows), rows_stream_stride_rows * kNumChannels, n_rows, d_probs, probs_stride, n,
+                               h->sm_count, st));
+        h->launches += 1;
+        return MWW_OK;
+    }
     CU(h, launch_nn_f32(h->W, static_cast<float *>(h->d_nn_state) + (size_t)first * h->state_elems,
                         static_cast<float *>(h->d_pend) + (size_t)first * h->pend_cap * kNumChannels, h->n_pend, d_rows,
                         rows_stream_stride_rows * kNumChannels * (long long)rb, n_rows, row_type == MWW_ROWS_F32, d_probs, probs_stride,
@@ -472,6 +485,34 @@ int upload_weights(mww_t *h, const uint8_t *blob, size_t n) {
         }
         if ((rc = get("head/w", 0, 17 * 64, (const void **)&h->W.head_w))) return rc;
         if ((rc = get("head/b", 0, 1, (const void **)&h->W.head_b))) return rc;
+        {
+            // tensor-core operands: 3xTF32 split + slot layout, once per model (mww_nn_tc.h)
+            Tensor tw0, tpw[4];
+            bool ok = find_tensor(blob, n, "first_conv/w", &tw0);
+            const float *pw_host[4];
+            for (int i = 0; i < 4 && ok; ++i) {
+                snprintf(name, sizeof name, "b%d/pw/w", i);
+                ok = find_tensor(blob, n, name, &tpw[i]);
+                pw_host[i] = reinterpret_cast<const float *>(tpw[i].data);
+            }
+            if (!ok) return fail(h, MWW_EMODEL, "model container: fp32 weights missing");
+            std::vector<float> w0_copy(5 * 40 * 32), pw_copy[4];
+            memcpy(w0_copy.data(), tw0.data, w0_copy.size() * 4);                    // container tensors are not necessarily 4-byte aligned
+            const float *pw_al[4];
+            for (int i = 0; i < 4; ++i) {
+                pw_copy[i].resize((size_t)cin[i] * 64);
+                memcpy(pw_copy[i].data(), pw_host[i], pw_copy[i].size() * 4);
+                pw_al[i] = pw_copy[i].data();
+            }
+            std::vector<unsigned char> tcb;
+            size_t offs[5];
+            build_tc_weights(w0_copy.data(), pw_al, &tcb, offs);
+            const unsigned char *dev_tc = nullptr;
+            if (cur + tcb.size() + 256 > total) return fail(h, MWW_EMODEL, "weight arena too small for the tensor-core operands");
+            if (!upload(h->d_weights, cur, tcb.data(), tcb.size(), &dev_tc, &e)) return cuda_fail(h, e, "weight upload");
+            h->TW.fc = dev_tc + offs[0];
+            for (int i = 0; i < 4; ++i) h->TW.pw[i] = dev_tc + offs[1 + i];
+        }
     } else {
         NnWeightsI8 &Q = h->Wq;
         if ((rc = get("q/first_conv/w", 1, 5 * 40 * 32, (const void **)&Q.w0))) return rc;
@@ -593,6 +634,7 @@ int mww_create(const void *model_blob, size_t n_bytes, int device, int n_streams
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     h->no_live = getenv("MWW_NO_LIVE") != nullptr;
     h->no_fuse = getenv("MWW_NO_FUSE") != nullptr;
+    h->no_tc = getenv("MWW_NO_TC") != nullptr;
     if (const char *mb = getenv("MWW_SCRATCH_MB")) { const long v = atol(mb); if (v > 0) h->scratch_budget = (size_t)v << 20; }
     if (const char *mt = getenv("MWW_MIN_TILE_STREAMS")) { const long v = atol(mt); if (v > 0) h->min_tile_streams = (int)v; }
     h->has_nn = model_blob != nullptr;

@@ -166,7 +166,9 @@ def test_predict_spectrogram_dtypes_and_quirks(torch_cuda):
     a = np.asarray(m.predict_spectrogram(feats)); m.reset()
     b = np.asarray(m.predict_spectrogram(feats.astype(np.float32) * np.float32(0.0390625))); m.reset()
     c = np.asarray(m.predict_spectrogram(feats.astype(np.float64) * 0.0390625)); m.reset()
-    assert len(a) == 30 and np.array_equal(a, b) and np.array_equal(a, c)        # 92 rows -> 30 chunks, 2 rows dropped
+    # 92 rows -> 30 chunks, 2 rows dropped.  uint16 rows take the tcgen05 clip kernel, float rows the mma.sync one: same values up
+    # to the order of fp32 additions inside the two tensor-core paths; float32 and float64 rows are the same path, bit for bit
+    assert len(a) == 30 and np.abs(a - b).max() <= 2e-6 and np.array_equal(b, c)
     assert m.predict_spectrogram(feats[:2]) == []
     # stride 1: overlapping chunks, each is one invoke (inference.py:98-105)
     m1 = Model(os.path.join(GOLDEN, "okay_nabu_synth_f32.mww"), stride=1)

@@ -161,6 +161,120 @@ probe_tcgen05(const float *__restrict__ w /* [N][K] */, const float *__restrict_
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(64));
 }
 
+// ------------------------------------------------------------------------------------------------ tcgen05, SWIZZLE_128B
+// The layout the product kernel uses: K is cut into slots of 32 tf32 = 128 bytes; a slot holds [rows][128 B] with the 16-byte
+// chunks of a row XOR-ed by (row % 8) (the hardware's 128-byte swizzle), so a warp that stores one row -- 32 consecutive k for
+// one time step, which is what a lane-per-channel producer does -- writes 128 contiguous bytes: no bank conflicts, unlike the
+// 8-way conflicts the no-swizzle core-matrix layout gives that access pattern.  Descriptor: layout type 2, stride byte offset
+// 1024 (8 rows), start address advanced by 32 bytes per K = 8 step inside the atom; slot base 1024-byte aligned.
+__host__ __device__ inline uint32_t sw128_off(int r, int kk /* 0..31 inside the slot */) {
+    return (uint32_t)r * 128 + (uint32_t)(((kk >> 2) ^ (r & 7)) << 4) + (uint32_t)(kk & 3) * 4;
+}
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                                      // leading byte offset: unused for swizzled K-major (one atom wide)
+    d |= (uint64_t)(1024 >> 4) << 32;                            // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;                                      // descriptor version 1
+    d |= (uint64_t)2 << 61;                                      // SWIZZLE_128B
+    return d;
+}
+__global__ void __launch_bounds__(kThreads, 1)
+probe_tcgen05_sw128(const float *__restrict__ w, const float *__restrict__ bias, float *__restrict__ out, int tiles_per_cta, int store_all) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // slot s of A: hi plane at s * 32 KB, lo plane at s * 32 KB + 16 KB;  slot s of B: 64 KB + s * 16 KB (+ 8 KB for lo)
+    unsigned char *a_base = smem, *b_base = smem + 65536;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < N * K; e += kThreads) {
+        const int n = e / K, k = e - n * K;
+        float hi, lo;
+        split_tf32(w[e], hi, lo);
+        unsigned char *slot = b_base + (k >> 5) * 16384;
+        *reinterpret_cast<float *>(slot + sw128_off(n, k & 31)) = hi;
+        *reinterpret_cast<float *>(slot + 8192 + sw128_off(n, k & 31)) = lo;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_base_smem)), "r"(64));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+    const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(a_base), b_s = (uint32_t)__cvta_generic_to_shared(b_base);
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&bar);
+    uint32_t phase = 0;
+    for (int it = 0; it < tiles_per_cta; ++it) {
+        const int tile = blockIdx.x * tiles_per_cta + it;
+        // produce with lanes along k (a warp stores whole 128-byte rows): thread -> (k = tid % 64, rows tid / 64 + 2 i)
+        {
+            const int k = tid & 63, r0 = tid >> 6;
+            unsigned char *slot = a_base + (k >> 5) * 32768;
+#pragma unroll 8
+            for (int r = r0; r < M; r += 2) {
+                float hi, lo;
+                split_tf32(a_value(tile, r, k), hi, lo);
+                *reinterpret_cast<float *>(slot + sw128_off(r, k & 31)) = hi;
+                *reinterpret_cast<float *>(slot + 16384 + sw128_off(r, k & 31)) = lo;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+            for (int ks = 0; ks < K / 8; ++ks) {
+                const uint32_t a_hi = a_s + (ks >> 2) * 32768 + (ks & 3) * 32, a_lo = a_hi + 16384;
+                const uint32_t b_hi = b_s + (ks >> 2) * 16384 + (ks & 3) * 32, b_lo = b_hi + 8192;
+                mma_tf32_ss(tmem_d, smem_desc_sw128(a_lo), smem_desc_sw128(b_hi), ks > 0);
+                mma_tf32_ss(tmem_d, smem_desc_sw128(a_hi), smem_desc_sw128(b_lo), 1);
+                mma_tf32_ss(tmem_d, smem_desc_sw128(a_hi), smem_desc_sw128(b_hi), 1);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_s) : "memory");
+        }
+        {
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                             : "=r"(done) : "r"(bar_s), "r"(phase) : "memory");
+            }
+            phase ^= 1;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        float *o = out + ((size_t)(store_all ? tile : blockIdx.x) * M + tid) * N;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 32);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+                         "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+                           "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                           "=r"(v[30]), "=r"(v[31])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 r4;
+                r4.x = fmaxf(__uint_as_float(v[j]) + bias[half * 32 + j], 0.f); r4.y = fmaxf(__uint_as_float(v[j + 1]) + bias[half * 32 + j + 1], 0.f);
+                r4.z = fmaxf(__uint_as_float(v[j + 2]) + bias[half * 32 + j + 2], 0.f); r4.w = fmaxf(__uint_as_float(v[j + 3]) + bias[half * 32 + j + 3], 0.f);
+                *reinterpret_cast<float4 *>(o + half * 32 + j) = r4;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(64));
+}
+
 // ------------------------------------------------------------------------------------------------ mma.sync variant
 constexpr int kPitchA = 136;      // [k][t] pitch: 136 = 8 (mod 32): conflict-free A fragments
 constexpr int kPitchB = 72;       // [k][n] pitch
@@ -237,12 +351,15 @@ int main() {
     const int smem_tc = (2 * M * K + 2 * N * K) * 4 + 1024, smem_mma = (K * kPitchA + K * kPitchB) * 4;
     CK(cudaFuncSetAttribute(probe_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
     CK(cudaFuncSetAttribute(probe_mma_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mma));
+    CK(cudaFuncSetAttribute(probe_tcgen05_sw128, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
+    const char *names[3] = {"tcgen05 kind::tf32 (no swizzle)", "mma.sync m16n8k8", "tcgen05 kind::tf32 (SWIZZLE_128B, K slots of 32)"};
     // ---- correctness: 2 tiles per CTA, every tile stored, against an fp64 reference
     std::vector<float> got((size_t)check_tiles * M * N);
-    for (int variant = 0; variant < 2; ++variant) {
+    for (int variant = 0; variant < 3; ++variant) {
         CK(cudaMemset(d_out, 0, got.size() * 4));
         if (variant == 0) probe_tcgen05<<<sms, kThreads, smem_tc>>>(d_w, d_b, d_out, 2, 1);
-        else probe_mma_sync<<<sms, kThreads, smem_mma>>>(d_w, d_b, d_out, 2, 1);
+        else if (variant == 1) probe_mma_sync<<<sms, kThreads, smem_mma>>>(d_w, d_b, d_out, 2, 1);
+        else probe_tcgen05_sw128<<<sms, kThreads, smem_tc>>>(d_w, d_b, d_out, 2, 1);
         CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(got.data(), d_out, got.size() * 4, cudaMemcpyDeviceToHost));
         double worst = 0;
@@ -254,24 +371,25 @@ int main() {
                     const double want = acc > 0 ? acc : 0;
                     worst = fmax(worst, fabs(want - (double)got[((size_t)tile * M + r) * N + n]));
                 }
-        printf("%s: max |error| vs fp64 reference %.3g (3xTF32 bound ~1e-5)\n", variant == 0 ? "tcgen05 kind::tf32" : "mma.sync m16n8k8", worst);
+        printf("%s: max |error| vs fp64 reference %.3g (3xTF32 bound ~1e-5)\n", names[variant], worst);
     }
     // ---- timing: T tiles per CTA, only the last tile of a CTA is kept (stores stay in L2), CUDA events
     const int T = 2000;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int variant = 0; variant < 2; ++variant) {
+    for (int variant = 0; variant < 3; ++variant) {
         for (int rep = 0; rep < 2; ++rep) {
             CK(cudaEventRecord(e0));
             if (variant == 0) probe_tcgen05<<<sms, kThreads, smem_tc>>>(d_w, d_b, d_out, T, 0);
-            else probe_mma_sync<<<sms, kThreads, smem_mma>>>(d_w, d_b, d_out, T, 0);
+            else if (variant == 1) probe_mma_sync<<<sms, kThreads, smem_mma>>>(d_w, d_b, d_out, T, 0);
+            else probe_tcgen05_sw128<<<sms, kThreads, smem_tc>>>(d_w, d_b, d_out, T, 0);
             CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         }
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, e0, e1));
         const double us_per_tile = ms * 1e3 / T;
         printf("%s: %.3f us per 128x64x64 3xTF32 tile per CTA (1 CTA/SM, %d SMs, produce + contract + epilogue); %.1f TFLOP/s chip-wide (3 x 2MNK)\n",
-               variant == 0 ? "tcgen05 kind::tf32" : "mma.sync m16n8k8", us_per_tile, sms, 3.0 * 2 * M * N * K * sms / (us_per_tile * 1e-6) / 1e12);
+               names[variant], us_per_tile, sms, 3.0 * 2 * M * N * K * sms / (us_per_tile * 1e-6) / 1e12);
     }
     return 0;
 }
