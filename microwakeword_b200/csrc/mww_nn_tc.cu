@@ -220,10 +220,14 @@ __device__ __forceinline__ void epilogue(int tid, int n, uint32_t tmem_d, float 
     tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * half), v);
     if (t < n) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int o = 32 * half + j;
-            const float r = v[j] + (bias ? bias[o] : 0.f);
-            x[o * kLdx + HIST + t] = r > 0.f ? r : 0.f;
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = bias ? __ldg(reinterpret_cast<const float4 *>(bias + 32 * half + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float r = v[j + q] + bb[q];
+                x[(32 * half + j + q) * kLdx + HIST + t] = r > 0.f ? r : 0.f;
+            }
         }
     }
 }
@@ -340,7 +344,14 @@ nn_f32_clip_tc_kernel(NnWeightsF32 W, TcWeights TW, float *__restrict__ state, f
                 const int kk = tid & 31, k = 32 * slot + kk;
                 const int j = k / kNumChannels, f = k - j * kNumChannels;
                 if (k < 200) {                                             // slot 6 only has the K = 8 step 192..199
-                    for (int t = tid >> 5; t < ((n + 7) & ~7); t += 8) store_split(a_base, t, kk, t < n ? feature(vr0 + 3 * t + j, f) : 0.f);
+                    // steps 0 and 1 of a call's first chunk can touch the first-conv ring / the pending rows; every other element is a raw
+                    // uint16 row of this call at an index affine in t: one 16-bit load, convert, scale, split, two stores
+                    const int t_pad = (n + 7) & ~7;
+                    int t = tid >> 5;
+                    for (; t < 2 && t < t_pad; t += 8) store_split(a_base, t, kk, t < n ? feature(vr0 + 3 * t + j, f) : 0.f);
+                    const uint16_t *src = feat + (vr0 + j - n_pend - row_lo) * kNumChannels + f;
+                    for (; t < n; t += 8) store_split(a_base, t, kk, (float)src[3 * kNumChannels * t] * kFeatureScale);
+                    for (; t < t_pad; t += 8) store_split(a_base, t, kk, 0.f);
                 }
                 contract_slot(slot, 32, slot < 6 ? 4 : 1, slot == 0);
             }
@@ -373,21 +384,43 @@ nn_f32_clip_tc_kernel(NnWeightsF32 W, TcWeights TW, float *__restrict__ state, f
             cp_wait<0>();
             // ---- head: 17-row window over the last block's outputs, dense(1), sigmoid ----
             {
-                // thread -> (step t = tid % 128, channel half tid / 128); a warp reads 32 consecutive steps of one channel (conflict-free),
-                // the weight is the same for the whole warp (one broadcast load)
-                const int t = tid & 127, c0 = 32 * (tid >> 7);
-                float acc = 0.f;
-                if (t < n) {
-                    for (int c = c0; c < c0 + 32; ++c) {
-                        const float *xc = x + c * kLdx + t;
+                // thread -> (channel c = tid % 64, 32-step segment tid / 64): 17 taps in registers, X values reused along time; the
+                // per-channel partial sums go through the idle operand buffers as [128 steps][pitch 65] (conflict-free both ways: lanes
+                // are channels on the way in, steps on the way out), then one thread per step adds its 64
+                float *part = reinterpret_cast<float *>(a_base);
+                constexpr int kPp = 65;
+                static_assert(128 * kPp * 4 <= 32768 + 2 * kBSlotBytes, "partial sums fit the A slot + B buffers");
+                const int c = tid & 63, t0 = 32 * (tid >> 6);
+                if (t0 < n) {
+                    float w[17];
 #pragma unroll
-                        for (int r = 0; r < 17; ++r) acc = fmaf(__ldg(W.head_w + r * 64 + c), xc[r], acc);
+                    for (int r = 0; r < 17; ++r) w[r] = W.head_w[r * 64 + c];
+                    const float *xc = x + c * kLdx + t0;
+#pragma unroll 1
+                    for (int tb = 0; tb < 32; tb += 8) {
+                        float acc[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8 + 16; ++i) {
+                            const float xv = xc[tb + i];
+#pragma unroll
+                            for (int tt = 0; tt < 8; ++tt) {
+                                const int r = i - tt;
+                                if (r >= 0 && r < 17) acc[tt] = fmaf(w[r], xv, acc[tt]);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) part[(t0 + tb + i) * kPp + c] = acc[i];
                     }
                 }
-                float *part = reinterpret_cast<float *>(a_base);                // the A slot is idle: [2][128] partial sums
-                part[tid] = acc;
                 __syncthreads();
-                if (tid < n) probs[s * probs_stream_stride + step0 + tid] = nn_sigmoid(part[tid] + part[128 + tid] + W.head_b[0]);
+                if (tid < n) {
+                    float acc = 0.f;
+#pragma unroll 8
+                    for (int cc = 0; cc < 64; ++cc) acc += part[tid * kPp + cc];
+                    probs[s * probs_stream_stride + step0 + tid] = nn_sigmoid(acc + W.head_b[0]);
+                }
             }
             x_to_ring<4>(tid, x, my_state, n);
             __syncthreads();                                        // X (and the feature alias) are rewritten by the next chunk
