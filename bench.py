@@ -381,6 +381,18 @@ def run_gpu(args):
         l0 = sh.engine.launch_count
         ms_per_step = timed(ingest_step, args.steps)
         launches = sh.engine.launch_count - l0
+        # who is the slow one: every rank's own device time for the same steps (the timed value is the max)
+        barrier()
+        r0e, r1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0e.record()
+        for _ in range(args.steps):
+            ingest_step()
+        r1e.record()
+        torch.cuda.synchronize()
+        mine_ms = torch.tensor([r0e.elapsed_time(r1e) / args.steps], dtype=torch.float64, device=device)
+        all_ms = [torch.zeros_like(mine_ms) for _ in range(world)]
+        dist.all_gather(all_ms, mine_ms)
+        per_rank_ms = [float(t.item()) for t in all_ms]
         ingest_checksum = float(probs[:, :100].double().sum().item())
         # side legs, for the record: (i) where the time goes: the pull alone (copy engine, no kernels);
         # (ii) the plain serialised NCCL scatter -> compute -> gather
@@ -425,7 +437,7 @@ def run_gpu(args):
             "how": "audio for all %d streams in rank 0's HBM; every rank pulls its 65 536-stream block tile by tile with its own copy engine over "
                    "NVLink peer access (CUDA IPC) while the previous tile computes (mww_predict_clip_remote), scores gathered to rank 0 with NCCL; "
                    "a tiny all-reduce per step orders the pulls after the ingest rank's writes" % total,
-            "tiles_per_rank": args.tiles or 16,
+            "tiles_per_rank": args.tiles or 16, "per_rank_ms_per_step": per_rank_ms,
             "nvlink_bytes_out_of_rank0_per_step": S * SAMPLES_PER_STEP * 2 * (world - 1),
             "egress_floor_ms": pull_ms, "pull_only_gbs_out_of_rank0": S * SAMPLES_PER_STEP * 2 * (world - 1) / (pull_ms / 1e3) / 1e9,
             "value_presharded": frames_per_step_all / (ms_resident / 1e3), "ms_per_step_presharded": ms_resident,

@@ -68,6 +68,7 @@ struct mww_handle {
     NnWeightsF32 W;
     TcWeights TW{};                 // fp32 okay_nabu: pre-split weights for the tcgen05 clip kernel (mww_nn_tc.cu)
     bool no_tc = false;             // MWW_NO_TC: keep the mma.sync clip kernel (A/B measurements)
+    int live_variant = 1;           // MWW_LIVE_V2: the warp-specialised live kernel (mww_nn_live.cuh, the r02 measurement instrument)
     NnWeightsI8 Wq;
     float in_scale = 0.f, out_scale = 0.f;
     int in_zp = 0, out_zp = 0;
@@ -310,7 +311,7 @@ int run_nn_tile(mww_t *h, int first, int n, const void *d_rows, int row_type, lo
         CU(h, launch_nn_f32_live(h->W, static_cast<float *>(h->d_nn_state) + (size_t)first * h->state_elems,
                                  static_cast<float *>(h->d_pend) + (size_t)first * h->pend_cap * kNumChannels, h->n_pend, d_rows,
                                  rows_stream_stride_rows * kNumChannels * (long long)rb, row_type == MWW_ROWS_F32, d_probs, probs_stride, n,
-                                 h->live_heads, h->sm_count, st));
+                                 h->live_heads, h->sm_count, h->live_variant, st));
         h->launches += 1;
         return MWW_OK;
     }
@@ -635,6 +636,7 @@ int mww_create(const void *model_blob, size_t n_bytes, int device, int n_streams
     h->no_live = getenv("MWW_NO_LIVE") != nullptr;
     h->no_fuse = getenv("MWW_NO_FUSE") != nullptr;
     h->no_tc = getenv("MWW_NO_TC") != nullptr;
+    h->live_variant = getenv("MWW_LIVE_V2") != nullptr ? 2 : 1;
     if (const char *mb = getenv("MWW_SCRATCH_MB")) { const long v = atol(mb); if (v > 0) h->scratch_budget = (size_t)v << 20; }
     if (const char *mt = getenv("MWW_MIN_TILE_STREAMS")) { const long v = atol(mt); if (v > 0) h->min_tile_streams = (int)v; }
     h->has_nn = model_blob != nullptr;

@@ -65,7 +65,7 @@ namespace mww {
 // the caller advances every head by one (mod its ring length) after the launch.
 cudaError_t launch_nn_f32_live(const NnWeightsF32 &W, float *state, float *pend, int n_pend, const void *rows,
                                long long rows_stream_stride_bytes, int rows_are_f32, float *probs, long long probs_stride,
-                               int n_streams, const LiveHeads &heads, int sm_count, cudaStream_t st);
+                               int n_streams, const LiveHeads &heads, int sm_count, int variant, cudaStream_t st);
 // rotate every ring of every stream back to the canonical oldest-first layout (no-op rings with head 0 are skipped)
 cudaError_t launch_nn_live_canonicalise(float *state, int n_streams, const LiveHeads &heads, cudaStream_t st);
 // int8 live-step path (mww_nn_i8_live.cuh); rows must be 16-byte aligned with a 16-byte-multiple stream stride

@@ -127,10 +127,10 @@ nn_f32_live2_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict
 
 cudaError_t launch_nn_f32_live(const NnWeightsF32 &W, float *state, float *pend, int n_pend, const void *rows,
                                long long rows_stream_stride_bytes, int rows_are_f32, float *probs, long long probs_stride,
-                               int n_streams, const LiveHeads &heads, int sm_count, cudaStream_t st) {
+                               int n_streams, const LiveHeads &heads, int sm_count, int variant, cudaStream_t st) {
     if (n_streams <= 0) return cudaSuccess;
     static bool attr_done[64] = {};
-    static const bool v1 = getenv("MWW_LIVE_V1") != nullptr;        // A/B switch kept for the r02 measurement
+    const bool v1 = variant != 2;       // 2 = the warp-specialised kernel (MWW_LIVE_V2 at mww_create): the r02 measurement instrument, same speed
     static const int debug_mode = getenv("MWW_LIVE_MODE") ? atoi(getenv("MWW_LIVE_MODE")) : 0;
     if (first_launch_on_this_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(nn_f32_live_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLiveSmemBytes);
