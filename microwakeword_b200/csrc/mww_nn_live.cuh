@@ -306,19 +306,21 @@ constexpr int kLive2OffP = kLiveSmemFloats;                   // the chain's reg
 // L2 / L1, every dependent global access of the latency-bound chain slowed down 2-3x while the streamers saturated the memory
 // system.  (The streamers' old-row taps moved the other way, to L1-cached global reads, to make room.)
 constexpr int kLive2W0Pitch = 40;                             // first-conv weights [200][40]: pitch = 8 (mod 32) like kWLd
-constexpr int kLive2OffW0 = kLive2OffP + 2 * kLive2PFloats;
-constexpr int kLive2OffPw0 = kLive2OffW0 + 200 * kLive2W0Pitch;
+constexpr int kLive2OffPw0 = kLive2OffP + 2 * kLive2PFloats;
 constexpr int kLive2OffSmall = kLive2OffPw0 + 32 * kWLd;      // newest taps [288], depthwise... 1x1 biases [4][64], head bias
 constexpr int kLive2SmallTaps = 0, kLive2SmallPwBias = kLive2Cols, kLive2SmallHeadBias = kLive2Cols + 256;
-constexpr int kLive2SmemFloats = kLive2OffSmall + kLive2Cols + 256 + 8;
-constexpr int kLive2SmemBytes = kLive2SmemFloats * 4;         // 227.2 KB of the 227 KB (232 448 B) a CTA may have
+constexpr int kLive2OffW0 = kLive2OffSmall + kLive2Cols + 256 + 32;   // last: v3 puts its bulk-copy stages here instead (128-byte aligned)
+constexpr int kLive2SmemFloats = kLive2OffW0 + 200 * kLive2W0Pitch;
+constexpr int kLive2SmemBytes = kLive2SmemFloats * 4;         // 227.3 KB of the 227 KB (232 448 B) a CTA may have
+static_assert((kLive2OffW0 * 4) % 128 == 0, "stage alignment");
 static_assert(kLive2SmemBytes <= 232448, "shared memory per CTA");
 MWW_HD constexpr int live2_col_base(int i) { return i == 0 ? 0 : 32 + 64 * (i - 1); }
 MWW_HD constexpr int live2_wrot_base(int i) { return i == 0 ? 0 : (i == 1 ? 128 : (i == 2 ? 128 + 640 : (i == 3 ? 128 + 640 + 896 : 128 + 640 + 896 + 1408))); }
 
 // once per CTA: the chain's constants
-MWW_HD void live2_stage_chain_tables(int tid, int n_threads, float *sm, const NnWeightsF32 &W) {
-    for (int e = tid; e < 200 * 32; e += n_threads) sm[kLive2OffW0 + (e >> 5) * kLive2W0Pitch + (e & 31)] = W.w0[e];
+MWW_HD void live2_stage_chain_tables(int tid, int n_threads, float *sm, const NnWeightsF32 &W, bool with_w0 = true) {
+    if (with_w0)
+        for (int e = tid; e < 200 * 32; e += n_threads) sm[kLive2OffW0 + (e >> 5) * kLive2W0Pitch + (e & 31)] = W.w0[e];
     for (int e = tid; e < 32 * 64; e += n_threads) sm[kLive2OffPw0 + (e >> 6) * kWLd + (e & 63)] = W.pw_w[0][e];
     float *small = sm + kLive2OffSmall;
     for (int e = tid; e < kLive2Cols; e += n_threads) {        // newest tap (row R of the [R + 1][C] table) of every ring column
@@ -439,6 +441,80 @@ MWW_HD void live2_build_a(int tid, float *sm, const LiveInput &in, long long s0,
     if (in.rows_are_f32) live2_build_a_t<true, NT>(tid, sm, in, s0, n_valid);
     else live2_build_a_t<false, NT>(tid, sm, in, s0, n_valid);
 }
+// v3: the same window in two halves -- the loads of group k + 1 are issued (into registers) right after group k's window went
+// to shared memory, i.e. a whole chain period before they are needed: under the bulk copies' HBM load a round of global
+// loads costs microseconds, and A is free only after the first conv of the previous group (r02 ncu: with two window warps
+// loading on demand the chain spent 33 % of its samples waiting for A).  The same warps also move the call's last n_pend
+// rows into the pending-row buffer (v1 / v2: the chain does, with loads on its critical path): a stream's old pending rows
+// are read (they are part of the window) and its new ones written by the same warp, separated by __syncwarp.
+// 128 threads: warp w owns streams 8 w .. 8 w + 7, lane l the window elements l, l + 32, ...
+constexpr int kLive3AStreamsPerWarp = 8;
+template <bool F32ROWS>
+MWW_HD void live3_window_load_t(int at, const LiveInput &in, float *pend_out, long long s0, int n_valid, float (&v)[kLive3AStreamsPerWarp][7]) {
+    const int warp = at >> 5;
+    const unsigned lane = (unsigned)(at & 31), np40 = (unsigned)in.n_pend * (unsigned)kNumChannels;
+#pragma unroll
+    for (int q = 0; q < kLive3AStreamsPerWarp; ++q) {
+        const int sl = warp * kLive3AStreamsPerWarp + q;
+        const bool ok = sl < n_valid;
+        const size_t su = (size_t)(s0 + (ok ? sl : 0));
+        const float *st = in.state + su * (size_t)kStateFloats;
+        const float *pd = in.pend + su * (size_t)(2 * kNumChannels);
+        const char *rb = static_cast<const char *>(in.rows) + su * (size_t)in.rows_stream_stride_bytes;
+        const float *rf = reinterpret_cast<const float *>(rb);
+        const uint16_t *r16 = reinterpret_cast<const uint16_t *>(rb);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const unsigned k = lane + 32u * (unsigned)i, kk = k < 199u ? k : 199u;
+            const bool in_ring = kk < 80u, in_pend = !in_ring && kk < 80u + np40, is_row = !in_ring && !in_pend;
+            const unsigned e = is_row ? kk - 80u - np40 : 0u;
+            const float *fp = in_ring ? st + kk : (in_pend ? pd + (kk - 80u) : (F32ROWS ? rf + e : st));
+            float x = *fp;
+            if (!F32ROWS) {
+                const float u = (float)r16[e] * kFeatureScale;
+                x = is_row ? u : x;
+            }
+            v[q][i] = (ok && k < 200u) ? x : 0.f;
+        }
+    }
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+    if (np40 != 0u) {
+        for (int q = 0; q < kLive3AStreamsPerWarp; ++q) {
+            const int sl = warp * kLive3AStreamsPerWarp + q;
+            if (sl >= n_valid) break;
+            const size_t su = (size_t)(s0 + sl);
+            for (unsigned e = lane; e < np40; e += 32u)
+                pend_out[su * (size_t)(2 * kNumChannels) + e] = live_row_value(in, su, (unsigned)(3 * kNumChannels) - np40 + e);
+        }
+    }
+}
+MWW_HD void live3_window_load(int at, const LiveInput &in, float *pend_out, long long s0, int n_valid, float (&v)[kLive3AStreamsPerWarp][7]) {
+    if (in.rows_are_f32) live3_window_load_t<true>(at, in, pend_out, s0, n_valid, v);
+    else live3_window_load_t<false>(at, in, pend_out, s0, n_valid, v);
+}
+MWW_HD void live3_window_store(int at, float *sm, const float (&v)[kLive3AStreamsPerWarp][7]) {
+    const int warp = at >> 5;
+    const unsigned lane = (unsigned)(at & 31);
+    float *a = sm + kLiveOffA;
+#pragma unroll
+    for (int q = 0; q < kLive3AStreamsPerWarp; ++q) {
+        const int sl = warp * kLive3AStreamsPerWarp + q;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const unsigned k = lane + 32u * (unsigned)i;
+            if (k < 200u) a[k * (unsigned)kLivePitch + (unsigned)sl] = v[q][i];
+        }
+    }
+}
+// the chain's half of the tail in v3: new first-conv ring = window[120:200], read back from the A operand
+MWW_HD void live3_write_ring0(int tid, const float *sm, float *state, long long s0, int n_valid) {
+    const int sl = tid >> 3, part = tid & 7;
+    if (sl >= n_valid) return;
+    const float *a = sm + kLiveOffA;
+    for (int k = part; k < 80; k += 8) state[(size_t)(s0 + sl) * kStateFloats + k] = a[(120 + k) * kLivePitch + sl];
+}
 // after the first conv has consumed A (and a barrier): new first-conv ring = window[120:200], read back from the A operand;
 // new pending rows = the call's last n_pend rows, which are NOT part of the window -- read from the caller's rows (only when
 // rows are pending at all; the steady state of hop-aligned 30 ms steps has none, so the chain then issues no global load).
@@ -530,6 +606,36 @@ MWW_D void live_first_conv_mma(int tid, float *sm, const float *w0, int w0_pitch
         FragA a;
         FragB b;
         load_frag_b(w0, w0_pitch, 8 * ks, n0, lane, b);
+        load_frag_a(a_base, kLivePitch, 8 * ks, r0, lane, a);
+        mma_tf32(c, a.lo, b.hi);
+        mma_tf32(c, a.hi, b.lo);
+        mma_tf32(c, a.hi, b.hi);
+    }
+    live_fc_store_tile(sm, r0, n0, lane, c);
+}
+// v3: the first conv's B fragments are the same 50 values per thread for every group.  They are loaded (from L2) a layer
+// BEFORE they are needed -- while the chain of the previous group is in its head -- so their latency, 2-3x longer while the
+// bulk copies saturate the memory system, is off the critical path; `volatile` pins the loads where they are written.
+MWW_D void live_first_conv_load_b(int tid, const float *w0, float (&bw)[50]) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const float *p = w0 + (lane & 3) * 32 + 8 * (warp & 3) + (lane >> 2);
+#pragma unroll
+    for (int ks = 0; ks < 25; ++ks) {
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(bw[2 * ks]) : "l"(p + (8 * ks) * 32));
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(bw[2 * ks + 1]) : "l"(p + (8 * ks + 4) * 32));
+    }
+}
+MWW_D void live_first_conv_mma_regs(int tid, float *sm, const float (&bw)[50]) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int r0 = 16 * (warp >> 2), n0 = 8 * (warp & 3);
+    const float *a_base = sm + kLiveOffA;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < 25; ++ks) {
+        FragA a;
+        FragB b;
+        split_tf32(bw[2 * ks], b.hi[0], b.lo[0]);
+        split_tf32(bw[2 * ks + 1], b.hi[1], b.lo[1]);
         load_frag_a(a_base, kLivePitch, 8 * ks, r0, lane, a);
         mma_tf32(c, a.lo, b.hi);
         mma_tf32(c, a.hi, b.lo);

@@ -255,10 +255,10 @@ def test_nn_state_roundtrip_and_reset_ids(torch_cuda):
     assert not st["nn"][2].any() and not st["estimate"][2].any() and st["nn"][1].any()
 
 
-@pytest.mark.parametrize("kind", ["f32", "int8", "f32_v2"])
+@pytest.mark.parametrize("kind", ["f32", "int8", "f32_v2", "f32_v3"])
 def test_live_rings_rotate_and_canonicalise(torch_cuda, kind, monkeypatch):
-    if kind == "f32_v2":           # the warp-specialised live kernel (MWW_LIVE_V2 is read at mww_create)
-        monkeypatch.setenv("MWW_LIVE_V2", "1")
+    if kind.startswith("f32_v"):   # the warp-specialised live kernels (MWW_LIVE_VARIANT is read at mww_create)
+        monkeypatch.setenv("MWW_LIVE_VARIANT", kind[-1])
         kind = "f32"
     """Live calls keep the NN rings rotated (only the new row is written); a snapshot, a clip call or a mode switch
     rotates them back.  Every hand-over must continue the same probability chain as the oracle."""

@@ -31,6 +31,6 @@ p = eng.profile_read()
 eb = 4 if kind == "f32" else 1
 step_bytes = 4176 * eb + 368 * eb + 240 + 4
 nn = p["mixednet"][0] / max(p["mixednet"][1], 1)
-print("%s mode=%s v2=%s: call %.4f ms, frontend %.4f, nn %.4f ms = %.0f GB/s (%.3f of 6576.7)" % (
-    kind, os.environ.get("MWW_LIVE_MODE", "0"), os.environ.get("MWW_LIVE_V2", "-"), a.elapsed_time(b) / calls, p["k1_spectral"][0] / calls, nn,
+print("%s mode=%s variant=%s: call %.4f ms, frontend %.4f, nn %.4f ms = %.0f GB/s (%.3f of 6576.7)" % (
+    kind, os.environ.get("MWW_LIVE_MODE", "0"), os.environ.get("MWW_LIVE_VARIANT", "-"), a.elapsed_time(b) / calls, p["k1_spectral"][0] / calls, nn,
     S * step_bytes / nn / 1e6, S * step_bytes / nn / 1e6 / 6576.7))
