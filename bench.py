@@ -508,7 +508,7 @@ def run_gpu(args):
         out = {"workload": "configs[1]/[2] streams stepped live: %d calls of %d new samples (one model step) for %d streams, %s" % (calls, n_live, S, kind),
                "samples_per_call": n_live, "calls": calls, "value": frames / (live_ms / 1e3), "unit": UNIT, "ms_per_call": live_ms,
                "kernels_ms_per_call": {k: v[0] / calls for k, v in lp.items()},
-               "roofline": {"bound": "hbm", "kernel": "nn_%s_live_kernel" % ("f32" if kind == "f32" else "i8"), "achieved": nn_gbs, "peak": peak,
+               "roofline": {"bound": "hbm", "kernel": "nn_f32_live3_kernel" if kind == "f32" else "nn_i8_live_kernel", "achieved": nn_gbs, "peak": peak,
                             "unit": "GB/s", "frac": nn_gbs / peak if nn_gbs else None, "peak_source": peak_src,
                             "alg_bytes_per_stream_step": step_bytes, "kernel_ms": nn_ms, "traffic": None},
                "realtime_streams_capacity": S * world * (n_live / 16.0) / live_ms}

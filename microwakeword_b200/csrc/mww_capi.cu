@@ -68,7 +68,7 @@ struct mww_handle {
     NnWeightsF32 W;
     TcWeights TW{};                 // fp32 okay_nabu: pre-split weights for the tcgen05 clip kernel (mww_nn_tc.cu)
     bool no_tc = false;             // MWW_NO_TC: keep the mma.sync clip kernel (A/B measurements)
-    int live_variant = 1;           // MWW_LIVE_V2: the warp-specialised live kernel (mww_nn_live.cuh, the r02 measurement instrument)
+    int live_variant = 3;           // MWW_LIVE_VARIANT: 3 = bulk-copy stages (default), 2 = warp-specialised with register loads, 1 = r01 kernel
     NnWeightsI8 Wq;
     float in_scale = 0.f, out_scale = 0.f;
     int in_zp = 0, out_zp = 0;
@@ -636,7 +636,7 @@ int mww_create(const void *model_blob, size_t n_bytes, int device, int n_streams
     h->no_live = getenv("MWW_NO_LIVE") != nullptr;
     h->no_fuse = getenv("MWW_NO_FUSE") != nullptr;
     h->no_tc = getenv("MWW_NO_TC") != nullptr;
-    h->live_variant = getenv("MWW_LIVE_VARIANT") != nullptr ? atoi(getenv("MWW_LIVE_VARIANT")) : (getenv("MWW_LIVE_V2") != nullptr ? 2 : 1);
+    h->live_variant = getenv("MWW_LIVE_VARIANT") != nullptr ? atoi(getenv("MWW_LIVE_VARIANT")) : (getenv("MWW_LIVE_V2") != nullptr ? 2 : 3);
     if (const char *mb = getenv("MWW_SCRATCH_MB")) { const long v = atol(mb); if (v > 0) h->scratch_budget = (size_t)v << 20; }
     if (const char *mt = getenv("MWW_MIN_TILE_STREAMS")) { const long v = atol(mt); if (v > 0) h->min_tile_streams = (int)v; }
     h->has_nn = model_blob != nullptr;

@@ -132,13 +132,13 @@ nn_f32_live2_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict
 // streamers' global loads queue in the same LSU / L1 miss pipeline.  Here one elected thread issues one
 // cp.async.bulk (global -> shared, 16 384 B = rings 1..5 of one stream, contiguous in the state layout) per stream into a
 // ring of four stages; nine "P" warps (one ring column per thread, its R rotated taps in registers) turn each stage into the
-// stream's 288 partial sums; four warps build the first-conv window one group ahead; the 8 chain warps are v2's.
+// stream's 288 partial sums; six warps build the first-conv window one group ahead; the 8 chain warps are v2's.
 // P is single-buffered: a P thread keeps the 32 sums of the NEXT group in registers and writes them once the chain's layer of
 // the current group has read the buffer (one full / empty named-barrier pair per ring) -- the second P buffer of v2 became
 // two more stages (bytes in flight are what an HBM-bound kernel is made of: 2 stages 0.30 ms, 4 stages see DESIGN.md).
 // The sums and their order are v2's (= v1's): the three kernels are bit-identical.
 constexpr int kLive3PThreads = kLive2Cols;                            // 288: one thread per ring column
-constexpr int kLive3AThreads = 128;
+constexpr int kLive3AThreads = kLive3WindowThreads;
 constexpr int kLive3Threads = kLive2ChainThreads + kLive3PThreads + kLive3AThreads + 32;   // + the producer's warp
 constexpr int kLive3PBase = kLive2ChainThreads, kLive3ABase = kLive3PBase + kLive3PThreads, kLive3ProdBase = kLive3ABase + kLive3AThreads;
 constexpr int kLive3StageFloats = kStateFloats - kStateOff[1];        // rings 1..5 of one stream
@@ -155,7 +155,7 @@ static_assert(kLive3PThreads / 32 == 9 && kLiveStreams % kLive3Stages == 0 && (k
               "P warps 1 + 2 + 2 + 2 + 2; stage index and parity of a stream are compile-time");
 __host__ __device__ constexpr int live3_stage_off(int s) { return s < 2 ? kLive3OffStageLo + s * kLive3StageFloats : kLive3OffStageHi + (s - 2) * kLive3StageFloats; }
 // named barriers of v3
-constexpr int kBar3Chain = 1, kBar3AFull = 2, kBar3AEmpty = 3, kBar3RingFull = 4, kBar3RingEmpty = 9;
+constexpr int kBar3Chain = 1, kBar3AFull = 2, kBar3AEmpty = 3, kBar3RingFull = 4, kBar3RingEmpty = 9, kBar3Window = 14;
 __host__ __device__ constexpr int live3_ring_count(int i) { return kLive2ChainThreads + live_ring_cols(i); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -269,17 +269,24 @@ nn_f32_live3_kernel(NnWeightsF32 W, float *__restrict__ state, float *__restrict
     if (tid >= kLive3ABase) {
         // ---- first-conv window of group k into A as soon as the chain's first conv of group k - 1 has let go of it ----
         const int at = tid - kLive3ABase;
-        float v[kLive3AStreamsPerWarp][7];
+        float v[kLive3WindowPerThread];
         int k = 0;
-        if ((int)blockIdx.x < n_groups && debug_mode != 1)
-            live3_window_load(at, in, pend, (long long)blockIdx.x * kLiveStreams, min(kLiveStreams, n_streams - (int)blockIdx.x * kLiveStreams), v);
+        auto load = [&](int gl) {
+            const long long s0 = (long long)gl * kLiveStreams;
+            const int n_valid = min(kLiveStreams, n_streams - (int)s0);
+            live3_window_load(at, in, s0, n_valid, v);
+            if (n_pend != 0) {
+                bar_sync(kBar3Window, kLive3AThreads);                             // every old pending row of the group has been read
+                live3_pend_store(at, in, pend, s0, n_valid);
+            }
+        };
+        if ((int)blockIdx.x < n_groups && debug_mode != 1) load((int)blockIdx.x);
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++k) {
             if (k >= 1) bar_sync(kBar3AEmpty, kLive2ChainThreads + kLive3AThreads);
             if (debug_mode != 1) live3_window_store(at, sm, v);
             bar_arrive(kBar3AFull, kLive2ChainThreads + kLive3AThreads);
             const int gn = g + (int)gridDim.x;
-            if (gn < n_groups && debug_mode != 1)                                  // the next group's window, a chain period early
-                live3_window_load(at, in, pend, (long long)gn * kLiveStreams, min(kLiveStreams, n_streams - gn * kLiveStreams), v);
+            if (gn < n_groups && debug_mode != 1) load(gn);                        // the next group's window, a chain period early
         }
         return;
     }

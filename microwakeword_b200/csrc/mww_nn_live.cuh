@@ -446,66 +446,52 @@ MWW_HD void live2_build_a(int tid, float *sm, const LiveInput &in, long long s0,
 // loads costs microseconds, and A is free only after the first conv of the previous group (r02 ncu: with two window warps
 // loading on demand the chain spent 33 % of its samples waiting for A).  The same warps also move the call's last n_pend
 // rows into the pending-row buffer (v1 / v2: the chain does, with loads on its critical path): a stream's old pending rows
-// are read (they are part of the window) and its new ones written by the same warp, separated by __syncwarp.
-// 128 threads: warp w owns streams 8 w .. 8 w + 7, lane l the window elements l, l + 32, ...
-constexpr int kLive3AStreamsPerWarp = 8;
+// are read (they are part of the window) before its new ones are written (a named barrier among the window warps).
+// 192 threads: thread t owns the (stream, element) pairs t, t + 192, ... of the group's 32 x 200 -- 34 values per thread, no
+// spills at the kernel's 80 registers (128 threads x 56 values spilled, and their loads took 87 % of a chain period).
+constexpr int kLive3WindowThreads = 192;
+constexpr int kLive3WindowPerThread = (kLiveStreams * 200 + kLive3WindowThreads - 1) / kLive3WindowThreads;     // 34
 template <bool F32ROWS>
-MWW_HD void live3_window_load_t(int at, const LiveInput &in, float *pend_out, long long s0, int n_valid, float (&v)[kLive3AStreamsPerWarp][7]) {
-    const int warp = at >> 5;
-    const unsigned lane = (unsigned)(at & 31), np40 = (unsigned)in.n_pend * (unsigned)kNumChannels;
+MWW_HD void live3_window_load_t(int t, const LiveInput &in, long long s0, int n_valid, float (&v)[kLive3WindowPerThread]) {
+    const unsigned np40 = (unsigned)in.n_pend * (unsigned)kNumChannels;
 #pragma unroll
-    for (int q = 0; q < kLive3AStreamsPerWarp; ++q) {
-        const int sl = warp * kLive3AStreamsPerWarp + q;
-        const bool ok = sl < n_valid;
-        const size_t su = (size_t)(s0 + (ok ? sl : 0));
+    for (int i = 0; i < kLive3WindowPerThread; ++i) {
+        const unsigned idx = (unsigned)t + (unsigned)(kLive3WindowThreads * i), slr = idx / 200u, sl = slr < 31u ? slr : 31u, kk = idx - 200u * slr;
+        const bool ok = (int)sl < n_valid && idx < (unsigned)(kLiveStreams * 200);
+        const size_t su = (size_t)(s0 + (ok ? (int)sl : 0));
         const float *st = in.state + su * (size_t)kStateFloats;
         const float *pd = in.pend + su * (size_t)(2 * kNumChannels);
         const char *rb = static_cast<const char *>(in.rows) + su * (size_t)in.rows_stream_stride_bytes;
-        const float *rf = reinterpret_cast<const float *>(rb);
-        const uint16_t *r16 = reinterpret_cast<const uint16_t *>(rb);
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const unsigned k = lane + 32u * (unsigned)i, kk = k < 199u ? k : 199u;
-            const bool in_ring = kk < 80u, in_pend = !in_ring && kk < 80u + np40, is_row = !in_ring && !in_pend;
-            const unsigned e = is_row ? kk - 80u - np40 : 0u;
-            const float *fp = in_ring ? st + kk : (in_pend ? pd + (kk - 80u) : (F32ROWS ? rf + e : st));
-            float x = *fp;
-            if (!F32ROWS) {
-                const float u = (float)r16[e] * kFeatureScale;
-                x = is_row ? u : x;
-            }
-            v[q][i] = (ok && k < 200u) ? x : 0.f;
+        const bool in_ring = kk < 80u, in_pend = !in_ring && kk < 80u + np40, is_row = !in_ring && !in_pend && kk < 200u;
+        const unsigned e = is_row ? kk - 80u - np40 : 0u;
+        const float *fp = in_ring ? st + kk : (in_pend ? pd + (kk - 80u) : (F32ROWS ? reinterpret_cast<const float *>(rb) + e : st));
+        float x = *fp;
+        if (!F32ROWS) {
+            const float u = (float)reinterpret_cast<const uint16_t *>(rb)[e] * kFeatureScale;
+            x = is_row ? u : x;
         }
-    }
-#if defined(__CUDA_ARCH__)
-    __syncwarp();
-#endif
-    if (np40 != 0u) {
-        for (int q = 0; q < kLive3AStreamsPerWarp; ++q) {
-            const int sl = warp * kLive3AStreamsPerWarp + q;
-            if (sl >= n_valid) break;
-            const size_t su = (size_t)(s0 + sl);
-            for (unsigned e = lane; e < np40; e += 32u)
-                pend_out[su * (size_t)(2 * kNumChannels) + e] = live_row_value(in, su, (unsigned)(3 * kNumChannels) - np40 + e);
-        }
+        v[i] = ok ? x : 0.f;
     }
 }
-MWW_HD void live3_window_load(int at, const LiveInput &in, float *pend_out, long long s0, int n_valid, float (&v)[kLive3AStreamsPerWarp][7]) {
-    if (in.rows_are_f32) live3_window_load_t<true>(at, in, pend_out, s0, n_valid, v);
-    else live3_window_load_t<false>(at, in, pend_out, s0, n_valid, v);
+MWW_HD void live3_window_load(int t, const LiveInput &in, long long s0, int n_valid, float (&v)[kLive3WindowPerThread]) {
+    if (in.rows_are_f32) live3_window_load_t<true>(t, in, s0, n_valid, v);
+    else live3_window_load_t<false>(t, in, s0, n_valid, v);
 }
-MWW_HD void live3_window_store(int at, float *sm, const float (&v)[kLive3AStreamsPerWarp][7]) {
-    const int warp = at >> 5;
-    const unsigned lane = (unsigned)(at & 31);
+// the call's last n_pend rows -> pending-row buffer (after every window thread has read the old pending rows: caller's barrier)
+MWW_HD void live3_pend_store(int t, const LiveInput &in, float *pend_out, long long s0, int n_valid) {
+    const unsigned np40 = (unsigned)in.n_pend * (unsigned)kNumChannels;
+    for (unsigned idx = (unsigned)t; idx < (unsigned)n_valid * np40; idx += (unsigned)kLive3WindowThreads) {
+        const unsigned sl = idx / np40, e = idx - sl * np40;
+        const size_t su = (size_t)(s0 + sl);
+        pend_out[su * (size_t)(2 * kNumChannels) + e] = live_row_value(in, su, (unsigned)(3 * kNumChannels) - np40 + e);
+    }
+}
+MWW_HD void live3_window_store(int t, float *sm, const float (&v)[kLive3WindowPerThread]) {
     float *a = sm + kLiveOffA;
 #pragma unroll
-    for (int q = 0; q < kLive3AStreamsPerWarp; ++q) {
-        const int sl = warp * kLive3AStreamsPerWarp + q;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const unsigned k = lane + 32u * (unsigned)i;
-            if (k < 200u) a[k * (unsigned)kLivePitch + (unsigned)sl] = v[q][i];
-        }
+    for (int i = 0; i < kLive3WindowPerThread; ++i) {
+        const unsigned idx = (unsigned)t + (unsigned)(kLive3WindowThreads * i), sl = idx / 200u, kk = idx - 200u * sl;
+        if (idx < (unsigned)(kLiveStreams * 200)) a[kk * (unsigned)kLivePitch + sl] = v[i];
     }
 }
 // the chain's half of the tail in v3: new first-conv ring = window[120:200], read back from the A operand

@@ -255,9 +255,9 @@ def test_nn_state_roundtrip_and_reset_ids(torch_cuda):
     assert not st["nn"][2].any() and not st["estimate"][2].any() and st["nn"][1].any()
 
 
-@pytest.mark.parametrize("kind", ["f32", "int8", "f32_v2", "f32_v3"])
+@pytest.mark.parametrize("kind", ["f32", "int8", "f32_v1", "f32_v2"])
 def test_live_rings_rotate_and_canonicalise(torch_cuda, kind, monkeypatch):
-    if kind.startswith("f32_v"):   # the warp-specialised live kernels (MWW_LIVE_VARIANT is read at mww_create)
+    if kind.startswith("f32_v"):   # the default is variant 3 (bulk-copy stages); 1 and 2 stay as references (MWW_LIVE_VARIANT is read at mww_create)
         monkeypatch.setenv("MWW_LIVE_VARIANT", kind[-1])
         kind = "f32"
     """Live calls keep the NN rings rotated (only the new row is written); a snapshot, a clip call or a mode switch
