@@ -480,6 +480,13 @@ def run_gpu(args):
         del ha, hp
 
     # ---- the other single-GPU configurations of BASELINE.json, each with its own roofline (rank-local, every rank runs them) ----
+    def live_traffic(kind, n_streams):
+        """DRAM bytes per launch of the fp32 live NN kernel, from the committed ncu --set full capture (per stream-step x streams)"""
+        path = os.path.join(ROOT, "profiles", "live_traffic.json")
+        if kind != "f32" or not os.path.exists(path):
+            return None
+        return json.load(open(path))["dram_bytes_per_unit"] * n_streams
+
     def live_leg(kind, n_live=480):
         """live mode: step() calls with `n_live` new samples per stream; the ring state round-trips HBM on every call"""
         le = eng if kind == args.model else StreamEngine(model_blob(kind), n_streams=S, device=local_rank)
@@ -510,7 +517,7 @@ def run_gpu(args):
                "kernels_ms_per_call": {k: v[0] / calls for k, v in lp.items()},
                "roofline": {"bound": "hbm", "kernel": "nn_f32_live3_kernel" if kind == "f32" else "nn_i8_live_kernel", "achieved": nn_gbs, "peak": peak,
                             "unit": "GB/s", "frac": nn_gbs / peak if nn_gbs else None, "peak_source": peak_src,
-                            "alg_bytes_per_stream_step": step_bytes, "kernel_ms": nn_ms, "traffic": None},
+                            "alg_bytes_per_stream_step": step_bytes, "kernel_ms": nn_ms, "traffic": live_traffic(kind, S)},
                "realtime_streams_capacity": S * world * (n_live / 16.0) / live_ms}
         if le is not eng:
             le.close()
