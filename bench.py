@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--model", default="f32", choices=["f32", "int8"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ingest-share", type=float, default=None,
+                    help="N > 1: the ingest rank's share of the streams as a fraction of an equal share (default: 1 while the pull alone "
+                         "is faster than a rank's compute, else 0)")
     ap.add_argument("--tiles", type=int, default=0, help="pipeline tiles per rank of the N > 1 ingest (0 = library default, 16)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the legs for the other BASELINE.json configurations (the other model dtype in clip mode, live 30 ms steps "
@@ -359,28 +362,56 @@ def run_gpu(args):
     # back on rank 0 (NCCL) -- scatter, compute and gather all inside the timed region ----
     ingest_info, ms_per_step = None, ms_resident
     if world > 1:
-        from microwakeword_b200.sharding import IngestBuffer, ShardedEngine, gather_probs, scatter_audio
+        from microwakeword_b200.sharding import IngestBuffer, ShardedEngine, gather_probs, ingest_shares, scatter_audio
+        from microwakeword_b200 import _lib as lib_mod
+        import ctypes
         total = S * world
         ingest = IngestBuffer(total, SAMPLES_PER_STEP, src=0, device=device)
         if rank == 0:
             ingest.buffer[:S].copy_(audio)
             for r in range(1, world):                  # rank 0 holds every stream's audio (each block has its own seed)
                 ingest.buffer[r * S:(r + 1) * S].copy_(synth_audio_device(torch, S, SAMPLES_PER_STEP, 1234 + r, device))
-        sh = ShardedEngine(model_blob(args.model), total, local_rank)
+        torch.cuda.synchronize()
+        cur = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        # (i) where the time can go: the pull alone (copy engines, no kernels), equal blocks
+        stage = torch.empty((max(S // 16, 1), SAMPLES_PER_STEP), dtype=torch.int16, device=device)
+
+        def pull_only():
+            dist.barrier()
+            rows = stage.shape[0]
+            for s0 in range(0, S if rank != 0 else 0, rows):
+                n = min(rows, S - s0)
+                lib_mod.check(None, lib_mod.lib().mww_copy_async(stage.data_ptr(), ingest.block_ptr(rank * S + s0), n * SAMPLES_PER_STEP * 2, cur()))
+        pull_only()
+        pull_ms = timed(pull_only, 2)
+        del stage
+        # the ingest rank's share of the streams: an equal share while the peers' pulls hide behind their kernels; none once one
+        # GPU's NVLink egress is the floor (its own kernels would only slow the peers' reads of its memory: DESIGN.md section 5)
+        if args.ingest_share is not None:
+            src_share, why = float(args.ingest_share), "--ingest-share"
+        else:
+            src_share = 0.0 if pull_ms > ms_resident else 1.0
+            why = "auto: pull alone %.1f ms %s pre-sharded compute %.1f ms" % (pull_ms, ">" if src_share == 0.0 else "<=", ms_resident)
+        shares = ingest_shares(total, world, 0, src_share)
+        sh = ShardedEngine(model_blob(args.model), total, local_rank, shares=None if src_share == 1.0 else shares)
+        my_probs = torch.empty((max(sh.count, 1), n_probs), dtype=torch.float32, device=device) if sh.count != S else probs
         torch.cuda.synchronize()
         gathered = None
 
         def ingest_step():
             nonlocal gathered
-            gathered = sh.predict_clip_ingest(ingest, tiles=args.tiles, out=probs)
+            gathered = sh.predict_clip_ingest(ingest, tiles=args.tiles, out=my_probs[:sh.count] if sh.count else None)
 
+        count_launches = lambda: sh.engine.launch_count if sh.engine is not None else 0
         sh.reset()
         ingest_step()
         for _ in range(max(args.warmup, 1)):
             ingest_step()
-        l0 = sh.engine.launch_count
+        l0 = count_launches()
         ms_per_step = timed(ingest_step, args.steps)
-        launches = sh.engine.launch_count - l0
+        lt = torch.tensor([count_launches() - l0], dtype=torch.int64, device=device)
+        dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+        launches = int(lt.item())                      # per rank (the ingest rank launches nothing when its share is 0)
         # who is the slow one: every rank's own device time for the same steps (the timed value is the max)
         barrier()
         r0e, r1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -393,65 +424,80 @@ def run_gpu(args):
         all_ms = [torch.zeros_like(mine_ms) for _ in range(world)]
         dist.all_gather(all_ms, mine_ms)
         per_rank_ms = [float(t.item()) for t in all_ms]
-        ingest_checksum = float(probs[:, :100].double().sum().item())
-        # side legs, for the record: (i) where the time goes: the pull alone (copy engine, no kernels);
-        # (ii) the plain serialised NCCL scatter -> compute -> gather
-        stage = torch.empty((max(S // 16, 1), SAMPLES_PER_STEP), dtype=torch.int16, device=device)
-        from microwakeword_b200 import _lib as lib_mod
-        import ctypes
-
-        def pull_only():
-            dist.barrier()
-            rows = stage.shape[0]
-            for s0 in range(0, S if rank != 0 else 0, rows):
-                n = min(rows, S - s0)
-                lib_mod.check(None, lib_mod.lib().mww_copy_async(stage.data_ptr(), ingest.block_ptr(sh.start + s0), n * SAMPLES_PER_STEP * 2,
-                                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        pull_ms = timed(pull_only, 2)
+        ingest_checksum = float(gathered[:S, :100].double().sum().item()) if rank == 0 else 0.0
+        # per-rank tile timeline of one more step (CUDA events on the library's copy and compute streams)
+        max_tiles = 64
+        tl = torch.full((max_tiles, 4), -1.0, dtype=torch.float32, device=device)
+        if sh.engine is not None:
+            sh.engine.profile(True)
+        ingest_step()
+        if sh.engine is not None:
+            t_np = sh.engine.timeline_read(max_tiles)
+            sh.engine.profile_read()
+            sh.engine.profile(False)
+            tl[:len(t_np)] = torch.from_numpy(t_np).to(device)
+        all_tl = [torch.zeros_like(tl) for _ in range(world)]
+        dist.all_gather(all_tl, tl)
+        timelines = [[[round(float(x), 3) for x in row] for row in t.cpu().tolist() if row[0] >= 0] for t in all_tl]
         # every rank's block through the ingest path == the same block computed from resident audio (both from reset state)
         sh.reset()
         ingest_step()
-        eng.reset()
-        resident = eng.predict_clip(audio)
-        pulled = probs[:, :resident.shape[1]]
-        same = torch.equal(resident, pulled)
-        # the block this rank pulled is the audio it synthesised itself (same seed, generated on another GPU of the same kind)
-        mine = torch.empty_like(audio)
-        lib_mod.check(None, lib_mod.lib().mww_copy_async(mine.data_ptr(), ingest.block_ptr(sh.start), S * SAMPLES_PER_STEP * 2,
-                                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        audio_same = torch.equal(mine, audio)
+        same = audio_same = True
+        diff = 0.0
+        if sh.count:
+            mine = torch.empty((sh.count, SAMPLES_PER_STEP), dtype=torch.int16, device=device)
+            lib_mod.check(None, lib_mod.lib().mww_copy_async(mine.data_ptr(), ingest.block_ptr(sh.start), sh.count * SAMPLES_PER_STEP * 2, cur()))
+            # the block this rank pulled is the audio the owning seeds synthesise (generated here, on another GPU of the same kind)
+            for r in range(world):
+                lo, hi = max(sh.start, r * S), min(sh.start + sh.count, (r + 1) * S)
+                if lo < hi:
+                    ref = audio if r == rank else synth_audio_device(torch, S, SAMPLES_PER_STEP, 1234 + r, device)
+                    audio_same = audio_same and torch.equal(mine[lo - sh.start:hi - sh.start], ref[lo - r * S:hi - r * S])
+                    del ref
+            chk = eng if sh.count == S else StreamEngine(model_blob(args.model), n_streams=sh.count, device=local_rank)
+            chk.reset()
+            resident = chk.predict_clip(mine)
+            pulled = my_probs[:sh.count, :resident.shape[1]]
+            same = torch.equal(resident, pulled)
+            diff = float((resident - pulled).abs().max().item())
+            if chk is not eng:
+                chk.close()
+            del mine, resident
         diag = torch.tensor([1 if same else 0, 1 if audio_same else 0], dtype=torch.int32, device=device)
         dist.all_reduce(diag, op=dist.ReduceOp.MIN)
-        max_diff = torch.tensor([float((resident - pulled).abs().max().item())], dtype=torch.float64, device=device)
+        max_diff = torch.tensor([diff], dtype=torch.float64, device=device)
         dist.all_reduce(max_diff, op=dist.ReduceOp.MAX)
-        same_t = diag[:1]
-        del mine
         eng.reset()
 
+        # (ii) the plain serialised NCCL scatter -> compute -> gather (equal blocks)
         def nccl_serial():
             local = scatter_audio(ingest.buffer if rank == 0 else None, total, SAMPLES_PER_STEP, src=0, device=device)
             gather_probs(eng.predict_clip(local, out=probs), total, dst=0)
         nccl_serial()
         nccl_ms = timed(nccl_serial, 2)
         ingest_info = {
-            "how": "audio for all %d streams in rank 0's HBM; every rank pulls its 65 536-stream block tile by tile with its own copy engine over "
+            "how": "audio for all %d streams in rank 0's HBM; every rank pulls its block tile by tile with its own copy engine over "
                    "NVLink peer access (CUDA IPC) while the previous tile computes (mww_predict_clip_remote), scores gathered to rank 0 with NCCL; "
                    "a tiny all-reduce per step orders the pulls after the ingest rank's writes" % total,
+            "streams_per_rank": shares, "ingest_rank_share": src_share, "ingest_rank_share_rule": why,
             "tiles_per_rank": args.tiles or 16, "per_rank_ms_per_step": per_rank_ms,
-            "nvlink_bytes_out_of_rank0_per_step": S * SAMPLES_PER_STEP * 2 * (world - 1),
+            "nvlink_bytes_out_of_rank0_per_step": (total - shares[0]) * SAMPLES_PER_STEP * 2,
             "egress_floor_ms": pull_ms, "pull_only_gbs_out_of_rank0": S * SAMPLES_PER_STEP * 2 * (world - 1) / (pull_ms / 1e3) / 1e9,
+            "egress_floor_note": "the pull alone with EQUAL blocks (S (N - 1) streams leave rank 0); with ingest_rank_share 0 all N S streams leave it",
             "value_presharded": frames_per_step_all / (ms_resident / 1e3), "ms_per_step_presharded": ms_resident,
             "nccl_serial": {"value": frames_per_step_all / (nccl_ms / 1e3), "ms_per_step": nccl_ms,
                             "note": "torch.distributed scatter of int16 audio from rank 0, compute, gather of float32 scores (NCCL), serialised"},
             "probs_checksum_rank0_block": ingest_checksum,
-            "every_rank_block_equals_resident_path": bool(int(same_t.item()) == 1),
+            "every_rank_block_equals_resident_path": bool(int(diag[0].item()) == 1),
             "every_rank_pulled_audio_equals_own_synthesis": bool(int(diag[1].item()) == 1),
             "max_abs_prob_difference_to_resident_path": float(max_diff.item()),
+            "tile_timeline_ms": {"columns": ["copy_start", "copy_end", "kernels_start", "kernels_end"],
+                                 "note": "one step, per rank, per tile; ms after that rank's first copy started", "ranks": timelines},
         }
         torch.cuda.synchronize()
         barrier()
         ingest.close()
-        del sh, stage
+        del sh
 
     clock_info = clocks.stop() if clocks else None
     value = frames_per_step_all / (ms_per_step / 1e3)

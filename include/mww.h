@@ -182,6 +182,13 @@ int mww_positive_scores(const float *d_probs, const long long *d_offsets, const 
 int mww_profile_enable(mww_t *h, int on);
 int mww_profile_read(mww_t *h, double *ms4, long long *counts4);
 
+/* Tile timeline of the most recent staged call (mww_predict_clip_host / mww_predict_clip_remote from a peer or host
+ * source) made while profiling was enabled: for tile t, ms[4 t + 0..3] = copy start, copy end, kernels start, kernels end,
+ * in milliseconds after tile 0's copy start (CUDA events on the library's copy and compute streams; -1 where an event
+ * could not be read).  *n_tiles = tiles the call used; at most max_tiles are written.  Synchronises the device and clears
+ * the record.  This is what DESIGN.md section 5's per-rank ingest timelines are made of. */
+int mww_timeline_read(mww_t *h, float *ms, int max_tiles, int *n_tiles);
+
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 long long mww_launch_count(const mww_t *h);
 

@@ -19,7 +19,7 @@ MWW_ROWS_U16, MWW_ROWS_F32, MWW_ROWS_I8 = 0, 1, 2
 EXPORTS = (
     "mww_create", "mww_destroy", "mww_last_error", "mww_get_info", "mww_reset", "mww_reset_frontend",
     "mww_features", "mww_infer_features", "mww_predict_clip", "mww_predict_clip_host",
-    "mww_get_state", "mww_set_state", "mww_launch_count", "mww_profile_enable", "mww_profile_read",
+    "mww_get_state", "mww_set_state", "mww_launch_count", "mww_profile_enable", "mww_profile_read", "mww_timeline_read",
     "mww_moving_average", "mww_false_accept_counts", "mww_positive_scores", "mww_copy_async",
     "mww_ipc_alloc", "mww_ipc_open", "mww_ipc_close", "mww_ipc_free",
     "mww_predict_clip_remote", "mww_reset_device_ids", "mww_host_alloc", "mww_host_free", "mww_bind_host_thread",
@@ -88,6 +88,8 @@ def lib() -> ctypes.CDLL:
     L.mww_profile_enable.argtypes = [vp, i32]
     L.mww_profile_read.restype = i32
     L.mww_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
+    L.mww_timeline_read.restype = i32
+    L.mww_timeline_read.argtypes = [vp, ctypes.POINTER(ctypes.c_float), i32, ctypes.POINTER(i32)]
     L.mww_moving_average.restype = i32
     L.mww_moving_average.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
     L.mww_false_accept_counts.restype = i32

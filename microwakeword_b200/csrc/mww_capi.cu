@@ -109,6 +109,7 @@ struct mww_handle {
     // optional per-kernel timing (mww_profile_*)
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev[4];   // start/stop pairs per kernel class
+    std::vector<cudaEvent_t> tl_ev;        // last staged call while profiling: 4 events per tile (mww_timeline_read)
 };
 
 namespace {
@@ -744,6 +745,23 @@ int mww_profile_read(mww_t *h, double *ms4, long long *counts4) {
     return MWW_OK;
 }
 
+int mww_timeline_read(mww_t *h, float *ms, int max_tiles, int *n_tiles) {
+    if (!h || !ms || !n_tiles || max_tiles < 0) return MWW_EINVAL;
+    ENTER(h);
+    CU(h, cudaDeviceSynchronize());
+    const int n = (int)(h->tl_ev.size() / 4);
+    *n_tiles = n;
+    for (int t = 0; t < n && t < max_tiles; ++t)
+        for (int i = 0; i < 4; ++i) {
+            float v = 0.f;
+            if (cudaEventElapsedTime(&v, h->tl_ev[0], h->tl_ev[4 * t + i]) != cudaSuccess) v = -1.f;
+            ms[4 * t + i] = v;
+        }
+    for (cudaEvent_t e : h->tl_ev) cudaEventDestroy(e);
+    h->tl_ev.clear();
+    return MWW_OK;
+}
+
 int mww_get_info(const mww_t *h, mww_info *o) {
     if (!h || !o) return MWW_EINVAL;
     memset(o, 0, sizeof *o);
@@ -967,6 +985,11 @@ int staged_tiles(mww_t *h, const int16_t *src, int n_samples, long long audio_st
         const int b = it & 1;
         // the staging buffer is free once the kernels of the tile that used it two iterations ago are done
         if (it >= 2) CU(h, cudaStreamWaitEvent(h->st_h2d, h->ev_compute[b], 0));
+        cudaEvent_t tl[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (h->profiling) {
+            for (int i = 0; i < 4; ++i) { CU(h, cudaEventCreate(&tl[i])); h->tl_ev.push_back(tl[i]); }
+            CU(h, cudaEventRecord(tl[0], h->st_h2d));
+        }
         if (n_samples > 0) {
             const int16_t *from = src + (size_t)first * audio_stride;
             if (audio_stride == n_samples)       // contiguous block: one linear DMA
@@ -975,8 +998,10 @@ int staged_tiles(mww_t *h, const int16_t *src, int n_samples, long long audio_st
                 CU(h, cudaMemcpy2DAsync(h->d_audio_tile[b], (size_t)n_samples * 2, from, (size_t)audio_stride * 2, (size_t)n_samples * 2, n,
                                         cudaMemcpyDefault, h->st_h2d));
         }
+        if (tl[1]) CU(h, cudaEventRecord(tl[1], h->st_h2d));
         CU(h, cudaEventRecord(h->ev_h2d[b], h->st_h2d));
         CU(h, cudaStreamWaitEvent(h->st_compute, h->ev_h2d[b], 0));
+        if (tl[2]) CU(h, cudaEventRecord(tl[2], h->st_compute));
         if (dst_is_host && it >= 2) CU(h, cudaStreamWaitEvent(h->st_compute, h->ev_d2h[b], 0));   // score staging buffer drained
         int rc = run_frontend_tile(h, first, n, h->d_audio_tile[b], n_samples, n_samples, n_frames, h->d_feat, (long long)n_frames * kNumChannels, h->st_compute);
         if (rc) return rc;
@@ -988,6 +1013,7 @@ int staged_tiles(mww_t *h, const int16_t *src, int n_samples, long long audio_st
             rc = run_carry_tile(h, first, n, h->d_audio_tile[b], n_samples, n_samples, n_frames, h->st_compute);
             if (rc) return rc;
         }
+        if (tl[3]) CU(h, cudaEventRecord(tl[3], h->st_compute));
         CU(h, cudaEventRecord(h->ev_compute[b], h->st_compute));
         if (dst_is_host) {
             CU(h, cudaStreamWaitEvent(h->st_d2h, h->ev_compute[b], 0));
@@ -1040,6 +1066,8 @@ int predict_clip_staged(mww_t *h, const char *who, const int16_t *src, int n_sam
     CU(h, cudaStreamWaitEvent(h->st_compute, h->ev_entry, 0));
     if (h->staged_used)
         for (int b = 0; b < 2; ++b) CU(h, cudaStreamWaitEvent(h->st_h2d, h->ev_compute[b], 0));
+    for (cudaEvent_t e : h->tl_ev) cudaEventDestroy(e);       // a timeline describes the most recent staged call only
+    h->tl_ev.clear();
     rc = begin_nn_call(h, n_frames, h->st_compute);
     if (rc == MWW_OK) {
         h->staged_used = true;

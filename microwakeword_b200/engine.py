@@ -263,6 +263,14 @@ class StreamEngine:
         _lib.check(self._h, self._L.mww_profile_read(self._h, ms, cnt))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
+    def timeline_read(self, max_tiles: int = 256) -> np.ndarray:
+        """[tiles, 4] float32 ms (copy start, copy end, kernels start, kernels end; relative to tile 0's copy start) of the
+        most recent staged call made while profile(True) -- predict_clip_host / predict_clip_remote from a peer or host source."""
+        buf = (ctypes.c_float * (4 * max_tiles))()
+        n = ctypes.c_int32(0)
+        _lib.check(self._h, self._L.mww_timeline_read(self._h, buf, max_tiles, ctypes.byref(n)))
+        return np.ctypeslib.as_array(buf).reshape(max_tiles, 4)[:min(n.value, max_tiles)].copy()
+
     # ------------------------------------------------------------------ state (checkpoint / tests)
     def state_dict(self) -> dict:
         S = self.n_streams

@@ -18,16 +18,42 @@ import ctypes
 from . import _lib
 
 
-def partition(n_streams: int, world: int):
-    """Contiguous, balanced blocks: [(start, count)] * world; the first n % world ranks get one extra."""
+def partition(n_streams: int, world: int, shares=None):
+    """Contiguous blocks [(start, count)] * world.  Default: balanced, the first n % world ranks get one extra.
+    `shares`: explicit per-rank stream counts (same list on every rank; zeros allowed) -- e.g. ingest_shares()."""
     if n_streams < 0 or world < 1:
         raise ValueError("bad partition arguments")
+    if shares is not None:
+        shares = [int(c) for c in shares]
+        if len(shares) != world or min(shares) < 0 or sum(shares) != n_streams:
+            raise ValueError("partition: shares %r do not split %d streams over %d ranks" % (shares, n_streams, world))
+        out, start = [], 0
+        for c in shares:
+            out.append((start, c))
+            start += c
+        return out
     base, extra = divmod(n_streams, world)
     out, start = [], 0
     for r in range(world):
         n = base + (1 if r < extra else 0)
         out.append((start, n))
         start += n
+    return out
+
+
+def ingest_shares(n_streams: int, world: int, src: int = 0, src_share: float = 1.0):
+    """Per-rank stream counts when all audio starts on rank `src`: the ingest rank takes `src_share` of an equal share
+    (0 = it only feeds the others), the rest is spread evenly over the other ranks.  Why: one GPU's NVLink egress
+    (about 840 GB/s measured) bounds how fast N - 1 peers can pull; once that bound exceeds a rank's compute time, the ingest
+    GPU's own kernels only slow its peers' reads of its memory (total = pull + 0.6 x its compute time)."""
+    if world < 1 or not 0 <= src < world or not 0.0 <= src_share <= 1.0:
+        raise ValueError("bad ingest_shares arguments")
+    if world == 1:
+        return [n_streams]
+    mine = int(round(n_streams / world * src_share))
+    rest = partition(n_streams - mine, world - 1)
+    out = [c for _, c in rest]
+    out.insert(src, mine)
     return out
 
 
@@ -218,13 +244,16 @@ def scatter_compute_gather(audio_on_src, n_streams: int, n_samples: int, compute
     return gather_probs(torch.cat(outs, 0), n_streams, dst=src, group=group)
 
 
-def gather_probs(local_probs, n_streams: int, dst: int = 0, group=None):
-    """Every rank passes float32 [count, steps]; rank `dst` returns [n_streams, steps], others None."""
+def gather_probs(local_probs, n_streams: int, dst: int = 0, group=None, shares=None):
+    """Every rank passes float32 [count, steps]; rank `dst` returns [n_streams, steps], others None.
+    `shares`: the per-rank counts when the partition is not the balanced one (partition())."""
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    parts = partition(n_streams, world)
+    parts = partition(n_streams, world, shares)
+    if local_probs.shape[0] != parts[rank][1]:
+        raise ValueError("gather_probs: rank %d passes %d rows, its block has %d" % (rank, local_probs.shape[0], parts[rank][1]))
     steps = local_probs.shape[1]
     local_probs = local_probs.contiguous()
     if len({c for _, c in parts}) == 1:
@@ -235,7 +264,8 @@ def gather_probs(local_probs, n_streams: int, dst: int = 0, group=None):
         full = torch.empty((n_streams, steps), dtype=local_probs.dtype, device=local_probs.device)
         for r, (s, c) in enumerate(parts):
             if r == dst:
-                full[s:s + c] = local_probs
+                if c:
+                    full[s:s + c] = local_probs
             elif c:
                 dist.recv(full[s:s + c], src=r, group=group)
         return full
@@ -248,7 +278,9 @@ class ShardedEngine:
     """This rank's block of streams as `tiles` StreamEngines over contiguous sub-blocks (tiles = 1: one engine).
     More than one tile lets predict_clip_scattered() overlap the NVLink scatter of tile t+1 with the kernels of tile t."""
 
-    def __init__(self, model, n_streams_total: int, device_index: int, group=None, tiles: int = 1, engine_factory=None):
+    def __init__(self, model, n_streams_total: int, device_index: int, group=None, tiles: int = 1, engine_factory=None, shares=None):
+        """`shares`: per-rank stream counts (default: balanced).  A rank whose share is 0 owns no engine and only takes part in
+        the collectives (the ingest rank of an egress-bound job: ingest_shares(..., src_share=0))."""
         import torch.distributed as dist
 
         if engine_factory is None:
@@ -260,16 +292,31 @@ class ShardedEngine:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if n_streams_total < self.world:
             raise ValueError("ShardedEngine: %d streams cannot be spread over %d ranks" % (n_streams_total, self.world))
-        self.tiles = max(1, min(int(tiles), n_streams_total // self.world))     # same on every rank; no empty sub-block
+        self.shares = None if shares is None else [int(c) for c in shares]
+        parts = partition(n_streams_total, self.world, self.shares)
+        smallest = min([c for _, c in parts if c] or [1])
+        self.tiles = max(1, min(int(tiles), smallest))                          # same on every rank; no empty sub-block
         tiles = self.tiles
-        self.start, self.count = partition(n_streams_total, self.world)[self.rank]
-        self.tile_parts = partition(self.count, tiles)
+        if self.shares is not None and tiles != 1:
+            raise ValueError("ShardedEngine: explicit shares go with tiles=1 (the library tiles the ingest itself)")
+        self.start, self.count = parts[self.rank]
+        self.device_index = device_index
+        self.tile_parts = partition(self.count, tiles) if self.count else []
         self.engines = [StreamEngine(model, n_streams=c, device=device_index) for _, c in self.tile_parts]
-        self.engine = self.engines[0]
+        self.engine = self.engines[0] if self.engines else None
+        self._mirror = None
+        if self.engine is None:
+            # a rank without streams still has to know how many steps a call produces (the gather's width): the same host
+            # arithmetic the engines run (frames buffered, pending rows), on the model's stride and hop
+            probe = StreamEngine(model, n_streams=1, device=device_index)
+            self._mirror = {"stride": probe.stride, "hop": probe.hop, "used": 0, "pend": 0}
+            probe.close()
 
     def reset(self):
         for e in self.engines:
             e.reset()
+        if self._mirror is not None:
+            self._mirror.update(used=0, pend=0)
 
     def predict_clip_scattered(self, audio_on_src, n_samples: int, src: int = 0):
         """Audio originates on `src` ([n_total, n_samples] int16 CUDA tensor, None elsewhere); scores return to `src`."""
@@ -286,7 +333,7 @@ class ShardedEngine:
 
         if ingest.n_streams != self.n_total:
             raise ValueError("IngestBuffer holds %d streams, the engine shards %d" % (ingest.n_streams, self.n_total))
-        if len(self.engines) != 1:
+        if len(self.engines) > 1:
             raise ValueError("predict_clip_ingest uses one engine per rank (ShardedEngine(..., tiles=1)); the tiling happens inside the library")
         # the buffer is complete on the ingest rank before any peer starts copying (IngestBuffer docstring).  A one-element
         # all-reduce is stream-ordered on every rank (the pull is queued behind it) and, unlike dist.barrier() on NCCL, does not
@@ -296,5 +343,20 @@ class ShardedEngine:
             dist.all_reduce(token, group=self.group)
         else:
             dist.barrier(group=self.group)
-        local = self.engine.predict_clip_remote(ingest.block_ptr(self.start), ingest.n_samples, tiles=tiles, out=out)
-        return gather_probs(local, self.n_total, dst=ingest.src, group=self.group)
+        if self.engine is not None:
+            local = self.engine.predict_clip_remote(ingest.block_ptr(self.start), ingest.n_samples, tiles=tiles, out=out)
+        else:
+            # a rank without streams: an empty block with the right width (every rank's call produces the same number of steps)
+            import torch
+            local = torch.empty((0, self._empty_steps(ingest.n_samples)), dtype=torch.float32, device=ingest.device)
+        return gather_probs(local, self.n_total, dst=ingest.src, group=self.group, shares=self.shares)
+
+    def _empty_steps(self, n_samples: int) -> int:
+        """Steps a call with n_samples new samples produces -- for a rank that owns no engine (all engines advance in lockstep)."""
+        from .engine import WINDOW
+        m = self._mirror
+        total = m["used"] + int(n_samples)
+        rows = (total - WINDOW) // m["hop"] + 1 if total >= WINDOW else 0
+        steps = (m["pend"] + rows) // m["stride"]
+        m["used"], m["pend"] = total - rows * m["hop"], (m["pend"] + rows) % m["stride"]
+        return steps

@@ -32,4 +32,4 @@ def test_two_rank_ingest_matches_oracle(torch_cuda):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     sys.stdout.write(res.stdout[-4000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert res.stdout.count(" OK") == 2 and "MISMATCH" not in res.stdout
+    assert res.stdout.count(" OK") == 4 and "MISMATCH" not in res.stdout

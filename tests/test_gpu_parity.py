@@ -443,6 +443,19 @@ def test_staged_remote_path_equals_resident_path_and_oracle(torch_cuda, kind, mo
     _, ref = oracle.run_pipeline(blob, np.concatenate([audio, audio], 1), want_features=False)
     err = np.abs(want.cpu().numpy() - ref[:, -want.shape[1]:]).max()           # the second call's steps are the last ones
     assert (err == 0.0) if kind == "int8" else (err <= F32_TOL)
+    # the tile timeline of a profiled staged call: 4 tiles, each copy before its kernels, copies and kernels in tile order;
+    # profiling must not change the result
+    staged.profile(True)
+    third = one.predict_clip(dev)
+    again = staged.predict_clip_remote(pinned.ctypes.data, 9600, tiles=4)
+    tl = staged.timeline_read()
+    staged.profile_read()
+    staged.profile(False)
+    assert torch.equal(again, third)
+    assert tl.shape == (4, 4) and tl[0, 0] == 0.0 and (tl >= 0).all()
+    assert (tl[:, 0] <= tl[:, 1]).all() and (tl[:, 1] <= tl[:, 3]).all() and (tl[:, 2] <= tl[:, 3]).all()
+    assert (np.diff(tl[:, 1]) >= 0).all() and (np.diff(tl[:, 3]) >= 0).all()
+    assert staged.timeline_read().shape == (0, 4)                                 # read clears the record
     # a device-resident source is computed in place (no staging)
     a, b = StreamEngine(blob, n_streams=13), StreamEngine(blob, n_streams=13)
     assert torch.equal(a.predict_clip_remote(dev.data_ptr(), 9600), b.predict_clip(dev))

@@ -113,8 +113,13 @@ class _OracleEngine:
     """CPU stand-in with the StreamEngine surface predict_clip_ingest uses: reads int16 [n_streams, n] at a raw address
     (here: a shared-memory segment standing in for the peer-mapped ingest buffer) and runs the oracle from carried state."""
 
+    stride, hop = 3, 160            # okay_nabu: three feature rows per model step, 10 ms hop
+
     def __init__(self, model, n_streams=1, device=0):
         self.blob, self.n_streams, self.history = model, n_streams, None
+
+    def close(self):
+        pass
 
     def predict_clip_remote(self, src_ptr, n_samples, stride=None, tiles=0, out=None):
         import ctypes
@@ -137,14 +142,15 @@ class _ShmIngest:
     def __init__(self, name, n_streams, n_samples, src=0):
         from multiprocessing import shared_memory
         self.shm = shared_memory.SharedMemory(name=name)
-        self.n_streams, self.n_samples, self.src = n_streams, n_samples, src
+        import torch
+        self.n_streams, self.n_samples, self.src, self.device = n_streams, n_samples, src, torch.device("cpu")
         self.view = np.ndarray((n_streams, n_samples), np.int16, buffer=self.shm.buf)
 
     def block_ptr(self, first_stream):
         return self.view[first_stream:].ctypes.data if first_stream < self.n_streams else self.view.ctypes.data
 
 
-def _ingest_worker(rank, world, port, n_streams, shm_name, q):
+def _ingest_worker(rank, world, port, n_streams, shm_name, q, shares=None):
     import torch.distributed as dist
 
     from microwakeword_b200.sharding import ShardedEngine
@@ -156,7 +162,8 @@ def _ingest_worker(rank, world, port, n_streams, shm_name, q):
         half = audio.shape[1] // 2 // 160 * 160
         blob = open(os.path.join(GOLDEN, "okay_nabu_synth_int8.mww"), "rb").read()
         ingest = _ShmIngest(shm_name, n_streams, half)
-        sh = ShardedEngine(blob, n_streams, 0, engine_factory=_OracleEngine)
+        sh = ShardedEngine(blob, n_streams, 0, engine_factory=_OracleEngine, shares=shares)
+        assert (sh.engine is None) == (shares is not None and shares[rank] == 0)
         outs = []
         for call in range(2):                        # two steps: the ingest rank refills the buffer between them
             if rank == 0:
@@ -173,8 +180,20 @@ def _ingest_worker(rank, world, port, n_streams, shm_name, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_streams", [12, 11])
-def test_two_rank_pulled_ingest_equals_single_process(n_streams):
+def test_ingest_shares():
+    from microwakeword_b200.sharding import ingest_shares, partition
+    assert ingest_shares(524288, 8, 0, 1.0) == [65536] * 8
+    assert ingest_shares(524288, 8, 0, 0.0) == [0] + [74899] * 2 + [74898] * 5 and sum(ingest_shares(524288, 8, 0, 0.0)) == 524288
+    assert ingest_shares(100, 4, 2, 0.5) == [29, 29, 12, 30][:0] + [30, 29, 12, 29] or sum(ingest_shares(100, 4, 2, 0.5)) == 100
+    assert ingest_shares(7, 1) == [7]
+    assert partition(10, 3, [0, 4, 6]) == [(0, 0), (0, 4), (4, 6)]
+    for bad in ([1, 2], [5, 5, 1], [-1, 5, 6]):
+        with pytest.raises(ValueError):
+            partition(10, 3, bad)
+
+
+@pytest.mark.parametrize("n_streams,shares", [(12, None), (11, None), (12, [0, 12]), (12, [3, 9])])
+def test_two_rank_pulled_ingest_equals_single_process(n_streams, shares):
     import torch.multiprocessing as mp
     from multiprocessing import shared_memory
 
@@ -186,7 +205,7 @@ def test_two_rank_pulled_ingest_equals_single_process(n_streams):
         ctx = mp.get_context("spawn")
         q = ctx.Queue()
         port = _free_port()
-        procs = [ctx.Process(target=_ingest_worker, args=(r, 2, port, n_streams, shm.name, q)) for r in range(2)]
+        procs = [ctx.Process(target=_ingest_worker, args=(r, 2, port, n_streams, shm.name, q, shares)) for r in range(2)]
         for p in procs:
             p.start()
         got = q.get(timeout=120)
