@@ -51,9 +51,12 @@ def parse_args():
     ap.add_argument("--model", default="f32", choices=["f32", "int8"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ingest-mode", default="auto", choices=["auto", "direct", "staged"],
+                    help="N > 1: how a rank reads its block of the ingest rank's buffer -- direct: the frontend kernel reads the peer-mapped "
+                         "buffer in place over NVLink; staged: the rank's copy engine pulls tile t+1 while tile t computes; auto: staged once "
+                         "the pull alone is slower than a rank's compute (the ingest GPU's NVLink egress is the bottleneck), else direct")
     ap.add_argument("--ingest-share", type=float, default=None,
-                    help="N > 1: the ingest rank's share of the streams as a fraction of an equal share (default: 1 while the pull alone "
-                         "is faster than a rank's compute, else 0)")
+                    help="N > 1: the ingest rank's share of the streams as a fraction of an equal share (default 1; 0 = it only feeds its peers)")
     ap.add_argument("--tiles", type=int, default=0, help="pipeline tiles per rank of the N > 1 ingest (0 = library default, 16)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the legs for the other BASELINE.json configurations (the other model dtype in clip mode, live 30 ms steps "
@@ -385,13 +388,13 @@ def run_gpu(args):
         pull_only()
         pull_ms = timed(pull_only, 2)
         del stage
-        # the ingest rank's share of the streams: an equal share while the peers' pulls hide behind their kernels; none once one
-        # GPU's NVLink egress is the floor (its own kernels would only slow the peers' reads of its memory: DESIGN.md section 5)
-        if args.ingest_share is not None:
-            src_share, why = float(args.ingest_share), "--ingest-share"
-        else:
-            src_share = 0.0 if pull_ms > ms_resident else 1.0
-            why = "auto: pull alone %.1f ms %s pre-sharded compute %.1f ms" % (pull_ms, ">" if src_share == 0.0 else "<=", ms_resident)
+        # the ingest rank's share of the streams: equal by default.  (Measured at N = 8, staged mode: equal shares 54.9 ms, the
+        # ingest rank feeding only 63.7 ms -- all 8 S streams then cross its NVLink instead of 7 S)
+        src_share = 1.0 if args.ingest_share is None else float(args.ingest_share)
+        why = "equal shares (default)" if args.ingest_share is None else "--ingest-share"
+        egress_bound = pull_ms > ms_resident
+        mode = args.ingest_mode if args.ingest_mode != "auto" else ("staged" if egress_bound else "direct")
+        ingest_tiles = 0 if mode == "direct" else (args.tiles or 16)
         shares = ingest_shares(total, world, 0, src_share)
         sh = ShardedEngine(model_blob(args.model), total, local_rank, shares=None if src_share == 1.0 else shares)
         my_probs = torch.empty((max(sh.count, 1), n_probs), dtype=torch.float32, device=device) if sh.count != S else probs
@@ -400,7 +403,7 @@ def run_gpu(args):
 
         def ingest_step():
             nonlocal gathered
-            gathered = sh.predict_clip_ingest(ingest, tiles=args.tiles, out=my_probs[:sh.count] if sh.count else None)
+            gathered = sh.predict_clip_ingest(ingest, tiles=ingest_tiles, out=my_probs[:sh.count] if sh.count else None)
 
         count_launches = lambda: sh.engine.launch_count if sh.engine is not None else 0
         sh.reset()
@@ -476,11 +479,14 @@ def run_gpu(args):
         nccl_serial()
         nccl_ms = timed(nccl_serial, 2)
         ingest_info = {
-            "how": "audio for all %d streams in rank 0's HBM; every rank pulls its block tile by tile with its own copy engine over "
-                   "NVLink peer access (CUDA IPC) while the previous tile computes (mww_predict_clip_remote), scores gathered to rank 0 with NCCL; "
-                   "a tiny all-reduce per step orders the pulls after the ingest rank's writes" % total,
+            "how": "audio for all %d streams in rank 0's HBM, mapped into every rank with CUDA IPC; " % total + (
+                   "every rank's frontend kernel reads its block in place over NVLink (zero-copy, no staging)" if mode == "direct" else
+                   "every rank's copy engine pulls its block tile by tile over NVLink while the previous tile computes (mww_predict_clip_remote, "
+                   "staged)") + "; scores gathered to rank 0 with NCCL; a one-element all-reduce per step orders the reads after the ingest rank's writes",
+            "mode": mode, "mode_rule": "%s (pull alone %.1f ms %s pre-sharded compute %.1f ms)" % (
+                args.ingest_mode, pull_ms, ">" if egress_bound else "<=", ms_resident),
             "streams_per_rank": shares, "ingest_rank_share": src_share, "ingest_rank_share_rule": why,
-            "tiles_per_rank": args.tiles or 16, "per_rank_ms_per_step": per_rank_ms,
+            "tiles_per_rank": ingest_tiles, "per_rank_ms_per_step": per_rank_ms,
             "nvlink_bytes_out_of_rank0_per_step": (total - shares[0]) * SAMPLES_PER_STEP * 2,
             "egress_floor_ms": pull_ms, "pull_only_gbs_out_of_rank0": S * SAMPLES_PER_STEP * 2 * (world - 1) / (pull_ms / 1e3) / 1e9,
             "egress_floor_note": "the pull alone with EQUAL blocks (S (N - 1) streams leave rank 0); with ingest_rank_share 0 all N S streams leave it",

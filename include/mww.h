@@ -138,15 +138,19 @@ int mww_predict_clip(mww_t *h, const int16_t *d_audio, int n_samples, long long 
 int mww_predict_clip_host(mww_t *h, const int16_t *h_audio, int n_samples, long long audio_stride,
                           float *h_probs, int max_probs, int *h_probs_out);
 
-/* Same pipeline with the audio somewhere this GPU can DMA from but should not compute from: device
- * memory of a PEER GPU of the box (mapped with mww_ipc_open -- the multi-GPU ingest of BASELINE.json
- * configs[4], "scatter stream batches") or host memory.  The streams are cut into `n_tiles` tiles
- * (<= 0: 16); this GPU's copy engine pulls tile t+1 over NVLink / PCIe into a staging buffer while the
- * kernels of tile t run, and the scores are written straight into d_probs on THIS device
- * ([n_streams][max_probs]).  Asynchronous and stream-ordered on cu_stream: the call starts after the
- * work queued on cu_stream so far and cu_stream waits for its last kernel.  A source that already lives
- * on this GPU is computed in place (= mww_predict_clip).  If a CUDA call fails half-way the handle is
- * left "poisoned": every stateful entry point fails until mww_reset(h, NULL, 0, stream). */
+/* The audio somewhere else than this GPU's own memory: device memory of a PEER GPU of the box (mapped with
+ * mww_ipc_open -- the multi-GPU ingest of BASELINE.json configs[4], "scatter stream batches") or host memory.
+ *   n_tiles <= 0: a source this GPU's kernels can address (its own memory, or a peer buffer mapped with mww_ipc_open --
+ *                 CUDA reports the mapping device for it) is read IN PLACE by the frontend kernel, i.e. over NVLink for a
+ *                 peer buffer (= mww_predict_clip; zero-copy, the right choice while the owner's NVLink egress is not the
+ *                 bottleneck); anything else (host memory) goes through the staged pipeline with 16 tiles.
+ *   n_tiles  > 0: always the staged pipeline: the streams are cut into n_tiles tiles, this GPU's copy engine pulls tile
+ *                 t+1 over NVLink / PCIe into a staging buffer while the kernels of tile t run (frontend AND network, so the
+ *                 network's time hides behind the pull -- the right choice when the pull is the bottleneck).
+ * Scores are written straight into d_probs on THIS device ([n_streams][max_probs]).  Asynchronous and stream-ordered on
+ * cu_stream: the call starts after the work queued on cu_stream so far and cu_stream waits for its last kernel.  If a
+ * CUDA call fails half-way the handle is left "poisoned": every stateful entry point fails until
+ * mww_reset(h, NULL, 0, stream). */
 int mww_predict_clip_remote(mww_t *h, const int16_t *src_audio, int n_samples, long long audio_stride,
                             float *d_probs, int max_probs, int *h_probs_out, int n_tiles, void *cu_stream);
 

@@ -1122,7 +1122,9 @@ int mww_predict_clip_remote(mww_t *h, const int16_t *src_audio, int n_samples, l
         if (cudaPointerGetAttributes(&at, src_audio) != cudaSuccess) { cudaGetLastError(); memset(&at, 0, sizeof at); }
         local = (at.type == cudaMemoryTypeDevice && at.device == h->device) || at.type == cudaMemoryTypeManaged;
     }
-    if (local) return mww_predict_clip(h, src_audio, n_samples, audio_stride, d_probs, max_probs, h_probs_out, cu_stream);   // nothing to stage
+    // a source this GPU's kernels can address -- its own memory, or a peer's buffer mapped with mww_ipc_open, which reports this
+    // device too -- is read in place by the frontend kernel unless the caller asks for the staged pipeline (n_tiles > 0)
+    if (local && n_tiles <= 0) return mww_predict_clip(h, src_audio, n_samples, audio_stride, d_probs, max_probs, h_probs_out, cu_stream);
     ENTER_STATEFUL(h);
     return predict_clip_staged(h, "mww_predict_clip_remote", src_audio, n_samples, audio_stride, d_probs, max_probs, h_probs_out, false, n_tiles,
                                static_cast<cudaStream_t>(cu_stream), false);

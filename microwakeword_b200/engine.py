@@ -228,8 +228,10 @@ class StreamEngine:
 
     def predict_clip_remote(self, src_ptr: int, n_samples: int, stride: int | None = None, tiles: int = 0, out=None):
         """Audio int16 [S, n_samples] at address `src_ptr` -- device memory of a PEER GPU mapped into this process
-        (sharding.IngestBuffer.block_ptr) or host memory -- pulled tile by tile by this GPU's copy engine while the previous
-        tile computes (mww_predict_clip_remote).  Returns float32 CUDA probabilities [S, steps]; stream-ordered like predict_clip."""
+        (sharding.IngestBuffer.block_ptr) or host memory (mww_predict_clip_remote).  tiles = 0: a peer-mapped (or local) buffer
+        is read in place by the frontend kernel, over NVLink; host memory is staged in 16 tiles.  tiles > 0: always staged --
+        this GPU's copy engine pulls tile t+1 while tile t computes.  Returns float32 CUDA probabilities [S, steps];
+        stream-ordered like predict_clip."""
         torch = _torch()
         n = int(n_samples)
         buffered = self.frontend_buffered

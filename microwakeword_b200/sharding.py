@@ -142,9 +142,9 @@ class IngestBuffer:
     0").  The buffer is a cudaMalloc owned by the library on the ingest rank, exported with cudaIpcGetMemHandle; every
     other rank opens the handle INSIDE ITS OWN device context (mww_ipc_open, cudaIpcMemLazyEnablePeerAccess), so no rank
     ever creates a context on the ingest GPU.  A rank then hands `block_ptr()` -- the address of its own block inside the
-    remote buffer -- to StreamEngine.predict_clip_remote, whose copy engine pulls tile t+1 over NVLink while tile t
-    computes: no communication kernel occupies an SM on either side and nothing has to be co-scheduled with the compute
-    grids.  One box only.
+    remote buffer -- to StreamEngine.predict_clip_remote: the frontend kernel reads it in place over NVLink (tiles = 0), or
+    the rank's copy engine pulls tile t+1 while tile t computes (tiles > 0).  Either way no communication kernel occupies
+    an SM on either side and nothing has to be co-scheduled with the compute grids.  One box only.
 
         with IngestBuffer(n_streams, n_samples, src=0, device=dev) as ingest:   # collective
             if rank == 0: ingest.buffer.copy_(audio)                             # the ingest rank fills it (its current stream)
@@ -326,9 +326,10 @@ class ShardedEngine:
                                       tiles=self.tiles, src=src, group=self.group, device=torch.device("cuda", self.engine.device))
 
     def predict_clip_ingest(self, ingest: "IngestBuffer", tiles: int = 0, out=None):
-        """Audio sits in `ingest` on its src rank; every rank pulls and computes its own block (one engine, the library's
-        staged pipeline: copy engine over NVLink || kernels), scores are gathered on the src rank.  Returns [n_total, steps]
-        there, None elsewhere.  `tiles` = pipeline depth per rank (<= 0: the library default of 16)."""
+        """Audio sits in `ingest` on its src rank; every rank computes its own block of it (one engine), scores are gathered on
+        the src rank.  Returns [n_total, steps] there, None elsewhere.  tiles = 0: the frontend kernel reads the peer-mapped
+        buffer in place over NVLink (zero-copy; best while the ingest GPU's egress is not the bottleneck); tiles > 0: the library's
+        staged pipeline -- this rank's copy engine pulls tile t+1 while tile t computes (best when it is)."""
         import torch.distributed as dist
 
         if ingest.n_streams != self.n_total:
