@@ -184,14 +184,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 template <int I>
 __device__ __forceinline__ void live3_p_warp(int c, int lane, float *sm, uint64_t *full, uint64_t *empty, const NnWeightsF32 &W, int head,
                                              int n_groups, int debug_mode) {
-    constexpr int R = live_ring_rows(I), C = live_ring_cols(I);
-    constexpr int off = kStateOff[I + 1] - kStateOff[1];
+    constexpr int R = live_ring_rows(I);
     constexpr int per_group = kLiveStreams / kLive3Stages;             // uses of each stage per group (even: parity restarts every group)
-    const float *taps = (I < 4 ? W.dw_w[I < 4 ? I : 0] : W.head_w) + c;
-    float w[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) { const int j = r < head ? R - head + r : r - head; w[r] = __ldg(taps + j * C); }   // (r - head) mod R
-    const float bias = I < 4 ? __ldg(W.dw_b[I < 4 ? I : 0] + c) : 0.f;
+    float w[R], bias;
+    live3_p_taps<I>(W, c, head, w, bias);
     float *p_col = sm + kLive2OffP + (live2_col_base(I) + c) * kLive2PPitch;
     int k = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++k) {
@@ -207,11 +203,7 @@ __device__ __forceinline__ void live3_p_warp(int c, int lane, float *sm, uint64_
 #pragma unroll
                 for (int s = 0; s < kLive3Stages; ++s) {
                     mbar_wait(full + s, (unsigned)(round & 1));
-                    const float *x = sm + live3_stage_off(s) + off + c;
-                    float a = bias;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) a = fmaf(w[r], x[r * C], a);
-                    acc[kLiveStreams - kLive3Stages + s] = a;
+                    acc[kLiveStreams - kLive3Stages + s] = live3_p_sum<I>(sm + live3_stage_off(s), c, w, bias);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty + s);
                 }

@@ -494,6 +494,28 @@ MWW_HD void live3_window_store(int t, float *sm, const float (&v)[kLive3WindowPe
         if (idx < (unsigned)(kLiveStreams * 200)) a[kk * (unsigned)kLivePitch + sl] = v[i];
     }
 }
+// v3 "P" thread: ring I, column c of it.  Taps rotated once per launch so that tap r multiplies PHYSICAL row r of the rotated
+// ring (tap of physical row r = row (r - head) mod R of the [R + 1][C] table); the sum runs in physical row order from the
+// bias -- exactly live_ring_pass's / live2_stream_ring's order, so v1 = v2 = v3 bit for bit.
+// `rings` = the stream's state from ring 1 on (kStateOff[1]): what one bulk-copy stage holds.
+template <int I>
+MWW_HD void live3_p_taps(const NnWeightsF32 &W, int c, int head, float (&w)[live_ring_rows(I)], float &bias) {
+    constexpr int R = live_ring_rows(I), C = live_ring_cols(I);
+    const float *taps = (I < 4 ? W.dw_w[I < 4 ? I : 0] : W.head_w) + c;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { const int j = r < head ? R - head + r : r - head; w[r] = taps[j * C]; }
+    bias = I < 4 ? W.dw_b[I < 4 ? I : 0][c] : 0.f;
+}
+template <int I>
+MWW_HD float live3_p_sum(const float *rings, int c, const float (&w)[live_ring_rows(I)], float bias) {
+    constexpr int R = live_ring_rows(I), C = live_ring_cols(I);
+    constexpr int off = kStateOff[I + 1] - kStateOff[1];
+    const float *x = rings + off + c;
+    float a = bias;
+#pragma unroll
+    for (int r = 0; r < R; ++r) a = fmaf(w[r], x[r * C], a);
+    return a;
+}
 // the chain's half of the tail in v3: new first-conv ring = window[120:200], read back from the A operand
 MWW_HD void live3_write_ring0(int tid, const float *sm, float *state, long long s0, int n_valid) {
     const int sl = tid >> 3, part = tid & 7;

@@ -35,6 +35,7 @@ def lib():
         L.emul_nn_i8.restype = ctypes.c_int
         L.emul_nn_f32_live.restype = ctypes.c_int
         L.emul_nn_f32_live2.restype = ctypes.c_int
+        L.emul_nn_f32_live3.restype = ctypes.c_int
         L.emul_nn_live_canonicalise.restype = None
         L.emul_nn_i8_live.restype = ctypes.c_int
         L.emul_nn_i8_live_canonicalise.restype = None
@@ -135,7 +136,8 @@ class NnF32Live(NnF32):
     RING_ROWS = (4, 10, 14, 22, 16)
 
     def __init__(self, *a, version=2, order=0, **kw):
-        """version 1: the r01 kernel (every CTA alternates ring loads and layer chain); 2: the warp-specialised one"""
+        """version 1: the r01 kernel (every CTA alternates ring loads and layer chain); 2: the warp-specialised one (register-load
+        streamers); 3: the bulk-copy kernel's phase functions (P threads, window warps, v2's chain) -- the GPU default"""
         super().__init__(*a, **kw)
         self.heads = np.zeros(5, np.int32)
         self.version, self.order = version, order
@@ -145,7 +147,10 @@ class NnF32Live(NnF32):
         S = rows3.shape[0]
         assert rows3.shape[1:] == (3, 40)
         probs = np.zeros((S, 1), np.float32)
-        if self.version == 2:
+        if self.version == 3:
+            lib().emul_nn_f32_live3(self.wp, _p(self.state), _p(self.pend), self.n_pend, _p(rows3), int(rows3.dtype == np.float32), S, _p(probs), 1,
+                                    _p(self.heads), int(self.order))
+        elif self.version == 2:
             lib().emul_nn_f32_live2(self.wp, _p(self.state), _p(self.pend), self.n_pend, _p(rows3), int(rows3.dtype == np.float32), S, _p(probs), 1,
                                     _p(self.heads), int(self.order))
         else:

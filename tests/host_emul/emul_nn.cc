@@ -402,6 +402,77 @@ extern "C" int emul_nn_f32_live2(const float *const *wp, float *state, float *pe
     return 1;
 }
 
+// v3: the bulk-copy kernel (nn_f32_live3_kernel).  On the GPU a producer thread copies each stream's rings 1..5 into a shared
+// memory stage and nine "P" warps (one ring column per thread) reduce it; six window warps build the first-conv window (and move
+// the pending rows) a group ahead; the chain is v2's with the first conv's weights read from global memory.  The emulation runs
+// the same phase functions with the stage = the stream's state in place (a short last group re-reads its last valid stream, as
+// the producer does), window loads of a group before its chain.
+template <int I>
+static void emul_live3_p(const NnWeightsF32 &W, const float *state, long long s0, int n_valid, int head, float *sm, int order) {
+    constexpr int C = live_ring_cols(I);
+    for (int i_ = 0; i_ < C; ++i_) {
+        const int c = order ? C - 1 - i_ : i_;
+        float w[live_ring_rows(I)], bias;
+        live3_p_taps<I>(W, c, head, w, bias);
+        float *p_col = sm + kLive2OffP + (live2_col_base(I) + c) * kLive2PPitch;
+        for (int sl = 0; sl < kLiveStreams; ++sl) {
+            const long long stream = s0 + (sl < n_valid ? sl : n_valid - 1);
+            p_col[sl] = live3_p_sum<I>(state + (size_t)stream * kStateFloats + kStateOff[1], c, w, bias);
+        }
+    }
+}
+extern "C" int emul_nn_f32_live3(const float *const *wp, float *state, float *pend, int n_pend, const void *rows, int rows_are_f32,
+                                 int n_streams, float *probs, int probs_stride, const int *heads5, int order) {
+    NnWeightsF32 W;
+    W.w0 = wp[0];
+    for (int i = 0; i < 4; ++i) { W.dw_w[i] = wp[1 + i]; W.dw_b[i] = wp[5 + i]; W.pw_w[i] = wp[9 + i]; W.pw_b[i] = wp[13 + i]; }
+    W.head_w = wp[17]; W.head_b = wp[18];
+    LiveHeads heads;
+    for (int i = 0; i < 5; ++i) heads.h[i] = heads5[i];
+    LiveInput in;
+    in.state = state; in.pend = pend; in.n_pend = n_pend; in.rows = rows;
+    in.rows_stream_stride_bytes = 3 * kNumChannels * (rows_are_f32 ? 4 : 2); in.rows_are_f32 = rows_are_f32;
+    std::vector<float> smv(kLive2SmemFloats, -777.f);
+    float *sm = smv.data();
+#define CHAIN(stmt) for (int i_ = 0; i_ < kLive2ChainThreads; ++i_) { const int tid = order ? kLive2ChainThreads - 1 - i_ : i_; stmt; }
+#define WINDOW(stmt) for (int i_ = 0; i_ < kLive3WindowThreads; ++i_) { const int at = order ? kLive3WindowThreads - 1 - i_ : i_; stmt; }
+    for (int tid = 0; tid < kLive2Threads; ++tid)
+        for (int L = 1; L < 4; ++L) {
+            float *dst = sm + (L == 1 ? kLiveOffPw1 : (L == 2 ? kLiveOffPw2 : kLiveOffPw3));
+            for (int e = tid; e < 64 * 64; e += kLive2Threads) dst[(e >> 6) * kWLd + (e & 63)] = W.pw_w[L][e];
+        }
+    for (int tid = 0; tid < kLive2Threads; ++tid) live2_stage_chain_tables(tid, kLive2Threads, sm, W, false);
+    const int n_groups = (n_streams + kLiveStreams - 1) / kLiveStreams;
+    std::vector<float> vals((size_t)kLive3WindowThreads * kLive3WindowPerThread);
+    for (int g = 0; g < n_groups; ++g) {
+        const long long s0 = (long long)g * kLiveStreams;
+        const int n_valid = n_streams - (int)s0 < kLiveStreams ? n_streams - (int)s0 : kLiveStreams;
+        emul_live3_p<0>(W, state, s0, n_valid, heads.h[0], sm, order);
+        emul_live3_p<1>(W, state, s0, n_valid, heads.h[1], sm, order);
+        emul_live3_p<2>(W, state, s0, n_valid, heads.h[2], sm, order);
+        emul_live3_p<3>(W, state, s0, n_valid, heads.h[3], sm, order);
+        emul_live3_p<4>(W, state, s0, n_valid, heads.h[4], sm, order);
+        // window warps: every load of the group (old pending rows included) precedes the pending-row stores (named barrier)
+        WINDOW({ float (&v)[kLive3WindowPerThread] = *reinterpret_cast<float (*)[kLive3WindowPerThread]>(&vals[(size_t)at * kLive3WindowPerThread]);
+                 live3_window_load(at, in, s0, n_valid, v); });
+        if (n_pend != 0) WINDOW(live3_pend_store(at, in, pend, s0, n_valid));
+        WINDOW({ const float (&v)[kLive3WindowPerThread] = *reinterpret_cast<const float (*)[kLive3WindowPerThread]>(&vals[(size_t)at * kLive3WindowPerThread]);
+                 live3_window_store(at, sm, v); });
+        const float *p_buf = sm + kLive2OffP;
+        emul_live_first_conv(sm, W.w0, 32);
+        CHAIN(live3_write_ring0(tid, sm, state, s0, n_valid));
+        CHAIN(live2_dw_from_p<0>(tid, sm, state, s0, n_valid, heads.h[0], p_buf)); emul_live_pointwise<0, true>(sm, W);
+        CHAIN(live2_dw_from_p<1>(tid, sm, state, s0, n_valid, heads.h[1], p_buf)); emul_live_pointwise<1, true>(sm, W);
+        CHAIN(live2_dw_from_p<2>(tid, sm, state, s0, n_valid, heads.h[2], p_buf)); emul_live_pointwise<2, true>(sm, W);
+        CHAIN(live2_dw_from_p<3>(tid, sm, state, s0, n_valid, heads.h[3], p_buf)); emul_live_pointwise<3, true>(sm, W);
+        CHAIN(live2_dw_from_p<4>(tid, sm, state, s0, n_valid, heads.h[4], p_buf));
+        CHAIN(live_head_finish_b(tid, sm, sm[kLive2OffSmall + kLive2SmallHeadBias], s0, n_valid, probs, probs_stride));
+    }
+#undef CHAIN
+#undef WINDOW
+    return 1;
+}
+
 extern "C" void emul_nn_live_canonicalise(float *state, int n_streams, const int *heads5) {
     LiveHeads heads;
     for (int i = 0; i < 5; ++i) heads.h[i] = heads5[i];

@@ -226,7 +226,7 @@ def test_live_step_kernel_phases_match_oracle_and_interleave_with_clip():
     S = 70
     audio = np.stack([synth_audio(9600, 900 + i) for i in range(S)])
     feats, want = oracle.run_pipeline(MF.write_container(t), audio)            # 58 rows -> 19 probabilities
-    for n_first, version, order in ((3, 2, 0), (4, 2, 1), (5, 2, 0), (4, 1, 0)):   # first call leaves 0 / 1 / 2 rows pending
+    for n_first, version, order in ((3, 2, 0), (4, 2, 1), (5, 2, 0), (4, 1, 0), (3, 3, 1), (4, 3, 0), (5, 3, 1)):   # first call leaves 0 / 1 / 2 rows pending
         nn = emul.NnF32Live(t, S, version=version, order=order)
         got = [nn.infer(feats[:, :n_first])]                                   # clip-kernel phases: 1 step (+ pending)
         pos = n_first
@@ -245,11 +245,19 @@ def test_live_step_kernel_phases_match_oracle_and_interleave_with_clip():
         rest = nn.infer(feats[:, pos:])
         tail = want[:, got.shape[1]:got.shape[1] + rest.shape[1]]
         assert rest.shape == tail.shape and (rest.size == 0 or np.abs(rest - tail).max() <= 1e-5)
-    # the warp-specialised kernel performs the r01 kernel's arithmetic in the same order: bit-identical, state included
-    a, b = emul.NnF32Live(t, S, version=1), emul.NnF32Live(t, S, version=2)
-    for pos in range(0, 30, 3):
-        assert np.array_equal(a.step(feats[:, pos:pos + 3]), b.step(feats[:, pos:pos + 3]))
-    assert np.array_equal(a.state, b.state) and np.array_equal(a.pend, b.pend)
+    # the warp-specialised kernels perform the r01 kernel's arithmetic in the same order: bit-identical, state included -- also
+    # with rows pending (a clip call of 4 rows first) and with float32 feature rows
+    for first, dtype in ((0, np.float32), (4, np.float32), (5, np.uint16)):
+        rows_all = feats if dtype == np.float32 else np.round(feats / np.float32(0.0390625)).astype(np.uint16)
+        a, b, c = (emul.NnF32Live(t, S, version=v) for v in (1, 2, 3))
+        if first:
+            for e in (a, b, c):
+                e.infer(feats[:, :first])
+        for pos in range(first, first + 30, 3):
+            pa = a.step(rows_all[:, pos:pos + 3])
+            assert np.array_equal(pa, b.step(rows_all[:, pos:pos + 3])) and np.array_equal(pa, c.step(rows_all[:, pos:pos + 3]))
+        assert np.array_equal(a.state, b.state) and np.array_equal(a.pend, b.pend)
+        assert np.array_equal(a.state, c.state) and np.array_equal(a.pend, c.pend)
 
 
 def test_int8_live_step_kernel_phases_are_bit_exact():

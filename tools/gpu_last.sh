@@ -1,7 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 300 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo rc=$?; tail -c 600 gpurun_out/bench_n1.err
-timeout 120 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo rc=$?
-python -c "
-import __graft_entry__ as g
-g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 200 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+timeout 100 python tools/live_time.py f32 60 2>&1 | tail -1
