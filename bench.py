@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--model", default="f32", choices=["f32", "int8"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-wc", type=int, default=0, help="e2e leg: 1 = the host AUDIO buffer is write-combined pinned memory (mww_host_alloc_wc)")
     ap.add_argument("--ingest-mode", default="auto", choices=["auto", "direct", "staged"],
                     help="N > 1: how a rank reads its block of the ingest rank's buffer -- direct: the frontend kernel reads the peer-mapped "
                          "buffer in place over NVLink; staged: the rank's copy engine pulls tile t+1 while tile t computes; auto: staged once "
@@ -512,7 +513,7 @@ def run_gpu(args):
     # ---- e2e through the host-buffer C-ABI call (pinned buffers on this GPU's NUMA node) ----
     e2e = None
     if not args.no_e2e:
-        ha = host_array((S, SAMPLES_PER_STEP), np.int16, local_rank)
+        ha = host_array((S, SAMPLES_PER_STEP), np.int16, local_rank, write_combined=bool(args.e2e_wc))
         hp = host_array((S, n_probs), np.float32, local_rank)
         torch.from_numpy(ha).copy_(audio)
         torch.cuda.synchronize()
@@ -527,7 +528,7 @@ def run_gpu(args):
                "d2h_bytes_per_step": S * (FRAMES_PER_STEP // 3) * 4 * world, "ms_per_step": e2e_ms, "steps": e2e_steps,
                "h2d_gbs_per_gpu": S * SAMPLES_PER_STEP * 2 / (e2e_ms / 1e3) / 1e9,
                "api": "mww_predict_clip_host (pinned host int16 audio in, float32 probabilities out; buffers from mww_host_alloc)",
-               "host_buffers_numa_node": ha.base.base.numa_node, "rank_bound_to_numa_node": numa_node,
+               "audio_buffer_write_combined": bool(args.e2e_wc), "host_buffers_numa_node": ha.base.base.numa_node, "rank_bound_to_numa_node": numa_node,
                "checksum_matches_device_path": bool(abs(float(hp[:, :100].astype(np.float64).sum()) - checksum) < 1e-3 * max(1.0, abs(checksum)))}
         del ha, hp
 

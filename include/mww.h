@@ -224,6 +224,10 @@ int mww_ipc_free(void *d_ptr, int device);
  * the topology cannot be read (then this is a plain cudaHostAlloc).  mww_bind_host_thread moves the CALLING thread to
  * the GPU's node for good (a rank calls it once, before anything else allocates). */
 int mww_host_alloc(size_t bytes, int device, void **h_ptr, int *numa_node_out);
+/* Same, write-combined (cudaHostAllocWriteCombined): for INPUT buffers the CPU only writes (sequentially) and the GPU only
+ * reads -- audio on its way to mww_predict_clip_host.  Transfers of write-combined memory are not snooped on the PCIe bus;
+ * CPU reads of it are very slow, so never use it for the probability buffer.  Freed with mww_host_free. */
+int mww_host_alloc_wc(size_t bytes, int device, void **h_ptr, int *numa_node_out);
 int mww_host_free(void *h_ptr);
 int mww_bind_host_thread(int device, int *numa_node_out);
 

@@ -22,7 +22,7 @@ EXPORTS = (
     "mww_get_state", "mww_set_state", "mww_launch_count", "mww_profile_enable", "mww_profile_read", "mww_timeline_read",
     "mww_moving_average", "mww_false_accept_counts", "mww_positive_scores", "mww_copy_async",
     "mww_ipc_alloc", "mww_ipc_open", "mww_ipc_close", "mww_ipc_free",
-    "mww_predict_clip_remote", "mww_reset_device_ids", "mww_host_alloc", "mww_host_free", "mww_bind_host_thread",
+    "mww_predict_clip_remote", "mww_reset_device_ids", "mww_host_alloc", "mww_host_alloc_wc", "mww_host_free", "mww_bind_host_thread",
     "mww_set_window_step",
 )
 
@@ -114,6 +114,8 @@ def lib() -> ctypes.CDLL:
     L.mww_reset_device_ids.argtypes = [vp, vp, i32, vp]
     L.mww_host_alloc.restype = i32
     L.mww_host_alloc.argtypes = [sz, i32, ctypes.POINTER(vp), pi]
+    L.mww_host_alloc_wc.restype = i32
+    L.mww_host_alloc_wc.argtypes = [sz, i32, ctypes.POINTER(vp), pi]
     L.mww_host_free.restype = i32
     L.mww_host_free.argtypes = [vp]
     L.mww_set_window_step.restype = i32

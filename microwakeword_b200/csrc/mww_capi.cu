@@ -1200,7 +1200,17 @@ int mww_bind_host_thread(int device, int *numa_node_out) {
     return MWW_OK;
 }
 
+namespace {
+int host_alloc_impl(size_t bytes, int device, unsigned flags, void **h_ptr, int *numa_node_out);
+}
 int mww_host_alloc(size_t bytes, int device, void **h_ptr, int *numa_node_out) {
+    return host_alloc_impl(bytes, device, cudaHostAllocPortable, h_ptr, numa_node_out);
+}
+int mww_host_alloc_wc(size_t bytes, int device, void **h_ptr, int *numa_node_out) {
+    return host_alloc_impl(bytes, device, cudaHostAllocPortable | cudaHostAllocWriteCombined, h_ptr, numa_node_out);
+}
+namespace {
+int host_alloc_impl(size_t bytes, int device, unsigned flags, void **h_ptr, int *numa_node_out) {
     if (!h_ptr || bytes == 0) { g_create_error = "mww_host_alloc: bad argument"; return MWW_EINVAL; }
     *h_ptr = nullptr;
     DeviceGuard guard(device);
@@ -1214,12 +1224,13 @@ int mww_host_alloc(size_t bytes, int device, void **h_ptr, int *numa_node_out) {
     const bool moved = have_before && node_cpus(node, &cpus) && sched_setaffinity(0, sizeof cpus, &cpus) == 0;
     if (moved) prefer_node(node);
     void *p = nullptr;
-    const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    const cudaError_t e = cudaHostAlloc(&p, bytes, flags);
     if (moved) { prefer_node(-1); sched_setaffinity(0, sizeof before, &before); }
     if (e != cudaSuccess) return ipc_fail("mww_host_alloc: cudaHostAlloc", e);
     *h_ptr = p;
     return MWW_OK;
 }
+}  // namespace
 
 int mww_host_free(void *h_ptr) {
     if (!h_ptr) return MWW_OK;

@@ -30,10 +30,11 @@ def _torch():
 class _PinnedBlock:
     """Owner of one mww_host_alloc allocation; numpy arrays built on it keep it alive through their .base chain."""
 
-    def __init__(self, nbytes: int, device: int):
+    def __init__(self, nbytes: int, device: int, write_combined: bool = False):
         L = _lib.lib()
         ptr, node = ctypes.c_void_p(), ctypes.c_int(-1)
-        _lib.check(None, L.mww_host_alloc(max(int(nbytes), 1), int(device), ctypes.byref(ptr), ctypes.byref(node)))
+        alloc = L.mww_host_alloc_wc if write_combined else L.mww_host_alloc
+        _lib.check(None, alloc(max(int(nbytes), 1), int(device), ctypes.byref(ptr), ctypes.byref(node)))
         self.ptr, self.nbytes, self.numa_node = ptr.value, int(nbytes), node.value
         self.__array_interface__ = {"shape": (max(int(nbytes), 1),), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
 
@@ -46,11 +47,12 @@ class _PinnedBlock:
             pass
 
 
-def host_array(shape, dtype=np.int16, device: int = 0) -> np.ndarray:
-    """Pinned, GPU-local (NUMA) host array; `.base.base.numa_node` tells where it landed (-1: topology unknown)."""
+def host_array(shape, dtype=np.int16, device: int = 0, write_combined: bool = False) -> np.ndarray:
+    """Pinned, GPU-local (NUMA) host array; `.base.base.numa_node` tells where it landed (-1: topology unknown).
+    write_combined: for input buffers the CPU only writes and the GPU only reads (mww_host_alloc_wc; CPU reads are very slow)."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
-    block = _PinnedBlock(n, device)
+    block = _PinnedBlock(n, device, write_combined)
     return np.asarray(block)[:n].view(dtype).reshape(shape)
 
 
@@ -247,10 +249,10 @@ class StreamEngine:
         return out[:, :got.value]
 
     # ------------------------------------------------------------------ pinned host buffers next to the GPU
-    def host_buffer(self, shape, dtype=np.int16) -> np.ndarray:
+    def host_buffer(self, shape, dtype=np.int16, write_combined: bool = False) -> np.ndarray:
         """Pinned host array on the NUMA node this engine's GPU hangs off (mww_host_alloc): full-rate predict_clip_host copies
         on a two-socket box whatever CPU the caller runs on.  Freed when the array (and every view of it) is gone."""
-        return host_array(shape, dtype, self.device)
+        return host_array(shape, dtype, self.device, write_combined)
 
     # ------------------------------------------------------------------ per-kernel device timing
     KERNEL_CLASSES = ("k1_spectral", "k2_temporal", "mixednet", "carry_update")
