@@ -567,6 +567,11 @@ int upload_weights(mww_t *h, const uint8_t *blob, size_t n) {
                 up = upload(h->d_weights, cur, ops.pwt[i].data(), ops.pwt[i].size(), &Q.pwt[i], &e) &&
                      upload(h->d_weights, cur, ops.pw_bf[i].data(), ops.pw_bf[i].size() * 4, &Q.pw_bf[i], &e);
             if (!up) return cuda_fail(h, e, "weight upload");
+            if (getenv("MWW_NO_QLUT") == nullptr) {
+                std::vector<int8_t> qlut;
+                build_feature_qlut(Q.in_scale, Q.zp[0], &qlut);
+                if (!upload(h->d_weights, cur, qlut.data(), qlut.size(), &Q.qlut, &e)) return cuda_fail(h, e, "weight upload");
+            }
         }
         h->out_scale = scales[11]; h->out_zp = 0;   // uint8 output tensor: zero point -128 + 128 (utils.py:338)
     }

@@ -31,6 +31,10 @@ struct NnWeightsI8 {
     const int8_t *pwt[4];     // [64 n][kPwPitch]   1x1 weights, K-contiguous
     const int32_t *b0f;       // [32]  bias - zp_in * sum_k w   (the MMA runs on raw int8 activations)
     const int32_t *pw_bf[4];  // [64]  bias - zp_d  * sum_k w
+    // input quantisation of a uint16 feature as a table: qlut[u] = nnq_quantize(u * kFeatureScale, in_scale, zp[0]) for every
+    // u (64 KB, built by mww_create / the host emulation with that very expression, so exact by construction).  nullptr: compute.
+    // r02 profile of the clip kernel: the float division + conversions of this step were 14 % of its instructions.
+    const int8_t *qlut = nullptr;
 };
 
 // zero point of the tensor buffered by ring L (0..3: block inputs, 4: head input)
@@ -81,9 +85,12 @@ MWW_HD int32_t nnq_virtual_row(const NnInputI8 &in, const NnWeightsI8 &W, int vr
         const long long e = (long long)(vr - in.n_pend) * kNumChannels + f;
         if (in.row_type == 2) q = static_cast<const int8_t *>(in.rows)[e];
         else {
-            const float x = in.row_type == 1 ? static_cast<const float *>(in.rows)[e]
-                                             : (float)static_cast<const uint16_t *>(in.rows)[e] * kFeatureScale;
-            q = nnq_quantize(x, W.in_scale, W.zp[0]);
+            if (in.row_type == 0 && W.qlut) q = W.qlut[static_cast<const uint16_t *>(in.rows)[e]];
+            else {
+                const float x = in.row_type == 1 ? static_cast<const float *>(in.rows)[e]
+                                                 : (float)static_cast<const uint16_t *>(in.rows)[e] * kFeatureScale;
+                q = nnq_quantize(x, W.in_scale, W.zp[0]);
+            }
         }
     }
     return q - W.zp[0];
@@ -160,6 +167,14 @@ MWW_HD NnQ8 nnq_row_octet(const NnInputI8 &in, const NnWeightsI8 &W, int vr, int
     } else {
         struct alignas(16) U8 { uint16_t v[8]; };
         const U8 u = *reinterpret_cast<const U8 *>(static_cast<const uint16_t *>(in.rows) + e);
+        if (W.qlut) {
+            uint32_t t[2] = {0u, 0u};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i >> 2] |= (uint32_t)(uint8_t)W.qlut[u.v[i]] << (8 * (i & 3));
+            NnQ8 r;
+            r.lo = t[0]; r.hi = t[1];
+            return r;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = (float)u.v[i] * kFeatureScale;
     }

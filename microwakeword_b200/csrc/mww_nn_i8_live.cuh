@@ -54,6 +54,7 @@ MWW_HD uint32_t livq_row_word(const LiveInputI8 &in, const NnWeightsI8 &W, size_
     } else {
         struct alignas(8) U16x4 { uint16_t v[4]; };
         const U16x4 v = *reinterpret_cast<const U16x4 *>(base + 8 * (size_t)e4);
+        if (W.qlut) return livq_pack(W.qlut[v.v[0]], W.qlut[v.v[1]], W.qlut[v.v[2]], W.qlut[v.v[3]]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) x[q] = (float)v.v[q] * kFeatureScale;
     }

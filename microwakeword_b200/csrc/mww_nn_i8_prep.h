@@ -16,7 +16,14 @@ struct I8MmaOperands {
     std::vector<int8_t> pwt[4];       // [64][kPwPitch]
     std::vector<int32_t> b0f;         // [32]
     std::vector<int32_t> pw_bf[4];    // [64]
+    std::vector<int8_t> qlut;         // [65536] (build_feature_qlut; the host emulation keeps it here)
 };
+
+// NnWeightsI8::qlut: the input quantisation of every possible uint16 feature value, by the kernels' own expression
+inline void build_feature_qlut(float in_scale, int32_t zp_in, std::vector<int8_t> *out) {
+    out->resize(65536);
+    for (int u = 0; u < 65536; ++u) (*out)[u] = (int8_t)nnq_quantize((float)(uint16_t)u * kFeatureScale, in_scale, zp_in);
+}
 
 // w0: [200][32] int8, b0: [32]; pw_w[L]: [cin][64], pw_b[L]: [64]; zp: the 12 activation zero points
 inline void build_i8_mma_operands(const int8_t *w0, const int32_t *b0, const int8_t *const pw_w[4], const int32_t *const pw_b[4],

@@ -1,6 +1,7 @@
 // tests/host_emul/emul_nn.cc -- TEST INFRASTRUCTURE: CPU execution of the product's fp32 MixedNet phase
 // functions (microwakeword_b200/csrc/mww_nn_dev.cuh), barriers modelled as phase boundaries.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -232,6 +233,10 @@ extern "C" int emul_nn_i8(const void *const *wp /* see order below */, const int
     I8MmaOperands ops;
     build_i8_mma_operands(W.w0, W.b0, W.pw_w, W.pw_b, W.zp, &ops);
     W.w0t = ops.w0t.data(); W.b0f = ops.b0f.data();
+    if (getenv("MWW_NO_QLUT") == nullptr) {      // as mww_create does: uint16 features are quantised through the table
+        build_feature_qlut(W.in_scale, W.zp[0], &ops.qlut);
+        W.qlut = ops.qlut.data();
+    }
     for (int i = 0; i < 4; ++i) { W.pwt[i] = ops.pwt[i].data(); W.pw_bf[i] = ops.pw_bf[i].data(); }
     const int n_virtual = n_pend + n_rows;
     const int n_steps = n_virtual / 3;
@@ -481,6 +486,12 @@ extern "C" void emul_nn_live_canonicalise(float *state, int n_streams, const int
 }
 
 
+extern "C" void emul_feature_qlut(float in_scale, int zp_in, int8_t *out65536) {
+    std::vector<int8_t> t;
+    build_feature_qlut(in_scale, zp_in, &t);
+    memcpy(out65536, t.data(), t.size());
+}
+
 // ---- live-step int8 kernel (mww_nn_i8_live.cuh) -------------------------------------------------------------
 #include "../../microwakeword_b200/csrc/mww_nn_i8_live.cuh"
 namespace {
@@ -497,6 +508,10 @@ void unpack_i8_weights(const void *const *wp, const int32_t *zp12, const int32_t
     W.in_scale = in_scale;
     build_i8_mma_operands(W.w0, W.b0, W.pw_w, W.pw_b, W.zp, &ops);
     W.w0t = ops.w0t.data(); W.b0f = ops.b0f.data();
+    if (getenv("MWW_NO_QLUT") == nullptr) {      // as mww_create does: uint16 features are quantised through the table
+        build_feature_qlut(W.in_scale, W.zp[0], &ops.qlut);
+        W.qlut = ops.qlut.data();
+    }
     for (int i = 0; i < 4; ++i) { W.pwt[i] = ops.pwt[i].data(); W.pw_bf[i] = ops.pw_bf[i].data(); }
 }
 

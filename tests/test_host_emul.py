@@ -200,6 +200,19 @@ def test_nn_int8_phases_bit_exact():
     assert np.array_equal(np.concatenate(parts, 1)[0], np.load(os.path.join(GOLDEN, "config0_probs_int8.npy")))
 
 
+def test_feature_quantisation_table_is_the_reference_expression_for_every_uint16():
+    """NnWeightsI8::qlut (built by mww_create and by the emulation with build_feature_qlut): every one of the 65 536 possible
+    uint16 features maps to what Model.quantize_input_data computes for feature * 0.0390625 (inference.py:93-94, 127-147)."""
+    import ctypes
+    from oracle import mixednet_ref as R
+    u = np.arange(65536, dtype=np.uint16)
+    x = u.astype(np.float32) * np.float32(0.0390625)
+    for scale, zp in ((0.10196078568696976, -128), (0.0390625, -128), (0.25, 3), (1.0 / 3.0, -7), (26.0, 0)):
+        out = np.zeros(65536, np.int8)
+        emul.lib().emul_feature_qlut(ctypes.c_float(scale), int(zp), out.ctypes.data_as(ctypes.c_void_p))
+        assert np.array_equal(out, R.quantize_input(x, np.float32(scale), zp)), (scale, zp)
+
+
 def test_closed_form_requantisation_equals_tflite_reference():
     """The kernels' MultiplyByQuantizedMultiplier (arithmetic-shift closed form) == the literal SRDHM + RoundingDivideByPOT."""
     from oracle import mixednet_ref as R

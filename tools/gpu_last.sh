@@ -1,11 +1,7 @@
-# e2e A/B: pinned audio buffer plain vs write-combined
+# last check of the round: full GPU suite, then the int8 clip / live timings with the feature-quantisation table
 mkdir -p gpurun_out
-for wc in 1 0; do
-  timeout 60 python bench.py --no-extra --no-cpu --steps 4 --warmup 3 --e2e-wc $wc > gpurun_out/bench_e2e_wc$wc.json 2> gpurun_out/bench_e2e_wc$wc.err
-  python - <<PY
-import json
-d = json.load(open("gpurun_out/bench_e2e_wc$wc.json"))
-e = d["e2e"]
-print("wc=$wc e2e %.4g ms/step %.2f h2d %.2f GB/s checksum_ok %s" % (e["value"], e["ms_per_step"], e["h2d_gbs_per_gpu"], e["checksum_matches_device_path"]))
-PY
-done
+timeout 60 python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+timeout 40 python bench.py --model int8 --no-e2e --no-cpu --no-extra --steps 3 --warmup 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('int8 value %.4g ms %.2f nn %.2f' % (d['value'], d['ms_per_step'], d['kernels']['mixednet']['ms_per_step']))"
+timeout 30 python tools/live_time.py int8 40 2>&1 | tail -1
