@@ -197,14 +197,14 @@ int mww_timeline_read(mww_t *h, float *ms, int max_tiles, int *n_tiles);
 long long mww_launch_count(const mww_t *h);
 
 /* Stream-ordered device copy issued on the CALLER'S stream: cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, cu_stream).
- * Used by the multi-GPU ingest (microwakeword_b200/sharding.py::PeerAudio; the north_star's "scatter stream batches"):
+ * Used by the multi-GPU ingest (bench.py's pull-only probe and equality checks; the north_star's "scatter stream batches"):
  * `src` may be peer memory of another GPU of the box mapped through CUDA IPC, and because the stream belongs to the
  * DESTINATION device the transfer is a copy-engine pull inside the caller's own context -- no communication kernel and
  * no work in a second context on the source GPU.  The reference has no counterpart (it is single-process).
  * Returns 0 or a negative MWW_ECUDA; no handle is involved (the message goes to mww_last_error(NULL)). */
 int mww_copy_async(void *d_dst, const void *d_src, size_t bytes, void *cu_stream);
 
-/* CUDA IPC for the multi-GPU ingest buffer, opened in the CALLER'S device context (sharding.py::PeerAudio.allocate).
+/* CUDA IPC for the multi-GPU ingest buffer, opened in the CALLER'S device context (sharding.py::IngestBuffer).
  * mww_ipc_alloc: cudaMalloc on `device` + cudaIpcGetMemHandle (64 opaque bytes to hand to the other ranks of the box).
  * mww_ipc_open: cudaIpcOpenMemHandle(..., cudaIpcMemLazyEnablePeerAccess) with `device` (the OPENING rank's own GPU)
  * current, so the mapping lives in that rank's context and the rank never creates a context on the exporting GPU --
