@@ -30,6 +30,7 @@
 
 #include "mww_kernels.h"
 #include "mww_nn_tc.h"
+#include "mww_nn_tc_prep.h"
 
 namespace mww {
 
@@ -56,11 +57,7 @@ static_assert(2 * (kTcSmemBytes + 1024) <= 232448, "two CTAs per SM");
 static_assert(kFeatRows * kNumChannels * 2 <= 64 * kLdx * 4, "feature rows alias the activation buffer");
 static_assert(kOffA % 1024 == 0 && kOffB % 1024 == 0, "swizzled operand slots need 1024-byte alignment");
 
-// 128-byte-swizzled K-major slot: element (row, kk) with kk in [0, 32)
-__host__ __device__ inline uint32_t sw128_off(int row, int kk) {
-    return (uint32_t)row * 128u + (uint32_t)((((kk >> 2) ^ (row & 7)) << 4) + ((kk & 3) << 2));
-}
-
+// 128-byte-swizzled K-major slot: sw128_off(row, kk), mww_nn_tc_prep.h
 __device__ __forceinline__ void split_tf32f(float x, float &hi, float &lo) {
     hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
     lo = x - hi;
@@ -453,24 +450,6 @@ nn_f32_clip_tc_kernel(NnWeightsF32 W, TcWeights TW, float *__restrict__ state, f
 
 // 3xTF32 split and slot layout of one [K][N] weight matrix (the container's layout: input-major): slots of 32 K-values,
 // each [N rows][128 B] swizzled, hi plane then lo plane
-static void tc_layout(const float *w, int K, int N, std::vector<unsigned char> *out) {
-    const int slots = (K + 31) / 32, plane = N * 128;
-    out->assign((size_t)slots * 2 * plane, 0);
-    for (int k = 0; k < K; ++k)
-        for (int n = 0; n < N; ++n) {
-            const float v = w[(size_t)k * N + n];
-            uint32_t u;
-            memcpy(&u, &v, 4);
-            const uint32_t hu = u & 0xFFFFE000u;
-            float hi, lo;
-            memcpy(&hi, &hu, 4);
-            lo = v - hi;
-            unsigned char *slot = out->data() + (size_t)(k >> 5) * 2 * plane;
-            memcpy(slot + sw128_off(n, k & 31), &hi, 4);
-            memcpy(slot + plane + sw128_off(n, k & 31), &lo, 4);
-        }
-}
-
 void build_tc_weights(const float *w0 /* [200][32] */, const float *const pw[4] /* [cin][64] */, std::vector<unsigned char> *blob, size_t offsets[5]) {
     blob->clear();
     std::vector<unsigned char> part;

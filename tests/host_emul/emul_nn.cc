@@ -492,6 +492,17 @@ extern "C" void emul_feature_qlut(float in_scale, int zp_in, int8_t *out65536) {
     memcpy(out65536, t.data(), t.size());
 }
 
+// ---- tcgen05 clip kernel: operand layout (mww_nn_tc_prep.h) ------------------------------------------------------
+#include "../../microwakeword_b200/csrc/mww_nn_tc_prep.h"
+extern "C" unsigned emul_sw128_off(int row, int kk) { return sw128_off(row, kk); }
+// lays [K][N] weights out like mww_create does; returns the byte count (out may be NULL to query it)
+extern "C" long long emul_tc_layout(const float *w, int K, int N, unsigned char *out, long long cap) {
+    std::vector<unsigned char> blob;
+    tc_layout(w, K, N, &blob);
+    if (out && (long long)blob.size() <= cap) memcpy(out, blob.data(), blob.size());
+    return (long long)blob.size();
+}
+
 // ---- live-step int8 kernel (mww_nn_i8_live.cuh) -------------------------------------------------------------
 #include "../../microwakeword_b200/csrc/mww_nn_i8_live.cuh"
 namespace {

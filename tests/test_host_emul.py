@@ -200,6 +200,41 @@ def test_nn_int8_phases_bit_exact():
     assert np.array_equal(np.concatenate(parts, 1)[0], np.load(os.path.join(GOLDEN, "config0_probs_int8.npy")))
 
 
+def test_tcgen05_operand_layout_round_trips_and_is_a_swizzle_bijection():
+    """The tcgen05 clip kernel's shared-memory operand layout (mww_nn_tc_prep.h; GPU parity proves the kernel, this pins the
+    layout on the CPU): within a K-slot [rows][128 B] the swizzle permutes the eight 16-byte chunks of a row by (row & 7) --
+    a bijection onto the slot, a row stays 128 contiguous bytes (the conflict-free store the kernel relies on); the weight
+    planes read back through the same map give hi + lo == w exactly, hi is a TF32 (13 low mantissa bits clear), |lo| <= 2^-10 |w|,
+    and the tail of the last slot is zero."""
+    import ctypes
+    L = emul.lib()
+    L.emul_sw128_off.restype = ctypes.c_uint
+    L.emul_tc_layout.restype = ctypes.c_longlong
+    for rows in (32, 64, 128):
+        off = np.array([[L.emul_sw128_off(r, kk) for kk in range(32)] for r in range(rows)], np.int64)
+        assert np.array_equal(np.sort(off.ravel()), 4 * np.arange(rows * 32))                       # bijection onto the slot, 4-byte aligned
+        assert all(np.array_equal(np.sort(off[r]), r * 128 + 4 * np.arange(32)) for r in range(rows))   # a row = 128 contiguous bytes
+        chunk = (off % 128) // 16
+        assert np.array_equal(chunk, (np.arange(32)[None, :] // 4) ^ (np.arange(rows)[:, None] & 7))      # the hardware's 128-byte XOR swizzle
+    rng = np.random.default_rng(3)
+    for K, N in ((200, 32), (32, 64), (64, 64)):
+        w = (rng.standard_normal((K, N)) * rng.choice([1e-3, 1.0, 50.0], (K, N))).astype(np.float32)
+        n = L.emul_tc_layout(w.ctypes.data_as(ctypes.c_void_p), K, N, None, 0)
+        slots, plane = (K + 31) // 32, N * 128
+        assert n == slots * 2 * plane
+        blob = np.zeros(n, np.uint8)
+        L.emul_tc_layout(w.ctypes.data_as(ctypes.c_void_p), K, N, blob.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(n))
+        f = blob.view(np.float32)
+        hi, lo = np.zeros((slots * 32, N), np.float32), np.zeros((slots * 32, N), np.float32)
+        for k in range(slots * 32):
+            for col in range(N):
+                o = (k // 32) * 2 * plane + L.emul_sw128_off(col, k % 32)
+                hi[k, col], lo[k, col] = f[o // 4], f[(o + plane) // 4]
+        assert np.array_equal(hi[:K] + lo[:K], w) and not hi[K:].any() and not lo[K:].any()
+        assert not (hi.view(np.uint32) & 0x1FFF).any()
+        assert (np.abs(lo[:K]) <= np.abs(w) * 2.0 ** -10).all()
+
+
 def test_feature_quantisation_table_is_the_reference_expression_for_every_uint16():
     """NnWeightsI8::qlut (built by mww_create and by the emulation with build_feature_qlut): every one of the 65 536 possible
     uint16 features maps to what Model.quantize_input_data computes for feature * 0.0390625 (inference.py:93-94, 127-147)."""
