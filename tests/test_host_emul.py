@@ -306,6 +306,14 @@ def test_live_step_kernel_phases_match_oracle_and_interleave_with_clip():
             assert np.array_equal(pa, b.step(rows_all[:, pos:pos + 3])) and np.array_equal(pa, c.step(rows_all[:, pos:pos + 3]))
         assert np.array_equal(a.state, b.state) and np.array_equal(a.pend, b.pend)
         assert np.array_equal(a.state, c.state) and np.array_equal(a.pend, c.pend)
+    # group-size edge cases: a single stream, one stream more than a full group
+    for S2 in (1, 33):
+        a, c = emul.NnF32Live(t, S2, version=1), emul.NnF32Live(t, S2, version=3, order=1)
+        for e in (a, c):
+            e.infer(feats[:S2, :4])
+        for pos in range(4, 4 + 24, 3):
+            assert np.array_equal(a.step(feats[:S2, pos:pos + 3]), c.step(feats[:S2, pos:pos + 3])), (S2, pos)
+        assert np.array_equal(a.state, c.state) and np.array_equal(a.pend, c.pend)
 
 
 def test_int8_live_step_kernel_phases_are_bit_exact():
